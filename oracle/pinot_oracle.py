@@ -1,0 +1,276 @@
+"""ctypes binding of the CPU parity oracle -- TEST INFRASTRUCTURE ONLY (see oracle/pinot_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from pinot_b200.query import Filter, Predicate, QueryContext, postfix
+
+from . import segment_builder as sb
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libpinot_oracle.so")
+
+_TYPE_CODES = {"AND": 0, "OR": 1, "NOT": 2, "EQ": 3, "NEQ": 4, "IN": 5, "NOT_IN": 6, "RANGE": 7}
+_FN_CODES = {"COUNT": 0, "SUM": 1, "MIN": 2, "MAX": 3, "AVG": 4, "DISTINCTCOUNT": 5}
+REGIMES = {0: "NONE", 1: "ARRAY", 2: "INT_MAP", 3: "LONG_MAP", 4: "ARRAY_MAP"}
+
+
+class _Column(C.Structure):
+    _fields_ = [("data_type", C.c_int32), ("has_dictionary", C.c_int32), ("bits_per_value", C.c_int32),
+                ("cardinality", C.c_int32), ("is_sorted", C.c_int32), ("dict_entry_bytes", C.c_int32),
+                ("fwd", C.c_void_p), ("fwd_len", C.c_int64), ("dict", C.c_void_p), ("dict_len", C.c_int64),
+                ("inv", C.c_void_p), ("inv_len", C.c_int64)]
+
+
+class _Segment(C.Structure):
+    _fields_ = [("num_docs", C.c_int32), ("num_columns", C.c_int32), ("columns", C.POINTER(_Column))]
+
+
+class _Literal(C.Structure):
+    _fields_ = [("i", C.c_int64), ("d", C.c_double), ("s", C.c_char_p)]
+
+
+class _FilterNode(C.Structure):
+    _fields_ = [("type", C.c_int32), ("column", C.c_int32), ("num_children", C.c_int32),
+                ("lower_inclusive", C.c_int32), ("upper_inclusive", C.c_int32), ("lower_unbounded", C.c_int32),
+                ("upper_unbounded", C.c_int32), ("num_values", C.c_int32), ("values_offset", C.c_int32)]
+
+
+class _Agg(C.Structure):
+    _fields_ = [("function", C.c_int32), ("column", C.c_int32)]
+
+
+class _Query(C.Structure):
+    _fields_ = [("num_filter_nodes", C.c_int32), ("filter", C.POINTER(_FilterNode)), ("literals", C.POINTER(_Literal)),
+                ("num_group_by", C.c_int32), ("group_by_columns", C.POINTER(C.c_int32)), ("num_aggs", C.c_int32),
+                ("aggs", C.POINTER(_Agg)), ("num_groups_limit", C.c_int32),
+                ("max_initial_result_holder_capacity", C.c_int32), ("and_scan_reordering", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    """Compiles oracle/_build/libpinot_oracle.so with the committed Makefile (g++)."""
+    src = os.path.join(_HERE, "pinot_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "pinot_oracle.h"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class OracleResult:
+    """One segment's results block (AggregationResultsBlock / GroupByResultsBlock + ExecutionStatistics)."""
+    num_groups: int  # -1 = aggregation only
+    regime: str
+    groups_limit_reached: bool
+    stats: Tuple[int, int, int, int]  # docsScanned, entriesInFilter, entriesPostFilter, totalDocs
+    keys: np.ndarray  # [G, k] dictIds
+    doubles: List[np.ndarray]  # per aggregation [G or 1]
+    longs: List[np.ndarray]
+    distinct: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)  # (agg, group) -> sorted dictIds
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(build())
+        L = self.lib
+        L.po_execute.restype = C.c_void_p
+        L.po_execute.argtypes = [C.POINTER(_Segment), C.POINTER(_Query)]
+        L.po_result_error.restype = C.c_char_p
+        L.po_result_error.argtypes = [C.c_void_p]
+        for f in ("po_result_num_groups", "po_result_regime", "po_result_groups_limit_reached"):
+            getattr(L, f).restype = C.c_int32
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.po_result_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.po_result_group_keys.argtypes = [C.c_void_p, C.c_void_p]
+        L.po_result_agg_double.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.po_result_agg_long.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.po_result_distinct.restype = C.c_int64
+        L.po_result_distinct.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+        L.po_result_free.argtypes = [C.c_void_p]
+        L.po_filter_doc_ids.restype = C.c_int64
+        L.po_filter_doc_ids.argtypes = [C.POINTER(_Segment), C.POINTER(_Query), C.c_void_p, C.c_int64,
+                                        C.POINTER(C.c_int64)]
+        L.po_num_bits_per_value.restype = C.c_int32
+        L.po_bitset_write.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p]
+        L.po_bitset_read.restype = C.c_int32
+        L.po_bitset_read.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
+        L.po_fixedbit_read_unchecked.restype = C.c_int32
+        L.po_fixedbit_read_unchecked.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
+        L.po_fixedbit_read32.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+        L.po_fwd_read_dict_ids.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.po_roaring_serialize.restype = C.c_int64
+        L.po_roaring_serialize.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64]
+        L.po_roaring_deserialize.restype = C.c_int64
+        L.po_roaring_deserialize.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.po_inverted_index_build.restype = C.c_int64
+        L.po_inverted_index_build.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+
+    # ---------------------------------------------------------------- formats
+    def bitset_write(self, values: np.ndarray, bits: int) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.int32)
+        out = np.zeros((len(v) * bits + 7) // 8, dtype=np.uint8)
+        self.lib.po_bitset_write(_ptr(out), 0, bits, len(v), _ptr(v))
+        return out
+
+    def bitset_read(self, buf: np.ndarray, index: int, bits: int) -> int:
+        return self.lib.po_bitset_read(_ptr(buf), index, bits)
+
+    def read_unchecked(self, buf: np.ndarray, index: int, bits: int) -> int:
+        return self.lib.po_fixedbit_read_unchecked(_ptr(buf), index, bits)
+
+    def read32(self, buf: np.ndarray, index: int, bits: int) -> np.ndarray:
+        out = np.zeros(32, dtype=np.int32)
+        self.lib.po_fixedbit_read32(_ptr(buf), index, bits, _ptr(out))
+        return out
+
+    def read_dict_ids(self, buf: np.ndarray, num_docs: int, bits: int, doc_ids: np.ndarray) -> np.ndarray:
+        d = np.ascontiguousarray(doc_ids, dtype=np.int32)
+        out = np.zeros(len(d), dtype=np.int32)
+        self.lib.po_fwd_read_dict_ids(_ptr(buf), num_docs, bits, _ptr(d), len(d), _ptr(out))
+        return out
+
+    def roaring_serialize(self, values: np.ndarray, run_optimize: bool = True) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.uint32)
+        n = self.lib.po_roaring_serialize(_ptr(v), len(v), int(run_optimize), None, 0)
+        out = np.zeros(n, dtype=np.uint8)
+        self.lib.po_roaring_serialize(_ptr(v), len(v), int(run_optimize), _ptr(out), n)
+        return out
+
+    def roaring_deserialize(self, buf: np.ndarray) -> np.ndarray:
+        b = np.ascontiguousarray(buf, dtype=np.uint8)
+        n = self.lib.po_roaring_deserialize(_ptr(b), len(b), None, 0)
+        if n < 0:
+            raise ValueError("malformed roaring bitmap")
+        out = np.zeros(n, dtype=np.uint32)
+        self.lib.po_roaring_deserialize(_ptr(b), len(b), _ptr(out), n)
+        return out
+
+    def inverted_index_build(self, dict_ids: np.ndarray, cardinality: int) -> np.ndarray:
+        d = np.ascontiguousarray(dict_ids, dtype=np.int32)
+        n = self.lib.po_inverted_index_build(_ptr(d), len(d), cardinality, None, 0)
+        out = np.zeros(n, dtype=np.uint8)
+        self.lib.po_inverted_index_build(_ptr(d), len(d), cardinality, _ptr(out), n)
+        return out
+
+    # ---------------------------------------------------------------- segments / queries
+    def build_segment(self, name, columns, inverted=(), raw=()) -> sb.SegmentData:
+        return sb.build_segment(name, columns, inverted=inverted, raw=raw, lib=self)
+
+    @staticmethod
+    def _c_segment(seg: sb.SegmentData):
+        cols = (_Column * len(seg.columns))()
+        for i, c in enumerate(seg.columns):
+            cols[i] = _Column(c.data_type, int(c.has_dictionary), c.bits, c.cardinality, int(c.is_sorted),
+                              c.dict_entry_bytes, _ptr(c.fwd), len(c.fwd), _ptr(c.dict),
+                              0 if c.dict is None else len(c.dict), _ptr(c.inv), 0 if c.inv is None else len(c.inv))
+        return _Segment(seg.num_docs, len(seg.columns), cols), cols
+
+    @staticmethod
+    def _c_query(seg: sb.SegmentData, q: QueryContext):
+        nodes = postfix(q.filter)
+        lits: List[_Literal] = []
+        keep = []  # keep byte strings alive
+
+        def lit(col: sb.ColumnData, v):
+            if col.data_type == sb.STRING:
+                b = v.encode("utf-8") if isinstance(v, str) else bytes(v)
+                keep.append(b)
+                return _Literal(0, 0.0, b)
+            if col.data_type in (sb.INT, sb.LONG):
+                # NumericalFilterOptimizer semantics are the caller's business; tests use integral literals here
+                return _Literal(int(v), float(v), None)
+            return _Literal(0, float(v), None)
+
+        c_nodes = (_FilterNode * max(1, len(nodes)))()
+        for i, n in enumerate(nodes):
+            if isinstance(n, Filter):
+                c_nodes[i] = _FilterNode(_TYPE_CODES[n.type], -1, len(n.children), 0, 0, 0, 0, 0, 0)
+                continue
+            ci = seg.column_index(n.column)
+            col = seg.columns[ci]
+            off = len(lits)
+            if n.type == "RANGE":
+                lits.append(lit(col, n.lower if n.lower is not None else 0))
+                lits.append(lit(col, n.upper if n.upper is not None else 0))
+                c_nodes[i] = _FilterNode(_TYPE_CODES["RANGE"], ci, 0, int(n.lower_inclusive), int(n.upper_inclusive),
+                                         int(n.lower is None), int(n.upper is None), 2, off)
+            else:
+                for v in n.values:
+                    lits.append(lit(col, v))
+                c_nodes[i] = _FilterNode(_TYPE_CODES[n.type], ci, 0, 0, 0, 0, 0, len(n.values), off)
+        c_lits = (_Literal * max(1, len(lits)))(*lits)
+        gb = (C.c_int32 * max(1, len(q.group_by)))(*[seg.column_index(c) for c in q.group_by])
+        aggs = (_Agg * max(1, len(q.aggregations)))()
+        for i, a in enumerate(q.aggregations):
+            aggs[i] = _Agg(_FN_CODES[a.function], -1 if a.column is None else seg.column_index(a.column))
+        cq = _Query(len(nodes), c_nodes, c_lits, len(q.group_by), gb, len(q.aggregations), aggs, q.num_groups_limit,
+                    q.max_initial_result_holder_capacity, int(q.and_scan_reordering))
+        return cq, (c_nodes, c_lits, gb, aggs, keep)
+
+    def execute(self, seg: sb.SegmentData, q: QueryContext) -> OracleResult:
+        """== getOperator(query).nextBlock() on one segment (BaseQueriesTest.java:97-102)."""
+        cseg, _k1 = self._c_segment(seg)
+        cq, _k2 = self._c_query(seg, q)
+        r = self.lib.po_execute(C.byref(cseg), C.byref(cq))
+        try:
+            err = self.lib.po_result_error(r)
+            if err:
+                raise RuntimeError(err.decode())
+            g = self.lib.po_result_num_groups(r)
+            rows = 1 if g < 0 else g
+            stats = (C.c_int64 * 4)()
+            self.lib.po_result_stats(r, stats)
+            k = len(q.group_by)
+            keys = np.zeros((max(g, 0), k), dtype=np.int32)
+            if g > 0 and k > 0:
+                self.lib.po_result_group_keys(r, _ptr(keys))
+            doubles, longs, distinct = [], [], {}
+            for a, agg in enumerate(q.aggregations):
+                d = np.zeros(rows, dtype=np.float64)
+                l = np.zeros(rows, dtype=np.int64)
+                if rows:
+                    self.lib.po_result_agg_double(r, a, _ptr(d))
+                    self.lib.po_result_agg_long(r, a, _ptr(l))
+                doubles.append(d)
+                longs.append(l)
+                if agg.function == "DISTINCTCOUNT":
+                    for grp in range(rows):
+                        ids = np.zeros(int(l[grp]), dtype=np.int32)
+                        self.lib.po_result_distinct(r, a, grp, _ptr(ids), len(ids))
+                        distinct[(a, grp)] = ids
+            return OracleResult(g, REGIMES[self.lib.po_result_regime(r)],
+                                bool(self.lib.po_result_groups_limit_reached(r)), tuple(stats), keys, doubles, longs,
+                                distinct)
+        finally:
+            self.lib.po_result_free(r)
+
+    def filter_doc_ids(self, seg: sb.SegmentData, q: QueryContext):
+        cseg, _k1 = self._c_segment(seg)
+        cq, _k2 = self._c_query(seg, q)
+        out = np.zeros(seg.num_docs, dtype=np.int32)
+        entries = C.c_int64(0)
+        n = self.lib.po_filter_doc_ids(C.byref(cseg), C.byref(cq), _ptr(out), len(out), C.byref(entries))
+        return out[:n].copy(), int(entries.value)
+
+
+_ORACLE: Optional[Oracle] = None
+
+
+def oracle() -> Oracle:
+    global _ORACLE
+    if _ORACLE is None:
+        _ORACLE = Oracle()
+    return _ORACLE
