@@ -1,0 +1,235 @@
+/*
+ * pinot_b200.h -- C-ABI of libpinot_b200.so: the B200-native implementation of Apache Pinot's per-segment
+ * scan -> filter -> project -> (group-by) aggregate operator chain.
+ *
+ * This is the drop-in boundary.  In the reference the path is entered through the plan-maker plugin seam
+ *   PlanMaker.makeSegmentPlanNode(SegmentContext, QueryContext)
+ *     (pinot-core/src/main/java/org/apache/pinot/core/plan/maker/PlanMaker.java:37-67, selected with
+ *      pinot.server.query.executor.plan.maker.class, pinot-spi/.../utils/CommonConstants.java:690-691)
+ * and the operator it returns is driven by  Operator.nextBlock()
+ *     (core/operator/BaseOperator.java:39-50; called once per segment from
+ *      core/operator/combine/BaseSingleBlockCombineOperator.java:85-108).
+ * A Java `B200PlanMaker` (java/ in this repo, binding shown in INTEGRATION.md) keeps doing everything that is
+ * dictionary / SQL / object work on the JVM side -- value -> dictId resolution with Pinot's own PredicateEvaluators,
+ * filter-operator selection, result-block construction -- and calls the functions below through a thin JNI layer.
+ * Everything crossing this boundary is plain pointers, sizes and fixed-width integers: no JNI, torch or C++ types.
+ *
+ * Conventions
+ *  - every function returns 0 (PB200_OK) or a negative PB200_E_* code; pb200_last_error() gives the message of the
+ *    calling thread's last failure.  No exceptions or longjmp cross the boundary.
+ *  - thread safety: a pb200_ctx may be shared by any number of threads (Pinot runs one operator per worker thread,
+ *    concurrently for many queries); pb200_segment handles are immutable after registration; pb200_result handles
+ *    belong to the caller that received them.
+ *  - ownership: index buffers passed to pb200_segment_register stay owned by the caller and are only read during the
+ *    call (they are copied into 256-byte aligned HBM allocations; PinotDataBuffer.toDirectByteBuffer memory may be
+ *    unmapped afterwards -- pinot-segment-spi/.../memory/PinotDataBuffer.java:632-654).
+ */
+#ifndef PINOT_B200_H_
+#define PINOT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_ABI_VERSION 1
+
+enum {
+  PB200_OK = 0,
+  PB200_E_INVALID = -1,     /* bad argument / malformed index bytes */
+  PB200_E_UNSUPPORTED = -2, /* query shape outside the accelerated set: caller falls back to the Java operator */
+  PB200_E_CUDA = -3,        /* CUDA runtime failure (message has the cudaError string) */
+  PB200_E_NOMEM = -4,
+  PB200_E_LIMIT = -5        /* numGroupsLimit would bind (first-seen order semantics): fall back */
+};
+
+typedef struct pb200_ctx pb200_ctx;
+typedef struct pb200_segment pb200_segment;
+typedef struct pb200_result pb200_result;
+
+/* ---- context ------------------------------------------------------------------------------------------------- */
+/* One context per (process, GPU).  `device` is the CUDA ordinal. Replaces nothing in the reference (there is no device
+ * in it); lifetime == the server's QueryExecutor (ServerQueryExecutorV1Impl.init/shutDown :104-139). */
+int32_t pb200_init(int32_t device, pb200_ctx** ctx);
+int32_t pb200_shutdown(pb200_ctx* ctx);
+const char* pb200_last_error(void);
+int32_t pb200_abi_version(void);
+/* Device facts for the caller's bookkeeping: {sm_count, major, minor, total_mem_mb, free_mem_mb}. */
+int32_t pb200_device_info(pb200_ctx* ctx, int64_t out[5]);
+
+/* ---- segments ------------------------------------------------------------------------------------------------ */
+/* Stored types (FieldSpec.DataType.getStoredType()). */
+enum { PB200_INT = 0, PB200_LONG = 1, PB200_FLOAT = 2, PB200_DOUBLE = 3, PB200_STRING = 4 };
+
+/* Forward-index kinds (ForwardIndexReaderFactory.createIndexReader dispatch,
+ * pinot-segment-local/.../segment/index/forward/ForwardIndexReaderFactory.java:74-91). */
+enum {
+  PB200_FWD_DICT_FIXEDBIT = 0, /* FixedBitSVForwardIndexReaderV2: MSB-first big-endian bit stream of dictIds */
+  PB200_FWD_DICT_SORTED = 1,   /* SortedIndexReaderImpl: (startDocId, endDocId) BE int pairs per dictId */
+  PB200_FWD_RAW_FIXEDBYTE = 2  /* FixedByteChunkSVForwardIndexReader, PASS_THROUGH chunks (file incl. header) */
+};
+
+#define PB200_COL_DEVICE_BUFFERS 1 /* flags: fwd/dict/inv already are device pointers in the layout below (adopted,
+                                      not copied, not freed) -- used by the synthetic segment generator */
+
+typedef struct {
+  int32_t fwd_kind;       /* PB200_FWD_* */
+  int32_t stored_type;    /* PB200_INT ... ; STRING dictionaries stay on the host (keys are dictIds on device) */
+  int32_t bits_per_value; /* column.<c>.bitsPerElement (V1Constants.MetadataKeys.Column.BITS_PER_ELEMENT) */
+  int32_t cardinality;    /* column.<c>.cardinality == Dictionary.length() */
+  int32_t flags;
+  int32_t reserved;
+  const void* fwd;        /* forward index bytes exactly as in columns.psf / <col>.sv.unsorted.fwd */
+  uint64_t fwd_bytes;
+  const void* dict;       /* fixed-width BIG-endian sorted dictionary (<col>.dict without its 8-byte-less header: the
+                             raw value array, cardinality * width bytes); NULL for STRING or no dictionary */
+  uint64_t dict_bytes;
+  const void* inv;        /* bitmap inverted index file (<col>.bitmap.inv) or NULL:
+                             BitmapInvertedIndexWriter layout, seglocal/.../inv/BitmapInvertedIndexWriter.java:33-50 */
+  uint64_t inv_bytes;
+} pb200_col_desc;
+
+/* Uploads the listed columns of one immutable segment into HBM (once, at segment load: the analogue of
+ * ImmutableSegmentLoader.load + PhysicalColumnIndexContainer; evict with pb200_segment_release from
+ * IndexSegment.destroy()).  Column order defines the column ids used in queries. */
+int32_t pb200_segment_register(pb200_ctx* ctx, const char* segment_name, int32_t num_docs, int32_t num_columns,
+                               const pb200_col_desc* columns, pb200_segment** segment);
+int32_t pb200_segment_release(pb200_ctx* ctx, pb200_segment* segment);
+/* Bytes of HBM held by the segment. */
+int64_t pb200_segment_device_bytes(const pb200_segment* segment);
+
+/* ---- query (dictId space) ------------------------------------------------------------------------------------ */
+/* Filter tree in POSTFIX order (children before parent, root last), per SEGMENT because dictIds are segment local.
+ * Leaves are what the reference's leaf filter operators consume AFTER PredicateEvaluator construction
+ * (core/operator/filter/FilterOperatorUtils.java:74-133):                                                          */
+enum {
+  PB200_F_AND = 0,         /* AndFilterOperator      -- num_children operands */
+  PB200_F_OR = 1,          /* OrFilterOperator */
+  PB200_F_NOT = 2,         /* NotFilterOperator      -- 1 operand */
+  PB200_F_MATCH_ALL = 3,   /* MatchAllFilterOperator */
+  PB200_F_EMPTY = 4,       /* EmptyFilterOperator */
+  PB200_F_SCAN_RANGE = 5,  /* ScanBasedFilterOperator + SortedDictionaryBasedRangePredicateEvaluator:
+                              dictId in [lo, hi)  (RangePredicateEvaluatorFactory.java:220-222) */
+  PB200_F_SCAN_IN = 6,     /* ScanBasedFilterOperator + EQ/IN evaluator: dictId in ids[] */
+  PB200_F_SCAN_NOT_IN = 7, /* ... NEQ/NOT_IN: dictId not in ids[] */
+  PB200_F_INV_IN = 8,      /* InvertedIndexFilterOperator: OR of the bitmaps of ids[] (InvertedIndexFilterOperator.java
+                              :60-96); column must have been registered with an inverted index */
+  PB200_F_INV_NOT_IN = 9,  /* ... flipped over [0, numDocs) */
+  PB200_F_DOC_RANGES = 10, /* SortedIndexBasedFilterOperator: ids[] holds num_ids/2 inclusive (start,end) docId pairs */
+  PB200_F_RAW_RANGE = 11   /* scan of a raw INT/LONG/FLOAT/DOUBLE column: raw_lo <= v <= raw_hi with the flags below */
+};
+
+typedef struct {
+  int32_t op;           /* PB200_F_* */
+  int32_t column;       /* leaf: column id (index into the columns given at registration) */
+  int32_t num_children; /* AND / OR */
+  int32_t lo, hi;       /* SCAN_RANGE: [lo, hi) in dictId space */
+  int32_t num_ids;
+  const int32_t* ids;   /* host pointer; sorted ascending */
+  double raw_lo, raw_hi;
+  int32_t raw_flags;    /* bit0 lower unbounded, bit1 upper unbounded, bit2 lower exclusive, bit3 upper exclusive */
+  int32_t reserved;
+} pb200_filter_node;
+
+/* Aggregation functions accelerated on this path (core/query/aggregation/function/{Count,Sum,Min,Max,Avg,
+ * DistinctCount}AggregationFunction.java). */
+enum { PB200_AGG_COUNT = 0, PB200_AGG_SUM = 1, PB200_AGG_MIN = 2, PB200_AGG_MAX = 3, PB200_AGG_AVG = 4,
+       PB200_AGG_DISTINCTCOUNT = 5 };
+
+typedef struct {
+  int32_t function; /* PB200_AGG_* */
+  int32_t column;   /* -1 for COUNT(*) */
+} pb200_agg;
+
+typedef struct {
+  int32_t num_filter_nodes; /* 0 = match all */
+  int32_t num_group_by;
+  int32_t num_aggs;
+  int32_t num_groups_limit;                   /* QueryContext.getNumGroupsLimit(), default 100000 */
+  int32_t max_initial_result_holder_capacity; /* default 10000; selects the ARRAY regime like
+                                                 DictionaryBasedGroupKeyGenerator.java:150-185 */
+  int32_t flags;
+  const pb200_filter_node* filter;            /* per segment: num_segments * num_filter_nodes entries when
+                                                 PB200_Q_PER_SEGMENT_FILTER is set, else shared by all segments */
+  const int32_t* group_by_columns;
+  const pb200_agg* aggs;
+} pb200_query;
+
+#define PB200_Q_PER_SEGMENT_FILTER 1 /* filter[] holds one tree per segment (segment-local dictIds) */
+#define PB200_Q_MERGE_SEGMENTS 2     /* all segments share dictionaries: accumulate into ONE result (device-side
+                                        combine, the GroupByCombineOperator/AggregationCombineOperator analogue) */
+
+/* Runs the operator chain DocIdSet -> Projection -> Aggregation/GroupBy for `num_segments` segments in one device
+ * submission (one persistent kernel over all segments' tiles).  Writes num_segments result handles (or exactly one
+ * with PB200_Q_MERGE_SEGMENTS).  == Operator.nextBlock() of GroupByOperator / AggregationOperator
+ * (core/operator/query/GroupByOperator.java:101-140, AggregationOperator.java:64-80). */
+int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200_segment* const* segments,
+                      int32_t num_segments, pb200_result** results);
+
+/* ---- results (the data a GroupByResultsBlock / AggregationResultsBlock is built from) ---------------------------- */
+enum { PB200_REGIME_NONE = 0, PB200_REGIME_ARRAY = 1, PB200_REGIME_INT_MAP = 2, PB200_REGIME_LONG_MAP = 3,
+       PB200_REGIME_ARRAY_MAP = 4 };
+
+typedef struct {
+  int32_t num_groups;          /* -1: aggregation only (one row) */
+  int32_t num_group_by;
+  int32_t num_aggs;
+  int32_t regime;              /* which key-holder regime the reference would have used (informational) */
+  int32_t groups_limit_reached;
+  int32_t reserved;
+  /* ExecutionStatistics (core/operator/ExecutionStatistics.java) */
+  int64_t num_docs_scanned;
+  int64_t num_entries_scanned_in_filter; /* see DESIGN.md: device semantics = docs x scan leaves evaluated */
+  int64_t num_entries_scanned_post_filter;
+  int64_t num_total_docs;
+  double device_ms;            /* CUDA-event time of the scan kernel(s) of this pb200_execute call */
+} pb200_result_meta;
+
+int32_t pb200_result_meta_get(const pb200_result* result, pb200_result_meta* meta);
+/* group keys as dictIds, group-major [num_groups x num_group_by] (dictId -> value via Dictionary.getInternal on the
+ * caller's side, as DictionaryBasedGroupKeyGenerator.getKeys does :577-605) */
+int32_t pb200_result_group_keys(const pb200_result* result, int32_t* out);
+/* aggregation `agg`: per group (or 1 row) the double intermediate (SUM, MIN, MAX, AVG's sum, COUNT as double) and the
+ * long intermediate (COUNT, AVG's count, DISTINCTCOUNT's set size).  MIN/MAX of an empty input are +inf/-inf. */
+int32_t pb200_result_agg(const pb200_result* result, int32_t agg, double* out_double, int64_t* out_long);
+/* MIN/MAX as dictIds (dict-encoded columns; -1 when empty), for exact value lookup on the caller's side */
+int32_t pb200_result_agg_dict_ids(const pb200_result* result, int32_t agg, int32_t* out);
+/* DISTINCTCOUNT: the dictId set of row `row` (ascending); returns the count (or < 0 on error), writes <= capacity */
+int64_t pb200_result_distinct(const pb200_result* result, int32_t agg, int32_t row, int32_t* out, int64_t capacity);
+int32_t pb200_result_free(pb200_result* result);
+
+/* ---- multi-GPU combine support (dense group tables with shared dictionaries) ----------------------------------- */
+/* Device pointers + element counts of the dense accumulator arrays of a merged group-by result, so that the caller's
+ * collective layer (torch.distributed / NCCL) can all-reduce them in place across ranks:
+ *   kind 0: int64 sums/counts (reduce SUM)   kind 1: double sums (SUM)   kind 2: uint32 max-encoded (reduce MAX)
+ * After the collective, pb200_result_finalize() re-extracts the groups on the root rank. */
+int32_t pb200_result_device_buffers(pb200_result* result, int32_t kind, void** device_ptr, int64_t* num_elements);
+int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* result);
+
+/* ---- synthetic segments (SegmentIndexCreationDriverImpl stand-in for benchmarks; bytes are Pinot's formats) ---- */
+typedef struct {
+  int32_t cardinality;   /* dictionary = { value_base + value_step * i } (sorted INT) */
+  int32_t value_base;
+  int32_t value_step;
+  int32_t with_inverted; /* build the bitmap inverted index on the device too */
+  uint64_t seed;         /* dictId(doc) = mix64(seed, doc) % cardinality */
+} pb200_synth_col;
+
+/* Generates `num_columns` dict-encoded INT columns of `num_docs` rows directly in HBM, byte-identical to what
+ * FixedBitSVForwardIndexWriter / SegmentDictionaryCreator would have written for the same values, and registers them
+ * as a segment. */
+int32_t pb200_synth_segment(pb200_ctx* ctx, const char* segment_name, int32_t num_docs, int32_t num_columns,
+                            const pb200_synth_col* columns, pb200_segment** segment);
+/* Copies a column's index bytes back to the host (tests: compare against the oracle's writer; bench: host-resident
+ * copy for the end-to-end arm).  which: 0 fwd, 1 dict, 2 inv.  Returns bytes (or needed size when out == NULL). */
+int64_t pb200_segment_read_index(pb200_ctx* ctx, const pb200_segment* segment, int32_t column, int32_t which,
+                                 void* out, uint64_t capacity);
+/* Column facts of a registered segment: {fwd_kind, stored_type, bits, cardinality, has_inverted, fwd_bytes}. */
+int32_t pb200_segment_column_info(const pb200_segment* segment, int32_t column, int64_t out[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINOT_B200_H_ */

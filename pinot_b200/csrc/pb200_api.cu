@@ -1,0 +1,1068 @@
+// pb200_api.cu -- C-ABI implementation: context, segment residency, query planning and launch, result extraction.
+//
+// Host logic here is the device-facing half of what the reference does between PlanNode.run() and nextBlock():
+// choosing what to stream (ProjectPlanNode's column set, core/plan/ProjectPlanNode.java), laying out the group-key
+// space (DictionaryBasedGroupKeyGenerator.java:105-186) and extracting results (GroupByOperator.java:116-140,
+// AggregationFunction.extractAggregationResult).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+
+#include "pb200_internal.h"
+#include "pb200_scan.cuh"
+
+namespace pb200 {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof g_error, fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// caching allocator + stream pool
+// ------------------------------------------------------------------------------------------------------------------
+static size_t round_block(size_t b) {
+  size_t r = 512;
+  while (r < b) r <<= 1;
+  return b > (64u << 20) ? ((b + (2u << 20) - 1) / (2u << 20)) * (2u << 20) : r;
+}
+
+int dev_alloc(pb200_ctx* ctx, size_t bytes, void** out) {
+  size_t rb = round_block(bytes ? bytes : 1);
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    auto it = ctx->free_blocks.find(rb);
+    if (it != ctx->free_blocks.end()) {
+      *out = it->second;
+      ctx->free_blocks.erase(it);
+      return PB200_OK;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, rb);
+  if (e != cudaSuccess) {
+    // drop the cache and retry once
+    {
+      std::lock_guard<std::mutex> g(ctx->mu);
+      for (auto& kv : ctx->free_blocks) { cudaFree(kv.second); ctx->block_size.erase(kv.second); }
+      ctx->free_blocks.clear();
+    }
+    cudaGetLastError();
+    e = cudaMalloc(&p, rb);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", rb, cudaGetErrorString(e));
+      cudaGetLastError();
+      return PB200_E_NOMEM;
+    }
+  }
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->block_size[p] = rb;
+  *out = p;
+  return PB200_OK;
+}
+
+void dev_free(pb200_ctx* ctx, void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  auto it = ctx->block_size.find(p);
+  if (it == ctx->block_size.end()) return;
+  if (it->second > (2048ull << 20)) {  // do not hoard very large blocks
+    cudaFree(p);
+    ctx->block_size.erase(it);
+    return;
+  }
+  ctx->free_blocks.emplace(it->second, p);
+}
+
+cudaStream_t take_stream(pb200_ctx* ctx) {
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->free_streams.empty()) {
+      cudaStream_t s = ctx->free_streams.back();
+      ctx->free_streams.pop_back();
+      return s;
+    }
+  }
+  cudaStream_t s = nullptr;
+  cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  return s;
+}
+void give_stream(pb200_ctx* ctx, cudaStream_t s) {
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->free_streams.push_back(s);
+}
+
+struct DevBuf {  // RAII pooled device buffer
+  pb200_ctx* ctx = nullptr;
+  void* p = nullptr;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { dev_free(ctx, p); }
+  int alloc(pb200_ctx* c, size_t bytes) { ctx = c; return dev_alloc(c, bytes, &p); }
+  void* release() { void* r = p; p = nullptr; return r; }
+};
+
+static inline uint32_t be32(const unsigned char* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
+static inline uint64_t be64(const unsigned char* p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
+
+static uint64_t padded_fwd_bytes(long long num_docs, int bits) {
+  long long tiles = (num_docs + kMaxTileRows - 1) / kMaxTileRows;
+  if (tiles == 0) tiles = 1;
+  return (uint64_t)tiles * kMaxTileRows / 8 * bits + 64;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// compaction of a dense group table: indices of non-empty groups (any order)
+__global__ void compact_groups_kernel(const unsigned long long* __restrict__ count, long long groups,
+                                      unsigned long long* __restrict__ n_out, uint32_t* __restrict__ idx_out,
+                                      long long cap) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i < groups; i += (long long)gridDim.x * blockDim.x) {
+    if (count[i] != 0ull) {
+      unsigned long long pos = atomicAdd(n_out, 1ull);
+      if ((long long)pos < cap) idx_out[pos] = (uint32_t)i;
+    }
+  }
+}
+template <typename T>
+__global__ void gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, long long n, T* __restrict__ dst) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+// ------------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" const char* pb200_last_error(void) { return g_error; }
+extern "C" int32_t pb200_abi_version(void) { return PB200_ABI_VERSION; }
+
+extern "C" int32_t pb200_init(int32_t device, pb200_ctx** out) {
+  if (!out) { set_error("ctx out pointer is NULL"); return PB200_E_INVALID; }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s): libpinot_b200 has no CPU fallback", cudaGetErrorString(e));
+    cudaGetLastError();
+    return PB200_E_CUDA;
+  }
+  if (device < 0 || device >= n) { set_error("device %d out of range [0,%d)", device, n); return PB200_E_INVALID; }
+  PB200_CUDA(cudaSetDevice(device));
+  auto* ctx = new pb200_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  PB200_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (prop.major < 9) {
+    set_error("device sm_%d%d: this library is built for sm_100a (TMA bulk copies + mbarrier)", prop.major, prop.minor);
+    delete ctx;
+    return PB200_E_UNSUPPORTED;
+  }
+  *out = ctx;
+  return PB200_OK;
+}
+
+extern "C" int32_t pb200_shutdown(pb200_ctx* ctx) {
+  if (!ctx) return PB200_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto s : ctx->free_streams) cudaStreamDestroy(s);
+  for (auto& kv : ctx->block_size) cudaFree(kv.first);
+  delete ctx;
+  return PB200_OK;
+}
+
+extern "C" int32_t pb200_device_info(pb200_ctx* ctx, int64_t out[5]) {
+  if (!ctx || !out) { set_error("null argument"); return PB200_E_INVALID; }
+  PB200_CUDA(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  PB200_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+  size_t fr = 0, tot = 0;
+  PB200_CUDA(cudaMemGetInfo(&fr, &tot));
+  out[0] = prop.multiProcessorCount; out[1] = prop.major; out[2] = prop.minor;
+  out[3] = (int64_t)(tot >> 20); out[4] = (int64_t)(fr >> 20);
+  return PB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// segments
+// ------------------------------------------------------------------------------------------------------------------
+static void free_column(pb200_ctx* ctx, DeviceColumn& c) {
+  if (c.owns) {
+    if (c.fwd && c.pooled) dev_free(ctx, c.fwd);
+    else if (c.fwd) cudaFree(c.fwd);
+    if (c.inv) cudaFree(c.inv);
+  }
+  if (c.dict_native) cudaFree(c.dict_native);
+  c.fwd = nullptr; c.inv = nullptr; c.dict_native = nullptr;
+}
+
+static int convert_dictionary(const pb200_col_desc& d, DeviceColumn& c, const unsigned char* be) {
+  // BIG-endian fixed-width values (SegmentDictionaryCreator.java:117-177) -> native little-endian arrays
+  const int w = c.dict_width();
+  if (d.dict_bytes < (uint64_t)w * c.cardinality) { set_error("dictionary too short: %llu bytes for %d x %d", (unsigned long long)d.dict_bytes, c.cardinality, w); return PB200_E_INVALID; }
+  c.dict_be.assign(be, be + (size_t)w * c.cardinality);
+  c.dict_host.resize((size_t)w * c.cardinality);
+  for (int i = 0; i < c.cardinality; i++) {
+    if (w == 4) { uint32_t v = be32(be + 4ll * i); memcpy(&c.dict_host[4ull * i], &v, 4); }
+    else { uint64_t v = be64(be + 8ll * i); memcpy(&c.dict_host[8ull * i], &v, 8); }
+  }
+  PB200_CUDA(cudaMalloc(&c.dict_native, std::max<size_t>(c.dict_host.size(), 16)));
+  PB200_CUDA(cudaMemcpy(c.dict_native, c.dict_host.data(), c.dict_host.size(), cudaMemcpyHostToDevice));
+  return PB200_OK;
+}
+
+extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int32_t num_docs, int32_t ncols,
+                                          const pb200_col_desc* cols, pb200_segment** out) {
+  if (!ctx || !cols || !out || num_docs < 0 || ncols <= 0) { set_error("invalid argument to pb200_segment_register"); return PB200_E_INVALID; }
+  PB200_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<pb200_segment> seg(new pb200_segment());
+  seg->ctx = ctx;
+  seg->name = name ? name : "";
+  seg->num_docs = num_docs;
+  seg->cols.resize(ncols);
+  auto fail = [&](int rc) { for (auto& c : seg->cols) free_column(ctx, c); return rc; };
+  for (int i = 0; i < ncols; i++) {
+    const pb200_col_desc& d = cols[i];
+    DeviceColumn& c = seg->cols[i];
+    c.fwd_kind = d.fwd_kind; c.stored_type = d.stored_type; c.bits = d.bits_per_value; c.cardinality = d.cardinality;
+    const bool on_device = d.flags & PB200_COL_DEVICE_BUFFERS;
+    c.owns = !on_device;
+    if (d.fwd_kind == PB200_FWD_DICT_FIXEDBIT) {
+      if (c.bits < 1 || c.bits > 31) { set_error("column %d: bitsPerElement %d out of range", i, c.bits); return fail(PB200_E_INVALID); }
+      uint64_t need = ((uint64_t)num_docs * c.bits + 7) / 8;
+      if (d.fwd_bytes < need) { set_error("column %d: forward index has %llu bytes, need %llu", i, (unsigned long long)d.fwd_bytes, (unsigned long long)need); return fail(PB200_E_INVALID); }
+      c.fwd_file_bytes = need;
+      if (on_device) {
+        c.fwd = (uint32_t*)d.fwd;  // generator allocated it padded
+        c.fwd_alloc_bytes = d.fwd_bytes;
+      } else {
+        c.fwd_alloc_bytes = padded_fwd_bytes(num_docs, c.bits);
+        void* p = nullptr;
+        int rc = dev_alloc(ctx, c.fwd_alloc_bytes, &p);  // pooled: repeated load / evict cycles reuse HBM blocks
+        if (rc) return fail(rc);
+        c.fwd = (uint32_t*)p;
+        c.pooled = true;
+        const uint64_t body = need & ~15ull;  // zero only the padding behind the file's bytes
+        PB200_CUDA(cudaMemsetAsync((unsigned char*)c.fwd + body, 0, c.fwd_alloc_bytes - body, 0));
+        PB200_CUDA(cudaMemcpy(c.fwd, d.fwd, need, cudaMemcpyHostToDevice));
+      }
+    } else if (d.fwd_kind == PB200_FWD_DICT_SORTED) {
+      // SortedIndexReaderImpl: expand (start,end) pairs into a fixed-bit dictId stream so every kernel sees one format
+      if (on_device) { set_error("sorted columns must be registered from host buffers"); return fail(PB200_E_UNSUPPORTED); }
+      if (d.fwd_bytes < 8ull * c.cardinality) { set_error("column %d: sorted index too short", i); return fail(PB200_E_INVALID); }
+      if (c.bits < 1) c.bits = 1;
+      const unsigned char* p = (const unsigned char*)d.fwd;
+      c.fwd_file_bytes = ((uint64_t)num_docs * c.bits + 7) / 8;
+      c.fwd_alloc_bytes = padded_fwd_bytes(num_docs, c.bits);
+      std::vector<unsigned char> packed(c.fwd_alloc_bytes, 0);
+      for (int id = 0; id < c.cardinality; id++) {
+        int s = (int)be32(p + 8ll * id), e = (int)be32(p + 8ll * id + 4);
+        if (s < 0 || e >= num_docs || e < s) { set_error("column %d: bad sorted range", i); return fail(PB200_E_INVALID); }
+        for (long long doc = s; doc <= e; doc++) {
+          long long bit = doc * c.bits;
+          for (int b = c.bits - 1; b >= 0; b--, bit++)
+            if ((id >> b) & 1) packed[bit >> 3] |= (unsigned char)(0x80 >> (bit & 7));
+        }
+      }
+      PB200_CUDA(cudaMalloc(&c.fwd, c.fwd_alloc_bytes));
+      PB200_CUDA(cudaMemcpy(c.fwd, packed.data(), c.fwd_alloc_bytes, cudaMemcpyHostToDevice));
+      c.fwd_kind = PB200_FWD_DICT_FIXEDBIT;
+    } else if (d.fwd_kind == PB200_FWD_RAW_FIXEDBYTE) {
+      // BaseChunkForwardIndexReader header :60-106; only PASS_THROUGH 4-byte values are accelerated
+      if (on_device) { set_error("raw columns must be registered from host buffers"); return fail(PB200_E_UNSUPPORTED); }
+      const unsigned char* p = (const unsigned char*)d.fwd;
+      if (d.fwd_bytes < 28) { set_error("column %d: raw forward index too short", i); return fail(PB200_E_INVALID); }
+      int version = (int)be32(p), nchunks = (int)be32(p + 4), entry = (int)be32(p + 12);
+      if (version < 2 || be32(p + 20) != 0 || entry != 4 || (d.stored_type != PB200_INT && d.stored_type != PB200_FLOAT)) {
+        set_error("column %d: raw forward index version %d / compression %u / width %d not accelerated", i, version, be32(p + 20), entry);
+        return fail(PB200_E_UNSUPPORTED);
+      }
+      uint64_t start = be32(p + 24) + (uint64_t)nchunks * (version <= 2 ? 4 : 8);
+      if (d.fwd_bytes < start + 4ull * num_docs) { set_error("column %d: raw data truncated", i); return fail(PB200_E_INVALID); }
+      c.bits = 32;
+      c.fwd_file_bytes = 4ull * num_docs;
+      c.fwd_alloc_bytes = padded_fwd_bytes(num_docs, 32);
+      PB200_CUDA(cudaMalloc(&c.fwd, c.fwd_alloc_bytes));
+      PB200_CUDA(cudaMemset(c.fwd, 0, c.fwd_alloc_bytes));
+      PB200_CUDA(cudaMemcpy(c.fwd, p + start, 4ull * num_docs, cudaMemcpyHostToDevice));
+    } else {
+      set_error("column %d: unknown forward index kind %d", i, d.fwd_kind);
+      return fail(PB200_E_INVALID);
+    }
+    seg->device_bytes += (int64_t)c.fwd_alloc_bytes;
+    if (d.dict && d.stored_type != PB200_STRING && d.fwd_kind != PB200_FWD_RAW_FIXEDBYTE) {
+      std::vector<unsigned char> tmp;
+      const unsigned char* be = (const unsigned char*)d.dict;
+      if (on_device) {
+        tmp.resize(d.dict_bytes);
+        PB200_CUDA(cudaMemcpy(tmp.data(), d.dict, d.dict_bytes, cudaMemcpyDeviceToHost));
+        be = tmp.data();
+      }
+      int rc = convert_dictionary(d, c, be);
+      if (rc) return fail(rc);
+      seg->device_bytes += (int64_t)c.dict_host.size();
+    }
+    if (d.inv && d.inv_bytes) {
+      if (d.inv_bytes < 4ull * (c.cardinality + 1)) { set_error("column %d: inverted index too short", i); return fail(PB200_E_INVALID); }
+      c.inv_bytes = d.inv_bytes;
+      c.inv_offsets.resize(c.cardinality + 1);
+      std::vector<unsigned char> hdr(4ull * (c.cardinality + 1));
+      if (on_device) {
+        c.inv = (unsigned char*)d.inv;
+        PB200_CUDA(cudaMemcpy(hdr.data(), d.inv, hdr.size(), cudaMemcpyDeviceToHost));
+      } else {
+        PB200_CUDA(cudaMalloc(&c.inv, d.inv_bytes + 16));
+        PB200_CUDA(cudaMemcpy(c.inv, d.inv, d.inv_bytes, cudaMemcpyHostToDevice));
+        memcpy(hdr.data(), d.inv, hdr.size());
+      }
+      for (int k = 0; k <= c.cardinality; k++) c.inv_offsets[k] = be32(hdr.data() + 4ll * k);
+      if (c.inv_offsets[0] != 4u * (c.cardinality + 1) || c.inv_offsets[c.cardinality] > d.inv_bytes) {
+        set_error("column %d: inverted index offsets are not in BitmapInvertedIndexWriter layout", i);
+        return fail(PB200_E_INVALID);
+      }
+      seg->device_bytes += (int64_t)d.inv_bytes;
+    }
+  }
+  for (auto& c : seg->cols) c.owns = true;  // adopted device buffers belong to the segment from here on
+  *out = seg.release();
+  return PB200_OK;
+}
+
+extern "C" int32_t pb200_segment_release(pb200_ctx* ctx, pb200_segment* seg) {
+  if (!seg) return PB200_OK;
+  cudaSetDevice(seg->ctx->device);
+  for (auto& c : seg->cols) free_column(seg->ctx, c);
+  delete seg;
+  return PB200_OK;
+}
+
+extern "C" int64_t pb200_segment_device_bytes(const pb200_segment* seg) { return seg ? seg->device_bytes : 0; }
+
+extern "C" int32_t pb200_segment_column_info(const pb200_segment* seg, int32_t col, int64_t out[6]) {
+  if (!seg || col < 0 || col >= (int)seg->cols.size()) { set_error("bad column"); return PB200_E_INVALID; }
+  const DeviceColumn& c = seg->cols[col];
+  out[0] = c.fwd_kind; out[1] = c.stored_type; out[2] = c.bits; out[3] = c.cardinality; out[4] = c.inv != nullptr;
+  out[5] = (int64_t)c.fwd_file_bytes;
+  return PB200_OK;
+}
+
+extern "C" int64_t pb200_segment_read_index(pb200_ctx* ctx, const pb200_segment* seg, int32_t col, int32_t which,
+                                            void* out, uint64_t cap) {
+  if (!seg || col < 0 || col >= (int)seg->cols.size()) { set_error("bad column"); return PB200_E_INVALID; }
+  const DeviceColumn& c = seg->cols[col];
+  cudaSetDevice(seg->ctx->device);
+  if (which == 0) {
+    if (!out) return (int64_t)c.fwd_file_bytes;
+    if (cap < c.fwd_file_bytes) { set_error("buffer too small"); return PB200_E_INVALID; }
+    if (cudaMemcpy(out, c.fwd, c.fwd_file_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); return PB200_E_CUDA; }
+    return (int64_t)c.fwd_file_bytes;
+  } else if (which == 1) {
+    if (!out) return (int64_t)c.dict_be.size();
+    if (cap < c.dict_be.size()) { set_error("buffer too small"); return PB200_E_INVALID; }
+    memcpy(out, c.dict_be.data(), c.dict_be.size());
+    return (int64_t)c.dict_be.size();
+  } else if (which == 2) {
+    if (!out) return (int64_t)c.inv_bytes;
+    if (cap < c.inv_bytes) { set_error("buffer too small"); return PB200_E_INVALID; }
+    if (c.inv_bytes && cudaMemcpy(out, c.inv, c.inv_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); return PB200_E_CUDA; }
+    return (int64_t)c.inv_bytes;
+  }
+  set_error("which must be 0,1,2");
+  return PB200_E_INVALID;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// query planning
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Plan {
+  QueryDesc q{};
+  std::vector<SegDesc> segs;
+  std::vector<int> slot_cols;                 // slot -> column id
+  std::vector<int> leaf_node;                 // leaf -> index in the postfix node list
+  bool group_by = false;
+  int cw = 8;
+  size_t smem_bytes = 0;
+  std::vector<std::unique_ptr<DevBuf>> temps; // LUTs, doc masks, range lists (freed after the launch)
+};
+
+int slot_of(Plan& p, int col, uint32_t role) {
+  for (size_t s = 0; s < p.slot_cols.size(); s++)
+    if (p.slot_cols[s] == col) { p.q.slot_roles[s] |= role; return (int)s; }
+  if ((int)p.slot_cols.size() >= kMaxSlots) return -1;
+  p.slot_cols.push_back(col);
+  p.q.slot_roles[p.slot_cols.size() - 1] = role;
+  return (int)p.slot_cols.size() - 1;
+}
+
+bool is_scan_leaf(int op) { return op == PB200_F_SCAN_RANGE || op == PB200_F_SCAN_IN || op == PB200_F_SCAN_NOT_IN; }
+bool is_leaf(int op) { return op >= PB200_F_MATCH_ALL; }
+
+int regime_of(const std::vector<int>& cards, int array_threshold) {
+  // DictionaryBasedGroupKeyGenerator.java:128-185
+  long long product = 1;
+  bool overflow = false;
+  for (int c : cards) {
+    if (!overflow) {
+      if (c > 0 && product > std::numeric_limits<long long>::max() / c) overflow = true; else product *= c;
+    }
+  }
+  if (overflow) return PB200_REGIME_ARRAY_MAP;
+  if (product > std::numeric_limits<int>::max()) return PB200_REGIME_LONG_MAP;
+  return product > array_threshold ? PB200_REGIME_INT_MAP : PB200_REGIME_ARRAY;
+}
+
+template <int CW, bool GB>
+cudaError_t launch_scan(const Plan& p, const SegDesc* dsegs, int grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(scan_kernel<CW, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+  if (e != cudaSuccess) return e;
+  scan_kernel<CW, GB><<<grid, (CW + 1) * 32, p.smem_bytes, st>>>(p.q, dsegs);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200_segment* const* segments,
+                                 int32_t nseg, pb200_result** results) {
+  if (!ctx || !query || !segments || !results || nseg <= 0) { set_error("invalid argument to pb200_execute"); return PB200_E_INVALID; }
+  PB200_CUDA(cudaSetDevice(ctx->device));
+  const bool per_seg_filter = query->flags & PB200_Q_PER_SEGMENT_FILTER;
+  const bool merge = query->flags & PB200_Q_MERGE_SEGMENTS;
+  const int nnodes = query->num_filter_nodes, nagg = query->num_aggs, ngb = query->num_group_by;
+  if (nagg < 0 || nagg > kMaxAggs || ngb < 0 || ngb > kMaxGroupBy || nnodes < 0 || nnodes > kMaxNodes) {
+    set_error("query exceeds device limits (aggs %d/%d, group-by %d/%d, filter nodes %d/%d)", nagg, kMaxAggs, ngb, kMaxGroupBy, nnodes, kMaxNodes);
+    return PB200_E_UNSUPPORTED;
+  }
+  if (nagg == 0) { set_error("at least one aggregation is required on this path"); return PB200_E_INVALID; }
+  const int ncols = (int)segments[0]->cols.size();
+  for (int s = 0; s < nseg; s++) {
+    if (!segments[s] || segments[s]->ctx != ctx || (int)segments[s]->cols.size() != ncols) { set_error("segment %d does not belong to this context / schema", s); return PB200_E_INVALID; }
+  }
+
+  Plan plan;
+  QueryDesc& q = plan.q;
+  plan.group_by = ngb > 0;
+  q.num_segments = nseg;
+  q.num_aggs = nagg;
+  q.num_group_by = ngb;
+
+  // ---- slots: filter scan columns, then group-by keys, then aggregation arguments ----
+  const pb200_filter_node* f0 = query->filter;
+  for (int s = 0; s < (per_seg_filter ? nseg : 1); s++) {
+    for (int i = 0; i < nnodes; i++) {
+      const pb200_filter_node& n = f0[(size_t)s * nnodes + i];
+      if (n.op == PB200_F_RAW_RANGE) { set_error("raw-value range predicates are not accelerated yet"); return PB200_E_UNSUPPORTED; }
+      if (is_leaf(n.op) != is_leaf(f0[i].op) || (!is_leaf(n.op) && (n.op != f0[i].op || n.num_children != f0[i].num_children))) {
+        set_error("per-segment filter trees must share their shape"); return PB200_E_INVALID;
+      }
+      if (is_scan_leaf(n.op)) {
+        if (n.column < 0 || n.column >= ncols) { set_error("filter column %d out of range", n.column); return PB200_E_INVALID; }
+        if (slot_of(plan, n.column, ROLE_FILTER) < 0) { set_error("too many distinct columns (max %d)", kMaxSlots); return PB200_E_UNSUPPORTED; }
+      }
+    }
+  }
+  for (int g = 0; g < ngb; g++) {
+    int c = query->group_by_columns[g];
+    if (c < 0 || c >= ncols) { set_error("group-by column %d out of range", c); return PB200_E_INVALID; }
+    int s = slot_of(plan, c, ROLE_GROUP);
+    if (s < 0) { set_error("too many distinct columns (max %d)", kMaxSlots); return PB200_E_UNSUPPORTED; }
+    q.group_slot[g] = s;
+  }
+  for (int a = 0; a < nagg; a++) {
+    const pb200_agg& ag = query->aggs[a];
+    q.aggs[a].function = ag.function;
+    q.aggs[a].slot = -1;
+    q.aggs[a].val_kind = VAL_NONE;
+    if (ag.function == PB200_AGG_COUNT) continue;
+    if (ag.function < 0 || ag.function > PB200_AGG_DISTINCTCOUNT) { set_error("unknown aggregation function %d", ag.function); return PB200_E_INVALID; }
+    if (ag.column < 0 || ag.column >= ncols) { set_error("aggregation column %d out of range", ag.column); return PB200_E_INVALID; }
+    if (ag.function == PB200_AGG_DISTINCTCOUNT && ngb > 0) { set_error("DISTINCTCOUNT with GROUP BY is not accelerated"); return PB200_E_UNSUPPORTED; }
+    int s = slot_of(plan, ag.column, ROLE_AGG);
+    if (s < 0) { set_error("too many distinct columns (max %d)", kMaxSlots); return PB200_E_UNSUPPORTED; }
+    q.aggs[a].slot = s;
+    const DeviceColumn& c0 = segments[0]->cols[ag.column];
+    int vk = VAL_NONE;
+    if (c0.bits == 32 && c0.dict_native == nullptr) {
+      if (c0.stored_type != PB200_INT) { set_error("raw column type %d not accelerated", c0.stored_type); return PB200_E_UNSUPPORTED; }
+      vk = VAL_RAW_I32;
+      if (ag.function == PB200_AGG_DISTINCTCOUNT) { set_error("DISTINCTCOUNT on raw column not accelerated"); return PB200_E_UNSUPPORTED; }
+    } else {
+      switch (c0.stored_type) {
+        case PB200_INT: vk = VAL_DICT_I32; break;
+        case PB200_LONG: vk = VAL_DICT_I64; break;
+        case PB200_FLOAT: vk = VAL_DICT_F32; break;
+        case PB200_DOUBLE: vk = VAL_DICT_F64; break;
+        default:  // STRING: only functions that work on dictIds (MIN/MAX come back as dictIds, DISTINCTCOUNT as a set)
+          if (ag.function == PB200_AGG_SUM || ag.function == PB200_AGG_AVG) { set_error("SUM/AVG over STRING column"); return PB200_E_UNSUPPORTED; }
+          vk = VAL_DICT_I32;
+      }
+    }
+    q.aggs[a].val_kind = vk;
+  }
+  q.num_slots = (int)plan.slot_cols.size();
+
+  // ---- filter program (shape shared by all segments) ----
+  int nleaves = 0;
+  for (int i = 0; i < nnodes; i++) {
+    const pb200_filter_node& n = f0[i];
+    if (is_leaf(n.op)) {
+      if (nleaves >= kMaxLeaves) { set_error("too many filter leaves (max %d)", kMaxLeaves); return PB200_E_UNSUPPORTED; }
+      q.prog_op[i] = OP_LEAF;
+      q.prog_arg[i] = (uint8_t)nleaves++;
+      plan.leaf_node.push_back(i);
+    } else if (n.op == PB200_F_NOT) {
+      q.prog_op[i] = OP_NOT; q.prog_arg[i] = 1;
+    } else if (n.op == PB200_F_AND || n.op == PB200_F_OR) {
+      if (n.num_children < 1 || n.num_children > kMaxStack) { set_error("AND/OR with %d operands not supported", n.num_children); return PB200_E_UNSUPPORTED; }
+      q.prog_op[i] = n.op == PB200_F_AND ? OP_AND : OP_OR;
+      q.prog_arg[i] = (uint8_t)n.num_children;
+    } else {
+      set_error("unknown filter op %d", n.op);
+      return PB200_E_INVALID;
+    }
+  }
+  q.num_nodes = nnodes;
+  q.num_leaves = nleaves;
+  q.conj = nnodes == 0 || (nnodes == 1 && nleaves == 1) ||
+           (nnodes == nleaves + 1 && f0[nnodes - 1].op == PB200_F_AND && f0[nnodes - 1].num_children == nleaves);
+  {  // validate stack discipline once
+    int sp = 0, maxsp = 0;
+    for (int i = 0; i < nnodes; i++) {
+      if (q.prog_op[i] == OP_LEAF) sp++;
+      else if (q.prog_op[i] == OP_NOT) { if (sp < 1) sp = -99; }
+      else { sp -= q.prog_arg[i] - 1; }
+      if (sp < 1) { set_error("malformed postfix filter"); return PB200_E_INVALID; }
+      maxsp = std::max(maxsp, sp);
+    }
+    if (nnodes > 0 && sp != 1) { set_error("malformed postfix filter (stack %d at end)", sp); return PB200_E_INVALID; }
+    if (maxsp > kMaxStack) { set_error("filter too deep"); return PB200_E_UNSUPPORTED; }
+  }
+
+  // ---- tile geometry ----
+  int max_bits_sum = 0;
+  for (int s = 0; s < nseg; s++) {
+    int sum = 0;
+    for (int c : plan.slot_cols) sum += segments[s]->cols[c].bits;
+    max_bits_sum = std::max(max_bits_sum, sum);
+  }
+  const size_t hdr_bytes = (sizeof(SmemHeader) + 127) / 128 * 128;
+  int cw = 8, stages = 0;
+  for (; cw >= 4; cw -= 4) {
+    size_t stage_bytes = (size_t)cw * 1024 / 8 * max_bits_sum;
+    size_t stack_bytes = q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4;
+    size_t budget = (size_t)ctx->max_smem_optin - hdr_bytes - stack_bytes - 256;
+    if (cw == 4) budget = (size_t)ctx->max_smem_optin / 2 - hdr_bytes - stack_bytes - 2048;  // 2 CTAs / SM
+    stages = stage_bytes == 0 ? 2 : (int)std::min<size_t>(8, budget / stage_bytes);
+    if (stages >= 2) break;
+  }
+  if (stages < 2) { set_error("touched columns too wide for the shared-memory pipeline (%d bits per row)", max_bits_sum); return PB200_E_UNSUPPORTED; }
+  if (getenv("PB200_STAGES")) stages = std::max(2, std::min(stages, atoi(getenv("PB200_STAGES"))));
+  plan.cw = cw;
+  q.tile_rows = cw * 1024;
+  q.num_stages = stages;
+  q.stage_words = (uint32_t)((size_t)q.tile_rows / 32 * max_bits_sum);
+  q.use_pipe = q.num_slots > 0;
+  plan.smem_bytes = hdr_bytes + (size_t)stages * q.stage_words * 4 + (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4);
+
+  cudaStream_t st = take_stream(ctx);
+  struct StreamReturn { pb200_ctx* c; cudaStream_t s; ~StreamReturn() { give_stream(c, s); } } stream_return{ctx, st};
+
+  // ---- group table geometry / result buffers ----
+  std::vector<std::unique_ptr<pb200_result>> res;
+  const int nres = merge ? 1 : nseg;
+  for (int r = 0; r < nres; r++) res.emplace_back(new pb200_result());
+  struct ResultCleanup {  // frees dense device state if we fail midway
+    std::vector<std::unique_ptr<pb200_result>>* r;
+    bool armed = true;
+    ~ResultCleanup() { if (armed) for (auto& x : *r) if (x) pb200_result_free(x.release()); }
+  } cleanup{&res};
+
+  std::vector<DevBuf> accum_bufs(nres);
+  std::vector<std::vector<std::unique_ptr<DevBuf>>> distinct_bufs(nres);
+  plan.segs.resize(nseg);
+  long long tile_cursor = 0;
+  for (int s = 0; s < nseg; s++) {
+    const pb200_segment* seg = segments[s];
+    SegDesc& sd = plan.segs[s];
+    memset(&sd, 0, sizeof sd);
+    sd.num_docs = seg->num_docs;
+    sd.first_tile = tile_cursor;
+    sd.num_tiles = (seg->num_docs + q.tile_rows - 1) / q.tile_rows;
+    tile_cursor += sd.num_tiles;
+    uint32_t word_off = 0, tx = 0;
+    for (int k = 0; k < q.num_slots; k++) {
+      const DeviceColumn& c = seg->cols[plan.slot_cols[k]];
+      sd.slots[k].data = c.fwd;
+      sd.slots[k].bits = c.bits;
+      sd.slots[k].stage_words = word_off;
+      sd.slots[k].tile_bytes = (uint32_t)(q.tile_rows / 8 * c.bits);
+      word_off += sd.slots[k].tile_bytes / 4;
+      tx += sd.slots[k].tile_bytes;
+    }
+    sd.stage_tx = tx;
+  }
+  q.total_tiles = tile_cursor;
+
+  // ---- per segment leaves ----
+  for (int s = 0; s < nseg; s++) {
+    const pb200_segment* seg = segments[s];
+    SegDesc& sd = plan.segs[s];
+    const pb200_filter_node* fs = per_seg_filter ? query->filter + (size_t)s * nnodes : query->filter;
+    for (int l = 0; l < nleaves; l++) {
+      const pb200_filter_node& n = fs[plan.leaf_node[l]];
+      const pb200_filter_node& n0 = f0[plan.leaf_node[l]];
+      LeafDesc& lf = sd.leaves[l];
+      lf.slot = -1;
+      if (n.op == PB200_F_MATCH_ALL) { lf.kind = LEAF_ALL; continue; }
+      if (n.op == PB200_F_EMPTY) { lf.kind = LEAF_NONE; continue; }
+      (void)n0;
+      if (n.column < 0 || n.column >= ncols) { set_error("filter column out of range"); return PB200_E_INVALID; }
+      const DeviceColumn& c = seg->cols[n.column];
+      if (is_scan_leaf(n.op)) {
+        int slot = -1;
+        for (int k = 0; k < q.num_slots; k++) if (plan.slot_cols[k] == n.column) slot = k;
+        if (slot < 0) { set_error("scan leaf column %d has no slot (per-segment trees must scan the same columns)", n.column); return PB200_E_INVALID; }
+        lf.slot = slot;
+        if (n.op == PB200_F_SCAN_RANGE) {
+          lf.kind = LEAF_RANGE;
+          int lo = std::max(n.lo, 0), hi = std::max(n.hi, lo);
+          lf.lo = (uint32_t)lo; lf.span = (uint32_t)(hi - lo);
+        } else {
+          lf.negate = n.op == PB200_F_SCAN_NOT_IN;
+          if (n.num_ids == 1) {
+            lf.kind = LEAF_RANGE; lf.lo = (uint32_t)n.ids[0]; lf.span = 1;
+          } else if (n.num_ids == 0) {
+            lf.kind = LEAF_NONE;
+          } else {
+            // dictId set -> bitmap over the dictionary (what PredicateEvaluator.getMatchingDictIds feeds the scan)
+            size_t words = ((size_t)std::max(c.cardinality, 1) + 31) / 32 + 1;
+            if (c.bits == 32) { set_error("IN on raw column not accelerated"); return PB200_E_UNSUPPORTED; }
+            words = std::max(words, ((size_t)1 << c.bits) / 32 + 1);  // every representable dictId is addressable
+            std::vector<uint32_t> lut(words, 0);
+            for (int k = 0; k < n.num_ids; k++) {
+              int id = n.ids[k];
+              if (id < 0 || id >= c.cardinality) { set_error("dictId %d out of range", id); return PB200_E_INVALID; }
+              lut[id >> 5] |= 1u << (id & 31);
+            }
+            plan.temps.emplace_back(new DevBuf());
+            int rc = plan.temps.back()->alloc(ctx, words * 4);
+            if (rc) return rc;
+            PB200_CUDA(cudaMemcpyAsync(plan.temps.back()->p, lut.data(), words * 4, cudaMemcpyHostToDevice, st));
+            PB200_CUDA(cudaStreamSynchronize(st));  // lut is a local
+            lf.kind = LEAF_LUT;
+            lf.bits = (const uint32_t*)plan.temps.back()->p;
+          }
+        }
+      } else if (n.op == PB200_F_INV_IN || n.op == PB200_F_INV_NOT_IN) {
+        if (!c.inv) { set_error("column %d has no inverted index", n.column); return PB200_E_INVALID; }
+        size_t words = ((size_t)seg->num_docs + 31) / 32 + 8;
+        plan.temps.emplace_back(new DevBuf());
+        int rc = plan.temps.back()->alloc(ctx, words * 4);
+        if (rc) return rc;
+        uint32_t* mask = (uint32_t*)plan.temps.back()->p;
+        PB200_CUDA(cudaMemsetAsync(mask, 0, words * 4, st));
+        rc = roaring_or_into_mask(ctx, st, c, n.ids, n.num_ids, mask, seg->num_docs);
+        if (rc) return rc;
+        lf.kind = LEAF_DOCMASK;
+        lf.bits = mask;
+        lf.negate = n.op == PB200_F_INV_NOT_IN;
+      } else if (n.op == PB200_F_DOC_RANGES) {
+        if (n.num_ids % 2) { set_error("DOC_RANGES needs (start,end) pairs"); return PB200_E_INVALID; }
+        if (n.num_ids == 0) { lf.kind = LEAF_NONE; continue; }
+        plan.temps.emplace_back(new DevBuf());
+        int rc = plan.temps.back()->alloc(ctx, (size_t)n.num_ids * 4);
+        if (rc) return rc;
+        PB200_CUDA(cudaMemcpyAsync(plan.temps.back()->p, n.ids, (size_t)n.num_ids * 4, cudaMemcpyHostToDevice, st));
+        PB200_CUDA(cudaStreamSynchronize(st));
+        lf.kind = LEAF_DOCRANGES;
+        lf.ranges = (const int32_t*)plan.temps.back()->p;
+        lf.num_ranges = n.num_ids / 2;
+      } else {
+        set_error("unsupported leaf op %d", n.op);
+        return PB200_E_UNSUPPORTED;
+      }
+    }
+  }
+
+  // ---- outputs ----
+  AggAccum init_acc;
+  memset(&init_acc, 0, sizeof init_acc);
+  for (int a = 0; a < kMaxAggs; a++) init_acc.min_id[a] = 0xFFFFFFFFu;
+  for (int r = 0; r < nres; r++) {
+    int rc = accum_bufs[r].alloc(ctx, sizeof(AggAccum));
+    if (rc) return rc;
+    PB200_CUDA(cudaMemcpyAsync(accum_bufs[r].p, &init_acc, sizeof init_acc, cudaMemcpyHostToDevice, st));
+  }
+  for (int s = 0; s < nseg; s++) {
+    const pb200_segment* seg = segments[s];
+    SegDesc& sd = plan.segs[s];
+    const int r = merge ? 0 : s;
+    sd.accum = (AggAccum*)accum_bufs[r].p;
+    for (int a = 0; a < nagg; a++) {
+      if (q.aggs[a].slot < 0) continue;
+      const DeviceColumn& c = seg->cols[query->aggs[a].column];
+      sd.dict[a] = c.dict_native;
+      if ((q.aggs[a].function == PB200_AGG_SUM || q.aggs[a].function == PB200_AGG_AVG) && q.aggs[a].val_kind != VAL_RAW_I32 && !c.dict_native) {
+        set_error("SUM/AVG over column %d needs its dictionary on the device", query->aggs[a].column);
+        return PB200_E_INVALID;
+      }
+    }
+  }
+  if (!plan.group_by) {
+    for (int r = 0; r < nres; r++) distinct_bufs[r].resize(nagg);
+    for (int s = 0; s < nseg; s++) {
+      const int r = merge ? 0 : s;
+      for (int a = 0; a < nagg; a++) {
+        if (q.aggs[a].function != PB200_AGG_DISTINCTCOUNT) continue;
+        const DeviceColumn& c = segments[s]->cols[query->aggs[a].column];
+        if (!distinct_bufs[r][a]) {
+          size_t words = ((size_t)1 << c.bits) / 32 + 1;
+          distinct_bufs[r][a].reset(new DevBuf());
+          int rc = distinct_bufs[r][a]->alloc(ctx, words * 4);
+          if (rc) return rc;
+          PB200_CUDA(cudaMemsetAsync(distinct_bufs[r][a]->p, 0, words * 4, st));
+        }
+        plan.segs[s].distinct_bits[a] = (uint32_t*)distinct_bufs[r][a]->p;
+      }
+    }
+  } else {
+    // dense group table over the raw key space (column 0 least significant, DictionaryBasedGroupKeyGenerator :311-346)
+    for (int r = 0; r < nres; r++) {
+      const pb200_segment* seg = segments[merge ? 0 : r];
+      pb200_result::Dense& d = res[r]->dense;
+      d.ctx = ctx;
+      long long groups = 1;
+      for (int g = 0; g < ngb; g++) {
+        int card = seg->cols[query->group_by_columns[g]].cardinality;
+        if (merge) for (int s = 1; s < nseg; s++) if (segments[s]->cols[query->group_by_columns[g]].cardinality != card) {
+          set_error("PB200_Q_MERGE_SEGMENTS needs identical dictionaries (cardinality of group-by column %d differs)", g);
+          return PB200_E_INVALID;
+        }
+        card = std::max(card, 1);
+        // every representable dictId must stay inside the table even for padded / corrupt rows
+        d.mult.push_back((uint32_t)groups);
+        d.cards.push_back(card);
+        if (groups > (1ll << 31) / card) { set_error("group key space too large for the dense device table"); return PB200_E_UNSUPPORTED; }
+        groups *= card;
+      }
+      if (groups > (1ll << 27)) { set_error("group key space of %lld exceeds the dense device table limit", groups); return PB200_E_UNSUPPORTED; }
+      d.groups = groups;
+      d.num_groups_limit = query->num_groups_limit;
+      for (int a = 0; a < nagg; a++) { d.aggs.push_back(query->aggs[a]); d.val_kind.push_back(q.aggs[a].val_kind); d.agg_cols.push_back(q.aggs[a].slot < 0 ? nullptr : &seg->cols[query->aggs[a].column]); }
+      // one block per element kind
+      long long n_i64 = 1, n_f64 = 0, n_max = 0, n_min = 0;
+      for (int a = 0; a < nagg; a++) {
+        const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
+        if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) { if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) n_f64++; else n_i64++; }
+        else if (fn == PB200_AGG_MIN) n_min++;
+        else if (fn == PB200_AGG_MAX) n_max++;
+      }
+      auto alloc_block = [&](void** p, long long elems, size_t esz, int fill) -> int {
+        if (!elems) return PB200_OK;
+        int rc = dev_alloc(ctx, (size_t)elems * esz, p);
+        if (rc) return rc;
+        PB200_CUDA(cudaMemsetAsync(*p, fill, (size_t)elems * esz, st));
+        return PB200_OK;
+      };
+      d.i64_elems = n_i64 * groups; d.f64_elems = n_f64 * groups; d.u32max_elems = n_max * groups; d.u32min_elems = n_min * groups;
+      int rc;
+      if ((rc = alloc_block(&d.i64_block, d.i64_elems, 8, 0))) return rc;
+      if ((rc = alloc_block(&d.f64_block, d.f64_elems, 8, 0))) return rc;
+      if ((rc = alloc_block(&d.u32max_block, d.u32max_elems, 4, 0))) return rc;
+      if ((rc = alloc_block(&d.u32min_block, d.u32min_elems, 4, 0xFF))) return rc;
+      d.count = (unsigned long long*)d.i64_block;
+      long long ii = 1, fi = 0, xi = 0, ni = 0;
+      for (int a = 0; a < nagg; a++) {
+        const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
+        if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
+          if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) d.dsum[a] = (double*)d.f64_block + (fi++) * groups;
+          else d.isum[a] = (long long*)d.i64_block + (ii++) * groups;
+        } else if (fn == PB200_AGG_MIN) d.gmin[a] = (uint32_t*)d.u32min_block + (ni++) * groups;
+        else if (fn == PB200_AGG_MAX) d.gmax[a] = (uint32_t*)d.u32max_block + (xi++) * groups;
+      }
+    }
+    for (int s = 0; s < nseg; s++) {
+      SegDesc& sd = plan.segs[s];
+      pb200_result::Dense& d = res[merge ? 0 : s]->dense;
+      sd.g_count = d.count;
+      for (int a = 0; a < nagg; a++) { sd.g_isum[a] = d.isum[a]; sd.g_dsum[a] = d.dsum[a]; sd.g_min[a] = d.gmin[a]; sd.g_max[a] = d.gmax[a]; }
+      for (int g = 0; g < ngb; g++) sd.group_mult[g] = d.mult[g];
+    }
+  }
+
+  // ---- launch ----
+  DevBuf dsegs;
+  int rc = dsegs.alloc(ctx, sizeof(SegDesc) * nseg);
+  if (rc) return rc;
+  PB200_CUDA(cudaMemcpyAsync(dsegs.p, plan.segs.data(), sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, st));
+  const int ctas_per_sm = cw == 4 ? 2 : 1;
+  int grid = (int)std::min<long long>((long long)ctx->sm_count * ctas_per_sm, std::max<long long>(q.total_tiles, 1));
+  if (getenv("PB200_GRID")) grid = std::max(1, atoi(getenv("PB200_GRID")));
+  cudaEvent_t e0, e1;
+  PB200_CUDA(cudaEventCreate(&e0));
+  PB200_CUDA(cudaEventCreate(&e1));
+  PB200_CUDA(cudaEventRecord(e0, st));
+  cudaError_t le;
+  if (cw == 8) le = plan.group_by ? launch_scan<8, true>(plan, (const SegDesc*)dsegs.p, grid, st) : launch_scan<8, false>(plan, (const SegDesc*)dsegs.p, grid, st);
+  else le = plan.group_by ? launch_scan<4, true>(plan, (const SegDesc*)dsegs.p, grid, st) : launch_scan<4, false>(plan, (const SegDesc*)dsegs.p, grid, st);
+  if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }
+  PB200_CUDA(cudaEventRecord(e1, st));
+  cudaError_t se = cudaStreamSynchronize(st);
+  if (se != cudaSuccess) { set_error("scan kernel failed: %s", cudaGetErrorString(se)); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+
+  // ---- results ----
+  int projected = 0;
+  for (int k = 0; k < q.num_slots; k++) if (q.slot_roles[k] & (ROLE_GROUP | ROLE_AGG)) projected++;
+  for (int r = 0; r < nres; r++) {
+    pb200_result& R = *res[r];
+    AggAccum acc;
+    PB200_CUDA(cudaMemcpy(&acc, accum_bufs[r].p, sizeof acc, cudaMemcpyDeviceToHost));
+    long long total_docs = 0;
+    if (merge) for (int s = 0; s < nseg; s++) total_docs += segments[s]->num_docs; else total_docs = segments[r]->num_docs;
+    R.meta.num_group_by = ngb;
+    R.meta.num_aggs = nagg;
+    R.meta.num_docs_scanned = (int64_t)acc.count;
+    long long in_filter = 0;  // device semantics: every scan leaf looks at every doc of its segment
+    for (int s = 0; s < nseg; s++) {
+      if (!merge && s != r) continue;
+      const pb200_filter_node* fs = per_seg_filter ? query->filter + (size_t)s * nnodes : query->filter;
+      for (int l = 0; l < nleaves; l++) if (is_scan_leaf(fs[plan.leaf_node[l]].op)) in_filter += segments[s]->num_docs;
+    }
+    R.meta.num_entries_scanned_in_filter = in_filter;
+    R.meta.num_entries_scanned_post_filter = (int64_t)acc.count * projected;
+    R.meta.num_total_docs = total_docs;
+    R.meta.device_ms = ms;
+    R.dbl.resize(nagg); R.lng.resize(nagg); R.ids.resize(nagg); R.distinct.resize(nagg);
+    if (!plan.group_by) {
+      R.meta.num_groups = -1;
+      R.meta.regime = PB200_REGIME_NONE;
+      const pb200_segment* seg = segments[merge ? 0 : r];
+      for (int a = 0; a < nagg; a++) {
+        const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
+        double d = 0; int64_t l = 0; int32_t id = -1;
+        const DeviceColumn* c = q.aggs[a].slot < 0 ? nullptr : &seg->cols[query->aggs[a].column];
+        auto value_of = [&](uint32_t x) -> double {
+          if (vk == VAL_RAW_I32) return (double)(int32_t)(x ^ 0x80000000u);
+          const unsigned char* h = c->dict_host.data();
+          switch (vk) {
+            case VAL_DICT_I32: { int32_t v; memcpy(&v, h + 4ull * x, 4); return (double)v; }
+            case VAL_DICT_I64: { int64_t v; memcpy(&v, h + 8ull * x, 8); return (double)v; }
+            case VAL_DICT_F32: { float v; memcpy(&v, h + 4ull * x, 4); return (double)v; }
+            default: { double v; memcpy(&v, h + 8ull * x, 8); return v; }
+          }
+        };
+        if (fn == PB200_AGG_COUNT) { l = (int64_t)acc.count; d = (double)l; }
+        else if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
+          d = (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) ? acc.dsum[a] : (double)acc.isum[a];
+          l = (int64_t)acc.count;
+        } else if (fn == PB200_AGG_MIN) {
+          if (acc.min_id[a] == 0xFFFFFFFFu || acc.count == 0) d = INFINITY; else { id = (int32_t)acc.min_id[a]; d = c->dict_host.empty() && vk != VAL_RAW_I32 ? (double)id : value_of(acc.min_id[a]); }
+        } else if (fn == PB200_AGG_MAX) {
+          if (acc.max_id_plus1[a] == 0) d = -INFINITY; else { id = (int32_t)(acc.max_id_plus1[a] - 1); d = c->dict_host.empty() && vk != VAL_RAW_I32 ? (double)id : value_of(acc.max_id_plus1[a] - 1); }
+        } else if (fn == PB200_AGG_DISTINCTCOUNT) {
+          size_t words = ((size_t)1 << c->bits) / 32 + 1;
+          std::vector<uint32_t> bits(words);
+          PB200_CUDA(cudaMemcpy(bits.data(), distinct_bufs[r][a]->p, words * 4, cudaMemcpyDeviceToHost));
+          std::vector<int32_t> idsv;
+          for (size_t w = 0; w < words; w++) { uint32_t x = bits[w]; while (x) { idsv.push_back((int32_t)(w * 32 + __builtin_ctz(x))); x &= x - 1; } }
+          l = (int64_t)idsv.size(); d = (double)l;
+          R.distinct[a].push_back(std::move(idsv));
+        }
+        R.dbl[a].push_back(d); R.lng[a].push_back(l); R.ids[a].push_back(id);
+      }
+    } else {
+      std::vector<int> cards = R.dense.cards;
+      R.meta.regime = regime_of(cards, query->max_initial_result_holder_capacity);
+      int frc = pb200_result_finalize(ctx, &R);
+      if (frc) return frc;
+      if (!merge) {  // per-segment results do not need the dense state any more
+        pb200_result::Dense& d = R.dense;
+        dev_free(ctx, d.i64_block); dev_free(ctx, d.f64_block); dev_free(ctx, d.u32max_block); dev_free(ctx, d.u32min_block);
+        d.i64_block = d.f64_block = d.u32max_block = d.u32min_block = nullptr;
+      }
+    }
+  }
+  cleanup.armed = false;
+  for (int r = 0; r < nres; r++) results[r] = res[r].release();
+  return PB200_OK;
+}
+
+// Extracts the non-empty groups of the (possibly all-reduced) dense table into the host-side result arrays.
+extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
+  if (!ctx || !R) { set_error("null argument"); return PB200_E_INVALID; }
+  pb200_result::Dense& d = R->dense;
+  if (!d.i64_block) { set_error("result has no dense device state"); return PB200_E_INVALID; }
+  PB200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = take_stream(ctx);
+  struct StreamReturn { pb200_ctx* c; cudaStream_t s; ~StreamReturn() { give_stream(c, s); } } stream_return{ctx, st};
+  const int nagg = (int)d.aggs.size(), ngb = (int)d.cards.size();
+  const long long G = d.groups;
+  DevBuf counter, idx;
+  int rc;
+  if ((rc = counter.alloc(ctx, 8))) return rc;
+  if ((rc = idx.alloc(ctx, (size_t)G * 4))) return rc;
+  PB200_CUDA(cudaMemsetAsync(counter.p, 0, 8, st));
+  int blocks = (int)std::min<long long>((G + 255) / 256, 148 * 8);
+  compact_groups_kernel<<<blocks, 256, 0, st>>>(d.count, G, (unsigned long long*)counter.p, (uint32_t*)idx.p, G);
+  PB200_CUDA(cudaGetLastError());
+  unsigned long long n = 0;
+  PB200_CUDA(cudaMemcpyAsync(&n, counter.p, 8, cudaMemcpyDeviceToHost, st));
+  PB200_CUDA(cudaStreamSynchronize(st));
+  R->meta.num_groups = (int32_t)n;
+  R->meta.groups_limit_reached = (long long)n >= d.num_groups_limit;
+  if ((long long)n > d.num_groups_limit) {
+    // the reference admits groups in doc order until the limit binds (IntGroupIdMap.getGroupId :1022-1047); that order
+    // is not reproducible by a parallel scan -> the caller must run the Java operator for this segment
+    set_error("numGroupsLimit %d would bind (%llu groups): fall back to the reference operator", d.num_groups_limit, n);
+    return PB200_E_LIMIT;
+  }
+  std::vector<uint32_t> hidx(n);
+  if (n) PB200_CUDA(cudaMemcpy(hidx.data(), idx.p, n * 4, cudaMemcpyDeviceToHost));
+  std::sort(hidx.begin(), hidx.end());  // ascending raw key == ArrayBasedHolder's iteration order
+  if (n) PB200_CUDA(cudaMemcpy(idx.p, hidx.data(), n * 4, cudaMemcpyHostToDevice));
+  R->keys.assign((size_t)n * ngb, 0);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t raw = hidx[i];
+    for (int g = 0; g < ngb; g++) { R->keys[i * ngb + g] = (int32_t)(raw % (uint32_t)d.cards[g]); raw /= (uint32_t)d.cards[g]; }
+  }
+  R->dbl.assign(nagg, {}); R->lng.assign(nagg, {}); R->ids.assign(nagg, {}); R->distinct.assign(nagg, {});
+  DevBuf g64, g32;
+  if ((rc = g64.alloc(ctx, std::max<size_t>(n, 1) * 8))) return rc;
+  if ((rc = g32.alloc(ctx, std::max<size_t>(n, 1) * 4))) return rc;
+  const int gb = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n + 255) / 256, 148 * 8));
+  std::vector<unsigned long long> counts(n);
+  if (n) {
+    gather_kernel<unsigned long long><<<gb, 256, 0, st>>>(d.count, (const uint32_t*)idx.p, (long long)n, (unsigned long long*)g64.p);
+    PB200_CUDA(cudaMemcpyAsync(counts.data(), g64.p, n * 8, cudaMemcpyDeviceToHost, st));
+    PB200_CUDA(cudaStreamSynchronize(st));
+  }
+  for (int a = 0; a < nagg; a++) {
+    const int fn = d.aggs[a].function, vk = d.val_kind[a];
+    std::vector<double>& D = R->dbl[a];
+    std::vector<int64_t>& L = R->lng[a];
+    std::vector<int32_t>& I = R->ids[a];
+    D.assign(n, 0.0); L.assign(n, 0); I.assign(n, -1);
+    const DeviceColumn* c = d.agg_cols[a];
+    auto value_of = [&](uint32_t x) -> double {
+      if (vk == VAL_RAW_I32) return (double)(int32_t)(x ^ 0x80000000u);
+      if (c->dict_host.empty()) return (double)x;
+      const unsigned char* h = c->dict_host.data();
+      switch (vk) {
+        case VAL_DICT_I32: { int32_t v; memcpy(&v, h + 4ull * x, 4); return (double)v; }
+        case VAL_DICT_I64: { int64_t v; memcpy(&v, h + 8ull * x, 8); return (double)v; }
+        case VAL_DICT_F32: { float v; memcpy(&v, h + 4ull * x, 4); return (double)v; }
+        default: { double v; memcpy(&v, h + 8ull * x, 8); return v; }
+      }
+    };
+    if (fn == PB200_AGG_COUNT) {
+      for (size_t i = 0; i < n; i++) { L[i] = (int64_t)counts[i]; D[i] = (double)counts[i]; }
+    } else if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
+      if (n) {
+        if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
+          gather_kernel<double><<<gb, 256, 0, st>>>(d.dsum[a], (const uint32_t*)idx.p, (long long)n, (double*)g64.p);
+          PB200_CUDA(cudaMemcpyAsync(D.data(), g64.p, n * 8, cudaMemcpyDeviceToHost, st));
+          PB200_CUDA(cudaStreamSynchronize(st));
+        } else {
+          std::vector<long long> tmp(n);
+          gather_kernel<long long><<<gb, 256, 0, st>>>(d.isum[a], (const uint32_t*)idx.p, (long long)n, (long long*)g64.p);
+          PB200_CUDA(cudaMemcpyAsync(tmp.data(), g64.p, n * 8, cudaMemcpyDeviceToHost, st));
+          PB200_CUDA(cudaStreamSynchronize(st));
+          for (size_t i = 0; i < n; i++) D[i] = (double)tmp[i];
+        }
+      }
+      for (size_t i = 0; i < n; i++) L[i] = (int64_t)counts[i];
+    } else if (fn == PB200_AGG_MIN || fn == PB200_AGG_MAX) {
+      std::vector<uint32_t> tmp(n);
+      if (n) {
+        gather_kernel<uint32_t><<<gb, 256, 0, st>>>(fn == PB200_AGG_MIN ? d.gmin[a] : d.gmax[a], (const uint32_t*)idx.p, (long long)n, (uint32_t*)g32.p);
+        PB200_CUDA(cudaMemcpyAsync(tmp.data(), g32.p, n * 4, cudaMemcpyDeviceToHost, st));
+        PB200_CUDA(cudaStreamSynchronize(st));
+      }
+      for (size_t i = 0; i < n; i++) {
+        if (fn == PB200_AGG_MIN) {
+          if (tmp[i] == 0xFFFFFFFFu) D[i] = INFINITY; else { I[i] = (int32_t)tmp[i]; D[i] = value_of(tmp[i]); }
+        } else {
+          if (tmp[i] == 0) D[i] = -INFINITY; else { I[i] = (int32_t)(tmp[i] - 1); D[i] = value_of(tmp[i] - 1); }
+        }
+      }
+    }
+  }
+  PB200_CUDA(cudaGetLastError());
+  return PB200_OK;
+}
+
+extern "C" int32_t pb200_result_device_buffers(pb200_result* R, int32_t kind, void** p, int64_t* n) {
+  if (!R || !p || !n) { set_error("null argument"); return PB200_E_INVALID; }
+  pb200_result::Dense& d = R->dense;
+  switch (kind) {
+    case 0: *p = d.i64_block; *n = d.i64_elems; break;
+    case 1: *p = d.f64_block; *n = d.f64_elems; break;
+    case 2: *p = d.u32max_block; *n = d.u32max_elems; break;
+    case 3: *p = d.u32min_block; *n = d.u32min_elems; break;
+    default: set_error("kind must be 0..3"); return PB200_E_INVALID;
+  }
+  return PB200_OK;
+}
+
+extern "C" int32_t pb200_result_meta_get(const pb200_result* R, pb200_result_meta* m) {
+  if (!R || !m) { set_error("null argument"); return PB200_E_INVALID; }
+  *m = R->meta;
+  return PB200_OK;
+}
+extern "C" int32_t pb200_result_group_keys(const pb200_result* R, int32_t* out) {
+  if (!R || (!out && !R->keys.empty())) { set_error("null argument"); return PB200_E_INVALID; }
+  if (!R->keys.empty()) memcpy(out, R->keys.data(), R->keys.size() * 4);
+  return PB200_OK;
+}
+extern "C" int32_t pb200_result_agg(const pb200_result* R, int32_t a, double* od, int64_t* ol) {
+  if (!R || a < 0 || a >= (int)R->dbl.size()) { set_error("bad aggregation index"); return PB200_E_INVALID; }
+  if (od && !R->dbl[a].empty()) memcpy(od, R->dbl[a].data(), R->dbl[a].size() * 8);
+  if (ol && !R->lng[a].empty()) memcpy(ol, R->lng[a].data(), R->lng[a].size() * 8);
+  return PB200_OK;
+}
+extern "C" int32_t pb200_result_agg_dict_ids(const pb200_result* R, int32_t a, int32_t* out) {
+  if (!R || a < 0 || a >= (int)R->ids.size() || !out) { set_error("bad aggregation index"); return PB200_E_INVALID; }
+  if (!R->ids[a].empty()) memcpy(out, R->ids[a].data(), R->ids[a].size() * 4);
+  return PB200_OK;
+}
+extern "C" int64_t pb200_result_distinct(const pb200_result* R, int32_t a, int32_t row, int32_t* out, int64_t cap) {
+  if (!R || a < 0 || a >= (int)R->distinct.size() || row < 0 || row >= (int)R->distinct[a].size()) { set_error("bad distinct index"); return PB200_E_INVALID; }
+  const auto& v = R->distinct[a][row];
+  for (int64_t i = 0; i < (int64_t)v.size() && i < cap; i++) out[i] = v[i];
+  return (int64_t)v.size();
+}
+extern "C" int32_t pb200_result_free(pb200_result* R) {
+  if (!R) return PB200_OK;
+  pb200_result::Dense& d = R->dense;
+  if (d.ctx) { dev_free(d.ctx, d.i64_block); dev_free(d.ctx, d.f64_block); dev_free(d.ctx, d.u32max_block); dev_free(d.ctx, d.u32min_block); }
+  delete R;
+  return PB200_OK;
+}

@@ -1,0 +1,102 @@
+// pb200_desc.h -- launch descriptors shared by the host planner (pb200_api.cu) and the scan kernels.
+#pragma once
+#include <cstdint>
+
+namespace pb200 {
+
+constexpr int kMaxSlots = 8;     // distinct columns one query may touch on the device
+constexpr int kMaxLeaves = 8;    // filter leaves
+constexpr int kMaxNodes = 16;    // filter tree nodes (postfix program length)
+constexpr int kMaxAggs = 6;      // aggregation functions per query
+constexpr int kMaxGroupBy = 4;   // group-by columns (dense key space)
+constexpr int kRowsPerThread = 32;
+constexpr int kMaxStack = 8;
+
+// slot roles
+enum : uint32_t { ROLE_FILTER = 1, ROLE_GROUP = 2, ROLE_AGG = 4 };
+
+// device leaf kinds
+enum : int32_t { LEAF_ALL = 0, LEAF_NONE = 1, LEAF_RANGE = 2, LEAF_LUT = 3, LEAF_DOCMASK = 4, LEAF_DOCRANGES = 5 };
+
+// program ops (postfix over 32-row masks)
+enum : uint8_t { OP_LEAF = 0, OP_AND = 1, OP_OR = 2, OP_NOT = 3 };
+
+// aggregation value kinds (how a dictId / raw word becomes a number)
+enum : int32_t { VAL_NONE = 0, VAL_DICT_I32 = 1, VAL_DICT_I64 = 2, VAL_DICT_F32 = 3, VAL_DICT_F64 = 4, VAL_RAW_I32 = 5 };
+
+struct SlotDesc {
+  const uint32_t* data;  // device: packed words, padded to whole tiles
+  int32_t bits;          // 1..32 (32 = raw big-endian 32-bit values)
+  uint32_t stage_words;  // offset of this slot inside a stage buffer, in 32-bit words
+  uint32_t tile_bytes;   // bytes of this slot per tile (multiple of 16)
+  uint32_t pad;
+};
+
+struct LeafDesc {
+  int32_t kind;
+  int32_t slot;
+  uint32_t lo;      // RANGE: dictId lower bound
+  uint32_t span;    // RANGE: hi - lo  (match iff (v - lo) < span, unsigned)
+  const uint32_t* bits;  // LUT: bitmap over dictIds; DOCMASK: 1 bit per doc (bit j of word w = doc 32w+j)
+  const int32_t* ranges; // DOCRANGES: inclusive (start,end) pairs
+  int32_t num_ranges;
+  int32_t negate;
+};
+
+// Per-aggregation outputs of the aggregation-only kernel (one per segment or one merged)
+struct AggAccum {
+  unsigned long long count;             // matched docs
+  long long isum[kMaxAggs];             // exact integer sums (INT / LONG dictionaries)
+  double dsum[kMaxAggs];                // FLOAT / DOUBLE sums
+  uint32_t min_id[kMaxAggs];            // dictId (or order-preserving raw encoding); 0xFFFFFFFF = empty
+  uint32_t max_id_plus1[kMaxAggs];      // dictId + 1; 0 = empty
+};
+
+struct SegDesc {
+  long long num_docs;
+  long long first_tile;   // index of this segment's first tile in the launch-wide tile sequence
+  long long num_tiles;
+  uint32_t stage_tx;      // bytes TMA delivers per stage for THIS segment (sum of its slots' tile_bytes)
+  uint32_t pad0;
+  SlotDesc slots[kMaxSlots];
+  LeafDesc leaves[kMaxLeaves];
+  const void* dict[kMaxAggs];          // native (little-endian) dictionary value array of the aggregation's column
+  uint32_t* distinct_bits[kMaxAggs];   // DISTINCTCOUNT (aggregation only): bitset over dictIds
+  AggAccum* accum;                     // aggregation-only output
+  // dense group table (group-by): indexed by raw key = sum_j dictId_j * mult_j
+  unsigned long long* g_count;
+  long long* g_isum[kMaxAggs];
+  double* g_dsum[kMaxAggs];
+  uint32_t* g_min[kMaxAggs];
+  uint32_t* g_max[kMaxAggs];
+  uint32_t group_mult[kMaxGroupBy];
+};
+
+struct AggDesc {
+  int32_t function;  // PB200_AGG_*
+  int32_t slot;      // -1 for COUNT(*)
+  int32_t val_kind;  // VAL_*
+  int32_t pad;
+};
+
+struct QueryDesc {
+  int32_t num_segments;
+  int32_t num_slots;
+  int32_t num_leaves;
+  int32_t num_nodes;       // program length; 0 = match all
+  int32_t conj;            // 1: root is a flat AND (or single leaf) of leaves -> no stack
+  int32_t num_aggs;
+  int32_t num_group_by;
+  int32_t tile_rows;       // consumer_warps * 1024
+  int32_t num_stages;
+  uint32_t stage_words;    // words per stage buffer (max over segments)
+  uint32_t use_pipe;       // 0: no column is streamed (e.g. COUNT(*) over doc masks only)
+  uint32_t slot_roles[kMaxSlots];
+  int32_t group_slot[kMaxGroupBy];
+  uint8_t prog_op[kMaxNodes];
+  uint8_t prog_arg[kMaxNodes];  // OP_LEAF: leaf index; AND/OR: operand count
+  AggDesc aggs[kMaxAggs];
+  long long total_tiles;
+};
+
+}  // namespace pb200

@@ -1,0 +1,110 @@
+// pb200_internal.h -- host-side objects behind the opaque C-ABI handles.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pinot_b200.h"
+#include "pb200_desc.h"
+
+namespace pb200 {
+
+void set_error(const char* fmt, ...);
+#define PB200_CUDA(call)                                                                         \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      ::pb200::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return PB200_E_CUDA;                                                                       \
+    }                                                                                            \
+  } while (0)
+
+// Largest tile the scan kernel uses: 8 consumer warps x 1024 rows.  Forward indexes are padded to whole tiles.
+constexpr int kMaxTileRows = 8192;
+
+struct DeviceColumn {
+  int fwd_kind = 0, stored_type = 0, bits = 0, cardinality = 0;
+  uint32_t* fwd = nullptr;        // packed words, padded to whole max tiles (+ slack)
+  uint64_t fwd_file_bytes = 0;    // length of the original index file: ceil(N*bits/8)
+  uint64_t fwd_alloc_bytes = 0;
+  void* dict_native = nullptr;    // device: little-endian value array
+  std::vector<unsigned char> dict_host;  // host copy of the native array (finalisation: dictId -> value)
+  std::vector<unsigned char> dict_be;    // original big-endian bytes (read-back / tests)
+  unsigned char* inv = nullptr;   // device: inverted index file bytes
+  uint64_t inv_bytes = 0;
+  std::vector<uint32_t> inv_offsets;  // host: (card+1) offsets into inv (file-relative)
+  bool owns = true;
+  bool pooled = false;            // fwd came from the context's caching allocator
+  int dict_width() const { return (stored_type == PB200_LONG || stored_type == PB200_DOUBLE) ? 8 : 4; }
+};
+
+}  // namespace pb200
+
+struct pb200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  std::mutex mu;
+  std::vector<cudaStream_t> free_streams;
+  std::multimap<size_t, void*> free_blocks;  // caching allocator: size -> block
+  std::map<void*, size_t> block_size;
+  size_t pooled_bytes = 0;
+};
+
+struct pb200_segment {
+  pb200_ctx* ctx = nullptr;
+  std::string name;
+  int num_docs = 0;
+  std::vector<pb200::DeviceColumn> cols;
+  int64_t device_bytes = 0;
+};
+
+struct pb200_result {
+  pb200_result_meta meta{};
+  std::vector<int32_t> keys;                     // [G x k]
+  std::vector<std::vector<double>> dbl;          // per agg [rows]
+  std::vector<std::vector<int64_t>> lng;
+  std::vector<std::vector<int32_t>> ids;         // per agg [rows] MIN/MAX dictIds (-1 empty)
+  std::vector<std::vector<std::vector<int32_t>>> distinct;  // per agg, per row
+  // merged dense-table state kept on the device for multi-GPU combine
+  struct Dense {
+    pb200_ctx* ctx = nullptr;
+    long long groups = 0;                        // size of the dense key space
+    unsigned long long* count = nullptr;
+    long long* isum[pb200::kMaxAggs] = {};
+    double* dsum[pb200::kMaxAggs] = {};
+    uint32_t* gmin[pb200::kMaxAggs] = {};
+    uint32_t* gmax[pb200::kMaxAggs] = {};
+    std::vector<uint32_t> mult;
+    std::vector<int> cards;
+    std::vector<pb200_agg> aggs;
+    std::vector<int> val_kind;
+    std::vector<const pb200::DeviceColumn*> agg_cols;
+    int num_groups_limit = 0;
+    // one contiguous allocation per kind so a collective can reduce it in place
+    void* i64_block = nullptr; long long i64_elems = 0;
+    void* f64_block = nullptr; long long f64_elems = 0;
+    void* u32max_block = nullptr; long long u32max_elems = 0;
+    void* u32min_block = nullptr; long long u32min_elems = 0;
+  } dense;
+};
+
+namespace pb200 {
+// caching device allocator + stream pool (thread safe)
+int dev_alloc(pb200_ctx* ctx, size_t bytes, void** out);
+void dev_free(pb200_ctx* ctx, void* p);
+cudaStream_t take_stream(pb200_ctx* ctx);
+void give_stream(pb200_ctx* ctx, cudaStream_t s);
+
+// pb200_roaring.cu
+// Decodes the bitmaps of `ids` (inverted index of `col`) OR-ed together into `mask` (1 bit per doc, bit j of 32-bit word
+// w = doc 32*w + j). mask must be zeroed by the caller.
+int roaring_or_into_mask(pb200_ctx* ctx, cudaStream_t stream, const DeviceColumn& col, const int32_t* ids, int num_ids,
+                         uint32_t* mask, long long num_docs);
+// pb200_synth.cu
+int synth_build_inverted(pb200_ctx* ctx, cudaStream_t stream, DeviceColumn& col, long long num_docs);
+}  // namespace pb200

@@ -1,0 +1,420 @@
+// pb200_scan.cuh -- the fused scan kernel: DocIdSet -> Projection -> Aggregation / GroupBy in one pass over HBM.
+//
+// What the reference does per segment, block (<=10 000 docs) at a time, on one CPU thread
+//   FilterOperator tree -> DocIdSetOperator -> ProjectionOperator -> GroupByOperator/AggregationOperator
+//   (core/operator/DocIdSetOperator.java:59-86, ProjectionOperator.java:68-79, query/GroupByOperator.java:101-140,
+//    query/AggregationOperator.java:64-80; bit unpack in seglocal/io/reader/impl/FixedBitIntReader.java)
+// is done here for ALL segments of a query by one persistent kernel:
+//
+//   * tile = consumer_warps x 1024 rows of every touched column; a producer thread streams tiles HBM -> shared memory
+//     with TMA 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) through an N-stage full/empty mbarrier ring;
+//   * each consumer thread owns 32 consecutive rows: unpacks its B big-endian words per column (pb200_unpack.cuh),
+//     evaluates every filter leaf into a 32-bit row mask, combines masks with the filter's boolean program,
+//     then aggregates the surviving rows: register accumulators + warp reduction + one atomic per warp for
+//     aggregation-only queries, atomics into a dense group table (raw key = sum dictId_j * mult_j, the same key
+//     DictionaryBasedGroupKeyGenerator computes, :311-346) for group-by;
+//   * integer work only: no tensor cores; the bound is HBM bandwidth (algorithmic bytes = sum of bits/8 per row).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "pb200_desc.h"
+#include "pb200_unpack.cuh"
+
+namespace pb200 {
+
+// ------------------------------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy primitives (PTX ISA 8.x; SASS: SYNCS.*, UBLKCP)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`; streaming data: L2 evict-first policy.
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void consumer_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// leaf evaluation on a thread's 32 unpacked dictIds
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t eval_range(const uint32_t (&v)[32], uint32_t lo, uint32_t span) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) m |= ((v[j] - lo) < span ? 1u : 0u) << j;
+  return m;
+}
+__device__ __forceinline__ uint32_t eval_lut(const uint32_t (&v)[32], const uint32_t* __restrict__ bits) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) m |= ((__ldg(bits + (v[j] >> 5)) >> (v[j] & 31)) & 1u) << j;
+  return m;
+}
+// rows [row0, row0+32) against inclusive doc-id ranges
+__device__ __forceinline__ uint32_t eval_doc_ranges(long long row0, const int32_t* __restrict__ r, int n) {
+  uint32_t m = 0;
+  for (int i = 0; i < n; ++i) {
+    long long lo = (long long)__ldg(r + 2 * i) - row0, hi = (long long)__ldg(r + 2 * i + 1) - row0 + 1;  // [lo, hi)
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > 32 ? 32 : hi;
+    if (hi > lo) {
+      uint32_t upto_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+      uint32_t upto_lo = (1u << lo) - 1u;  // lo < 32 here
+      m |= upto_hi & ~upto_lo;
+    }
+  }
+  return m;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+  return x;
+}
+__device__ __forceinline__ uint32_t warp_min(uint32_t x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = min(x, __shfl_xor_sync(0xFFFFFFFFu, x, o));
+  return x;
+}
+__device__ __forceinline__ uint32_t warp_max(uint32_t x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(0xFFFFFFFFu, x, o));
+  return x;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------------
+struct SmemHeader {
+  SegDesc seg;            // consumer-side copy of the current segment's descriptor
+  uint64_t full[8];       // stage filled by TMA
+  uint64_t empty[8];      // stage drained by all consumer warps
+};
+
+template <int CW, bool GROUPBY>
+__global__ void __launch_bounds__((CW + 1) * 32, (CW <= 4 ? 2 : 1))
+scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ segs) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
+  constexpr int kHdrBytes = (sizeof(SmemHeader) + 127) / 128 * 128;
+  uint32_t* stages = reinterpret_cast<uint32_t*>(smem_raw + kHdrBytes);
+  uint32_t* fstack = stages + (size_t)q.num_stages * q.stage_words;  // generic-filter mask stack (if !conj)
+  constexpr int kConsumers = CW * 32;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool use_pipe = q.use_pipe != 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < q.num_stages; ++s) {
+      mbar_init(&hdr->full[s], 1);
+      mbar_init(&hdr->empty[s], CW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == CW) {
+    // ============================== producer: one thread drives TMA ==============================
+    if (lane == 0 && use_pipe) {
+      const uint64_t policy = policy_evict_first();
+      int sidx = 0, stage = 0;
+      uint32_t phase = 0;
+      for (long long T = blockIdx.x; T < q.total_tiles; T += gridDim.x) {
+        while (T >= segs[sidx].first_tile + segs[sidx].num_tiles) ++sidx;
+        const SegDesc* sd = segs + sidx;
+        const long long t = T - sd->first_tile;
+        mbar_wait(&hdr->empty[stage], phase ^ 1u);
+        mbar_expect_tx(&hdr->full[stage], sd->stage_tx);
+        uint32_t* dst = stages + (size_t)stage * q.stage_words;
+        for (int s = 0; s < q.num_slots; ++s) {
+          const uint32_t tb = sd->slots[s].tile_bytes;
+          tma_load_1d(dst + sd->slots[s].stage_words, reinterpret_cast<const unsigned char*>(sd->slots[s].data) + t * tb,
+                      tb, &hdr->full[stage], policy);
+        }
+        if (++stage == q.num_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ================================== consumers ==================================
+  const int group = threadIdx.x;  // 32-row group inside the tile
+  const SegDesc& sd = hdr->seg;
+
+  // per-thread accumulators (aggregation-only kernel)
+  unsigned long long cnt = 0;
+  long long isum[kMaxAggs];
+  double dsum[kMaxAggs];
+  uint32_t mn[kMaxAggs], mx[kMaxAggs];
+#pragma unroll
+  for (int a = 0; a < kMaxAggs; ++a) { isum[a] = 0; dsum[a] = 0.0; mn[a] = 0xFFFFFFFFu; mx[a] = 0u; }
+
+  auto flush = [&]() {
+    // one atomic per warp per accumulator into the segment's AggAccum
+    unsigned long long c = warp_sum(cnt);
+    if (lane == 0 && c) atomicAdd(&sd.accum->count, c);
+    cnt = 0;
+    if (!GROUPBY) {
+#pragma unroll
+      for (int a = 0; a < kMaxAggs; ++a) {
+        if (a < q.num_aggs && q.aggs[a].slot >= 0) {
+          const int fn = q.aggs[a].function;
+          if (fn == 1 || fn == 4) {  // SUM / AVG
+            if (q.aggs[a].val_kind == VAL_DICT_F32 || q.aggs[a].val_kind == VAL_DICT_F64) {
+              double d = warp_sum(dsum[a]);
+              if (lane == 0) atomicAdd(&sd.accum->dsum[a], d);
+            } else {
+              long long s = warp_sum(isum[a]);
+              if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&sd.accum->isum[a]), (unsigned long long)s);
+            }
+          } else if (fn == 2) {
+            uint32_t m = warp_min(mn[a]);
+            if (lane == 0) atomicMin(&sd.accum->min_id[a], m);
+          } else if (fn == 3) {
+            uint32_t m = warp_max(mx[a]);
+            if (lane == 0) atomicMax(&sd.accum->max_id_plus1[a], m);
+          }
+          isum[a] = 0; dsum[a] = 0.0; mn[a] = 0xFFFFFFFFu; mx[a] = 0u;
+        }
+      }
+    }
+  };
+
+  int sidx = -1, stage = 0;
+  uint32_t phase = 0;
+  for (long long T = blockIdx.x; T < q.total_tiles; T += gridDim.x) {
+    // ---- segment change: flush accumulators, refresh the shared descriptor copy ----
+    int ns = sidx < 0 ? 0 : sidx;
+    while (T >= __ldg(&segs[ns].first_tile) + __ldg(&segs[ns].num_tiles)) ++ns;
+    if (ns != sidx) {
+      if (sidx >= 0) flush();
+      consumer_bar_sync(kConsumers);  // everyone done reading the old descriptor
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(segs + ns);
+      uint32_t* dstw = reinterpret_cast<uint32_t*>(&hdr->seg);
+      for (int i = threadIdx.x; i < (int)(sizeof(SegDesc) / 4); i += kConsumers) dstw[i] = __ldg(src + i);
+      consumer_bar_sync(kConsumers);
+      sidx = ns;
+    }
+    const long long t = T - sd.first_tile;
+    const long long row0 = t * q.tile_rows + (long long)group * kRowsPerThread;
+    const long long left = sd.num_docs - row0;
+    uint32_t m = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+
+    if (use_pipe) mbar_wait(&hdr->full[stage], phase);
+    const uint32_t* st = stages + (size_t)stage * q.stage_words;
+    uint32_t v[32];
+
+    // ---------------- phase 1: filter -> row mask ----------------
+    if (q.num_nodes > 0) {
+      uint32_t lm[kMaxLeaves];
+#pragma unroll
+      for (int l = 0; l < kMaxLeaves; ++l) {
+        lm[l] = 0xFFFFFFFFu;
+        if (l < q.num_leaves) {
+          const LeafDesc& lf = sd.leaves[l];
+          if (lf.kind == LEAF_NONE) lm[l] = 0u;
+          else if (lf.kind == LEAF_DOCMASK) lm[l] = left > 0 ? __ldg(lf.bits + (row0 >> 5)) : 0u;
+          else if (lf.kind == LEAF_DOCRANGES) lm[l] = eval_doc_ranges(row0, lf.ranges, lf.num_ranges);
+        }
+      }
+      for (int s = 0; s < q.num_slots; ++s) {
+        if (!(q.slot_roles[s] & ROLE_FILTER)) continue;
+        unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
+#pragma unroll
+        for (int l = 0; l < kMaxLeaves; ++l) {
+          if (l < q.num_leaves && sd.leaves[l].slot == s) {
+            const LeafDesc& lf = sd.leaves[l];
+            if (lf.kind == LEAF_RANGE) lm[l] = eval_range(v, lf.lo, lf.span);
+            else if (lf.kind == LEAF_LUT) lm[l] = eval_lut(v, lf.bits);
+          }
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < kMaxLeaves; ++l)
+        if (l < q.num_leaves && sd.leaves[l].negate) lm[l] = ~lm[l];
+      if (q.conj) {
+#pragma unroll
+        for (int l = 0; l < kMaxLeaves; ++l)
+          if (l < q.num_leaves) m &= lm[l];
+      } else {
+        // postfix boolean program over masks; the stack lives in shared memory (column per thread: conflict free)
+        uint32_t* stk = fstack + group;
+        int sp = 0;
+        for (int i = 0; i < q.num_nodes; ++i) {
+          const int op = q.prog_op[i], arg = q.prog_arg[i];
+          if (op == OP_LEAF) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int l = 0; l < kMaxLeaves; ++l) x = (l == arg) ? lm[l] : x;
+            stk[(sp++) * kConsumers] = x;
+          } else if (op == OP_NOT) {
+            stk[(sp - 1) * kConsumers] = ~stk[(sp - 1) * kConsumers];
+          } else {
+            uint32_t x = stk[(sp - 1) * kConsumers];
+            for (int c = 1; c < arg; ++c) {
+              uint32_t y = stk[(sp - 1 - c) * kConsumers];
+              x = op == OP_AND ? (x & y) : (x | y);
+            }
+            sp -= arg;
+            stk[(sp++) * kConsumers] = x;
+          }
+        }
+        m &= stk[0];
+      }
+    }
+
+    // ---------------- phase 2: aggregate the surviving rows ----------------
+    cnt += __popc(m);
+    const bool warp_any = __any_sync(0xFFFFFFFFu, m != 0u);
+    if (warp_any) {
+      uint32_t gid[32];
+      if (GROUPBY) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gid[j] = 0;
+        for (int s = 0; s < q.num_slots; ++s) {
+          if (!(q.slot_roles[s] & ROLE_GROUP)) continue;
+          unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
+#pragma unroll
+          for (int g = 0; g < kMaxGroupBy; ++g) {
+            if (g < q.num_group_by && q.group_slot[g] == s) {
+              const uint32_t mult = sd.group_mult[g];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) gid[j] += v[j] * mult;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if ((m >> j) & 1u) atomicAdd(sd.g_count + gid[j], 1ull);
+      }
+      for (int s = 0; s < q.num_slots; ++s) {
+        if (!(q.slot_roles[s] & ROLE_AGG)) continue;
+        unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
+#pragma unroll
+        for (int a = 0; a < kMaxAggs; ++a) {
+          if (a < q.num_aggs && q.aggs[a].slot == s) {
+            const int fn = q.aggs[a].function;
+            const int vk = q.aggs[a].val_kind;
+            if (fn == 1 || fn == 4) {  // SUM / AVG: value = dictionary[dictId]
+              if (vk == VAL_DICT_I32) {
+                const int* __restrict__ d = static_cast<const int*>(sd.dict[a]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if ((m >> j) & 1u) {
+                    long long x = __ldg(d + v[j]);
+                    if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)x);
+                    else isum[a] += x;
+                  }
+                }
+              } else if (vk == VAL_DICT_I64) {
+                const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if ((m >> j) & 1u) {
+                    long long x = __ldg(d + v[j]);
+                    if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)x);
+                    else isum[a] += x;
+                  }
+                }
+              } else if (vk == VAL_DICT_F32) {
+                const float* __restrict__ d = static_cast<const float*>(sd.dict[a]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if ((m >> j) & 1u) {
+                    double x = (double)__ldg(d + v[j]);
+                    if (GROUPBY) atomicAdd(sd.g_dsum[a] + gid[j], x);
+                    else dsum[a] += x;
+                  }
+                }
+              } else if (vk == VAL_DICT_F64) {
+                const double* __restrict__ d = static_cast<const double*>(sd.dict[a]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if ((m >> j) & 1u) {
+                    double x = __ldg(d + v[j]);
+                    if (GROUPBY) atomicAdd(sd.g_dsum[a] + gid[j], x);
+                    else dsum[a] += x;
+                  }
+                }
+              } else if (vk == VAL_RAW_I32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if ((m >> j) & 1u) {
+                    long long x = (int)v[j];
+                    if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)x);
+                    else isum[a] += x;
+                  }
+                }
+              }
+            } else if (fn == 2 || fn == 3) {  // MIN / MAX on dictIds (dictionaries are sorted: order preserving)
+              const uint32_t bias = vk == VAL_RAW_I32 ? 0x80000000u : 0u;  // raw INT: signed -> unsigned order
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if ((m >> j) & 1u) {
+                  const uint32_t x = v[j] ^ bias;
+                  if (GROUPBY) {
+                    if (fn == 2) atomicMin(sd.g_min[a] + gid[j], x);
+                    else atomicMax(sd.g_max[a] + gid[j], x + 1u);
+                  } else {
+                    mn[a] = min(mn[a], x);
+                    mx[a] = max(mx[a], x + 1u);
+                  }
+                }
+              }
+            } else if (fn == 5 && !GROUPBY) {  // DISTINCTCOUNT: bitset of dictIds (RoaringBitmap.addN in the reference)
+              uint32_t* bits = sd.distinct_bits[a];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if ((m >> j) & 1u) atomicOr(bits + (v[j] >> 5), 1u << (v[j] & 31));
+            }
+          }
+        }
+      }
+    }
+
+    if (use_pipe) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&hdr->empty[stage]);
+      if (++stage == q.num_stages) { stage = 0; phase ^= 1u; }
+    }
+  }
+  if (sidx >= 0) flush();
+}
+
+}  // namespace pb200

@@ -1,0 +1,336 @@
+"""Python face of the host layer: the reference's plan-maker / operator interface for this path.
+
+Names follow the reference so that tests read like its own (``pinot-core/src/test/java/org/apache/pinot/queries/
+BaseQueriesTest.java:97-102``: ``PLAN_MAKER.makeSegmentPlanNode(new SegmentContext(segment), queryContext).run()``):
+
+    ctx      = B200Context(device=0)
+    segment  = IndexSegment.from_columns(ctx, "seg", num_docs, columns)          # ImmutableSegmentLoader.load
+    operator = B200PlanMaker(ctx).make_segment_plan_node(segment, query).run()    # PlanMaker.makeSegmentPlanNode
+    block    = operator.next_block()                                              # Operator.nextBlock()
+    block.get_results() / block.group_keys / operator.get_execution_statistics()
+
+All work happens in libpinot_b200.so (C++ plan maker above the C-ABI + CUDA kernels below it); this module only
+marshals.  There is no CPU fallback: queries outside the accelerated set raise ``UnsupportedQueryError`` (the Java
+``B200PlanMaker`` would call ``super.makeSegmentPlanNode`` there).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import UnsupportedQueryError  # noqa: F401  (re-export)
+from .query import Filter, QueryContext, postfix
+
+
+class B200Context:
+    """One per (process, GPU): owns the CUDA context, stream pool and device memory pool."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.pb200_init(device, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def device_info(self) -> Dict[str, int]:
+        out = (C.c_int64 * 5)()
+        _lib.check(self.lib.pb200_device_info(self.handle, out))
+        return {"sm_count": out[0], "major": out[1], "minor": out[2], "total_mem_mb": out[3], "free_mem_mb": out[4]}
+
+    def close(self):
+        if self.handle:
+            self.lib.pb200_shutdown(self.handle)
+            self.handle = None
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class IndexSegment:
+    """An immutable segment resident in HBM (+ host dictionaries). Mirrors ``IndexSegment`` / ``SegmentContext``."""
+
+    def __init__(self, ctx: B200Context, handle, name: str):
+        self.ctx = ctx
+        self.handle = handle
+        self.name = name
+        L = ctx.lib
+        self.num_docs = L.pb200h_segment_num_docs(handle)
+        self.column_names = [L.pb200h_segment_column_name(handle, i).decode() for i in
+                             range(L.pb200h_segment_num_columns(handle))]
+
+    # ---- constructors -------------------------------------------------------------------------------------------
+    @classmethod
+    def from_columns(cls, ctx: B200Context, name: str, num_docs: int, columns: Sequence) -> "IndexSegment":
+        """`columns`: objects with name, data_type, has_dictionary, bits, cardinality, is_sorted, dict_entry_bytes and
+        numpy uint8 buffers fwd / dict / inv holding Pinot's index file bytes."""
+        arr = (_lib.HColumn * len(columns))()
+        keep = []
+        for i, c in enumerate(columns):
+            nm = c.name.encode()
+            keep.append(nm)
+            arr[i] = _lib.HColumn(nm, c.data_type, int(c.has_dictionary), c.bits, c.cardinality, int(c.is_sorted),
+                                  c.dict_entry_bytes, _ptr(c.fwd), len(c.fwd), _ptr(c.dict),
+                                  0 if c.dict is None else len(c.dict), _ptr(c.inv),
+                                  0 if c.inv is None else len(c.inv))
+        h = C.c_void_p()
+        _lib.check(ctx.lib.pb200h_segment_create(ctx.handle, name.encode(), num_docs, len(columns), arr, C.byref(h)))
+        return cls(ctx, h, name)
+
+    @classmethod
+    def synthetic(cls, ctx: B200Context, name: str, num_docs: int, columns: Sequence[dict]) -> "IndexSegment":
+        """Generates dict-encoded INT columns directly in HBM (pb200_synth_segment).  Each column dict:
+        {name, cardinality, seed, value_base=0, value_step=1, inverted=False}."""
+        arr = (_lib.SynthCol * len(columns))()
+        for i, c in enumerate(columns):
+            arr[i] = _lib.SynthCol(c["cardinality"], c.get("value_base", 0), c.get("value_step", 1),
+                                   int(c.get("inverted", False)), c["seed"])
+        dev = C.c_void_p()
+        _lib.check(ctx.lib.pb200_synth_segment(ctx.handle, name.encode(), num_docs, len(columns), arr, C.byref(dev)))
+        names = (C.c_char_p * len(columns))(*[c["name"].encode() for c in columns])
+        h = C.c_void_p()
+        _lib.check(ctx.lib.pb200h_segment_adopt(ctx.handle, dev, num_docs, len(columns), names, C.byref(h)))
+        return cls(ctx, h, name)
+
+    @classmethod
+    def load(cls, ctx: B200Context, index_dir: str) -> "IndexSegment":
+        """ImmutableSegmentLoader.load(indexDir): reads metadata.properties + v1 / v3 index files from disk."""
+        h = C.c_void_p()
+        _lib.check(ctx.lib.pb200h_segment_load_dir(ctx.handle, index_dir.encode(), C.byref(h)))
+        return cls(ctx, h, index_dir)
+
+    # ---- accessors ----------------------------------------------------------------------------------------------
+    def column_index(self, name: str) -> int:
+        return self.ctx.lib.pb200h_segment_column_index(self.handle, name.encode())
+
+    def column_info(self, name: str) -> Dict[str, int]:
+        out = (C.c_int32 * 6)()
+        _lib.check(self.ctx.lib.pb200h_segment_column_info(self.handle, self.column_index(name), out))
+        return dict(zip(("data_type", "has_dictionary", "bits", "cardinality", "is_sorted", "has_inverted"), out))
+
+    def dictionary_value(self, column: str, dict_id: int):
+        """Dictionary.getInternal(dictId)."""
+        ci = self.column_index(column)
+        info = self.column_info(column)
+        d, l = C.c_double(), C.c_int64()
+        buf = C.create_string_buffer(4096)
+        _lib.check(self.ctx.lib.pb200h_dictionary_get(self.handle, ci, int(dict_id), C.byref(d), C.byref(l), buf, 4096))
+        if info["data_type"] == _lib.STRING:
+            return buf.value.decode("utf-8")
+        return int(l.value) if info["data_type"] in (_lib.INT, _lib.LONG) else float(d.value)
+
+    def read_index(self, column: str, which: str) -> np.ndarray:
+        """Index file bytes as held on the device: which in {"fwd", "dict", "inv"}."""
+        L = self.ctx.lib
+        dev = L.pb200h_segment_device(self.handle)
+        w = {"fwd": 0, "dict": 1, "inv": 2}[which]
+        ci = self.column_index(column)
+        n = L.pb200_segment_read_index(self.ctx.handle, dev, ci, w, None, 0)
+        if n < 0:
+            _lib.check(int(n))
+        out = np.zeros(int(n), dtype=np.uint8)
+        if n:
+            r = L.pb200_segment_read_index(self.ctx.handle, dev, ci, w, _ptr(out), int(n))
+            if r < 0:
+                _lib.check(int(r))
+        return out
+
+    def device_bytes(self) -> int:
+        return int(self.ctx.lib.pb200_segment_device_bytes(self.ctx.lib.pb200h_segment_device(self.handle)))
+
+    def destroy(self):
+        if self.handle:
+            self.ctx.lib.pb200h_segment_destroy(self.handle)
+            self.handle = None
+
+
+@dataclass
+class ExecutionStatistics:
+    """core/operator/ExecutionStatistics.java"""
+    num_docs_scanned: int
+    num_entries_scanned_in_filter: int
+    num_entries_scanned_post_filter: int
+    num_total_docs: int
+
+
+@dataclass
+class ResultsBlock:
+    """What an AggregationResultsBlock / GroupByResultsBlock is built from (intermediate results, dictId keys)."""
+    num_groups: int  # -1: aggregation only
+    regime: str
+    groups_limit_reached: bool
+    stats: ExecutionStatistics
+    keys: np.ndarray  # [G, k] dictIds
+    doubles: List[np.ndarray]
+    longs: List[np.ndarray]
+    dict_ids: List[np.ndarray]
+    distinct: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)
+    device_ms: float = 0.0
+    operator_kind: str = "AGGREGATION"
+    handle: Optional[C.c_void_p] = None  # kept only for merged results (multi-GPU combine)
+
+    def get_results(self, query: QueryContext) -> List[object]:
+        """AggregationResultsBlock.getResults(): Long for COUNT, Double for SUM/MIN/MAX, (sum, count) for AVG,
+        set size for DISTINCTCOUNT -- row 0 (aggregation only)."""
+        out = []
+        for a, agg in enumerate(query.aggregations):
+            if agg.function == "COUNT":
+                out.append(int(self.longs[a][0]))
+            elif agg.function == "AVG":
+                out.append((float(self.doubles[a][0]), int(self.longs[a][0])))
+            elif agg.function == "DISTINCTCOUNT":
+                out.append(int(self.longs[a][0]))
+            else:
+                out.append(float(self.doubles[a][0]))
+        return out
+
+
+def _marshal_query(q: QueryContext, merge: bool):
+    nodes = postfix(q.filter)
+    keep: List[bytes] = []
+    lits: List[_lib.HLiteral] = []
+
+    def lit(v):
+        if isinstance(v, str):
+            b = v.encode("utf-8")
+            keep.append(b)
+            return _lib.HLiteral(0, 0.0, b)
+        if isinstance(v, bytes):
+            keep.append(v)
+            return _lib.HLiteral(0, 0.0, v)
+        iv = int(v) if float(v).is_integer() else int(np.floor(v))
+        return _lib.HLiteral(iv, float(v), None)
+
+    c_nodes = (_lib.HFilterNode * max(1, len(nodes)))()
+    for i, n in enumerate(nodes):
+        if isinstance(n, Filter):
+            c_nodes[i] = _lib.HFilterNode(_lib.FILTER_CODES[n.type], None, len(n.children), 0, 0, 0, 0, 0, 0)
+            continue
+        cname = n.column.encode()
+        keep.append(cname)
+        off = len(lits)
+        if n.type == "RANGE":
+            lits.append(lit(n.lower if n.lower is not None else 0))
+            lits.append(lit(n.upper if n.upper is not None else 0))
+            c_nodes[i] = _lib.HFilterNode(_lib.FILTER_CODES["RANGE"], cname, 0, int(n.lower_inclusive),
+                                          int(n.upper_inclusive), int(n.lower is None), int(n.upper is None), 2, off)
+        else:
+            for v in n.values:
+                lits.append(lit(v))
+            c_nodes[i] = _lib.HFilterNode(_lib.FILTER_CODES[n.type], cname, 0, 0, 0, 0, 0, len(n.values), off)
+    c_lits = (_lib.HLiteral * max(1, len(lits)))(*lits)
+    gb_names = [c.encode() for c in q.group_by]
+    gb = (C.c_char_p * max(1, len(gb_names)))(*gb_names)
+    aggs = (_lib.HAgg * max(1, len(q.aggregations)))()
+    for i, a in enumerate(q.aggregations):
+        nm = None if a.column is None else a.column.encode()
+        keep.append(nm)
+        aggs[i] = _lib.HAgg(_lib.AGG_CODES[a.function], nm)
+    hq = _lib.HQuery(len(nodes), c_nodes, c_lits, len(q.group_by), gb, len(q.aggregations), aggs, q.num_groups_limit,
+                     q.max_initial_result_holder_capacity, int(merge))
+    return hq, (c_nodes, c_lits, gb, gb_names, aggs, keep)
+
+
+def _read_result(ctx: B200Context, handle, q: QueryContext, kind: int, keep_handle: bool) -> ResultsBlock:
+    L = ctx.lib
+    meta = _lib.ResultMeta()
+    _lib.check(L.pb200_result_meta_get(handle, C.byref(meta)))
+    g = meta.num_groups
+    rows = 1 if g < 0 else g
+    k = len(q.group_by)
+    keys = np.zeros((max(g, 0), k), dtype=np.int32)
+    if g > 0 and k > 0:
+        _lib.check(L.pb200_result_group_keys(handle, _ptr(keys)))
+    doubles, longs, ids, distinct = [], [], [], {}
+    for a, agg in enumerate(q.aggregations):
+        d = np.zeros(rows, dtype=np.float64)
+        l = np.zeros(rows, dtype=np.int64)
+        di = np.full(rows, -1, dtype=np.int32)
+        if rows:
+            _lib.check(L.pb200_result_agg(handle, a, _ptr(d), _ptr(l)))
+            _lib.check(L.pb200_result_agg_dict_ids(handle, a, _ptr(di)))
+        doubles.append(d)
+        longs.append(l)
+        ids.append(di)
+        if agg.function == "DISTINCTCOUNT":
+            for row in range(rows):
+                buf = np.zeros(int(l[row]), dtype=np.int32)
+                n = L.pb200_result_distinct(handle, a, row, _ptr(buf), len(buf))
+                if n < 0:
+                    _lib.check(int(n))
+                distinct[(a, row)] = buf
+    stats = ExecutionStatistics(meta.num_docs_scanned, meta.num_entries_scanned_in_filter,
+                                meta.num_entries_scanned_post_filter, meta.num_total_docs)
+    block = ResultsBlock(g, _lib.REGIMES[meta.regime], bool(meta.groups_limit_reached), stats, keys, doubles, longs,
+                         ids, distinct, meta.device_ms, _lib.OPERATOR_KINDS.get(kind, "AGGREGATION"))
+    if keep_handle:
+        block.handle = handle
+    else:
+        L.pb200_result_free(handle)
+    return block
+
+
+class Operator:
+    """GroupByOperator / AggregationOperator stand-in: next_block() may be called once."""
+
+    def __init__(self, plan_maker: "B200PlanMaker", segment: IndexSegment, query: QueryContext):
+        self._pm, self._segment, self._query = plan_maker, segment, query
+        self._block: Optional[ResultsBlock] = None
+
+    def next_block(self) -> ResultsBlock:
+        if self._block is None:
+            self._block = self._pm.execute_segments([self._segment], self._query)[0]
+        return self._block
+
+    def get_execution_statistics(self) -> ExecutionStatistics:
+        return self.next_block().stats
+
+    def get_index_segment(self) -> IndexSegment:
+        return self._segment
+
+    def to_explain_string(self) -> str:
+        return self._pm.explain(self._segment, self._query)
+
+
+class PlanNode:
+    def __init__(self, plan_maker, segment, query):
+        self._args = (plan_maker, segment, query)
+
+    def run(self) -> Operator:
+        return Operator(*self._args)
+
+
+class B200PlanMaker:
+    """``PlanMaker`` for this path (core/plan/maker/PlanMaker.java:37-67)."""
+
+    def __init__(self, ctx: B200Context):
+        self.ctx = ctx
+
+    def make_segment_plan_node(self, segment: IndexSegment, query: QueryContext) -> PlanNode:
+        return PlanNode(self, segment, query)
+
+    def explain(self, segment: IndexSegment, query: QueryContext) -> str:
+        hq, _keep = _marshal_query(query, False)
+        buf = C.create_string_buffer(8192)
+        n = self.ctx.lib.pb200h_explain(self.ctx.handle, C.byref(hq), segment.handle, buf, 8192)
+        if n < 0:
+            _lib.check(n)
+        return buf.value.decode()
+
+    def execute_segments(self, segments: Sequence[IndexSegment], query: QueryContext, merge: bool = False,
+                         keep_handle: bool = False) -> List[ResultsBlock]:
+        """All segments of one query in ONE device submission (makeInstancePlan-level batching).  With merge=True the
+        segments (sharing dictionaries) are combined on the device and one block is returned."""
+        hq, _keep = _marshal_query(query, merge)
+        n = len(segments)
+        segs = (C.c_void_p * n)(*[s.handle for s in segments])
+        nres = 1 if merge else n
+        res = (C.c_void_p * nres)()
+        kinds = (C.c_int32 * n)()
+        _lib.check(self.ctx.lib.pb200h_execute(self.ctx.handle, C.byref(hq), segs, n, res, kinds))
+        return [_read_result(self.ctx, C.c_void_p(res[i]), query, kinds[i if not merge else 0], keep_handle and merge)
+                for i in range(nres)]

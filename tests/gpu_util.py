@@ -1,0 +1,46 @@
+"""Helpers shared by the -m gpu tests: run one query through the product (C-ABI) and through the oracle, compare."""
+from __future__ import annotations
+
+import numpy as np
+
+from pinot_b200.plan_maker import IndexSegment
+from reduce_util import normalise
+
+SUM_REL_TOL = 1e-6  # BASELINE.json north_star: SUM / AVG within 1e-6 relative; everything else bit exact
+
+
+def to_device(ctx, seg_data) -> IndexSegment:
+    """Registers oracle-built Pinot index buffers with the device library (host pointers -> HBM)."""
+    return IndexSegment.from_columns(ctx, seg_data.name, seg_data.num_docs, seg_data.columns)
+
+
+def gpu_table(seg_data, q, block):
+    return normalise(seg_data, q, block.num_groups, block.keys, block.doubles, block.longs, block.distinct)
+
+
+def oracle_table(seg_data, q, r):
+    return normalise(seg_data, q, r.num_groups, r.keys, r.doubles, r.longs, r.distinct)
+
+
+def assert_tables_equal(q, got, want, what=""):
+    assert set(got.keys()) == set(want.keys()), f"{what}: group keys differ: {len(got)} vs {len(want)}"
+    for key, wv in want.items():
+        gv = got[key]
+        for a, agg in enumerate(q.aggregations):
+            fn = agg.function
+            if fn in ("SUM",):
+                assert gv[a] == wv[a] or abs(gv[a] - wv[a]) <= SUM_REL_TOL * abs(wv[a]), (what, key, fn, gv[a], wv[a])
+            elif fn == "AVG":
+                assert gv[a][1] == wv[a][1], (what, key, fn, gv[a], wv[a])
+                assert gv[a][0] == wv[a][0] or abs(gv[a][0] - wv[a][0]) <= SUM_REL_TOL * abs(wv[a][0]), (what, key, fn)
+            else:  # COUNT / MIN / MAX / DISTINCTCOUNT: bit exact
+                assert gv[a] == wv[a], (what, key, fn, gv[a], wv[a])
+
+
+def check_query(oracle, pm, seg_data, dev_seg, q, what=""):
+    r = oracle.execute(seg_data, q)
+    block = pm.make_segment_plan_node(dev_seg, q).run().next_block()
+    assert_tables_equal(q, gpu_table(seg_data, q, block), oracle_table(seg_data, q, r), what)
+    assert block.stats.num_docs_scanned == r.stats[0], what
+    assert block.stats.num_total_docs == r.stats[3], what
+    return r, block

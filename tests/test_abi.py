@@ -1,0 +1,56 @@
+"""CPU-side checks of the boundary: the shared library loads and exports every symbol the headers declare."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb200h?_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pinot_b200 import _lib
+    from pinot_b200.build import build
+    build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared("pinot_b200.h") + _declared("pinot_b200_host.h")
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert sorted(set(_lib.EXPORTED_SYMBOLS)) == sorted(set(declared))
+    assert lib.pb200_abi_version() == 1
+
+
+def test_init_fails_loudly_without_gpu():
+    """No CPU fallback: without a CUDA device pb200_init must fail with a message (skipped on the GPU box)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pinot_b200 import _lib
+    from pinot_b200.plan_maker import B200Context
+    with pytest.raises(_lib.Pb200Error) as e:
+        B200Context(0)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_sql_front_end_shapes():
+    from pinot_b200 import sql
+    import golden_cases as G
+    q = sql.parse(G.AGGREGATION_QUERY + G.FILTER + G.MEDIUM_GROUP_BY)
+    assert [a.function for a in q.aggregations] == ["COUNT", "SUM", "MAX", "MIN", "AVG"]
+    assert q.group_by == ["column9", "column11", "column12"]
+    assert q.filter.type == "AND" and len(q.filter.children) == 5
+    assert q.filter.children[3].type == "OR"
+    q = sql.parse("SELECT SUM(a) FROM t WHERE a > 3 AND a <= 10 AND b = 1")
+    rng = [c for c in q.filter.children if c.type == "RANGE"]
+    assert len(rng) == 1 and rng[0].lower == 3 and not rng[0].lower_inclusive and rng[0].upper == 10  # MergeRange
+    q = sql.parse("SELECT COUNT(*) FROM t WHERE a = 1 OR a = 2 OR b = 3")
+    assert sorted(c.type for c in q.filter.children) == ["EQ", "IN"]  # MergeEqIn
+    with pytest.raises(sql.SqlError):
+        sql.parse("SELECT a FROM t")
