@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--selectivity", type=float, default=0.25)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000, help="rows per oracle work item")
+    ap.add_argument("--quick", action="store_true", help="tuning runs: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -288,6 +289,19 @@ def main():
     k_ms = statistics.mean(kernel_ms)
     peak, peak_src = measured_peak_gbs()
     achieved = rows_per_step * bpr / (k_ms * 1e-3) / 1e9
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_per_step, "kernel_ms": k_ms,
+                              "achieved_gbs": achieved, "frac": achieved / peak, "clocks": clocks,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("PB200_")},
+                              "selectivity": args.selectivity, "count": c}))
+        for sgm in segs:
+            sgm.destroy()
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
 
     # ---- e2e: host-resident index buffers, H2D inside the timed region (rank-local; N>1: max over ranks) ----
     pinned = []

@@ -117,8 +117,8 @@ static inline uint32_t be32(const unsigned char* p) { return (uint32_t)p[0] << 2
 static inline uint64_t be64(const unsigned char* p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
 
 static uint64_t padded_fwd_bytes(long long num_docs, int bits) {
-  long long tiles = (num_docs + kMaxTileRows - 1) / kMaxTileRows;
-  if (tiles == 0) tiles = 1;
+  // whole tiles for ANY tile size <= kMaxTileRows: ceil(N/t)*t < N + t <= alloc rows
+  long long tiles = (num_docs + kMaxTileRows - 1) / kMaxTileRows + 1;
   return (uint64_t)tiles * kMaxTileRows / 8 * bits + 64;
 }
 
@@ -570,14 +570,19 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     max_bits_sum = std::max(max_bits_sum, sum);
   }
   const size_t hdr_bytes = (sizeof(SmemHeader) + 127) / 128 * 128;
-  int cw = 8, stages = 0;
-  for (; cw >= 4; cw -= 4) {
+  // tile = CW consumer warps x 1024 rows.  CW = 7 -> 256-thread CTA, one per SM (255 registers available);
+  // CW = 3 -> 128-thread CTA, three per SM.
+  int cw = 7, stages = 0;
+  if (getenv("PB200_CW") && atoi(getenv("PB200_CW")) == 3) cw = 3;  // tuning knob
+  q.sparse_max = getenv("PB200_SPARSE_MAX") ? atoi(getenv("PB200_SPARSE_MAX")) : 16;
+  for (;;) {
+    const int ctas = cw == 7 ? 1 : 3;
     size_t stage_bytes = (size_t)cw * 1024 / 8 * max_bits_sum;
     size_t stack_bytes = q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4;
-    size_t budget = (size_t)ctx->max_smem_optin - hdr_bytes - stack_bytes - 256;
-    if (cw == 4) budget = (size_t)ctx->max_smem_optin / 2 - hdr_bytes - stack_bytes - 2048;  // 2 CTAs / SM
-    stages = stage_bytes == 0 ? 2 : (int)std::min<size_t>(8, budget / stage_bytes);
-    if (stages >= 2) break;
+    long long budget = (long long)ctx->max_smem_optin / ctas - (long long)hdr_bytes - (long long)stack_bytes - 1024 * ctas;
+    stages = stage_bytes == 0 ? 2 : (budget <= 0 ? 0 : (int)std::min<long long>(8, budget / (long long)stage_bytes));
+    if (stages >= 2 || cw == 3) break;
+    cw = 3;
   }
   if (stages < 2) { set_error("touched columns too wide for the shared-memory pipeline (%d bits per row)", max_bits_sum); return PB200_E_UNSUPPORTED; }
   if (getenv("PB200_STAGES")) stages = std::max(2, std::min(stages, atoi(getenv("PB200_STAGES"))));
@@ -708,6 +713,24 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     }
   }
 
+  // ---- conjunctions: cheapest / most selective leaf first (per segment; AND is commutative).  The reference orders
+  //      AND children by operator priority (FilterOperatorUtils.java:205-251) and, with AndScanReordering, by estimated
+  //      cardinality (AndDocIdSet.java:118-120); here the estimate is the matching fraction of the dictionary. ----
+  if (q.conj && nleaves > 1) {
+    for (int s = 0; s < nseg; s++) {
+      SegDesc& sd = plan.segs[s];
+      auto cost = [&](const LeafDesc& lf) -> double {
+        if (lf.slot < 0) return -1.0;  // doc masks / ranges / constants: no column to unpack
+        const DeviceColumn& c = segments[s]->cols[plan.slot_cols[lf.slot]];
+        double frac = 1.0;
+        if (lf.kind == LEAF_RANGE) frac = (double)lf.span / std::max(c.cardinality, 1);
+        else if (lf.kind == LEAF_LUT) frac = 0.5;
+        return lf.negate ? 1.0 - frac : frac;
+      };
+      std::stable_sort(sd.leaves, sd.leaves + nleaves, [&](const LeafDesc& a, const LeafDesc& b) { return cost(a) < cost(b); });
+    }
+  }
+
   // ---- outputs ----
   AggAccum init_acc;
   memset(&init_acc, 0, sizeof init_acc);
@@ -819,7 +842,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   int rc = dsegs.alloc(ctx, sizeof(SegDesc) * nseg);
   if (rc) return rc;
   PB200_CUDA(cudaMemcpyAsync(dsegs.p, plan.segs.data(), sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, st));
-  const int ctas_per_sm = cw == 4 ? 2 : 1;
+  const int ctas_per_sm = cw == 3 ? 3 : 1;
   int grid = (int)std::min<long long>((long long)ctx->sm_count * ctas_per_sm, std::max<long long>(q.total_tiles, 1));
   if (getenv("PB200_GRID")) grid = std::max(1, atoi(getenv("PB200_GRID")));
   cudaEvent_t e0, e1;
@@ -827,8 +850,8 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   PB200_CUDA(cudaEventCreate(&e1));
   PB200_CUDA(cudaEventRecord(e0, st));
   cudaError_t le;
-  if (cw == 8) le = plan.group_by ? launch_scan<8, true>(plan, (const SegDesc*)dsegs.p, grid, st) : launch_scan<8, false>(plan, (const SegDesc*)dsegs.p, grid, st);
-  else le = plan.group_by ? launch_scan<4, true>(plan, (const SegDesc*)dsegs.p, grid, st) : launch_scan<4, false>(plan, (const SegDesc*)dsegs.p, grid, st);
+  if (cw == 7) le = plan.group_by ? launch_scan<7, true>(plan, (const SegDesc*)dsegs.p, grid, st) : launch_scan<7, false>(plan, (const SegDesc*)dsegs.p, grid, st);
+  else le = plan.group_by ? launch_scan<3, true>(plan, (const SegDesc*)dsegs.p, grid, st) : launch_scan<3, false>(plan, (const SegDesc*)dsegs.p, grid, st);
   if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }
   PB200_CUDA(cudaEventRecord(e1, st));
   cudaError_t se = cudaStreamSynchronize(st);

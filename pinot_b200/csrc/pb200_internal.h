@@ -23,7 +23,8 @@ void set_error(const char* fmt, ...);
     }                                                                                            \
   } while (0)
 
-// Largest tile the scan kernel uses: 8 consumer warps x 1024 rows.  Forward indexes are padded to whole tiles.
+// Upper bound of the scan kernel's tile (consumer warps x 1024 rows).  Forward indexes are padded so that whole tiles
+// of any size up to this can be streamed.
 constexpr int kMaxTileRows = 8192;
 
 struct DeviceColumn {

@@ -101,6 +101,28 @@ __device__ __forceinline__ uint32_t eval_doc_ranges(long long row0, const int32_
   return m;
 }
 
+
+// One value of a thread's 32-row group straight from the tile: bit offset j*bits inside the group's `bits` words.
+__device__ __forceinline__ uint32_t read_one_group(const uint32_t* __restrict__ p, int j, int bits) {
+  const int bit = j * bits;
+  const int k = bit >> 5, s = bit & 31;
+  const uint32_t hi = bswap32(p[k]);
+  const uint32_t lo = (s + bits > 32) ? bswap32(p[k + 1]) : 0u;
+  const uint32_t x = __funnelshift_l(lo, hi, s);
+  return bits == 32 ? x : (x >> (32 - bits));
+}
+// Branch-free predicated gathers: the load is skipped (not just masked) for rows that did not survive the filter.
+__device__ __forceinline__ int ldg_pred_s32(const int* p, uint32_t pred) {
+  int x;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(x) : "l"(p), "r"(pred));
+  return x;
+}
+__device__ __forceinline__ long long ldg_pred_s64(const long long* p, uint32_t pred) {
+  long long x;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b64 %0, 0;\n\t@p ld.global.nc.b64 %0, [%1];\n\t}" : "=l"(x) : "l"(p), "r"(pred));
+  return x;
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T x) {
 #pragma unroll
@@ -128,7 +150,7 @@ struct SmemHeader {
 };
 
 template <int CW, bool GROUPBY>
-__global__ void __launch_bounds__((CW + 1) * 32, (CW <= 4 ? 2 : 1))
+__global__ void __launch_bounds__((CW + 1) * 32, (CW <= 3 ? 3 : 1))
 scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ segs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
@@ -241,38 +263,76 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
     uint32_t v[32];
 
     // ---------------- phase 1: filter -> row mask ----------------
+    // Conjunctions (the common case) evaluate leaf by leaf, most selective first (host order); once few rows per
+    // thread survive, the remaining columns are probed per surviving row straight from the shared-memory tile
+    // (the GPU form of ScanBasedDocIdIterator.applyAnd on the bitmap of survivors, AndDocIdSet.java:167-169)
+    // instead of unpacking all 32 values.
+    int v_slot = -1;  // which slot v[] currently holds (dense unpack), -1 = none
     if (q.num_nodes > 0) {
-      uint32_t lm[kMaxLeaves];
-#pragma unroll
-      for (int l = 0; l < kMaxLeaves; ++l) {
-        lm[l] = 0xFFFFFFFFu;
-        if (l < q.num_leaves) {
-          const LeafDesc& lf = sd.leaves[l];
-          if (lf.kind == LEAF_NONE) lm[l] = 0u;
-          else if (lf.kind == LEAF_DOCMASK) lm[l] = left > 0 ? __ldg(lf.bits + (row0 >> 5)) : 0u;
-          else if (lf.kind == LEAF_DOCRANGES) lm[l] = eval_doc_ranges(row0, lf.ranges, lf.num_ranges);
-        }
-      }
-      for (int s = 0; s < q.num_slots; ++s) {
-        if (!(q.slot_roles[s] & ROLE_FILTER)) continue;
-        unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
-#pragma unroll
-        for (int l = 0; l < kMaxLeaves; ++l) {
-          if (l < q.num_leaves && sd.leaves[l].slot == s) {
-            const LeafDesc& lf = sd.leaves[l];
-            if (lf.kind == LEAF_RANGE) lm[l] = eval_range(v, lf.lo, lf.span);
-            else if (lf.kind == LEAF_LUT) lm[l] = eval_lut(v, lf.bits);
-          }
-        }
-      }
-#pragma unroll
-      for (int l = 0; l < kMaxLeaves; ++l)
-        if (l < q.num_leaves && sd.leaves[l].negate) lm[l] = ~lm[l];
       if (q.conj) {
 #pragma unroll
-        for (int l = 0; l < kMaxLeaves; ++l)
-          if (l < q.num_leaves) m &= lm[l];
+        for (int l = 0; l < kMaxLeaves; ++l) {
+          if (l < q.num_leaves) {
+            const LeafDesc& lf = sd.leaves[l];
+            uint32_t lm;
+            if (lf.kind == LEAF_ALL) lm = 0xFFFFFFFFu;
+            else if (lf.kind == LEAF_NONE) lm = 0u;
+            else if (lf.kind == LEAF_DOCMASK) lm = left > 0 ? __ldg(lf.bits + (row0 >> 5)) : 0u;
+            else if (lf.kind == LEAF_DOCRANGES) lm = eval_doc_ranges(row0, lf.ranges, lf.num_ranges);
+            else {
+              const int wmax = __reduce_max_sync(0xFFFFFFFFu, __popc(m));
+              const SlotDesc& sl = sd.slots[lf.slot];
+              if (wmax == 0) {
+                lm = 0u;  // nothing left to test (m == 0 in every lane)
+              } else if (wmax <= q.sparse_max && v_slot != lf.slot) {
+                const uint32_t* p = st + sl.stage_words + group * sl.bits;
+                uint32_t keep = 0, mm = m;
+                while (mm) {
+                  const int j = __ffs(mm) - 1;
+                  mm &= mm - 1;
+                  const uint32_t id = read_one_group(p, j, sl.bits);
+                  const bool hit = lf.kind == LEAF_RANGE ? ((id - lf.lo) < lf.span)
+                                                         : (((__ldg(lf.bits + (id >> 5)) >> (id & 31)) & 1u) != 0u);
+                  keep |= (hit ? 1u : 0u) << j;
+                }
+                lm = keep;  // bits outside m are irrelevant (m &= lm below)
+              } else {
+                if (v_slot != lf.slot) { unpack_group(sl.bits, st + sl.stage_words, group, v); v_slot = lf.slot; }
+                lm = lf.kind == LEAF_RANGE ? eval_range(v, lf.lo, lf.span) : eval_lut(v, lf.bits);
+              }
+            }
+            if (lf.negate) lm = ~lm;
+            m &= lm;
+          }
+        }
       } else {
+        uint32_t lm[kMaxLeaves];
+#pragma unroll
+        for (int l = 0; l < kMaxLeaves; ++l) {
+          lm[l] = 0xFFFFFFFFu;
+          if (l < q.num_leaves) {
+            const LeafDesc& lf = sd.leaves[l];
+            if (lf.kind == LEAF_NONE) lm[l] = 0u;
+            else if (lf.kind == LEAF_DOCMASK) lm[l] = left > 0 ? __ldg(lf.bits + (row0 >> 5)) : 0u;
+            else if (lf.kind == LEAF_DOCRANGES) lm[l] = eval_doc_ranges(row0, lf.ranges, lf.num_ranges);
+          }
+        }
+        for (int s = 0; s < q.num_slots; ++s) {
+          if (!(q.slot_roles[s] & ROLE_FILTER)) continue;
+          unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
+          v_slot = s;
+#pragma unroll
+          for (int l = 0; l < kMaxLeaves; ++l) {
+            if (l < q.num_leaves && sd.leaves[l].slot == s) {
+              const LeafDesc& lf = sd.leaves[l];
+              if (lf.kind == LEAF_RANGE) lm[l] = eval_range(v, lf.lo, lf.span);
+              else if (lf.kind == LEAF_LUT) lm[l] = eval_lut(v, lf.bits);
+            }
+          }
+        }
+#pragma unroll
+        for (int l = 0; l < kMaxLeaves; ++l)
+          if (l < q.num_leaves && sd.leaves[l].negate) lm[l] = ~lm[l];
         // postfix boolean program over masks; the stack lives in shared memory (column per thread: conflict free)
         uint32_t* stk = fstack + group;
         int sp = 0;
@@ -300,16 +360,64 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
     }
 
     // ---------------- phase 2: aggregate the surviving rows ----------------
-    cnt += __popc(m);
-    const bool warp_any = __any_sync(0xFFFFFFFFu, m != 0u);
-    if (warp_any) {
+    const int pc = __popc(m);
+    cnt += pc;
+    const int wmax2 = __reduce_max_sync(0xFFFFFFFFu, pc);
+    if (wmax2 > 0 && wmax2 <= q.sparse_max) {
+      // ---- sparse projection: per surviving row, read its dictIds from the tile (FixedBitIntReader.readUnchecked
+      //      shape; what DataFetcher does with sparse docIds, core/common/DataFetcher.java:335-338) ----
+      uint32_t mm = m;
+      while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
+        uint32_t g = 0;
+        if (GROUPBY) {
+#pragma unroll
+          for (int gi = 0; gi < kMaxGroupBy; ++gi) {
+            if (gi < q.num_group_by) {
+              const SlotDesc& sl = sd.slots[q.group_slot[gi]];
+              g += read_one_group(st + sl.stage_words + group * sl.bits, j, sl.bits) * sd.group_mult[gi];
+            }
+          }
+          atomicAdd(sd.g_count + g, 1ull);
+        }
+#pragma unroll
+        for (int a = 0; a < kMaxAggs; ++a) {
+          if (a < q.num_aggs && q.aggs[a].slot >= 0) {
+            const SlotDesc& sl = sd.slots[q.aggs[a].slot];
+            const uint32_t id = read_one_group(st + sl.stage_words + group * sl.bits, j, sl.bits);
+            const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
+            if (fn == 1 || fn == 4) {
+              if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
+                const double x = vk == VAL_DICT_F32 ? (double)__ldg(static_cast<const float*>(sd.dict[a]) + id)
+                                                    : __ldg(static_cast<const double*>(sd.dict[a]) + id);
+                if (GROUPBY) atomicAdd(sd.g_dsum[a] + g, x); else dsum[a] += x;
+              } else {
+                const long long x = vk == VAL_DICT_I32 ? (long long)__ldg(static_cast<const int*>(sd.dict[a]) + id)
+                                    : vk == VAL_DICT_I64 ? __ldg(static_cast<const long long*>(sd.dict[a]) + id)
+                                                         : (long long)(int)id;
+                if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + g), (unsigned long long)x);
+                else isum[a] += x;
+              }
+            } else if (fn == 2 || fn == 3) {
+              const uint32_t x = id ^ (vk == VAL_RAW_I32 ? 0x80000000u : 0u);
+              if (GROUPBY) { if (fn == 2) atomicMin(sd.g_min[a] + g, x); else atomicMax(sd.g_max[a] + g, x + 1u); }
+              else { mn[a] = min(mn[a], x); mx[a] = max(mx[a], x + 1u); }
+            } else if (fn == 5 && !GROUPBY) {
+              atomicOr(sd.distinct_bits[a] + (id >> 5), 1u << (id & 31));
+            }
+          }
+        }
+      }
+    } else if (wmax2 > 0) {
+      // ---- dense projection: unpack all 32 values of each needed column ----
       uint32_t gid[32];
       if (GROUPBY) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) gid[j] = 0;
         for (int s = 0; s < q.num_slots; ++s) {
           if (!(q.slot_roles[s] & ROLE_GROUP)) continue;
-          unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
+          if (v_slot != s) { unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v); v_slot = s; }
 #pragma unroll
           for (int g = 0; g < kMaxGroupBy; ++g) {
             if (g < q.num_group_by && q.group_slot[g] == s) {
@@ -325,61 +433,61 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
       }
       for (int s = 0; s < q.num_slots; ++s) {
         if (!(q.slot_roles[s] & ROLE_AGG)) continue;
-        unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
+        if (v_slot != s) { unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v); v_slot = s; }
 #pragma unroll
         for (int a = 0; a < kMaxAggs; ++a) {
           if (a < q.num_aggs && q.aggs[a].slot == s) {
             const int fn = q.aggs[a].function;
             const int vk = q.aggs[a].val_kind;
             if (fn == 1 || fn == 4) {  // SUM / AVG: value = dictionary[dictId]
-              if (vk == VAL_DICT_I32) {
+              if (vk == VAL_DICT_I32 || vk == VAL_RAW_I32) {
                 const int* __restrict__ d = static_cast<const int*>(sd.dict[a]);
+                int x[32];
+                // all (predicated) gathers are issued before the first use: one L2 latency per tile, not 32
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if ((m >> j) & 1u) {
-                    long long x = __ldg(d + v[j]);
-                    if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)x);
-                    else isum[a] += x;
-                  }
+                for (int j = 0; j < 32; ++j) x[j] = vk == VAL_RAW_I32 ? (((m >> j) & 1u) ? (int)v[j] : 0) : ldg_pred_s32(d + v[j], (m >> j) & 1u);
+                if (GROUPBY) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if ((m >> j) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)(long long)x[j]);
+                } else {
+                  long long acc = 0;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) acc += x[j];
+                  isum[a] += acc;
                 }
               } else if (vk == VAL_DICT_I64) {
                 const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
+                long long x[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if ((m >> j) & 1u) {
-                    long long x = __ldg(d + v[j]);
-                    if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)x);
-                    else isum[a] += x;
-                  }
+                for (int j = 0; j < 32; ++j) x[j] = ldg_pred_s64(d + v[j], (m >> j) & 1u);
+                if (GROUPBY) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if ((m >> j) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)x[j]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) isum[a] += x[j];
                 }
               } else if (vk == VAL_DICT_F32) {
                 const float* __restrict__ d = static_cast<const float*>(sd.dict[a]);
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = __int_as_float(ldg_pred_s32(reinterpret_cast<const int*>(d + v[j]), (m >> j) & 1u));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                  if ((m >> j) & 1u) {
-                    double x = (double)__ldg(d + v[j]);
-                    if (GROUPBY) atomicAdd(sd.g_dsum[a] + gid[j], x);
-                    else dsum[a] += x;
-                  }
+                  if (GROUPBY) { if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], (double)x[j]); }
+                  else dsum[a] += (double)x[j];
                 }
               } else if (vk == VAL_DICT_F64) {
                 const double* __restrict__ d = static_cast<const double*>(sd.dict[a]);
+                double x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = __longlong_as_double(ldg_pred_s64(reinterpret_cast<const long long*>(d + v[j]), (m >> j) & 1u));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                  if ((m >> j) & 1u) {
-                    double x = __ldg(d + v[j]);
-                    if (GROUPBY) atomicAdd(sd.g_dsum[a] + gid[j], x);
-                    else dsum[a] += x;
-                  }
-                }
-              } else if (vk == VAL_RAW_I32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if ((m >> j) & 1u) {
-                    long long x = (int)v[j];
-                    if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)x);
-                    else isum[a] += x;
-                  }
+                  if (GROUPBY) { if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], x[j]); }
+                  else dsum[a] += x[j];
                 }
               }
             } else if (fn == 2 || fn == 3) {  // MIN / MAX on dictIds (dictionaries are sorted: order preserving)

@@ -220,7 +220,7 @@ extern "C" int32_t pb200_synth_segment(pb200_ctx* ctx, const char* name, int32_t
     if (sc.cardinality < 1) { set_error("cardinality must be >= 1"); cleanup(false); return PB200_E_INVALID; }
     int bits = 1;
     while (bits < 31 && (1ll << bits) < sc.cardinality) bits++;  // PinotDataBitSet.getNumBitsPerValue(card - 1)
-    long long tiles = ((long long)num_docs + kMaxTileRows - 1) / kMaxTileRows;
+    long long tiles = ((long long)num_docs + kMaxTileRows - 1) / kMaxTileRows + 1;  // see padded_fwd_bytes()
     uint64_t alloc = (uint64_t)tiles * kMaxTileRows / 8 * bits + 64;
     uint32_t* fwd = nullptr;
     cudaError_t e = cudaMalloc(&fwd, alloc);

@@ -194,8 +194,9 @@ def test_parity_wide_columns(oracle, ctx, pm, bits):
     kcol = sb.build_column("k", k)
     xcol = sb.ColumnData("x", sb.INT, True, bits, card, False, 4, fwd, None, None)
     # registering needs card*4 dictionary bytes: allocate lazily-zero pages
-    full = np.zeros(card, dtype=">i4")
+    full = np.empty(card, dtype=">i4")
     full[:lim] = dict_vals
+    full[lim:] = int(dict_vals[-1]) + 1 + np.arange(card - lim, dtype=np.int64)  # dictionaries are strictly sorted
     xcol.dict = np.frombuffer(full.tobytes(), dtype=np.uint8)
     xcol.dict_values = full.astype(np.int32)
     seg = sb.SegmentData("wide", n, [xcol, kcol])
