@@ -230,7 +230,15 @@ static int convert_dictionary(const pb200_col_desc& d, DeviceColumn& c, const un
     else { uint64_t v = be64(be + 8ll * i); memcpy(&c.dict_host[8ull * i], &v, 8); }
   }
   PB200_CUDA(cudaMalloc(&c.dict_native, std::max<size_t>(c.dict_host.size(), 16)));
-  PB200_CUDA(cudaMemcpy(c.dict_native, c.dict_host.data(), c.dict_host.size(), cudaMemcpyHostToDevice));
+  if (c.stored_type == PB200_INT) {
+    // the DEVICE copy of an INT dictionary is biased (value ^ 0x80000000 == value + 2^31 as unsigned): the scan kernel
+    // sums unsigned words with 3-input adds and removes count * 2^31 once per tile (SumBiasedU32)
+    std::vector<uint32_t> biased(c.cardinality);
+    for (int i = 0; i < c.cardinality; i++) { uint32_t v; memcpy(&v, &c.dict_host[4ull * i], 4); biased[i] = v ^ 0x80000000u; }
+    PB200_CUDA(cudaMemcpy(c.dict_native, biased.data(), biased.size() * 4, cudaMemcpyHostToDevice));
+  } else {
+    PB200_CUDA(cudaMemcpy(c.dict_native, c.dict_host.data(), c.dict_host.size(), cudaMemcpyHostToDevice));
+  }
   return PB200_OK;
 }
 
@@ -436,6 +444,15 @@ int regime_of(const std::vector<int>& cards, int array_threshold) {
   return product > array_threshold ? PB200_REGIME_INT_MAP : PB200_REGIME_ARRAY;
 }
 
+// one-sided ranges: every stored dictId is < cardinality, so "hi covers the dictionary" needs no upper compare
+void set_cmp(LeafDesc& lf, const DeviceColumn& c) {
+  const unsigned long long hi = (unsigned long long)lf.lo + lf.span;
+  if (lf.span == 0) { lf.kind = LEAF_NONE; return; }
+  if (hi >= (unsigned long long)c.cardinality || hi >= (1ull << c.bits)) lf.cmp = CMP_GE;
+  else if (lf.lo == 0) lf.cmp = CMP_LT;
+  else lf.cmp = CMP_BOTH;
+}
+
 template <int CW, bool GB>
 cudaError_t launch_scan(const Plan& p, const SegDesc* dsegs, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(scan_kernel<CW, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
@@ -570,16 +587,18 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     max_bits_sum = std::max(max_bits_sum, sum);
   }
   const size_t hdr_bytes = (sizeof(SmemHeader) + 127) / 128 * 128;
-  // tile = CW consumer warps x 1024 rows.  CW = 7 -> 256-thread CTA, one per SM (255 registers available);
-  // CW = 3 -> 128-thread CTA, three per SM.
-  int cw = 7, stages = 0;
+  // tile = CW consumer warps x 1024 rows.  CW = 7 -> 256-thread CTA: two per SM for aggregation-only queries
+  // (<= 128 registers), one per SM for group-by; CW = 3 -> 128-thread CTA, three per SM.
+  int cw = 7, stages = 0, ctas_per_sm = 1;
   if (getenv("PB200_CW") && atoi(getenv("PB200_CW")) == 3) cw = 3;  // tuning knob
-  q.sparse_max = getenv("PB200_SPARSE_MAX") ? atoi(getenv("PB200_SPARSE_MAX")) : 16;
+  q.sparse_max = getenv("PB200_SPARSE_MAX") ? atoi(getenv("PB200_SPARSE_MAX")) : 4;
+  size_t extra_bytes = 0;
   for (;;) {
-    const int ctas = cw == 7 ? 1 : 3;
+    ctas_per_sm = cw == 7 ? (plan.group_by ? 1 : 2) : 3;
+    if (getenv("PB200_CTAS")) ctas_per_sm = std::max(1, atoi(getenv("PB200_CTAS")));
     size_t stage_bytes = (size_t)cw * 1024 / 8 * max_bits_sum;
-    size_t stack_bytes = q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4;
-    long long budget = (long long)ctx->max_smem_optin / ctas - (long long)hdr_bytes - (long long)stack_bytes - 1024 * ctas;
+    extra_bytes = (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4) + (plan.group_by ? 0 : (size_t)nagg * cw * 32 * 16);
+    long long budget = (long long)ctx->max_smem_optin / ctas_per_sm - (long long)hdr_bytes - (long long)extra_bytes - 1024 - 256;
     stages = stage_bytes == 0 ? 2 : (budget <= 0 ? 0 : (int)std::min<long long>(8, budget / (long long)stage_bytes));
     if (stages >= 2 || cw == 3) break;
     cw = 3;
@@ -591,7 +610,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   q.num_stages = stages;
   q.stage_words = (uint32_t)((size_t)q.tile_rows / 32 * max_bits_sum);
   q.use_pipe = q.num_slots > 0;
-  plan.smem_bytes = hdr_bytes + (size_t)stages * q.stage_words * 4 + (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4);
+  plan.smem_bytes = hdr_bytes + (size_t)stages * q.stage_words * 4 + extra_bytes;
 
   cudaStream_t st = take_stream(ctx);
   struct StreamReturn { pb200_ctx* c; cudaStream_t s; ~StreamReturn() { give_stream(c, s); } } stream_return{ctx, st};
@@ -656,10 +675,12 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
           lf.kind = LEAF_RANGE;
           int lo = std::max(n.lo, 0), hi = std::max(n.hi, lo);
           lf.lo = (uint32_t)lo; lf.span = (uint32_t)(hi - lo);
+          set_cmp(lf, c);
         } else {
           lf.negate = n.op == PB200_F_SCAN_NOT_IN;
           if (n.num_ids == 1) {
             lf.kind = LEAF_RANGE; lf.lo = (uint32_t)n.ids[0]; lf.span = 1;
+            set_cmp(lf, c);
           } else if (n.num_ids == 0) {
             lf.kind = LEAF_NONE;
           } else {
@@ -842,7 +863,6 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   int rc = dsegs.alloc(ctx, sizeof(SegDesc) * nseg);
   if (rc) return rc;
   PB200_CUDA(cudaMemcpyAsync(dsegs.p, plan.segs.data(), sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, st));
-  const int ctas_per_sm = cw == 3 ? 3 : 1;
   int grid = (int)std::min<long long>((long long)ctx->sm_count * ctas_per_sm, std::max<long long>(q.total_tiles, 1));
   if (getenv("PB200_GRID")) grid = std::max(1, atoi(getenv("PB200_GRID")));
   cudaEvent_t e0, e1;

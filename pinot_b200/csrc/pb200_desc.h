@@ -21,6 +21,9 @@ enum : int32_t { LEAF_ALL = 0, LEAF_NONE = 1, LEAF_RANGE = 2, LEAF_LUT = 3, LEAF
 // program ops (postfix over 32-row masks)
 enum : uint8_t { OP_LEAF = 0, OP_AND = 1, OP_OR = 2, OP_NOT = 3 };
 
+// LEAF_RANGE comparison shape (one-sided ranges need one compare per value instead of subtract + compare)
+enum : int32_t { CMP_BOTH = 0, CMP_GE = 1, CMP_LT = 2 };
+
 // aggregation value kinds (how a dictId / raw word becomes a number)
 enum : int32_t { VAL_NONE = 0, VAL_DICT_I32 = 1, VAL_DICT_I64 = 2, VAL_DICT_F32 = 3, VAL_DICT_F64 = 4, VAL_RAW_I32 = 5 };
 
@@ -41,6 +44,8 @@ struct LeafDesc {
   const int32_t* ranges; // DOCRANGES: inclusive (start,end) pairs
   int32_t num_ranges;
   int32_t negate;
+  int32_t cmp;      // LEAF_RANGE: CMP_*
+  int32_t pad;
 };
 
 // Per-aggregation outputs of the aggregation-only kernel (one per segment or one merged)

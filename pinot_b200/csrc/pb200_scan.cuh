@@ -140,6 +140,61 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t x) {
   return x;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// streaming functors for dispatch_left_aligned(): consume one left-aligned value at a time (pb200_unpack.cuh)
+// ------------------------------------------------------------------------------------------------------------------
+// dictId range predicate -> 32-bit row mask.  Four partial masks keep the OR chain short (ILP).
+struct RangeBoth {   // lo <= v < hi   as   (xl - LO) < SPAN,  LO = lo << (32-B), SPAN = (hi-lo) << (32-B)
+  uint32_t LO, SPAN, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  __device__ __forceinline__ void operator()(int j, uint32_t xl) {
+    const uint32_t bit = ((xl - LO) < SPAN) ? (1u << j) : 0u;
+    if ((j & 3) == 0) m0 |= bit; else if ((j & 3) == 1) m1 |= bit; else if ((j & 3) == 2) m2 |= bit; else m3 |= bit;
+  }
+  __device__ __forceinline__ uint32_t mask() const { return (m0 | m1) | (m2 | m3); }
+};
+struct RangeGE {     // v >= lo  (upper bound is the whole dictionary: every stored dictId is < cardinality)
+  uint32_t LO, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  __device__ __forceinline__ void operator()(int j, uint32_t xl) {
+    const uint32_t bit = (xl >= LO) ? (1u << j) : 0u;
+    if ((j & 3) == 0) m0 |= bit; else if ((j & 3) == 1) m1 |= bit; else if ((j & 3) == 2) m2 |= bit; else m3 |= bit;
+  }
+  __device__ __forceinline__ uint32_t mask() const { return (m0 | m1) | (m2 | m3); }
+};
+struct RangeLT {     // v < hi  (lower bound 0)
+  uint32_t HI, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  __device__ __forceinline__ void operator()(int j, uint32_t xl) {
+    const uint32_t bit = (xl < HI) ? (1u << j) : 0u;
+    if ((j & 3) == 0) m0 |= bit; else if ((j & 3) == 1) m1 |= bit; else if ((j & 3) == 2) m2 |= bit; else m3 |= bit;
+  }
+  __device__ __forceinline__ uint32_t mask() const { return (m0 | m1) | (m2 | m3); }
+};
+// SUM over an INT dictionary: gather the BIASED value (value ^ 0x80000000, i.e. value + 2^31 as unsigned) of every
+// surviving row and add pairs with one 3-input 64-bit add; the bias is removed once per tile (popc * 2^31).
+struct SumBiasedU32 {
+  const uint32_t* __restrict__ d;
+  uint32_t m, sh;
+  unsigned long long a0 = 0, a1 = 0;
+  uint32_t pend = 0;
+  __device__ __forceinline__ void operator()(int j, uint32_t xl) {
+    const uint32_t x = (uint32_t)ldg_pred_s32(reinterpret_cast<const int*>(d + (xl >> sh)), (m >> j) & 1u);
+    if ((j & 1) == 0) {
+      pend = x;
+    } else if ((j & 2) == 0) {
+      a0 += (unsigned long long)pend + (unsigned long long)x;
+    } else {
+      a1 += (unsigned long long)pend + (unsigned long long)x;
+    }
+  }
+};
+// MIN / MAX of dictIds on the left-aligned form (order preserving; shift back once at the end)
+struct MinMaxLeft {
+  uint32_t m, mn = 0xFFFFFFFFu, mx = 0u;
+  __device__ __forceinline__ void operator()(int j, uint32_t xl) {
+    if ((m >> j) & 1u) { mn = min(mn, xl); mx = max(mx, xl); }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
@@ -149,15 +204,21 @@ struct SmemHeader {
   uint64_t empty[8];      // stage drained by all consumer warps
 };
 
+// Shared-memory layout (dynamic):  [SmemHeader][stages x stage_words][filter stack (generic filters only)]
+//                                   [acc64: num_aggs x consumers x 8 B][accmm: num_aggs x consumers x 8 B]
+// acc64/accmm are the per-thread running aggregates of the aggregation-only kernel; they live in shared memory (one
+// private slot per thread, touched once per tile) instead of registers so that two CTAs fit on an SM.
 template <int CW, bool GROUPBY>
-__global__ void __launch_bounds__((CW + 1) * 32, (CW <= 3 ? 3 : 1))
+__global__ void __launch_bounds__((CW + 1) * 32, (CW <= 3 ? 3 : (GROUPBY ? 1 : 2)))
 scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ segs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
   constexpr int kHdrBytes = (sizeof(SmemHeader) + 127) / 128 * 128;
+  constexpr int kConsumers = CW * 32;
   uint32_t* stages = reinterpret_cast<uint32_t*>(smem_raw + kHdrBytes);
   uint32_t* fstack = stages + (size_t)q.num_stages * q.stage_words;  // generic-filter mask stack (if !conj)
-  constexpr int kConsumers = CW * 32;
+  unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(fstack + (q.conj ? 0 : kConsumers * kMaxStack));
+  uint2* accmm = reinterpret_cast<uint2*>(acc64 + (size_t)q.num_aggs * kConsumers);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool use_pipe = q.use_pipe != 0;
@@ -198,45 +259,44 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
   // ================================== consumers ==================================
   const int group = threadIdx.x;  // 32-row group inside the tile
   const SegDesc& sd = hdr->seg;
-
-  // per-thread accumulators (aggregation-only kernel)
   unsigned long long cnt = 0;
-  long long isum[kMaxAggs];
-  double dsum[kMaxAggs];
-  uint32_t mn[kMaxAggs], mx[kMaxAggs];
-#pragma unroll
-  for (int a = 0; a < kMaxAggs; ++a) { isum[a] = 0; dsum[a] = 0.0; mn[a] = 0xFFFFFFFFu; mx[a] = 0u; }
 
+  auto reset_acc = [&]() {
+    if (!GROUPBY) {
+      for (int a = 0; a < q.num_aggs; ++a) {
+        acc64[a * kConsumers + group] = 0ull;
+        accmm[a * kConsumers + group] = make_uint2(0xFFFFFFFFu, 0u);
+      }
+    }
+  };
   auto flush = [&]() {
     // one atomic per warp per accumulator into the segment's AggAccum
     unsigned long long c = warp_sum(cnt);
     if (lane == 0 && c) atomicAdd(&sd.accum->count, c);
     cnt = 0;
     if (!GROUPBY) {
-#pragma unroll
-      for (int a = 0; a < kMaxAggs; ++a) {
-        if (a < q.num_aggs && q.aggs[a].slot >= 0) {
-          const int fn = q.aggs[a].function;
-          if (fn == 1 || fn == 4) {  // SUM / AVG
-            if (q.aggs[a].val_kind == VAL_DICT_F32 || q.aggs[a].val_kind == VAL_DICT_F64) {
-              double d = warp_sum(dsum[a]);
-              if (lane == 0) atomicAdd(&sd.accum->dsum[a], d);
-            } else {
-              long long s = warp_sum(isum[a]);
-              if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&sd.accum->isum[a]), (unsigned long long)s);
-            }
-          } else if (fn == 2) {
-            uint32_t m = warp_min(mn[a]);
-            if (lane == 0) atomicMin(&sd.accum->min_id[a], m);
-          } else if (fn == 3) {
-            uint32_t m = warp_max(mx[a]);
-            if (lane == 0) atomicMax(&sd.accum->max_id_plus1[a], m);
+      for (int a = 0; a < q.num_aggs; ++a) {
+        if (q.aggs[a].slot < 0) continue;
+        const int fn = q.aggs[a].function;
+        if (fn == 1 || fn == 4) {  // SUM / AVG
+          const unsigned long long raw = acc64[a * kConsumers + group];
+          if (q.aggs[a].val_kind == VAL_DICT_F32 || q.aggs[a].val_kind == VAL_DICT_F64) {
+            double d = warp_sum(__longlong_as_double((long long)raw));
+            if (lane == 0) atomicAdd(&sd.accum->dsum[a], d);
+          } else {
+            unsigned long long s = warp_sum(raw);
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&sd.accum->isum[a]), s);
           }
-          isum[a] = 0; dsum[a] = 0.0; mn[a] = 0xFFFFFFFFu; mx[a] = 0u;
+        } else if (fn == 2 || fn == 3) {
+          const uint2 mm = accmm[a * kConsumers + group];
+          if (fn == 2) { uint32_t x = warp_min(mm.x); if (lane == 0) atomicMin(&sd.accum->min_id[a], x); }
+          else { uint32_t x = warp_max(mm.y); if (lane == 0) atomicMax(&sd.accum->max_id_plus1[a], x); }
         }
       }
+      reset_acc();
     }
   };
+  reset_acc();
 
   int sidx = -1, stage = 0;
   uint32_t phase = 0;
@@ -260,50 +320,53 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
 
     if (use_pipe) mbar_wait(&hdr->full[stage], phase);
     const uint32_t* st = stages + (size_t)stage * q.stage_words;
-    uint32_t v[32];
 
     // ---------------- phase 1: filter -> row mask ----------------
     // Conjunctions (the common case) evaluate leaf by leaf, most selective first (host order); once few rows per
     // thread survive, the remaining columns are probed per surviving row straight from the shared-memory tile
     // (the GPU form of ScanBasedDocIdIterator.applyAnd on the bitmap of survivors, AndDocIdSet.java:167-169)
     // instead of unpacking all 32 values.
-    int v_slot = -1;  // which slot v[] currently holds (dense unpack), -1 = none
     if (q.num_nodes > 0) {
       if (q.conj) {
-#pragma unroll
-        for (int l = 0; l < kMaxLeaves; ++l) {
-          if (l < q.num_leaves) {
-            const LeafDesc& lf = sd.leaves[l];
-            uint32_t lm;
-            if (lf.kind == LEAF_ALL) lm = 0xFFFFFFFFu;
-            else if (lf.kind == LEAF_NONE) lm = 0u;
-            else if (lf.kind == LEAF_DOCMASK) lm = left > 0 ? __ldg(lf.bits + (row0 >> 5)) : 0u;
-            else if (lf.kind == LEAF_DOCRANGES) lm = eval_doc_ranges(row0, lf.ranges, lf.num_ranges);
-            else {
-              const int wmax = __reduce_max_sync(0xFFFFFFFFu, __popc(m));
-              const SlotDesc& sl = sd.slots[lf.slot];
-              if (wmax == 0) {
-                lm = 0u;  // nothing left to test (m == 0 in every lane)
-              } else if (wmax <= q.sparse_max && v_slot != lf.slot) {
-                const uint32_t* p = st + sl.stage_words + group * sl.bits;
-                uint32_t keep = 0, mm = m;
-                while (mm) {
-                  const int j = __ffs(mm) - 1;
-                  mm &= mm - 1;
-                  const uint32_t id = read_one_group(p, j, sl.bits);
-                  const bool hit = lf.kind == LEAF_RANGE ? ((id - lf.lo) < lf.span)
-                                                         : (((__ldg(lf.bits + (id >> 5)) >> (id & 31)) & 1u) != 0u);
-                  keep |= (hit ? 1u : 0u) << j;
-                }
-                lm = keep;  // bits outside m are irrelevant (m &= lm below)
-              } else {
-                if (v_slot != lf.slot) { unpack_group(sl.bits, st + sl.stage_words, group, v); v_slot = lf.slot; }
-                lm = lf.kind == LEAF_RANGE ? eval_range(v, lf.lo, lf.span) : eval_lut(v, lf.bits);
+#pragma unroll 1
+        for (int l = 0; l < q.num_leaves; ++l) {
+          const LeafDesc& lf = sd.leaves[l];
+          uint32_t lm;
+          if (lf.kind == LEAF_ALL) lm = 0xFFFFFFFFu;
+          else if (lf.kind == LEAF_NONE) lm = 0u;
+          else if (lf.kind == LEAF_DOCMASK) lm = left > 0 ? __ldg(lf.bits + (row0 >> 5)) : 0u;
+          else if (lf.kind == LEAF_DOCRANGES) lm = eval_doc_ranges(row0, lf.ranges, lf.num_ranges);
+          else {
+            const int wmax = __reduce_max_sync(0xFFFFFFFFu, __popc(m));
+            const SlotDesc& sl = sd.slots[lf.slot];
+            if (wmax == 0) {
+              lm = 0u;  // nothing left to test (m == 0 in every lane)
+            } else if (wmax <= q.sparse_max) {
+              const uint32_t* p = st + sl.stage_words + group * sl.bits;
+              uint32_t keep = 0, mm = m;
+              while (mm) {
+                const int j = 31 - __clz(mm);
+                mm &= ~(1u << j);
+                const uint32_t id = read_one_group(p, j, sl.bits);
+                const bool hit = lf.kind == LEAF_RANGE ? ((id - lf.lo) < lf.span)
+                                                       : (((__ldg(lf.bits + (id >> 5)) >> (id & 31)) & 1u) != 0u);
+                keep |= (hit ? 1u : 0u) << j;
               }
+              lm = keep;  // bits outside m are irrelevant (m &= lm below)
+            } else if (lf.kind == LEAF_RANGE) {
+              const int sh = 32 - sl.bits;
+              const uint32_t* base = st + sl.stage_words;
+              if (lf.cmp == CMP_GE) { RangeGE f; f.LO = lf.lo << sh; dispatch_left_aligned(sl.bits, base, group, f); lm = f.mask(); }
+              else if (lf.cmp == CMP_LT) { RangeLT f; f.HI = (lf.lo + lf.span) << sh; dispatch_left_aligned(sl.bits, base, group, f); lm = f.mask(); }
+              else { RangeBoth f; f.LO = lf.lo << sh; f.SPAN = lf.span << sh; dispatch_left_aligned(sl.bits, base, group, f); lm = f.mask(); }
+            } else {
+              uint32_t v[32];
+              unpack_group(sl.bits, st + sl.stage_words, group, v);
+              lm = eval_lut(v, lf.bits);
             }
-            if (lf.negate) lm = ~lm;
-            m &= lm;
           }
+          if (lf.negate) lm = ~lm;
+          m &= lm;
         }
       } else {
         uint32_t lm[kMaxLeaves];
@@ -319,8 +382,8 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
         }
         for (int s = 0; s < q.num_slots; ++s) {
           if (!(q.slot_roles[s] & ROLE_FILTER)) continue;
+          uint32_t v[32];
           unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
-          v_slot = s;
 #pragma unroll
           for (int l = 0; l < kMaxLeaves; ++l) {
             if (l < q.num_leaves && sd.leaves[l].slot == s) {
@@ -368,8 +431,8 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
       //      shape; what DataFetcher does with sparse docIds, core/common/DataFetcher.java:335-338) ----
       uint32_t mm = m;
       while (mm) {
-        const int j = __ffs(mm) - 1;
-        mm &= mm - 1;
+        const int j = 31 - __clz(mm);
+        mm &= ~(1u << j);
         uint32_t g = 0;
         if (GROUPBY) {
 #pragma unroll
@@ -381,43 +444,112 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
           }
           atomicAdd(sd.g_count + g, 1ull);
         }
-#pragma unroll
-        for (int a = 0; a < kMaxAggs; ++a) {
-          if (a < q.num_aggs && q.aggs[a].slot >= 0) {
-            const SlotDesc& sl = sd.slots[q.aggs[a].slot];
-            const uint32_t id = read_one_group(st + sl.stage_words + group * sl.bits, j, sl.bits);
-            const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
-            if (fn == 1 || fn == 4) {
-              if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
-                const double x = vk == VAL_DICT_F32 ? (double)__ldg(static_cast<const float*>(sd.dict[a]) + id)
-                                                    : __ldg(static_cast<const double*>(sd.dict[a]) + id);
-                if (GROUPBY) atomicAdd(sd.g_dsum[a] + g, x); else dsum[a] += x;
-              } else {
-                const long long x = vk == VAL_DICT_I32 ? (long long)__ldg(static_cast<const int*>(sd.dict[a]) + id)
-                                    : vk == VAL_DICT_I64 ? __ldg(static_cast<const long long*>(sd.dict[a]) + id)
-                                                         : (long long)(int)id;
-                if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + g), (unsigned long long)x);
-                else isum[a] += x;
-              }
-            } else if (fn == 2 || fn == 3) {
-              const uint32_t x = id ^ (vk == VAL_RAW_I32 ? 0x80000000u : 0u);
-              if (GROUPBY) { if (fn == 2) atomicMin(sd.g_min[a] + g, x); else atomicMax(sd.g_max[a] + g, x + 1u); }
-              else { mn[a] = min(mn[a], x); mx[a] = max(mx[a], x + 1u); }
-            } else if (fn == 5 && !GROUPBY) {
-              atomicOr(sd.distinct_bits[a] + (id >> 5), 1u << (id & 31));
+#pragma unroll 1
+        for (int a = 0; a < q.num_aggs; ++a) {
+          if (q.aggs[a].slot < 0) continue;
+          const SlotDesc& sl = sd.slots[q.aggs[a].slot];
+          const uint32_t id = read_one_group(st + sl.stage_words + group * sl.bits, j, sl.bits);
+          const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
+          if (fn == 1 || fn == 4) {
+            if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
+              const double x = vk == VAL_DICT_F32 ? (double)__ldg(static_cast<const float*>(sd.dict[a]) + id)
+                                                  : __ldg(static_cast<const double*>(sd.dict[a]) + id);
+              if (GROUPBY) atomicAdd(sd.g_dsum[a] + g, x);
+              else { double* slot = reinterpret_cast<double*>(acc64 + a * kConsumers + group); *slot += x; }
+            } else {
+              const long long x = vk == VAL_DICT_I32 ? (long long)(int)(__ldg(static_cast<const uint32_t*>(sd.dict[a]) + id) ^ 0x80000000u)
+                                  : vk == VAL_DICT_I64 ? __ldg(static_cast<const long long*>(sd.dict[a]) + id)
+                                                       : (long long)(int)id;
+              if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + g), (unsigned long long)x);
+              else acc64[a * kConsumers + group] += (unsigned long long)x;
             }
+          } else if (fn == 2 || fn == 3) {
+            const uint32_t x = id ^ (vk == VAL_RAW_I32 ? 0x80000000u : 0u);
+            if (GROUPBY) { if (fn == 2) atomicMin(sd.g_min[a] + g, x); else atomicMax(sd.g_max[a] + g, x + 1u); }
+            else { uint2 mmx = accmm[a * kConsumers + group]; mmx.x = min(mmx.x, x); mmx.y = max(mmx.y, x + 1u); accmm[a * kConsumers + group] = mmx; }
+          } else if (fn == 5 && !GROUPBY) {
+            atomicOr(sd.distinct_bits[a] + (id >> 5), 1u << (id & 31));
           }
         }
       }
     } else if (wmax2 > 0) {
-      // ---- dense projection: unpack all 32 values of each needed column ----
-      uint32_t gid[32];
-      if (GROUPBY) {
+      // ---- dense projection ----
+      if (!GROUPBY) {
+#pragma unroll 1
+        for (int a = 0; a < q.num_aggs; ++a) {
+          if (q.aggs[a].slot < 0) continue;
+          const SlotDesc& sl = sd.slots[q.aggs[a].slot];
+          const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
+          const uint32_t* base = st + sl.stage_words;
+          if ((fn == 1 || fn == 4) && vk == VAL_DICT_I32) {
+            // streaming gather of biased INT dictionary values (device copy holds value ^ 0x80000000)
+            SumBiasedU32 f;
+            f.d = static_cast<const uint32_t*>(sd.dict[a]); f.m = m; f.sh = 32 - sl.bits;
+            dispatch_left_aligned(sl.bits, base, group, f);
+            acc64[a * kConsumers + group] += (f.a0 + f.a1) - ((unsigned long long)pc << 31);
+          } else if ((fn == 2 || fn == 3) && vk != VAL_RAW_I32) {
+            MinMaxLeft f;
+            f.m = m;
+            dispatch_left_aligned(sl.bits, base, group, f);
+            if (pc) {
+              const int sh = 32 - sl.bits;
+              uint2 mmx = accmm[a * kConsumers + group];
+              mmx.x = min(mmx.x, f.mn >> sh);
+              mmx.y = max(mmx.y, (f.mx >> sh) + 1u);
+              accmm[a * kConsumers + group] = mmx;
+            }
+          } else {
+            uint32_t v[32];
+            unpack_group(sl.bits, base, group, v);
+            if (fn == 1 || fn == 4) {
+              if (vk == VAL_RAW_I32) {
+                long long acc = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc += ((m >> j) & 1u) ? (long long)(int)v[j] : 0ll;
+                acc64[a * kConsumers + group] += (unsigned long long)acc;
+              } else if (vk == VAL_DICT_I64) {
+                const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
+                long long acc = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc += ldg_pred_s64(d + v[j], (m >> j) & 1u);
+                acc64[a * kConsumers + group] += (unsigned long long)acc;
+              } else {
+                double acc = 0.0;
+                if (vk == VAL_DICT_F32) {
+                  const float* __restrict__ d = static_cast<const float*>(sd.dict[a]);
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) acc += (double)__int_as_float(ldg_pred_s32(reinterpret_cast<const int*>(d + v[j]), (m >> j) & 1u));
+                } else {
+                  const double* __restrict__ d = static_cast<const double*>(sd.dict[a]);
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) acc += __longlong_as_double(ldg_pred_s64(reinterpret_cast<const long long*>(d + v[j]), (m >> j) & 1u));
+                }
+                double* slot = reinterpret_cast<double*>(acc64 + a * kConsumers + group);
+                *slot += acc;
+              }
+            } else if (fn == 2 || fn == 3) {  // raw INT: signed -> unsigned order
+              uint32_t tmn = 0xFFFFFFFFu, tmx = 0u;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if ((m >> j) & 1u) { const uint32_t x = v[j] ^ 0x80000000u; tmn = min(tmn, x); tmx = max(tmx, x + 1u); }
+              uint2 mmx = accmm[a * kConsumers + group];
+              mmx.x = min(mmx.x, tmn); mmx.y = max(mmx.y, tmx);
+              accmm[a * kConsumers + group] = mmx;
+            } else if (fn == 5) {  // DISTINCTCOUNT: bitset of dictIds (RoaringBitmap.addN in the reference)
+              uint32_t* bits = sd.distinct_bits[a];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if ((m >> j) & 1u) atomicOr(bits + (v[j] >> 5), 1u << (v[j] & 31));
+            }
+          }
+        }
+      } else {
+        uint32_t gid[32], v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) gid[j] = 0;
         for (int s = 0; s < q.num_slots; ++s) {
           if (!(q.slot_roles[s] & ROLE_GROUP)) continue;
-          if (v_slot != s) { unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v); v_slot = s; }
+          unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
 #pragma unroll
           for (int g = 0; g < kMaxGroupBy; ++g) {
             if (g < q.num_group_by && q.group_slot[g] == s) {
@@ -430,86 +562,47 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if ((m >> j) & 1u) atomicAdd(sd.g_count + gid[j], 1ull);
-      }
-      for (int s = 0; s < q.num_slots; ++s) {
-        if (!(q.slot_roles[s] & ROLE_AGG)) continue;
-        if (v_slot != s) { unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v); v_slot = s; }
-#pragma unroll
-        for (int a = 0; a < kMaxAggs; ++a) {
-          if (a < q.num_aggs && q.aggs[a].slot == s) {
-            const int fn = q.aggs[a].function;
-            const int vk = q.aggs[a].val_kind;
-            if (fn == 1 || fn == 4) {  // SUM / AVG: value = dictionary[dictId]
-              if (vk == VAL_DICT_I32 || vk == VAL_RAW_I32) {
-                const int* __restrict__ d = static_cast<const int*>(sd.dict[a]);
-                int x[32];
-                // all (predicated) gathers are issued before the first use: one L2 latency per tile, not 32
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = vk == VAL_RAW_I32 ? (((m >> j) & 1u) ? (int)v[j] : 0) : ldg_pred_s32(d + v[j], (m >> j) & 1u);
-                if (GROUPBY) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if ((m >> j) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)(long long)x[j]);
-                } else {
-                  long long acc = 0;
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) acc += x[j];
-                  isum[a] += acc;
-                }
-              } else if (vk == VAL_DICT_I64) {
-                const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
-                long long x[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = ldg_pred_s64(d + v[j], (m >> j) & 1u);
-                if (GROUPBY) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if ((m >> j) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)x[j]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) isum[a] += x[j];
-                }
-              } else if (vk == VAL_DICT_F32) {
-                const float* __restrict__ d = static_cast<const float*>(sd.dict[a]);
-                float x[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = __int_as_float(ldg_pred_s32(reinterpret_cast<const int*>(d + v[j]), (m >> j) & 1u));
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if (GROUPBY) { if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], (double)x[j]); }
-                  else dsum[a] += (double)x[j];
-                }
-              } else if (vk == VAL_DICT_F64) {
-                const double* __restrict__ d = static_cast<const double*>(sd.dict[a]);
-                double x[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = __longlong_as_double(ldg_pred_s64(reinterpret_cast<const long long*>(d + v[j]), (m >> j) & 1u));
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if (GROUPBY) { if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], x[j]); }
-                  else dsum[a] += x[j];
-                }
-              }
-            } else if (fn == 2 || fn == 3) {  // MIN / MAX on dictIds (dictionaries are sorted: order preserving)
-              const uint32_t bias = vk == VAL_RAW_I32 ? 0x80000000u : 0u;  // raw INT: signed -> unsigned order
+#pragma unroll 1
+        for (int a = 0; a < q.num_aggs; ++a) {
+          if (q.aggs[a].slot < 0) continue;
+          const SlotDesc& sl = sd.slots[q.aggs[a].slot];
+          const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
+          unpack_group(sl.bits, st + sl.stage_words, group, v);
+          if (fn == 1 || fn == 4) {
+            if (vk == VAL_DICT_I32 || vk == VAL_RAW_I32) {
+              const uint32_t* __restrict__ d = static_cast<const uint32_t*>(sd.dict[a]);
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 if ((m >> j) & 1u) {
-                  const uint32_t x = v[j] ^ bias;
-                  if (GROUPBY) {
-                    if (fn == 2) atomicMin(sd.g_min[a] + gid[j], x);
-                    else atomicMax(sd.g_max[a] + gid[j], x + 1u);
-                  } else {
-                    mn[a] = min(mn[a], x);
-                    mx[a] = max(mx[a], x + 1u);
-                  }
+                  const long long x = vk == VAL_RAW_I32 ? (long long)(int)v[j] : (long long)(int)(__ldg(d + v[j]) ^ 0x80000000u);
+                  atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)x);
                 }
               }
-            } else if (fn == 5 && !GROUPBY) {  // DISTINCTCOUNT: bitset of dictIds (RoaringBitmap.addN in the reference)
-              uint32_t* bits = sd.distinct_bits[a];
+            } else if (vk == VAL_DICT_I64) {
+              const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if ((m >> j) & 1u) atomicOr(bits + (v[j] >> 5), 1u << (v[j] & 31));
+                if ((m >> j) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)__ldg(d + v[j]));
+            } else if (vk == VAL_DICT_F32) {
+              const float* __restrict__ d = static_cast<const float*>(sd.dict[a]);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], (double)__ldg(d + v[j]));
+            } else {
+              const double* __restrict__ d = static_cast<const double*>(sd.dict[a]);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], __ldg(d + v[j]));
+            }
+          } else if (fn == 2 || fn == 3) {
+            const uint32_t bias = vk == VAL_RAW_I32 ? 0x80000000u : 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if ((m >> j) & 1u) {
+                const uint32_t x = v[j] ^ bias;
+                if (fn == 2) atomicMin(sd.g_min[a] + gid[j], x);
+                else atomicMax(sd.g_max[a] + gid[j], x + 1u);
+              }
             }
           }
         }

@@ -69,6 +69,74 @@ struct Unpack32 {
   }
 };
 
+// Streaming form: calls f(j, xl) for the 32 values in order, j a compile-time constant after unrolling and xl the value
+// LEFT-aligned in 32 bits (top B bits = the value, lower bits = whatever follows it in the stream).  Left alignment
+// costs ONE shift (a funnel shift when the value straddles two words) and is enough for order comparisons:
+//   v >= lo  <=>  xl >= (lo << (32-B)),   v < hi  <=>  xl < (hi << (32-B))        (low garbage bits < 2^(32-B))
+// while v itself is xl >> (32-B).  Only the B loaded words stay live (no 32-value register array), which is what lets
+// two CTAs share an SM.
+template <int B, class F>
+__device__ __forceinline__ void for_each_left_aligned(const uint32_t* __restrict__ p, F& f) {
+  static_assert(B >= 1 && B <= 32, "bits per value");
+  uint32_t w[B];
+  if constexpr (B % 4 == 0) {
+    const uint4* p4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int k = 0; k < B / 4; ++k) {
+      uint4 x = p4[k];
+      w[4 * k + 0] = bswap32(x.x);
+      w[4 * k + 1] = bswap32(x.y);
+      w[4 * k + 2] = bswap32(x.z);
+      w[4 * k + 3] = bswap32(x.w);
+    }
+  } else if constexpr (B % 2 == 0) {
+    const uint2* p2 = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+    for (int k = 0; k < B / 2; ++k) {
+      uint2 x = p2[k];
+      w[2 * k + 0] = bswap32(x.x);
+      w[2 * k + 1] = bswap32(x.y);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < B; ++k) w[k] = bswap32(p[k]);
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int o = i * B;
+    const int k = o >> 5;
+    const int s = o & 31;
+    uint32_t xl;
+    if (s == 0) {
+      xl = w[k];
+    } else if (s + B <= 32) {
+      xl = w[k] << s;
+    } else {
+      const int k1 = (k + 1 < B) ? k + 1 : k;
+      xl = __funnelshift_l(w[k1], w[k], s);
+    }
+    f(i, xl);
+  }
+}
+
+template <class F>
+__device__ __forceinline__ void dispatch_left_aligned(int bits, const uint32_t* __restrict__ base, int group, F& f) {
+  switch (bits) {
+#define PB200_CASE(B) \
+  case B:             \
+    for_each_left_aligned<B>(base + group * B, f); \
+    break;
+    PB200_CASE(1) PB200_CASE(2) PB200_CASE(3) PB200_CASE(4) PB200_CASE(5) PB200_CASE(6) PB200_CASE(7) PB200_CASE(8)
+    PB200_CASE(9) PB200_CASE(10) PB200_CASE(11) PB200_CASE(12) PB200_CASE(13) PB200_CASE(14) PB200_CASE(15)
+    PB200_CASE(16) PB200_CASE(17) PB200_CASE(18) PB200_CASE(19) PB200_CASE(20) PB200_CASE(21) PB200_CASE(22)
+    PB200_CASE(23) PB200_CASE(24) PB200_CASE(25) PB200_CASE(26) PB200_CASE(27) PB200_CASE(28) PB200_CASE(29)
+    PB200_CASE(30) PB200_CASE(31) PB200_CASE(32)
+#undef PB200_CASE
+    default:
+      break;
+  }
+}
+
 // Width is a per-(segment, column) runtime value but uniform across the whole tile: one switch, 32 specialisations.
 // `group` is the thread's 32-row group index inside the tile; `base` the slot's first word in the stage buffer.
 __device__ __forceinline__ void unpack_group(int bits, const uint32_t* __restrict__ base, int group,
