@@ -457,7 +457,7 @@ template <int CW, bool GB>
 cudaError_t launch_scan(const Plan& p, const SegDesc* dsegs, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(scan_kernel<CW, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
   if (e != cudaSuccess) return e;
-  scan_kernel<CW, GB><<<grid, (CW + 1) * 32, p.smem_bytes, st>>>(p.q, dsegs);
+  scan_kernel<CW, GB><<<grid, CW * 32, p.smem_bytes, st>>>(p.q, dsegs);
   return cudaGetLastError();
 }
 
@@ -587,30 +587,36 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     max_bits_sum = std::max(max_bits_sum, sum);
   }
   const size_t hdr_bytes = (sizeof(SmemHeader) + 127) / 128 * 128;
-  // tile = CW consumer warps x 1024 rows.  CW = 7 -> 256-thread CTA: two per SM for aggregation-only queries
-  // (<= 128 registers), one per SM for group-by; CW = 3 -> 128-thread CTA, three per SM.
-  int cw = 7, stages = 0, ctas_per_sm = 1;
-  if (getenv("PB200_CW") && atoi(getenv("PB200_CW")) == 3) cw = 3;  // tuning knob
+  // CTA tile = W warps x 1024 rows; every warp streams its own 1024-row slices through a private TMA ring.
+  // Aggregation-only kernels run two CTAs per SM (<= 128 registers at W = 8), group-by one.
+  int cw = 8, stages = 0, ctas_per_sm = 1;
+  if (getenv("PB200_W")) { int w = atoi(getenv("PB200_W")); if (w == 6 || w == 7 || w == 8) cw = w; }  // tuning knob
   q.sparse_max = getenv("PB200_SPARSE_MAX") ? atoi(getenv("PB200_SPARSE_MAX")) : 4;
-  size_t extra_bytes = 0;
-  for (;;) {
-    ctas_per_sm = cw == 7 ? (plan.group_by ? 1 : 2) : 3;
-    if (getenv("PB200_CTAS")) ctas_per_sm = std::max(1, atoi(getenv("PB200_CTAS")));
-    size_t stage_bytes = (size_t)cw * 1024 / 8 * max_bits_sum;
-    extra_bytes = (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4) + (plan.group_by ? 0 : (size_t)nagg * cw * 32 * 16);
+  ctas_per_sm = plan.group_by ? 1 : 2;
+  if (getenv("PB200_CTAS")) ctas_per_sm = std::max(1, atoi(getenv("PB200_CTAS")));
+  const size_t warp_stage_bytes = (size_t)128 * max_bits_sum;
+  const size_t extra_bytes = (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4) + (plan.group_by ? 0 : (size_t)nagg * cw * 32 * 16);
+  {
     long long budget = (long long)ctx->max_smem_optin / ctas_per_sm - (long long)hdr_bytes - (long long)extra_bytes - 1024 - 256;
-    stages = stage_bytes == 0 ? 2 : (budget <= 0 ? 0 : (int)std::min<long long>(8, budget / (long long)stage_bytes));
-    if (stages >= 2 || cw == 3) break;
-    cw = 3;
+    stages = warp_stage_bytes == 0 ? 2 : (budget <= 0 ? 0 : (int)std::min<long long>(kMaxStages, budget / (long long)(warp_stage_bytes * cw)));
+    if (stages < 2 && ctas_per_sm > 1) {  // wide rows: fall back to one CTA per SM
+      ctas_per_sm = 1;
+      budget = (long long)ctx->max_smem_optin - (long long)hdr_bytes - (long long)extra_bytes - 1024 - 256;
+      stages = budget <= 0 ? 0 : (int)std::min<long long>(kMaxStages, budget / (long long)(warp_stage_bytes * cw));
+    }
   }
   if (stages < 2) { set_error("touched columns too wide for the shared-memory pipeline (%d bits per row)", max_bits_sum); return PB200_E_UNSUPPORTED; }
   if (getenv("PB200_STAGES")) stages = std::max(2, std::min(stages, atoi(getenv("PB200_STAGES"))));
   plan.cw = cw;
   q.tile_rows = cw * 1024;
   q.num_stages = stages;
-  q.stage_words = (uint32_t)((size_t)q.tile_rows / 32 * max_bits_sum);
+  q.stage_words = (uint32_t)(32 * max_bits_sum);
   q.use_pipe = q.num_slots > 0;
-  plan.smem_bytes = hdr_bytes + (size_t)stages * q.stage_words * 4 + extra_bytes;
+  q.defer_agg = -1;
+  if (!plan.group_by && !getenv("PB200_NO_DEFER"))
+    for (int a = 0; a < nagg; a++)
+      if ((q.aggs[a].function == PB200_AGG_SUM || q.aggs[a].function == PB200_AGG_AVG) && q.aggs[a].val_kind == VAL_DICT_I32) { q.defer_agg = a; break; }
+  plan.smem_bytes = hdr_bytes + (size_t)cw * stages * q.stage_words * 4 + extra_bytes;
 
   cudaStream_t st = take_stream(ctx);
   struct StreamReturn { pb200_ctx* c; cudaStream_t s; ~StreamReturn() { give_stream(c, s); } } stream_return{ctx, st};
@@ -643,7 +649,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       sd.slots[k].data = c.fwd;
       sd.slots[k].bits = c.bits;
       sd.slots[k].stage_words = word_off;
-      sd.slots[k].tile_bytes = (uint32_t)(q.tile_rows / 8 * c.bits);
+      sd.slots[k].tile_bytes = (uint32_t)(128 * c.bits);  // one warp slice = 1024 rows
       word_off += sd.slots[k].tile_bytes / 4;
       tx += sd.slots[k].tile_bytes;
     }
@@ -870,8 +876,9 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   PB200_CUDA(cudaEventCreate(&e1));
   PB200_CUDA(cudaEventRecord(e0, st));
   cudaError_t le;
-  if (cw == 7) le = plan.group_by ? launch_scan<7, true>(plan, (const SegDesc*)dsegs.p, grid, st) : launch_scan<7, false>(plan, (const SegDesc*)dsegs.p, grid, st);
-  else le = plan.group_by ? launch_scan<3, true>(plan, (const SegDesc*)dsegs.p, grid, st) : launch_scan<3, false>(plan, (const SegDesc*)dsegs.p, grid, st);
+  const SegDesc* dptr = (const SegDesc*)dsegs.p;
+  if (plan.group_by) le = cw == 8 ? launch_scan<8, true>(plan, dptr, grid, st) : cw == 7 ? launch_scan<7, true>(plan, dptr, grid, st) : launch_scan<6, true>(plan, dptr, grid, st);
+  else le = cw == 8 ? launch_scan<8, false>(plan, dptr, grid, st) : cw == 7 ? launch_scan<7, false>(plan, dptr, grid, st) : launch_scan<6, false>(plan, dptr, grid, st);
   if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }
   PB200_CUDA(cudaEventRecord(e1, st));
   cudaError_t se = cudaStreamSynchronize(st);

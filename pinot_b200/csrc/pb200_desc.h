@@ -30,8 +30,8 @@ enum : int32_t { VAL_NONE = 0, VAL_DICT_I32 = 1, VAL_DICT_I64 = 2, VAL_DICT_F32 
 struct SlotDesc {
   const uint32_t* data;  // device: packed words, padded to whole tiles
   int32_t bits;          // 1..32 (32 = raw big-endian 32-bit values)
-  uint32_t stage_words;  // offset of this slot inside a stage buffer, in 32-bit words
-  uint32_t tile_bytes;   // bytes of this slot per tile (multiple of 16)
+  uint32_t stage_words;  // offset of this slot inside a warp's stage buffer, in 32-bit words
+  uint32_t tile_bytes;   // bytes of this slot per 1024-row warp slice: 128 * bits
   uint32_t pad;
 };
 
@@ -61,7 +61,7 @@ struct SegDesc {
   long long num_docs;
   long long first_tile;   // index of this segment's first tile in the launch-wide tile sequence
   long long num_tiles;
-  uint32_t stage_tx;      // bytes TMA delivers per stage for THIS segment (sum of its slots' tile_bytes)
+  uint32_t stage_tx;      // bytes TMA delivers per warp slice for THIS segment (sum of its slots' tile_bytes)
   uint32_t pad0;
   SlotDesc slots[kMaxSlots];
   LeafDesc leaves[kMaxLeaves];
@@ -91,11 +91,12 @@ struct QueryDesc {
   int32_t num_nodes;       // program length; 0 = match all
   int32_t conj;            // 1: root is a flat AND (or single leaf) of leaves -> no stack
   int32_t sparse_max;      // per-row probing instead of unpacking when <= this many rows per thread survive
+  int32_t defer_agg;       // aggregation whose dictionary gathers are software-pipelined across tiles (-1: none)
   int32_t num_aggs;
   int32_t num_group_by;
-  int32_t tile_rows;       // consumer_warps * 1024
+  int32_t tile_rows;       // warps per CTA * 1024
   int32_t num_stages;
-  uint32_t stage_words;    // words per stage buffer (max over segments)
+  uint32_t stage_words;    // words per WARP stage buffer: 32 * sum of bits (max over segments)
   uint32_t use_pipe;       // 0: no column is streamed (e.g. COUNT(*) over doc masks only)
   uint32_t slot_roles[kMaxSlots];
   int32_t group_slot[kMaxGroupBy];

@@ -66,6 +66,7 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
@@ -115,6 +116,13 @@ __device__ __forceinline__ uint32_t read_one_group(const uint32_t* __restrict__ 
 __device__ __forceinline__ int ldg_pred_s32(const int* p, uint32_t pred) {
   int x;
   asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(x) : "l"(p), "r"(pred));
+  return x;
+}
+// same, predicate = (mask & bit) != 0 with `bit` a compile-time constant after unrolling: LOP3 + ISETP, no shift
+__device__ __forceinline__ uint32_t ldg_bit_u32(const uint32_t* p, uint32_t mask, uint32_t bit) {
+  uint32_t x;
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\tmov.b32 %0, 0;\n\t"
+      "@p ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(x) : "l"(p), "r"(mask), "r"(bit));
   return x;
 }
 __device__ __forceinline__ long long ldg_pred_s64(const long long* p, uint32_t pred) {
@@ -177,7 +185,7 @@ struct SumBiasedU32 {
   unsigned long long a0 = 0, a1 = 0;
   uint32_t pend = 0;
   __device__ __forceinline__ void operator()(int j, uint32_t xl) {
-    const uint32_t x = (uint32_t)ldg_pred_s32(reinterpret_cast<const int*>(d + (xl >> sh)), (m >> j) & 1u);
+    const uint32_t x = ldg_bit_u32(d + (xl >> sh), m, 1u << j);
     if ((j & 1) == 0) {
       pend = x;
     } else if ((j & 2) == 0) {
@@ -186,6 +194,13 @@ struct SumBiasedU32 {
       a1 += (unsigned long long)pend + (unsigned long long)x;
     }
   }
+};
+// Deferred variant: only issues the gathers (into x[j]); the caller sums them one tile later.
+struct GatherBiasedU32 {
+  const uint32_t* __restrict__ d;
+  uint32_t m, sh;
+  uint32_t (&x)[32];
+  __device__ __forceinline__ void operator()(int j, uint32_t xl) { x[j] = ldg_bit_u32(d + (xl >> sh), m, 1u << j); }
 };
 // MIN / MAX of dictIds on the left-aligned form (order preserving; shift back once at the end)
 struct MinMaxLeft {
@@ -198,68 +213,93 @@ struct MinMaxLeft {
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxWarps = 8;    // warps per CTA (all of them consume; there is no producer warp)
+constexpr int kMaxStages = 4;
+
 struct SmemHeader {
-  SegDesc seg;            // consumer-side copy of the current segment's descriptor
-  uint64_t full[8];       // stage filled by TMA
-  uint64_t empty[8];      // stage drained by all consumer warps
+  SegDesc seg;                              // CTA-wide copy of the current segment's descriptor
+  uint64_t full[kMaxWarps][kMaxStages];     // per-warp ring: "stage filled by TMA"
 };
 
-// Shared-memory layout (dynamic):  [SmemHeader][stages x stage_words][filter stack (generic filters only)]
-//                                   [acc64: num_aggs x consumers x 8 B][accmm: num_aggs x consumers x 8 B]
-// acc64/accmm are the per-thread running aggregates of the aggregation-only kernel; they live in shared memory (one
-// private slot per thread, touched once per tile) instead of registers so that two CTAs fit on an SM.
-template <int CW, bool GROUPBY>
-__global__ void __launch_bounds__((CW + 1) * 32, (CW <= 3 ? 3 : (GROUPBY ? 1 : 2)))
+// Execution model
+//   * a CTA tile is W x 1024 consecutive rows of ONE segment; CTA c takes CTA tiles c, c + grid, ...;
+//   * inside it every WARP owns a private slice of 1024 rows and a private TMA ring: lane 0 arms the warp's mbarrier
+//     with the slice's byte count and issues one 1-D bulk copy per touched column (128 x bits bytes each); when the
+//     warp has consumed a slice, the same lane refills that buffer with the slice `num_stages` CTA tiles ahead.  No
+//     producer warp, no CTA-wide barrier per tile -- warps only meet at segment boundaries (<= #segments times);
+//   * a THREAD owns 32 consecutive rows (one FixedBitIntReader.read32 group): B words per column.
+// Shared-memory layout (dynamic):
+//   [SmemHeader][W x num_stages x stage_words][filter stack (generic filters only)]
+//   [acc64: num_aggs x threads x 8 B][accmm: num_aggs x threads x 8 B]     (aggregation-only kernel)
+// acc64/accmm are the per-thread running aggregates; they live in shared memory (private slot per thread, touched once
+// per tile) instead of registers so that two CTAs fit on an SM.
+template <int W, bool GROUPBY>
+__global__ void __launch_bounds__(W * 32, GROUPBY ? 1 : 2)
 scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ segs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
   constexpr int kHdrBytes = (sizeof(SmemHeader) + 127) / 128 * 128;
-  constexpr int kConsumers = CW * 32;
-  uint32_t* stages = reinterpret_cast<uint32_t*>(smem_raw + kHdrBytes);
-  uint32_t* fstack = stages + (size_t)q.num_stages * q.stage_words;  // generic-filter mask stack (if !conj)
-  unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(fstack + (q.conj ? 0 : kConsumers * kMaxStack));
-  uint2* accmm = reinterpret_cast<uint2*>(acc64 + (size_t)q.num_aggs * kConsumers);
+  constexpr int kConsumers = W * 32;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  uint32_t* stages_all = reinterpret_cast<uint32_t*>(smem_raw + kHdrBytes);
+  uint32_t* wstages = stages_all + (size_t)warp * q.num_stages * q.stage_words;   // this warp's ring
+  uint32_t* fstack = stages_all + (size_t)W * q.num_stages * q.stage_words;       // generic-filter mask stack
+  unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(fstack + (q.conj ? 0 : kConsumers * kMaxStack));
+  uint2* accmm = reinterpret_cast<uint2*>(acc64 + (size_t)q.num_aggs * kConsumers);
   const bool use_pipe = q.use_pipe != 0;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < q.num_stages; ++s) {
-      mbar_init(&hdr->full[s], 1);
-      mbar_init(&hdr->empty[s], CW);
-    }
+  if (lane == 0) {
+    for (int s = 0; s < q.num_stages; ++s) mbar_init(&hdr->full[warp][s], 1);
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == CW) {
-    // ============================== producer: one thread drives TMA ==============================
-    if (lane == 0 && use_pipe) {
-      const uint64_t policy = policy_evict_first();
-      int sidx = 0, stage = 0;
-      uint32_t phase = 0;
-      for (long long T = blockIdx.x; T < q.total_tiles; T += gridDim.x) {
-        while (T >= segs[sidx].first_tile + segs[sidx].num_tiles) ++sidx;
-        const SegDesc* sd = segs + sidx;
-        const long long t = T - sd->first_tile;
-        mbar_wait(&hdr->empty[stage], phase ^ 1u);
-        mbar_expect_tx(&hdr->full[stage], sd->stage_tx);
-        uint32_t* dst = stages + (size_t)stage * q.stage_words;
-        for (int s = 0; s < q.num_slots; ++s) {
-          const uint32_t tb = sd->slots[s].tile_bytes;
-          tma_load_1d(dst + sd->slots[s].stage_words, reinterpret_cast<const unsigned char*>(sd->slots[s].data) + t * tb,
-                      tb, &hdr->full[stage], policy);
-        }
-        if (++stage == q.num_stages) { stage = 0; phase ^= 1u; }
-      }
-    }
-    return;
-  }
-
-  // ================================== consumers ==================================
-  const int group = threadIdx.x;  // 32-row group inside the tile
+  const int group = threadIdx.x;  // index of this thread's per-thread accumulators
   const SegDesc& sd = hdr->seg;
   unsigned long long cnt = 0;
+
+  // ---- warp-private TMA ring ----
+  uint64_t policy = 0;
+  int pidx = 0;  // lane 0: segment cursor of the prefetcher (runs ahead of the consumer cursor)
+  if (lane == 0) policy = policy_evict_first();
+  auto issue = [&](long long Tc, int stage) {  // lane 0 only
+    while (Tc >= __ldg(&segs[pidx].first_tile) + __ldg(&segs[pidx].num_tiles)) ++pidx;
+    const SegDesc* ps = segs + pidx;
+    const long long slice = (Tc - __ldg(&ps->first_tile)) * W + warp;  // 1024-row slice index inside the segment
+    fence_proxy_async();  // the buffer was read through the generic proxy; order those reads before the async write
+    mbar_expect_tx(&hdr->full[warp][stage], __ldg(&ps->stage_tx));
+    uint32_t* dst = wstages + (size_t)stage * q.stage_words;
+    for (int s = 0; s < q.num_slots; ++s) {
+      const uint32_t tb = __ldg(&ps->slots[s].tile_bytes);
+      tma_load_1d(dst + __ldg(&ps->slots[s].stage_words),
+                  reinterpret_cast<const unsigned char*>(ps->slots[s].data) + slice * tb, tb,
+                  &hdr->full[warp][stage], policy);
+    }
+  };
+  if (lane == 0 && use_pipe) {
+    for (int s = 0; s < q.num_stages; ++s) {
+      const long long Tc = blockIdx.x + (long long)s * gridDim.x;
+      if (Tc < q.total_tiles) issue(Tc, s);
+    }
+  }
+
+  // deferred dictionary gathers (software pipelining across tiles): the biased values of tile t's surviving rows are
+  // loaded into x[] while tile t+1 is being filtered and are summed afterwards -- one L2 latency hidden per tile
+  uint32_t x[32];
+  int pend_pc = -1;  // >= 0: x[] holds a tile's gathers (pend_pc surviving rows in this thread)
+  auto drain = [&]() {
+    if (pend_pc >= 0) {
+      unsigned long long a0 = 0, a1 = 0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        a0 += (unsigned long long)x[j] + (unsigned long long)x[j + 1];
+        a1 += (unsigned long long)x[j + 2] + (unsigned long long)x[j + 3];
+      }
+      acc64[q.defer_agg * kConsumers + group] += (a0 + a1) - ((unsigned long long)pend_pc << 31);
+      pend_pc = -1;
+    }
+  };
 
   auto reset_acc = [&]() {
     if (!GROUPBY) {
@@ -271,6 +311,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
   };
   auto flush = [&]() {
     // one atomic per warp per accumulator into the segment's AggAccum
+    drain();
     unsigned long long c = warp_sum(cnt);
     if (lane == 0 && c) atomicAdd(&sd.accum->count, c);
     cnt = 0;
@@ -289,8 +330,8 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
           }
         } else if (fn == 2 || fn == 3) {
           const uint2 mm = accmm[a * kConsumers + group];
-          if (fn == 2) { uint32_t x = warp_min(mm.x); if (lane == 0) atomicMin(&sd.accum->min_id[a], x); }
-          else { uint32_t x = warp_max(mm.y); if (lane == 0) atomicMax(&sd.accum->max_id_plus1[a], x); }
+          if (fn == 2) { uint32_t v = warp_min(mm.x); if (lane == 0) atomicMin(&sd.accum->min_id[a], v); }
+          else { uint32_t v = warp_max(mm.y); if (lane == 0) atomicMax(&sd.accum->max_id_plus1[a], v); }
         }
       }
       reset_acc();
@@ -301,7 +342,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
   int sidx = -1, stage = 0;
   uint32_t phase = 0;
   for (long long T = blockIdx.x; T < q.total_tiles; T += gridDim.x) {
-    // ---- segment change: flush accumulators, refresh the shared descriptor copy ----
+    // ---- segment change: flush accumulators, refresh the shared descriptor copy (the only CTA-wide barriers) ----
     int ns = sidx < 0 ? 0 : sidx;
     while (T >= __ldg(&segs[ns].first_tile) + __ldg(&segs[ns].num_tiles)) ++ns;
     if (ns != sidx) {
@@ -314,12 +355,13 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
       sidx = ns;
     }
     const long long t = T - sd.first_tile;
-    const long long row0 = t * q.tile_rows + (long long)group * kRowsPerThread;
+    const long long row0 = (t * W + warp) * 1024 + (long long)lane * kRowsPerThread;
     const long long left = sd.num_docs - row0;
     uint32_t m = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
 
-    if (use_pipe) mbar_wait(&hdr->full[stage], phase);
-    const uint32_t* st = stages + (size_t)stage * q.stage_words;
+    if (use_pipe) mbar_wait(&hdr->full[warp][stage], phase);
+    const uint32_t* st = wstages + (size_t)stage * q.stage_words;
+    const int group_in_stage = lane;  // the thread's 32-row group inside the warp's slice
 
     // ---------------- phase 1: filter -> row mask ----------------
     // Conjunctions (the common case) evaluate leaf by leaf, most selective first (host order); once few rows per
@@ -342,7 +384,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
             if (wmax == 0) {
               lm = 0u;  // nothing left to test (m == 0 in every lane)
             } else if (wmax <= q.sparse_max) {
-              const uint32_t* p = st + sl.stage_words + group * sl.bits;
+              const uint32_t* p = st + sl.stage_words + group_in_stage * sl.bits;
               uint32_t keep = 0, mm = m;
               while (mm) {
                 const int j = 31 - __clz(mm);
@@ -356,12 +398,12 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
             } else if (lf.kind == LEAF_RANGE) {
               const int sh = 32 - sl.bits;
               const uint32_t* base = st + sl.stage_words;
-              if (lf.cmp == CMP_GE) { RangeGE f; f.LO = lf.lo << sh; dispatch_left_aligned(sl.bits, base, group, f); lm = f.mask(); }
-              else if (lf.cmp == CMP_LT) { RangeLT f; f.HI = (lf.lo + lf.span) << sh; dispatch_left_aligned(sl.bits, base, group, f); lm = f.mask(); }
-              else { RangeBoth f; f.LO = lf.lo << sh; f.SPAN = lf.span << sh; dispatch_left_aligned(sl.bits, base, group, f); lm = f.mask(); }
+              if (lf.cmp == CMP_GE) { RangeGE f; f.LO = lf.lo << sh; dispatch_left_aligned(sl.bits, base, group_in_stage, f); lm = f.mask(); }
+              else if (lf.cmp == CMP_LT) { RangeLT f; f.HI = (lf.lo + lf.span) << sh; dispatch_left_aligned(sl.bits, base, group_in_stage, f); lm = f.mask(); }
+              else { RangeBoth f; f.LO = lf.lo << sh; f.SPAN = lf.span << sh; dispatch_left_aligned(sl.bits, base, group_in_stage, f); lm = f.mask(); }
             } else {
               uint32_t v[32];
-              unpack_group(sl.bits, st + sl.stage_words, group, v);
+              unpack_group(sl.bits, st + sl.stage_words, group_in_stage, v);
               lm = eval_lut(v, lf.bits);
             }
           }
@@ -383,7 +425,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
         for (int s = 0; s < q.num_slots; ++s) {
           if (!(q.slot_roles[s] & ROLE_FILTER)) continue;
           uint32_t v[32];
-          unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
+          unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group_in_stage, v);
 #pragma unroll
           for (int l = 0; l < kMaxLeaves; ++l) {
             if (l < q.num_leaves && sd.leaves[l].slot == s) {
@@ -422,6 +464,8 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
       }
     }
 
+    drain();  // the previous tile's gathers have had this tile's whole filter phase to arrive
+
     // ---------------- phase 2: aggregate the surviving rows ----------------
     const int pc = __popc(m);
     cnt += pc;
@@ -439,7 +483,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
           for (int gi = 0; gi < kMaxGroupBy; ++gi) {
             if (gi < q.num_group_by) {
               const SlotDesc& sl = sd.slots[q.group_slot[gi]];
-              g += read_one_group(st + sl.stage_words + group * sl.bits, j, sl.bits) * sd.group_mult[gi];
+              g += read_one_group(st + sl.stage_words + group_in_stage * sl.bits, j, sl.bits) * sd.group_mult[gi];
             }
           }
           atomicAdd(sd.g_count + g, 1ull);
@@ -448,7 +492,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
         for (int a = 0; a < q.num_aggs; ++a) {
           if (q.aggs[a].slot < 0) continue;
           const SlotDesc& sl = sd.slots[q.aggs[a].slot];
-          const uint32_t id = read_one_group(st + sl.stage_words + group * sl.bits, j, sl.bits);
+          const uint32_t id = read_one_group(st + sl.stage_words + group_in_stage * sl.bits, j, sl.bits);
           const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
           if (fn == 1 || fn == 4) {
             if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
@@ -481,16 +525,21 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
           const SlotDesc& sl = sd.slots[q.aggs[a].slot];
           const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
           const uint32_t* base = st + sl.stage_words;
-          if ((fn == 1 || fn == 4) && vk == VAL_DICT_I32) {
-            // streaming gather of biased INT dictionary values (device copy holds value ^ 0x80000000)
+          if ((fn == 1 || fn == 4) && vk == VAL_DICT_I32 && a == q.defer_agg) {
+            // gathers of biased INT dictionary values (device copy holds value ^ 0x80000000) are only ISSUED here;
+            // they are summed after the next tile's filter phase (drain())
+            GatherBiasedU32 f{static_cast<const uint32_t*>(sd.dict[a]), m, (uint32_t)(32 - sl.bits), x};
+            dispatch_left_aligned(sl.bits, base, group_in_stage, f);
+            pend_pc = pc;
+          } else if ((fn == 1 || fn == 4) && vk == VAL_DICT_I32) {
             SumBiasedU32 f;
             f.d = static_cast<const uint32_t*>(sd.dict[a]); f.m = m; f.sh = 32 - sl.bits;
-            dispatch_left_aligned(sl.bits, base, group, f);
+            dispatch_left_aligned(sl.bits, base, group_in_stage, f);
             acc64[a * kConsumers + group] += (f.a0 + f.a1) - ((unsigned long long)pc << 31);
           } else if ((fn == 2 || fn == 3) && vk != VAL_RAW_I32) {
             MinMaxLeft f;
             f.m = m;
-            dispatch_left_aligned(sl.bits, base, group, f);
+            dispatch_left_aligned(sl.bits, base, group_in_stage, f);
             if (pc) {
               const int sh = 32 - sl.bits;
               uint2 mmx = accmm[a * kConsumers + group];
@@ -500,7 +549,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
             }
           } else {
             uint32_t v[32];
-            unpack_group(sl.bits, base, group, v);
+            unpack_group(sl.bits, base, group_in_stage, v);
             if (fn == 1 || fn == 4) {
               if (vk == VAL_RAW_I32) {
                 long long acc = 0;
@@ -549,7 +598,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
         for (int j = 0; j < 32; ++j) gid[j] = 0;
         for (int s = 0; s < q.num_slots; ++s) {
           if (!(q.slot_roles[s] & ROLE_GROUP)) continue;
-          unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group, v);
+          unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group_in_stage, v);
 #pragma unroll
           for (int g = 0; g < kMaxGroupBy; ++g) {
             if (g < q.num_group_by && q.group_slot[g] == s) {
@@ -567,7 +616,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
           if (q.aggs[a].slot < 0) continue;
           const SlotDesc& sl = sd.slots[q.aggs[a].slot];
           const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
-          unpack_group(sl.bits, st + sl.stage_words, group, v);
+          unpack_group(sl.bits, st + sl.stage_words, group_in_stage, v);
           if (fn == 1 || fn == 4) {
             if (vk == VAL_DICT_I32 || vk == VAL_RAW_I32) {
               const uint32_t* __restrict__ d = static_cast<const uint32_t*>(sd.dict[a]);
@@ -610,8 +659,11 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
     }
 
     if (use_pipe) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&hdr->empty[stage]);
+      __syncwarp();  // every lane is done reading this buffer
+      if (lane == 0) {
+        const long long Tn = T + (long long)q.num_stages * gridDim.x;
+        if (Tn < q.total_tiles) issue(Tn, stage);
+      }
       if (++stage == q.num_stages) { stage = 0; phase ^= 1u; }
     }
   }
