@@ -454,10 +454,10 @@ void set_cmp(LeafDesc& lf, const DeviceColumn& c) {
 }
 
 template <int CW, bool GB>
-cudaError_t launch_scan(const Plan& p, const SegDesc* dsegs, int grid, cudaStream_t st) {
+cudaError_t launch_scan(const Plan& p, const QueryDesc& q, const TmaTable& tt, const SegDesc* dsegs, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(scan_kernel<CW, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
   if (e != cudaSuccess) return e;
-  scan_kernel<CW, GB><<<grid, CW * 32, p.smem_bytes, st>>>(p.q, dsegs);
+  scan_kernel<CW, GB><<<grid, CW * 32, p.smem_bytes, st>>>(q, tt, dsegs);
   return cudaGetLastError();
 }
 
@@ -589,7 +589,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   const size_t hdr_bytes = (sizeof(SmemHeader) + 127) / 128 * 128;
   // CTA tile = W warps x 1024 rows; every warp streams its own 1024-row slices through a private TMA ring.
   // Aggregation-only kernels run two CTAs per SM (<= 128 registers at W = 8), group-by one.
-  int cw = 8, stages = 0, ctas_per_sm = 1;
+  int cw = 6, stages = 0, ctas_per_sm = 1;  // W = 6: 192-thread CTAs, two per SM, 168 registers (no spills)
   if (getenv("PB200_W")) { int w = atoi(getenv("PB200_W")); if (w == 6 || w == 7 || w == 8) cw = w; }  // tuning knob
   q.sparse_max = getenv("PB200_SPARSE_MAX") ? atoi(getenv("PB200_SPARSE_MAX")) : 4;
   ctas_per_sm = plan.group_by ? 1 : 2;
@@ -864,21 +864,44 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     }
   }
 
-  // ---- launch ----
+  // ---- launch: chunks of <= kMaxLaunchSegs segments (their TMA table travels in the kernel parameters) ----
   DevBuf dsegs;
   int rc = dsegs.alloc(ctx, sizeof(SegDesc) * nseg);
   if (rc) return rc;
-  PB200_CUDA(cudaMemcpyAsync(dsegs.p, plan.segs.data(), sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, st));
-  int grid = (int)std::min<long long>((long long)ctx->sm_count * ctas_per_sm, std::max<long long>(q.total_tiles, 1));
-  if (getenv("PB200_GRID")) grid = std::max(1, atoi(getenv("PB200_GRID")));
   cudaEvent_t e0, e1;
   PB200_CUDA(cudaEventCreate(&e0));
   PB200_CUDA(cudaEventCreate(&e1));
+  cudaError_t le = cudaSuccess;
+  int grid = 0;
+  std::vector<SegDesc> launch_segs = plan.segs;
+  for (int c0 = 0; c0 < nseg; c0 += kMaxLaunchSegs) {  // first_tile is relative to the chunk
+    long long cursor = 0;
+    for (int s = c0; s < std::min(nseg, c0 + kMaxLaunchSegs); s++) { launch_segs[s].first_tile = cursor; cursor += launch_segs[s].num_tiles; }
+  }
+  PB200_CUDA(cudaMemcpyAsync(dsegs.p, launch_segs.data(), sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, st));
   PB200_CUDA(cudaEventRecord(e0, st));
-  cudaError_t le;
-  const SegDesc* dptr = (const SegDesc*)dsegs.p;
-  if (plan.group_by) le = cw == 8 ? launch_scan<8, true>(plan, dptr, grid, st) : cw == 7 ? launch_scan<7, true>(plan, dptr, grid, st) : launch_scan<6, true>(plan, dptr, grid, st);
-  else le = cw == 8 ? launch_scan<8, false>(plan, dptr, grid, st) : cw == 7 ? launch_scan<7, false>(plan, dptr, grid, st) : launch_scan<6, false>(plan, dptr, grid, st);
+  for (int c0 = 0; c0 < nseg && le == cudaSuccess; c0 += kMaxLaunchSegs) {
+    const int cn = std::min(nseg - c0, (int)kMaxLaunchSegs);
+    QueryDesc cq = q;
+    TmaTable tt;
+    memset(&tt, 0, sizeof tt);
+    cq.num_segments = cn;
+    cq.total_tiles = 0;
+    for (int s = 0; s < cn; s++) {
+      const SegDesc& sd = launch_segs[c0 + s];
+      tt.seg[s].first_tile = sd.first_tile;
+      tt.seg[s].num_tiles = sd.num_tiles;
+      tt.seg[s].stage_tx = sd.stage_tx;
+      for (int k = 0; k < q.num_slots; k++) tt.seg[s].slot[k] = TmaSlot{sd.slots[k].data, sd.slots[k].tile_bytes, sd.slots[k].stage_words};
+      cq.total_tiles += sd.num_tiles;
+    }
+    for (int s = cn; s < kMaxLaunchSegs; s++) { tt.seg[s].first_tile = cq.total_tiles; tt.seg[s].num_tiles = (1ll << 60); }  // sentinel
+    grid = (int)std::min<long long>((long long)ctx->sm_count * ctas_per_sm, std::max<long long>(cq.total_tiles, 1));
+    if (getenv("PB200_GRID")) grid = std::max(1, atoi(getenv("PB200_GRID")));
+    const SegDesc* dptr = (const SegDesc*)dsegs.p + c0;
+    if (plan.group_by) le = cw == 8 ? launch_scan<8, true>(plan, cq, tt, dptr, grid, st) : cw == 7 ? launch_scan<7, true>(plan, cq, tt, dptr, grid, st) : launch_scan<6, true>(plan, cq, tt, dptr, grid, st);
+    else le = cw == 8 ? launch_scan<8, false>(plan, cq, tt, dptr, grid, st) : cw == 7 ? launch_scan<7, false>(plan, cq, tt, dptr, grid, st) : launch_scan<6, false>(plan, cq, tt, dptr, grid, st);
+  }
   if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }
   PB200_CUDA(cudaEventRecord(e1, st));
   cudaError_t se = cudaStreamSynchronize(st);

@@ -77,6 +77,26 @@ struct SegDesc {
   uint32_t group_mult[kMaxGroupBy];
 };
 
+// Everything lane 0 needs to refill a warp's TMA ring, for every segment of the launch, passed BY VALUE as a kernel
+// parameter so it sits in the constant bank (a global-memory descriptor read per tile costs an L2 round trip because
+// the dictionary gathers keep evicting L1).
+constexpr int kMaxLaunchSegs = 16;
+struct TmaSlot {
+  const void* data;
+  uint32_t tile_bytes;
+  uint32_t stage_words;
+};
+struct TmaSeg {
+  long long first_tile;
+  long long num_tiles;
+  uint32_t stage_tx;
+  uint32_t pad;
+  TmaSlot slot[kMaxSlots];
+};
+struct TmaTable {
+  TmaSeg seg[kMaxLaunchSegs];
+};
+
 struct AggDesc {
   int32_t function;  // PB200_AGG_*
   int32_t slot;      // -1 for COUNT(*)

@@ -235,7 +235,7 @@ struct SmemHeader {
 // per tile) instead of registers so that two CTAs fit on an SM.
 template <int W, bool GROUPBY>
 __global__ void __launch_bounds__(W * 32, GROUPBY ? 1 : 2)
-scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ segs) {
+scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTable tt, const SegDesc* __restrict__ segs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
   constexpr int kHdrBytes = (sizeof(SmemHeader) + 127) / 128 * 128;
@@ -261,23 +261,25 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
 
   // ---- warp-private TMA ring ----
   uint64_t policy = 0;
-  int pidx = 0;  // lane 0: segment cursor of the prefetcher (runs ahead of the consumer cursor)
-  if (lane == 0) policy = policy_evict_first();
-  auto issue = [&](long long Tc, int stage) {  // lane 0 only
-    while (Tc >= __ldg(&segs[pidx].first_tile) + __ldg(&segs[pidx].num_tiles)) ++pidx;
-    const SegDesc* ps = segs + pidx;
-    const long long slice = (Tc - __ldg(&ps->first_tile)) * W + warp;  // 1024-row slice index inside the segment
-    fence_proxy_async();  // the buffer was read through the generic proxy; order those reads before the async write
-    mbar_expect_tx(&hdr->full[warp][stage], __ldg(&ps->stage_tx));
-    uint32_t* dst = wstages + (size_t)stage * q.stage_words;
-    for (int s = 0; s < q.num_slots; ++s) {
-      const uint32_t tb = __ldg(&ps->slots[s].tile_bytes);
-      tma_load_1d(dst + __ldg(&ps->slots[s].stage_words),
-                  reinterpret_cast<const unsigned char*>(ps->slots[s].data) + slice * tb, tb,
+  int pidx = 0;  // segment cursor of the prefetcher (runs ahead of the consumer cursor)
+  policy = policy_evict_first();
+  auto issue = [&](long long Tc, int stage) {  // whole warp: lane 0 arms the barrier, lane k < num_slots copies slot k
+    while (Tc >= tt.seg[pidx].first_tile + tt.seg[pidx].num_tiles) ++pidx;
+    const TmaSeg& ps = tt.seg[pidx];
+    const long long slice = (Tc - ps.first_tile) * W + warp;  // 1024-row slice index inside the segment
+    if (lane == 0) {
+      fence_proxy_async();  // the buffer was read through the generic proxy; order those reads before the async write
+      mbar_expect_tx(&hdr->full[warp][stage], ps.stage_tx);
+    }
+    __syncwarp();
+    if (lane < q.num_slots) {
+      const TmaSlot& sl = ps.slot[lane];
+      tma_load_1d(wstages + (size_t)stage * q.stage_words + sl.stage_words,
+                  reinterpret_cast<const unsigned char*>(sl.data) + slice * sl.tile_bytes, sl.tile_bytes,
                   &hdr->full[warp][stage], policy);
     }
   };
-  if (lane == 0 && use_pipe) {
+  if (use_pipe) {
     for (int s = 0; s < q.num_stages; ++s) {
       const long long Tc = blockIdx.x + (long long)s * gridDim.x;
       if (Tc < q.total_tiles) issue(Tc, s);
@@ -344,7 +346,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
   for (long long T = blockIdx.x; T < q.total_tiles; T += gridDim.x) {
     // ---- segment change: flush accumulators, refresh the shared descriptor copy (the only CTA-wide barriers) ----
     int ns = sidx < 0 ? 0 : sidx;
-    while (T >= __ldg(&segs[ns].first_tile) + __ldg(&segs[ns].num_tiles)) ++ns;
+    while (T >= tt.seg[ns].first_tile + tt.seg[ns].num_tiles) ++ns;
     if (ns != sidx) {
       if (sidx >= 0) flush();
       consumer_bar_sync(kConsumers);  // everyone done reading the old descriptor
@@ -660,10 +662,8 @@ scan_kernel(const __grid_constant__ QueryDesc q, const SegDesc* __restrict__ seg
 
     if (use_pipe) {
       __syncwarp();  // every lane is done reading this buffer
-      if (lane == 0) {
-        const long long Tn = T + (long long)q.num_stages * gridDim.x;
-        if (Tn < q.total_tiles) issue(Tn, stage);
-      }
+      const long long Tn = T + (long long)q.num_stages * gridDim.x;
+      if (Tn < q.total_tiles) issue(Tn, stage);
       if (++stage == q.num_stages) { stage = 0; phase ^= 1u; }
     }
   }
