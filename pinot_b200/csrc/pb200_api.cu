@@ -631,7 +631,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     ~ResultCleanup() { if (armed) for (auto& x : *r) if (x) pb200_result_free(x.release()); }
   } cleanup{&res};
 
-  std::vector<DevBuf> accum_bufs(nres);
+  DevBuf accum_buf;  // nres AggAccum records, initialised and read back with ONE copy each
   std::vector<std::vector<std::unique_ptr<DevBuf>>> distinct_bufs(nres);
   plan.segs.resize(nseg);
   long long tile_cursor = 0;
@@ -655,7 +655,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     }
     sd.stage_tx = tx;
   }
-  q.total_tiles = tile_cursor;
+  q.total_tiles = (int32_t)std::min<long long>(tile_cursor, 0x7FFFFFFF);
 
   // ---- per segment leaves ----
   for (int s = 0; s < nseg; s++) {
@@ -762,16 +762,17 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   AggAccum init_acc;
   memset(&init_acc, 0, sizeof init_acc);
   for (int a = 0; a < kMaxAggs; a++) init_acc.min_id[a] = 0xFFFFFFFFu;
-  for (int r = 0; r < nres; r++) {
-    int rc = accum_bufs[r].alloc(ctx, sizeof(AggAccum));
+  std::vector<AggAccum> host_acc(nres, init_acc);
+  {
+    int rc = accum_buf.alloc(ctx, sizeof(AggAccum) * nres);
     if (rc) return rc;
-    PB200_CUDA(cudaMemcpyAsync(accum_bufs[r].p, &init_acc, sizeof init_acc, cudaMemcpyHostToDevice, st));
+    PB200_CUDA(cudaMemcpyAsync(accum_buf.p, host_acc.data(), sizeof(AggAccum) * nres, cudaMemcpyHostToDevice, st));
   }
   for (int s = 0; s < nseg; s++) {
     const pb200_segment* seg = segments[s];
     SegDesc& sd = plan.segs[s];
     const int r = merge ? 0 : s;
-    sd.accum = (AggAccum*)accum_bufs[r].p;
+    sd.accum = (AggAccum*)accum_buf.p + r;
     for (int a = 0; a < nagg; a++) {
       if (q.aggs[a].slot < 0) continue;
       const DeviceColumn& c = seg->cols[query->aggs[a].column];
@@ -889,14 +890,16 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     cq.total_tiles = 0;
     for (int s = 0; s < cn; s++) {
       const SegDesc& sd = launch_segs[c0 + s];
-      tt.seg[s].first_tile = sd.first_tile;
-      tt.seg[s].num_tiles = sd.num_tiles;
+      tt.seg[s].first_tile = (int32_t)sd.first_tile;
+      tt.seg[s].end_tile = (int32_t)(sd.first_tile + sd.num_tiles);
       tt.seg[s].stage_tx = sd.stage_tx;
+      tt.seg[s].num_docs = (uint32_t)sd.num_docs;
       for (int k = 0; k < q.num_slots; k++) tt.seg[s].slot[k] = TmaSlot{sd.slots[k].data, sd.slots[k].tile_bytes, sd.slots[k].stage_words};
       cq.total_tiles += sd.num_tiles;
     }
-    for (int s = cn; s < kMaxLaunchSegs; s++) { tt.seg[s].first_tile = cq.total_tiles; tt.seg[s].num_tiles = (1ll << 60); }  // sentinel
+    for (int s = cn; s < kMaxLaunchSegs; s++) { tt.seg[s].first_tile = cq.total_tiles; tt.seg[s].end_tile = 0x7FFFFFFF; }  // sentinel
     grid = (int)std::min<long long>((long long)ctx->sm_count * ctas_per_sm, std::max<long long>(cq.total_tiles, 1));
+    if (cq.total_tiles >= (1 << 30)) { set_error("too many tiles in one launch"); return PB200_E_UNSUPPORTED; }
     if (getenv("PB200_GRID")) grid = std::max(1, atoi(getenv("PB200_GRID")));
     const SegDesc* dptr = (const SegDesc*)dsegs.p + c0;
     if (plan.group_by) le = cw == 8 ? launch_scan<8, true>(plan, cq, tt, dptr, grid, st) : cw == 7 ? launch_scan<7, true>(plan, cq, tt, dptr, grid, st) : launch_scan<6, true>(plan, cq, tt, dptr, grid, st);
@@ -906,6 +909,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   PB200_CUDA(cudaEventRecord(e1, st));
   cudaError_t se = cudaStreamSynchronize(st);
   if (se != cudaSuccess) { set_error("scan kernel failed: %s", cudaGetErrorString(se)); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }
+  PB200_CUDA(cudaMemcpy(host_acc.data(), accum_buf.p, sizeof(AggAccum) * nres, cudaMemcpyDeviceToHost));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0);
@@ -916,8 +920,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   for (int k = 0; k < q.num_slots; k++) if (q.slot_roles[k] & (ROLE_GROUP | ROLE_AGG)) projected++;
   for (int r = 0; r < nres; r++) {
     pb200_result& R = *res[r];
-    AggAccum acc;
-    PB200_CUDA(cudaMemcpy(&acc, accum_bufs[r].p, sizeof acc, cudaMemcpyDeviceToHost));
+    const AggAccum acc = host_acc[r];
     long long total_docs = 0;
     if (merge) for (int s = 0; s < nseg; s++) total_docs += segments[s]->num_docs; else total_docs = segments[r]->num_docs;
     R.meta.num_group_by = ngb;

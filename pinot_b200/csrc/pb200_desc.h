@@ -87,10 +87,10 @@ struct TmaSlot {
   uint32_t stage_words;
 };
 struct TmaSeg {
-  long long first_tile;
-  long long num_tiles;
+  int32_t first_tile;   // CTA-tile index (launch relative) of the segment's first tile
+  int32_t end_tile;     // exclusive
   uint32_t stage_tx;
-  uint32_t pad;
+  uint32_t num_docs;
   TmaSlot slot[kMaxSlots];
 };
 struct TmaTable {
@@ -123,7 +123,8 @@ struct QueryDesc {
   uint8_t prog_op[kMaxNodes];
   uint8_t prog_arg[kMaxNodes];  // OP_LEAF: leaf index; AND/OR: operand count
   AggDesc aggs[kMaxAggs];
-  long long total_tiles;
+  int32_t total_tiles;     // CTA tiles in this launch
+  int32_t pad_tail;
 };
 
 }  // namespace pb200

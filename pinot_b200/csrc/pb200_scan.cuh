@@ -87,7 +87,8 @@ __device__ __forceinline__ uint32_t eval_lut(const uint32_t (&v)[32], const uint
   return m;
 }
 // rows [row0, row0+32) against inclusive doc-id ranges
-__device__ __forceinline__ uint32_t eval_doc_ranges(long long row0, const int32_t* __restrict__ r, int n) {
+__device__ __forceinline__ uint32_t eval_doc_ranges(uint32_t row0u, const int32_t* __restrict__ r, int n) {
+  const long long row0 = row0u;
   uint32_t m = 0;
   for (int i = 0; i < n; ++i) {
     long long lo = (long long)__ldg(r + 2 * i) - row0, hi = (long long)__ldg(r + 2 * i + 1) - row0 + 1;  // [lo, hi)
@@ -259,31 +260,39 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
   const SegDesc& sd = hdr->seg;
   unsigned long long cnt = 0;
 
-  // ---- warp-private TMA ring ----
-  uint64_t policy = 0;
-  int pidx = 0;  // segment cursor of the prefetcher (runs ahead of the consumer cursor)
-  policy = policy_evict_first();
-  auto issue = [&](long long Tc, int stage) {  // whole warp: lane 0 arms the barrier, lane k < num_slots copies slot k
-    while (Tc >= tt.seg[pidx].first_tile + tt.seg[pidx].num_tiles) ++pidx;
-    const TmaSeg& ps = tt.seg[pidx];
-    const long long slice = (Tc - ps.first_tile) * W + warp;  // 1024-row slice index inside the segment
+  // ---- warp-private TMA ring.  Prefetch cursor state lives in registers and advances incrementally (lane k < num_slots
+  //      owns slot k's source pointer); the constant-bank table is consulted only when the cursor enters a new segment.
+  const uint64_t policy = policy_evict_first();
+  uint64_t* const fullw = &hdr->full[warp][0];
+  int pidx = 0, p_end = 0;            // prefetch segment cursor and its exclusive end tile
+  int Tp = blockIdx.x;                // next CTA tile to prefetch
+  const unsigned char* p_src = nullptr;
+  unsigned long long p_stride = 0;
+  uint32_t p_tb = 0, p_dst = 0, p_tx = 0;
+  auto issue = [&](int stage) {  // whole warp: lane 0 arms the barrier, lane k < num_slots copies slot k
+    if (Tp >= p_end) {
+      while (Tp >= tt.seg[pidx].end_tile) ++pidx;
+      const TmaSeg& ps = tt.seg[pidx];
+      p_end = ps.end_tile;
+      p_tx = ps.stage_tx;
+      const TmaSlot& sl = ps.slot[lane < q.num_slots ? lane : 0];
+      p_tb = sl.tile_bytes;
+      p_dst = sl.stage_words;
+      p_src = reinterpret_cast<const unsigned char*>(sl.data) + (unsigned long long)((Tp - ps.first_tile) * W + warp) * p_tb;
+      p_stride = (unsigned long long)p_tb * (unsigned)(W * gridDim.x);
+    }
     if (lane == 0) {
       fence_proxy_async();  // the buffer was read through the generic proxy; order those reads before the async write
-      mbar_expect_tx(&hdr->full[warp][stage], ps.stage_tx);
+      mbar_expect_tx(fullw + stage, p_tx);
     }
     __syncwarp();
-    if (lane < q.num_slots) {
-      const TmaSlot& sl = ps.slot[lane];
-      tma_load_1d(wstages + (size_t)stage * q.stage_words + sl.stage_words,
-                  reinterpret_cast<const unsigned char*>(sl.data) + slice * sl.tile_bytes, sl.tile_bytes,
-                  &hdr->full[warp][stage], policy);
-    }
+    if (lane < q.num_slots) tma_load_1d(wstages + stage * q.stage_words + p_dst, p_src, p_tb, fullw + stage, policy);
+    p_src += p_stride;
+    Tp += gridDim.x;
   };
   if (use_pipe) {
-    for (int s = 0; s < q.num_stages; ++s) {
-      const long long Tc = blockIdx.x + (long long)s * gridDim.x;
-      if (Tc < q.total_tiles) issue(Tc, s);
-    }
+    for (int s = 0; s < q.num_stages; ++s)
+      if (Tp < q.total_tiles) issue(s);
   }
 
   // deferred dictionary gathers (software pipelining across tiles): the biased values of tile t's surviving rows are
@@ -341,13 +350,13 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
   };
   reset_acc();
 
-  int sidx = -1, stage = 0;
-  uint32_t phase = 0;
-  for (long long T = blockIdx.x; T < q.total_tiles; T += gridDim.x) {
+  int sidx = -1, stage = 0, c_first = 0, c_end = 0;
+  uint32_t phase = 0, c_docs = 0;
+  for (int T = blockIdx.x; T < q.total_tiles; T += gridDim.x) {
     // ---- segment change: flush accumulators, refresh the shared descriptor copy (the only CTA-wide barriers) ----
-    int ns = sidx < 0 ? 0 : sidx;
-    while (T >= tt.seg[ns].first_tile + tt.seg[ns].num_tiles) ++ns;
-    if (ns != sidx) {
+    if (T >= c_end) {
+      int ns = sidx < 0 ? 0 : sidx;
+      while (T >= tt.seg[ns].end_tile) ++ns;
       if (sidx >= 0) flush();
       consumer_bar_sync(kConsumers);  // everyone done reading the old descriptor
       const uint32_t* src = reinterpret_cast<const uint32_t*>(segs + ns);
@@ -355,14 +364,16 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
       for (int i = threadIdx.x; i < (int)(sizeof(SegDesc) / 4); i += kConsumers) dstw[i] = __ldg(src + i);
       consumer_bar_sync(kConsumers);
       sidx = ns;
+      c_first = tt.seg[ns].first_tile;
+      c_end = tt.seg[ns].end_tile;
+      c_docs = tt.seg[ns].num_docs;
     }
-    const long long t = T - sd.first_tile;
-    const long long row0 = (t * W + warp) * 1024 + (long long)lane * kRowsPerThread;
-    const long long left = sd.num_docs - row0;
-    uint32_t m = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+    const uint32_t row0 = (uint32_t)((T - c_first) * W + warp) * 1024u + (uint32_t)lane * kRowsPerThread;
+    const int left = row0 >= c_docs ? 0 : (c_docs - row0 >= 32u ? 32 : (int)(c_docs - row0));
+    uint32_t m = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
 
-    if (use_pipe) mbar_wait(&hdr->full[warp][stage], phase);
-    const uint32_t* st = wstages + (size_t)stage * q.stage_words;
+    if (use_pipe) mbar_wait(fullw + stage, phase);
+    const uint32_t* st = wstages + stage * q.stage_words;
     const int group_in_stage = lane;  // the thread's 32-row group inside the warp's slice
 
     // ---------------- phase 1: filter -> row mask ----------------
@@ -662,8 +673,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 
     if (use_pipe) {
       __syncwarp();  // every lane is done reading this buffer
-      const long long Tn = T + (long long)q.num_stages * gridDim.x;
-      if (Tn < q.total_tiles) issue(Tn, stage);
+      if (Tp < q.total_tiles) issue(stage);
       if (++stage == q.num_stages) { stage = 0; phase ^= 1u; }
     }
   }
