@@ -371,7 +371,7 @@ def main():
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "pb200::scan_kernel<8,false>", "kernel_ms": k_ms,
+                             "kernel": "pb200::scan_kernel<6,false>", "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": rows_per_step * bpr},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d,

@@ -146,10 +146,51 @@ public class B200Operator extends BaseOperator<BaseResultsBlock> {
     }
   }
 
+  /** Inclusive (start, end) docId pairs -- the range arithmetic of SortedIndexBasedFilterOperator :60-135. */
   private int[] sortedDocRanges(DataSource ds, PredicateEvaluator evaluator) {
-    // same range arithmetic as SortedIndexBasedFilterOperator; omitted here for brevity: returns inclusive
-    // (start, end) pairs, already inverted for exclusive predicates
-    throw new UnsupportedOperationException("see pinot_b200/csrc/host/plan_maker.cpp sorted_doc_ranges()");
+    org.apache.pinot.segment.spi.index.reader.SortedIndexReader<?> sorted =
+        (org.apache.pinot.segment.spi.index.reader.SortedIndexReader<?>) ds.getInvertedIndex();
+    int numDocs = _segment.getSegmentMetadata().getTotalDocs();
+    List<IntPair> ranges = new ArrayList<>();
+    if (evaluator instanceof SortedDictionaryBasedRangePredicateEvaluator) {
+      SortedDictionaryBasedRangePredicateEvaluator range = (SortedDictionaryBasedRangePredicateEvaluator) evaluator;
+      ranges.add(new IntPair(sorted.getDocIds(range.getStartDictId()).getLeft(),
+          sorted.getDocIds(range.getEndDictId() - 1).getRight()));
+    } else {
+      boolean exclusive = evaluator.isExclusive();
+      int[] ids = exclusive ? evaluator.getNonMatchingDictIds() : evaluator.getMatchingDictIds();
+      IntPair last = sorted.getDocIds(ids[0]);
+      last = new IntPair(last.getLeft(), last.getRight());
+      for (int i = 1; i < ids.length; i++) {
+        IntPair cur = sorted.getDocIds(ids[i]);
+        if (cur.getLeft() == last.getRight() + 1) {
+          last.setRight(cur.getRight());
+        } else {
+          ranges.add(last);
+          last = new IntPair(cur.getLeft(), cur.getRight());
+        }
+      }
+      ranges.add(last);
+      if (exclusive) {
+        List<IntPair> inverted = new ArrayList<>();
+        if (ranges.get(0).getLeft() > 0) {
+          inverted.add(new IntPair(0, ranges.get(0).getLeft() - 1));
+        }
+        for (int i = 0; i + 1 < ranges.size(); i++) {
+          inverted.add(new IntPair(ranges.get(i).getRight() + 1, ranges.get(i + 1).getLeft() - 1));
+        }
+        if (ranges.get(ranges.size() - 1).getRight() < numDocs - 1) {
+          inverted.add(new IntPair(ranges.get(ranges.size() - 1).getRight() + 1, numDocs - 1));
+        }
+        ranges = inverted;
+      }
+    }
+    int[] flat = new int[2 * ranges.size()];
+    for (int i = 0; i < ranges.size(); i++) {
+      flat[2 * i] = ranges.get(i).getLeft();
+      flat[2 * i + 1] = ranges.get(i).getRight();
+    }
+    return flat;
   }
 
   @Override
@@ -269,7 +310,7 @@ public class B200Operator extends BaseOperator<BaseResultsBlock> {
         }
       }
     }
-    DataSchema schema = org.apache.pinot.core.operator.query.GroupByOperator.class == null ? null : buildSchema(functions, groupBy);
+    DataSchema schema = buildSchema(functions, groupBy);
     GroupByResultsBlock block =
         new GroupByResultsBlock(schema, new AggregationGroupByResult(generator, functions, holders), _queryContext);
     block.setNumGroupsLimitReached(meta[2] != 0);
