@@ -14,6 +14,9 @@
 #include <limits>
 #include <memory>
 
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
 #include "pb200_internal.h"
 #include "pb200_scan.cuh"
 
@@ -129,6 +132,11 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, long long n) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   for (; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
+
+struct NonEmptyGroup {
+  const unsigned long long* count;
+  __device__ __forceinline__ bool operator()(const uint32_t& i) const { return count[i] != 0ull; }
+};
 
 // compaction of a dense group table: indices of non-empty groups (any order)
 __global__ void compact_groups_kernel(const unsigned long long* __restrict__ count, long long groups,
@@ -658,6 +666,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   q.total_tiles = (int32_t)std::min<long long>(tile_cursor, 0x7FFFFFFF);
 
   // ---- per segment leaves ----
+  std::vector<DecodeJob> decode_jobs;  // every posting list the query needs, decoded by ONE launch
   for (int s = 0; s < nseg; s++) {
     const pb200_segment* seg = segments[s];
     SegDesc& sd = plan.segs[s];
@@ -711,14 +720,17 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         }
       } else if (n.op == PB200_F_INV_IN || n.op == PB200_F_INV_NOT_IN) {
         if (!c.inv) { set_error("column %d has no inverted index", n.column); return PB200_E_INVALID; }
-        size_t words = ((size_t)seg->num_docs + 31) / 32 + 8;
+        size_t words = (((size_t)seg->num_docs + kMaxTileRows - 1) / kMaxTileRows + 1) * (kMaxTileRows / 32) + 8;  // whole tiles
         plan.temps.emplace_back(new DevBuf());
         int rc = plan.temps.back()->alloc(ctx, words * 4);
         if (rc) return rc;
         uint32_t* mask = (uint32_t*)plan.temps.back()->p;
         PB200_CUDA(cudaMemsetAsync(mask, 0, words * 4, st));
-        rc = roaring_or_into_mask(ctx, st, c, n.ids, n.num_ids, mask, seg->num_docs);
-        if (rc) return rc;
+        for (int k = 0; k < n.num_ids; k++) {  // InvertedIndexFilterOperator: OR of the bitmaps of the dictIds
+          const int id = n.ids[k];
+          if (id < 0 || id >= c.cardinality) { set_error("dictId %d out of range for inverted index (card %d)", id, c.cardinality); return PB200_E_INVALID; }
+          decode_jobs.push_back(DecodeJob{c.inv, c.inv_offsets[id], (unsigned long long)c.inv_offsets[id + 1] - c.inv_offsets[id], mask, seg->num_docs});
+        }
         lf.kind = LEAF_DOCMASK;
         lf.bits = mask;
         lf.negate = n.op == PB200_F_INV_NOT_IN;
@@ -738,6 +750,14 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         return PB200_E_UNSUPPORTED;
       }
     }
+  }
+
+  if (!decode_jobs.empty()) {
+    plan.temps.emplace_back(new DevBuf());
+    int rc = plan.temps.back()->alloc(ctx, sizeof(DecodeJob) * decode_jobs.size());
+    if (rc) return rc;
+    rc = roaring_decode_batch(ctx, st, decode_jobs, plan.temps.back()->p);
+    if (rc) return rc;
   }
 
   // ---- conjunctions: cheapest / most selective leaf first (per segment; AND is commutative).  The reference orders
@@ -895,6 +915,11 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       tt.seg[s].stage_tx = sd.stage_tx;
       tt.seg[s].num_docs = (uint32_t)sd.num_docs;
       for (int k = 0; k < q.num_slots; k++) tt.seg[s].slot[k] = TmaSlot{sd.slots[k].data, sd.slots[k].tile_bytes, sd.slots[k].stage_words};
+      if (q.conj && q.num_slots > 0 && !getenv("PB200_NO_SKIP")) {
+        int nm = 0;
+        for (int l = 0; l < nleaves && nm < kMaxSkipMasks; l++)
+          if (sd.leaves[l].kind == LEAF_DOCMASK && !sd.leaves[l].negate) tt.seg[s].skip_mask[nm++] = sd.leaves[l].bits;
+      }
       cq.total_tiles += sd.num_tiles;
     }
     for (int s = cn; s < kMaxLaunchSegs; s++) { tt.seg[s].first_tile = cq.total_tiles; tt.seg[s].end_tile = 0x7FFFFFFF; }  // sentinel
@@ -1007,8 +1032,16 @@ extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
   if ((rc = idx.alloc(ctx, (size_t)G * 4))) return rc;
   PB200_CUDA(cudaMemsetAsync(counter.p, 0, 8, st));
   int blocks = (int)std::min<long long>((G + 255) / 256, 148 * 8);
-  compact_groups_kernel<<<blocks, 256, 0, st>>>(d.count, G, (unsigned long long*)counter.p, (uint32_t*)idx.p, G);
-  PB200_CUDA(cudaGetLastError());
+  (void)blocks;
+  {  // stream compaction of the non-empty groups IN raw-key order (== ArrayBasedHolder's iteration order): no host sort
+    cub::CountingInputIterator<uint32_t> first(0u);
+    size_t tmp_bytes = 0;
+    PB200_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, first, (uint32_t*)idx.p, (unsigned long long*)counter.p, (long long)G, NonEmptyGroup{d.count}, st));
+    DevBuf tmp;
+    if ((rc = tmp.alloc(ctx, tmp_bytes + 16))) return rc;
+    PB200_CUDA(cub::DeviceSelect::If(tmp.p, tmp_bytes, first, (uint32_t*)idx.p, (unsigned long long*)counter.p, (long long)G, NonEmptyGroup{d.count}, st));
+    PB200_CUDA(cudaStreamSynchronize(st));  // tmp is released at scope exit
+  }
   unsigned long long n = 0;
   PB200_CUDA(cudaMemcpyAsync(&n, counter.p, 8, cudaMemcpyDeviceToHost, st));
   PB200_CUDA(cudaStreamSynchronize(st));
@@ -1022,8 +1055,6 @@ extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
   }
   std::vector<uint32_t> hidx(n);
   if (n) PB200_CUDA(cudaMemcpy(hidx.data(), idx.p, n * 4, cudaMemcpyDeviceToHost));
-  std::sort(hidx.begin(), hidx.end());  // ascending raw key == ArrayBasedHolder's iteration order
-  if (n) PB200_CUDA(cudaMemcpy(idx.p, hidx.data(), n * 4, cudaMemcpyHostToDevice));
   R->keys.assign((size_t)n * ngb, 0);
   for (size_t i = 0; i < n; i++) {
     uint32_t raw = hidx[i];

@@ -81,6 +81,7 @@ struct SegDesc {
 // parameter so it sits in the constant bank (a global-memory descriptor read per tile costs an L2 round trip because
 // the dictionary gathers keep evicting L1).
 constexpr int kMaxLaunchSegs = 16;
+constexpr int kMaxSkipMasks = 3;
 struct TmaSlot {
   const void* data;
   uint32_t tile_bytes;
@@ -91,6 +92,9 @@ struct TmaSeg {
   int32_t end_tile;     // exclusive
   uint32_t stage_tx;
   uint32_t num_docs;
+  // doc masks (1 bit per doc) that are top-level AND operands of the filter: a 1024-row slice whose mask words are all
+  // zero is never loaded (the GPU analogue of iterating only the doc ids a bitmap index produced)
+  const uint32_t* skip_mask[kMaxSkipMasks];
   TmaSlot slot[kMaxSlots];
 };
 struct TmaTable {

@@ -102,10 +102,16 @@ cudaStream_t take_stream(pb200_ctx* ctx);
 void give_stream(pb200_ctx* ctx, cudaStream_t s);
 
 // pb200_roaring.cu
-// Decodes the bitmaps of `ids` (inverted index of `col`) OR-ed together into `mask` (1 bit per doc, bit j of 32-bit word
-// w = doc 32*w + j). mask must be zeroed by the caller.
-int roaring_or_into_mask(pb200_ctx* ctx, cudaStream_t stream, const DeviceColumn& col, const int32_t* ids, int num_ids,
-                         uint32_t* mask, long long num_docs);
+// One serialized RoaringBitmap (posting list of one dictId) to be OR-ed into `mask` (1 bit per doc, bit j of 32-bit
+// word w = doc 32*w + j; zeroed by the caller).
+struct DecodeJob {
+  const unsigned char* inv;     // device: inverted index file bytes
+  unsigned long long offset;    // byte offset of the bitmap inside the file
+  unsigned long long length;
+  uint32_t* mask;
+  long long num_docs;
+};
+int roaring_decode_batch(pb200_ctx* ctx, cudaStream_t stream, const std::vector<DecodeJob>& jobs, void* jobs_dev);
 // pb200_synth.cu
 int synth_build_inverted(pb200_ctx* ctx, cudaStream_t stream, DeviceColumn& col, long long num_docs);
 }  // namespace pb200

@@ -10,6 +10,7 @@
 // (array: a thread per value; run: a thread per run; bitmap: a thread per 32-bit word) with atomicOr into the mask.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "pb200_internal.h"
@@ -21,15 +22,11 @@ __device__ __forceinline__ uint32_t ld32(const unsigned char* p) {
   return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
 }
 
-struct BitmapRef {
-  unsigned long long offset;  // byte offset inside the inverted index file
-  unsigned long long length;
-};
-
-__global__ void __launch_bounds__(256) roaring_decode_kernel(const unsigned char* __restrict__ inv,
-                                                             const BitmapRef* __restrict__ refs,
-                                                             uint32_t* __restrict__ mask, long long num_docs) {
-  const BitmapRef ref = refs[blockIdx.y];
+__global__ void __launch_bounds__(256) roaring_decode_kernel(const DecodeJob* __restrict__ jobs) {
+  const DecodeJob ref = jobs[blockIdx.y];
+  const unsigned char* __restrict__ inv = ref.inv;
+  uint32_t* __restrict__ mask = ref.mask;
+  const long long num_docs = ref.num_docs;
   if (ref.length < 8) return;  // empty bitmap: cookie + size 0
   const unsigned char* b = inv + ref.offset;
   const uint32_t cookie = ld32(b);
@@ -107,30 +104,22 @@ __global__ void __launch_bounds__(256) roaring_decode_kernel(const unsigned char
   }
 }
 
-int roaring_or_into_mask(pb200_ctx* ctx, cudaStream_t stream, const DeviceColumn& col, const int32_t* ids, int num_ids,
-                         uint32_t* mask, long long num_docs) {
-  if (num_ids <= 0) return PB200_OK;
-  std::vector<BitmapRef> refs(num_ids);
-  for (int i = 0; i < num_ids; i++) {
-    int id = ids[i];
-    if (id < 0 || id >= col.cardinality) { set_error("dictId %d out of range for inverted index (card %d)", id, col.cardinality); return PB200_E_INVALID; }
-    refs[i].offset = col.inv_offsets[id];
-    refs[i].length = (unsigned long long)col.inv_offsets[id + 1] - col.inv_offsets[id];
+// One launch for ALL bitmaps a query needs (every segment, every inverted-index leaf): blockIdx.y = job.  Nothing here
+// synchronises the stream; `jobs_dev` must stay alive until the stream has passed the kernel (the caller owns it).
+int roaring_decode_batch(pb200_ctx* ctx, cudaStream_t stream, const std::vector<DecodeJob>& jobs, void* jobs_dev) {
+  if (jobs.empty()) return PB200_OK;
+  cudaError_t e = cudaMemcpyAsync(jobs_dev, jobs.data(), sizeof(DecodeJob) * jobs.size(), cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) { set_error("decode job upload failed: %s", cudaGetErrorString(e)); return PB200_E_CUDA; }
+  long long max_docs = 0;
+  for (const DecodeJob& j : jobs) max_docs = std::max(max_docs, j.num_docs);
+  const long long containers = (max_docs + 65535) / 65536;
+  for (size_t j0 = 0; j0 < jobs.size(); j0 += 65535) {
+    const unsigned ny = (unsigned)std::min<size_t>(65535, jobs.size() - j0);
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(containers, 512)), ny);
+    roaring_decode_kernel<<<grid, 256, 0, stream>>>((const DecodeJob*)jobs_dev + j0);
   }
-  void* drefs = nullptr;
-  int rc = dev_alloc(ctx, sizeof(BitmapRef) * num_ids, &drefs);
-  if (rc) return rc;
-  cudaError_t e = cudaMemcpyAsync(drefs, refs.data(), sizeof(BitmapRef) * num_ids, cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // refs is a local
-  if (e != cudaSuccess) { dev_free(ctx, drefs); set_error("bitmap ref upload failed: %s", cudaGetErrorString(e)); return PB200_E_CUDA; }
-  const long long containers = (num_docs + 65535) / 65536;
-  dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(containers, 2048)), (unsigned)num_ids);
-  roaring_decode_kernel<<<grid, 256, 0, stream>>>(col.inv, (const BitmapRef*)drefs, mask, num_docs);
   e = cudaGetLastError();
-  // drefs is read by the kernel: release it only after the stream has passed the kernel
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  dev_free(ctx, drefs);
-  if (e != cudaSuccess) { set_error("roaring decode failed: %s", cudaGetErrorString(e)); return PB200_E_CUDA; }
+  if (e != cudaSuccess) { set_error("roaring decode launch failed: %s", cudaGetErrorString(e)); return PB200_E_CUDA; }
   return PB200_OK;
 }
 

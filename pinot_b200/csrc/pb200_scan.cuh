@@ -268,12 +268,17 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
   int Tp = blockIdx.x;                // next CTA tile to prefetch
   const unsigned char* p_src = nullptr;
   unsigned long long p_stride = 0;
-  uint32_t p_tb = 0, p_dst = 0, p_tx = 0;
+  uint32_t p_tb = 0, p_dst = 0, p_tx = 0, p_docs = 0, skipbits = 0;
+  int p_first = 0;
+  const uint32_t *p_skip0 = nullptr, *p_skip1 = nullptr, *p_skip2 = nullptr;
   auto issue = [&](int stage) {  // whole warp: lane 0 arms the barrier, lane k < num_slots copies slot k
     if (Tp >= p_end) {
       while (Tp >= tt.seg[pidx].end_tile) ++pidx;
       const TmaSeg& ps = tt.seg[pidx];
       p_end = ps.end_tile;
+      p_first = ps.first_tile;
+      p_docs = ps.num_docs;
+      p_skip0 = ps.skip_mask[0]; p_skip1 = ps.skip_mask[1]; p_skip2 = ps.skip_mask[2];
       p_tx = ps.stage_tx;
       const TmaSlot& sl = ps.slot[lane < q.num_slots ? lane : 0];
       p_tb = sl.tile_bytes;
@@ -281,12 +286,31 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
       p_src = reinterpret_cast<const unsigned char*>(sl.data) + (unsigned long long)((Tp - ps.first_tile) * W + warp) * p_tb;
       p_stride = (unsigned long long)p_tb * (unsigned)(W * gridDim.x);
     }
-    if (lane == 0) {
-      fence_proxy_async();  // the buffer was read through the generic proxy; order those reads before the async write
-      mbar_expect_tx(fullw + stage, p_tx);
+    // bitmap-index driven skipping: if the AND of the slice's doc-mask words is zero, nothing in it can match
+    bool skip = false;
+    if (p_skip0 != nullptr) {
+      const uint32_t slice = (uint32_t)((Tp - p_first) * W + warp);
+      uint32_t wv = 0;
+      if (slice * 1024u < p_docs) {
+        const uint32_t wi = slice * 32u + lane;
+        wv = __ldg(p_skip0 + wi);
+        if (p_skip1) wv &= __ldg(p_skip1 + wi);
+        if (p_skip2) wv &= __ldg(p_skip2 + wi);
+      }
+      skip = !__any_sync(0xFFFFFFFFu, wv != 0u);
     }
-    __syncwarp();
-    if (lane < q.num_slots) tma_load_1d(wstages + stage * q.stage_words + p_dst, p_src, p_tb, fullw + stage, policy);
+    if (skip) {
+      skipbits |= 1u << stage;
+      if (lane == 0) mbar_arrive(fullw + stage);  // completes the phase without any bytes
+    } else {
+      skipbits &= ~(1u << stage);
+      if (lane == 0) {
+        fence_proxy_async();  // the buffer was read through the generic proxy; order those reads before the async write
+        mbar_expect_tx(fullw + stage, p_tx);
+      }
+      __syncwarp();
+      if (lane < q.num_slots) tma_load_1d(wstages + stage * q.stage_words + p_dst, p_src, p_tb, fullw + stage, policy);
+    }
     p_src += p_stride;
     Tp += gridDim.x;
   };
@@ -373,6 +397,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     uint32_t m = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
 
     if (use_pipe) mbar_wait(fullw + stage, phase);
+    if (use_pipe && ((skipbits >> stage) & 1u)) m = 0u;  // slice was never loaded: no doc of it passes the bitmap leaves
     const uint32_t* st = wstages + stage * q.stage_words;
     const int group_in_stage = lane;  // the thread's 32-row group inside the warp's slice
 
@@ -381,7 +406,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     // thread survive, the remaining columns are probed per surviving row straight from the shared-memory tile
     // (the GPU form of ScanBasedDocIdIterator.applyAnd on the bitmap of survivors, AndDocIdSet.java:167-169)
     // instead of unpacking all 32 values.
-    if (q.num_nodes > 0) {
+    if (q.num_nodes > 0 && __any_sync(0xFFFFFFFFu, m != 0u)) {
       if (q.conj) {
 #pragma unroll 1
         for (int l = 0; l < q.num_leaves; ++l) {
@@ -483,7 +508,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     const int pc = __popc(m);
     cnt += pc;
     const int wmax2 = __reduce_max_sync(0xFFFFFFFFu, pc);
-    if (wmax2 > 0 && wmax2 <= q.sparse_max) {
+    if (wmax2 > 0 && wmax2 <= (GROUPBY ? min(q.sparse_max, 2) : q.sparse_max)) {
       // ---- sparse projection: per surviving row, read its dictIds from the tile (FixedBitIntReader.readUnchecked
       //      shape; what DataFetcher does with sparse docIds, core/common/DataFetcher.java:335-338) ----
       uint32_t mm = m;
@@ -631,30 +656,41 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
           const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
           unpack_group(sl.bits, st + sl.stage_words, group_in_stage, v);
           if (fn == 1 || fn == 4) {
+            // all gathers of the tile are issued BEFORE the first atomic consumes one: one L2 latency per tile, not
+            // one per surviving row
             if (vk == VAL_DICT_I32 || vk == VAL_RAW_I32) {
               const uint32_t* __restrict__ d = static_cast<const uint32_t*>(sd.dict[a]);
+              uint32_t xv[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if ((m >> j) & 1u) {
-                  const long long x = vk == VAL_RAW_I32 ? (long long)(int)v[j] : (long long)(int)(__ldg(d + v[j]) ^ 0x80000000u);
-                  atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)x);
-                }
-              }
+              for (int j = 0; j < 32; ++j) xv[j] = vk == VAL_RAW_I32 ? (v[j] ^ 0x80000000u) : ldg_bit_u32(d + v[j], m, 1u << j);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if ((m >> j) & 1u)
+                  atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)(long long)(int)(xv[j] ^ 0x80000000u));
             } else if (vk == VAL_DICT_I64) {
               const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
+              long long xv[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) xv[j] = ldg_pred_s64(d + v[j], (m >> j) & 1u);
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if ((m >> j) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)__ldg(d + v[j]));
+                if ((m >> j) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)xv[j]);
             } else if (vk == VAL_DICT_F32) {
               const float* __restrict__ d = static_cast<const float*>(sd.dict[a]);
+              float xv[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) xv[j] = __int_as_float(ldg_pred_s32(reinterpret_cast<const int*>(d + v[j]), (m >> j) & 1u));
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], (double)__ldg(d + v[j]));
+                if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], (double)xv[j]);
             } else {
               const double* __restrict__ d = static_cast<const double*>(sd.dict[a]);
+              double xv[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) xv[j] = __longlong_as_double(ldg_pred_s64(reinterpret_cast<const long long*>(d + v[j]), (m >> j) & 1u));
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], __ldg(d + v[j]));
+                if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], xv[j]);
             }
           } else if (fn == 2 || fn == 3) {
             const uint32_t bias = vk == VAL_RAW_I32 ? 0x80000000u : 0u;
