@@ -658,15 +658,19 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
           if (fn == 1 || fn == 4) {
             // all gathers of the tile are issued BEFORE the first atomic consumes one: one L2 latency per tile, not
             // one per surviving row
-            if (vk == VAL_DICT_I32 || vk == VAL_RAW_I32) {
+            if (vk == VAL_DICT_I32) {
               const uint32_t* __restrict__ d = static_cast<const uint32_t*>(sd.dict[a]);
               uint32_t xv[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) xv[j] = vk == VAL_RAW_I32 ? (v[j] ^ 0x80000000u) : ldg_bit_u32(d + v[j], m, 1u << j);
+              for (int j = 0; j < 32; ++j) xv[j] = ldg_bit_u32(d + v[j], m, 1u << j);  // straight-line: 32 loads in flight
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if ((m >> j) & 1u)
                   atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)(long long)(int)(xv[j] ^ 0x80000000u));
+            } else if (vk == VAL_RAW_I32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if ((m >> j) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)(long long)(int)v[j]);
             } else if (vk == VAL_DICT_I64) {
               const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
               long long xv[32];
