@@ -133,9 +133,14 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, long long n) {
   for (; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
-struct NonEmptyGroup {
+struct NonEmptyGroup {  // a group exists iff any of its (present) markers says so
   const unsigned long long* count;
-  __device__ __forceinline__ bool operator()(const uint32_t& i) const { return count[i] != 0ull; }
+  const uint32_t* seen;
+  const uint32_t* maxk;
+  const uint32_t* mink;
+  __device__ __forceinline__ bool operator()(const uint32_t& i) const {
+    return (count && count[i] != 0ull) || (seen && seen[i] != 0u) || (maxk && maxk[i] != 0u) || (mink && mink[i] != 0xFFFFFFFFu);
+  }
 };
 
 // compaction of a dense group table: indices of non-empty groups (any order)
@@ -845,7 +850,16 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       d.num_groups_limit = query->num_groups_limit;
       for (int a = 0; a < nagg; a++) { d.aggs.push_back(query->aggs[a]); d.val_kind.push_back(q.aggs[a].val_kind); d.agg_cols.push_back(q.aggs[a].slot < 0 ? nullptr : &seg->cols[query->aggs[a].column]); }
       // one block per element kind
-      long long n_i64 = 1, n_f64 = 0, n_max = 0, n_min = 0;
+      // the exact per-group count is kept only when a function needs it; otherwise a MIN/MAX table (or a flag table)
+      // marks the groups that exist -- one atomic less per surviving row
+      bool need_count = getenv("PB200_ALWAYS_COUNT") != nullptr;
+      bool has_minmax = false;
+      for (int a = 0; a < nagg; a++) {
+        need_count |= q.aggs[a].function == PB200_AGG_COUNT || q.aggs[a].function == PB200_AGG_AVG;
+        has_minmax |= q.aggs[a].function == PB200_AGG_MIN || q.aggs[a].function == PB200_AGG_MAX;
+      }
+      const bool need_seen = !need_count && !has_minmax;
+      long long n_i64 = need_count ? 1 : 0, n_f64 = 0, n_max = need_seen ? 1 : 0, n_min = 0;
       for (int a = 0; a < nagg; a++) {
         const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
         if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) { if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) n_f64++; else n_i64++; }
@@ -865,21 +879,23 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       if ((rc = alloc_block(&d.f64_block, d.f64_elems, 8, 0))) return rc;
       if ((rc = alloc_block(&d.u32max_block, d.u32max_elems, 4, 0))) return rc;
       if ((rc = alloc_block(&d.u32min_block, d.u32min_elems, 4, 0xFF))) return rc;
-      d.count = (unsigned long long*)d.i64_block;
-      long long ii = 1, fi = 0, xi = 0, ni = 0;
+      d.count = need_count ? (unsigned long long*)d.i64_block : nullptr;
+      d.seen = need_seen ? (uint32_t*)d.u32max_block : nullptr;
+      long long ii = need_count ? 1 : 0, fi = 0, xi = need_seen ? 1 : 0, ni = 0;
       for (int a = 0; a < nagg; a++) {
         const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
         if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
           if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) d.dsum[a] = (double*)d.f64_block + (fi++) * groups;
           else d.isum[a] = (long long*)d.i64_block + (ii++) * groups;
-        } else if (fn == PB200_AGG_MIN) d.gmin[a] = (uint32_t*)d.u32min_block + (ni++) * groups;
-        else if (fn == PB200_AGG_MAX) d.gmax[a] = (uint32_t*)d.u32max_block + (xi++) * groups;
+        } else if (fn == PB200_AGG_MIN) { d.gmin[a] = (uint32_t*)d.u32min_block + (ni++) * groups; if (!need_count && !d.exists_max && !d.exists_min) d.exists_min = d.gmin[a]; }
+        else if (fn == PB200_AGG_MAX) { d.gmax[a] = (uint32_t*)d.u32max_block + (xi++) * groups; if (!need_count && !d.exists_max && !d.exists_min) d.exists_max = d.gmax[a]; }
       }
     }
     for (int s = 0; s < nseg; s++) {
       SegDesc& sd = plan.segs[s];
       pb200_result::Dense& d = res[merge ? 0 : s]->dense;
       sd.g_count = d.count;
+      sd.g_seen = d.seen;
       for (int a = 0; a < nagg; a++) { sd.g_isum[a] = d.isum[a]; sd.g_dsum[a] = d.dsum[a]; sd.g_min[a] = d.gmin[a]; sd.g_max[a] = d.gmax[a]; }
       for (int g = 0; g < ngb; g++) sd.group_mult[g] = d.mult[g];
     }
@@ -1036,10 +1052,10 @@ extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
   {  // stream compaction of the non-empty groups IN raw-key order (== ArrayBasedHolder's iteration order): no host sort
     cub::CountingInputIterator<uint32_t> first(0u);
     size_t tmp_bytes = 0;
-    PB200_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, first, (uint32_t*)idx.p, (unsigned long long*)counter.p, (long long)G, NonEmptyGroup{d.count}, st));
+    PB200_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, first, (uint32_t*)idx.p, (unsigned long long*)counter.p, (long long)G, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min}, st));
     DevBuf tmp;
     if ((rc = tmp.alloc(ctx, tmp_bytes + 16))) return rc;
-    PB200_CUDA(cub::DeviceSelect::If(tmp.p, tmp_bytes, first, (uint32_t*)idx.p, (unsigned long long*)counter.p, (long long)G, NonEmptyGroup{d.count}, st));
+    PB200_CUDA(cub::DeviceSelect::If(tmp.p, tmp_bytes, first, (uint32_t*)idx.p, (unsigned long long*)counter.p, (long long)G, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min}, st));
     PB200_CUDA(cudaStreamSynchronize(st));  // tmp is released at scope exit
   }
   unsigned long long n = 0;
@@ -1065,8 +1081,8 @@ extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
   if ((rc = g64.alloc(ctx, std::max<size_t>(n, 1) * 8))) return rc;
   if ((rc = g32.alloc(ctx, std::max<size_t>(n, 1) * 4))) return rc;
   const int gb = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n + 255) / 256, 148 * 8));
-  std::vector<unsigned long long> counts(n);
-  if (n) {
+  std::vector<unsigned long long> counts(n, 0ull);
+  if (n && d.count) {
     gather_kernel<unsigned long long><<<gb, 256, 0, st>>>(d.count, (const uint32_t*)idx.p, (long long)n, (unsigned long long*)g64.p);
     PB200_CUDA(cudaMemcpyAsync(counts.data(), g64.p, n * 8, cudaMemcpyDeviceToHost, st));
     PB200_CUDA(cudaStreamSynchronize(st));

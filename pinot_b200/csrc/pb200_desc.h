@@ -69,7 +69,8 @@ struct SegDesc {
   uint32_t* distinct_bits[kMaxAggs];   // DISTINCTCOUNT (aggregation only): bitset over dictIds
   AggAccum* accum;                     // aggregation-only output
   // dense group table (group-by): indexed by raw key = sum_j dictId_j * mult_j
-  unsigned long long* g_count;
+  unsigned long long* g_count;   // per-group row count; NULL when no COUNT / AVG needs it
+  uint32_t* g_seen;              // then: group-exists flags (NULL if a MIN/MAX table already tells)
   long long* g_isum[kMaxAggs];
   double* g_dsum[kMaxAggs];
   uint32_t* g_min[kMaxAggs];

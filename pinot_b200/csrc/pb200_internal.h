@@ -75,7 +75,10 @@ struct pb200_result {
   struct Dense {
     pb200_ctx* ctx = nullptr;
     long long groups = 0;                        // size of the dense key space
-    unsigned long long* count = nullptr;
+    unsigned long long* count = nullptr;         // NULL when no COUNT / AVG
+    uint32_t* seen = nullptr;                    // group-exists flags (inside the u32max block) or NULL
+    uint32_t* exists_max = nullptr;              // a MAX table doubling as the group-exists marker, or NULL
+    uint32_t* exists_min = nullptr;              // a MIN table doubling as the group-exists marker, or NULL
     long long* isum[pb200::kMaxAggs] = {};
     double* dsum[pb200::kMaxAggs] = {};
     uint32_t* gmin[pb200::kMaxAggs] = {};

@@ -150,6 +150,18 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t x) {
 }
 
 
+
+// Group bookkeeping of one surviving row: the exact count when some function needs it (COUNT / AVG), otherwise a
+// test-then-set "seen" flag (benign race: every writer stores 1), or nothing when a MIN/MAX table already marks groups.
+__device__ __forceinline__ void touch_group(const SegDesc& sd, uint32_t g) {
+  if (sd.g_count) atomicAdd(sd.g_count + g, 1ull);
+  else if (sd.g_seen) { if (__ldcg(sd.g_seen + g) == 0u) sd.g_seen[g] = 1u; }
+}
+// MIN / MAX tables only change for O(log n) of a group's rows: read the current value (L2) and skip the atomic when it
+// cannot win.  A stale read only costs a redundant atomic, never a wrong result.
+__device__ __forceinline__ void group_min(uint32_t* p, uint32_t x) { if (x < __ldcg(p)) atomicMin(p, x); }
+__device__ __forceinline__ void group_max(uint32_t* p, uint32_t x1) { if (x1 > __ldcg(p)) atomicMax(p, x1); }
+
 // ------------------------------------------------------------------------------------------------------------------
 // streaming functors for dispatch_left_aligned(): consume one left-aligned value at a time (pb200_unpack.cuh)
 // ------------------------------------------------------------------------------------------------------------------
@@ -524,7 +536,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
               g += read_one_group(st + sl.stage_words + group_in_stage * sl.bits, j, sl.bits) * sd.group_mult[gi];
             }
           }
-          atomicAdd(sd.g_count + g, 1ull);
+          touch_group(sd, g);
         }
 #pragma unroll 1
         for (int a = 0; a < q.num_aggs; ++a) {
@@ -547,7 +559,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
             }
           } else if (fn == 2 || fn == 3) {
             const uint32_t x = id ^ (vk == VAL_RAW_I32 ? 0x80000000u : 0u);
-            if (GROUPBY) { if (fn == 2) atomicMin(sd.g_min[a] + g, x); else atomicMax(sd.g_max[a] + g, x + 1u); }
+            if (GROUPBY) { if (fn == 2) group_min(sd.g_min[a] + g, x); else group_max(sd.g_max[a] + g, x + 1u); }
             else { uint2 mmx = accmm[a * kConsumers + group]; mmx.x = min(mmx.x, x); mmx.y = max(mmx.y, x + 1u); accmm[a * kConsumers + group] = mmx; }
           } else if (fn == 5 && !GROUPBY) {
             atomicOr(sd.distinct_bits[a] + (id >> 5), 1u << (id & 31));
@@ -648,7 +660,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if ((m >> j) & 1u) atomicAdd(sd.g_count + gid[j], 1ull);
+          if ((m >> j) & 1u) touch_group(sd, gid[j]);
 #pragma unroll 1
         for (int a = 0; a < q.num_aggs; ++a) {
           if (q.aggs[a].slot < 0) continue;
@@ -702,8 +714,8 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
             for (int j = 0; j < 32; ++j) {
               if ((m >> j) & 1u) {
                 const uint32_t x = v[j] ^ bias;
-                if (fn == 2) atomicMin(sd.g_min[a] + gid[j], x);
-                else atomicMax(sd.g_max[a] + gid[j], x + 1u);
+                if (fn == 2) group_min(sd.g_min[a] + gid[j], x);
+                else group_max(sd.g_max[a] + gid[j], x + 1u);
               }
             }
           }
