@@ -847,6 +847,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       }
       if (groups > (1ll << 27)) { set_error("group key space of %lld exceeds the dense device table limit", groups); return PB200_E_UNSUPPORTED; }
       d.groups = groups;
+      d.live = true;
       d.num_groups_limit = query->num_groups_limit;
       for (int a = 0; a < nagg; a++) { d.aggs.push_back(query->aggs[a]); d.val_kind.push_back(q.aggs[a].val_kind); d.agg_cols.push_back(q.aggs[a].slot < 0 ? nullptr : &seg->cols[query->aggs[a].column]); }
       // one block per element kind
@@ -1024,6 +1025,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         pb200_result::Dense& d = R.dense;
         dev_free(ctx, d.i64_block); dev_free(ctx, d.f64_block); dev_free(ctx, d.u32max_block); dev_free(ctx, d.u32min_block);
         d.i64_block = d.f64_block = d.u32max_block = d.u32min_block = nullptr;
+        d.live = false;
       }
     }
   }
@@ -1036,7 +1038,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
 extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
   if (!ctx || !R) { set_error("null argument"); return PB200_E_INVALID; }
   pb200_result::Dense& d = R->dense;
-  if (!d.i64_block) { set_error("result has no dense device state"); return PB200_E_INVALID; }
+  if (!d.ctx || d.groups <= 0 || !d.live) { set_error("result has no dense device state"); return PB200_E_INVALID; }
   PB200_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = take_stream(ctx);
   struct StreamReturn { pb200_ctx* c; cudaStream_t s; ~StreamReturn() { give_stream(c, s); } } stream_return{ctx, st};

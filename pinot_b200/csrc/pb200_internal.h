@@ -75,6 +75,7 @@ struct pb200_result {
   struct Dense {
     pb200_ctx* ctx = nullptr;
     long long groups = 0;                        // size of the dense key space
+    bool live = false;                           // device tables still allocated
     unsigned long long* count = nullptr;         // NULL when no COUNT / AVG
     uint32_t* seen = nullptr;                    // group-exists flags (inside the u32max block) or NULL
     uint32_t* exists_max = nullptr;              // a MAX table doubling as the group-exists marker, or NULL

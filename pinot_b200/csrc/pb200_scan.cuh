@@ -151,6 +151,13 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t x) {
 
 
 
+// L2-coherent (.cg) predicated load; masked rows get `otherwise`, chosen so that they never trigger an update
+__device__ __forceinline__ uint32_t ldcg_bit_u32(const uint32_t* p, uint32_t mask, uint32_t bit, uint32_t otherwise) {
+  uint32_t x;
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\tmov.b32 %0, %4;\n\t"
+               "@p ld.global.cg.b32 %0, [%1];\n\t}" : "=r"(x) : "l"(p), "r"(mask), "r"(bit), "r"(otherwise) : "memory");
+  return x;
+}
 // Group bookkeeping of one surviving row: the exact count when some function needs it (COUNT / AVG), otherwise a
 // test-then-set "seen" flag (benign race: every writer stores 1), or nothing when a MIN/MAX table already marks groups.
 __device__ __forceinline__ void touch_group(const SegDesc& sd, uint32_t g) {
@@ -658,9 +665,18 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
             }
           }
         }
+        if (sd.g_count) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if ((m >> j) & 1u) touch_group(sd, gid[j]);
+          for (int j = 0; j < 32; ++j)
+            if ((m >> j) & 1u) atomicAdd(sd.g_count + gid[j], 1ull);
+        } else if (sd.g_seen) {  // test-then-set flags: all tests first (one L2 latency), then the few stores
+          uint32_t cur[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cur[j] = ldcg_bit_u32(sd.g_seen + gid[j], m, 1u << j, 1u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cur[j] == 0u) sd.g_seen[gid[j]] = 1u;
+        }
 #pragma unroll 1
         for (int a = 0; a < q.num_aggs; ++a) {
           if (q.aggs[a].slot < 0) continue;
@@ -709,14 +725,18 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
                 if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], xv[j]);
             }
           } else if (fn == 2 || fn == 3) {
+            // MIN / MAX tables change for only O(log n) of a group's rows: read the current entries of the whole tile
+            // first (straight-line predicated loads, one L2 latency), then issue an atomic only where the row can win
             const uint32_t bias = vk == VAL_RAW_I32 ? 0x80000000u : 0u;
+            uint32_t* tab = fn == 2 ? sd.g_min[a] : sd.g_max[a];
+            uint32_t cur[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cur[j] = ldcg_bit_u32(tab + gid[j], m, 1u << j, fn == 2 ? 0u : 0xFFFFFFFFu);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if ((m >> j) & 1u) {
-                const uint32_t x = v[j] ^ bias;
-                if (fn == 2) group_min(sd.g_min[a] + gid[j], x);
-                else group_max(sd.g_max[a] + gid[j], x + 1u);
-              }
+              const uint32_t x = v[j] ^ bias;
+              if (fn == 2) { if (x < cur[j]) atomicMin(tab + gid[j], x); }
+              else { if (x + 1u > cur[j]) atomicMax(tab + gid[j], x + 1u); }
             }
           }
         }
