@@ -777,7 +777,9 @@ struct NotIterator : DocIdIterator {
 // A "DocIdSet" here is a factory producing the iterator (BlockDocIdSet.iterator()) exactly once.
 // ------------------------------------------------------------------------------------------------------------------
 struct FilterOp {
-  enum Kind { EMPTY, MATCH_ALL, SCAN, BITMAP, SORTED, AND, OR, NOT } kind = EMPTY;
+  enum Kind { EMPTY, MATCH_ALL, SCAN, BITMAP, SORTED, AND, OR, NOT, DOCIDS } kind = EMPTY;
+  const int32_t* doc_ids = nullptr;  // DOCIDS: BitmapBasedFilterOperator over an explicit doc-id list
+  int64_t num_doc_ids = 0;
   const Column* col = nullptr;
   Predicate pred;
   std::vector<std::unique_ptr<FilterOp>> children;
@@ -786,7 +788,7 @@ struct FilterOp {
   int priority() const {  // FilterOperatorUtils.java:205-251 (PrioritizedFilterOperator constants)
     switch (kind) {
       case SORTED: return 0;      // HIGH_PRIORITY
-      case BITMAP: return 100;    // MEDIUM_PRIORITY
+      case BITMAP: case DOCIDS: return 100;    // MEDIUM_PRIORITY
       case AND: return 300;       // AND_PRIORITY
       case OR: return 400;        // OR_PRIORITY
       case NOT: return children[0]->priority();
@@ -834,6 +836,12 @@ OpPtr build_filter(const Segment& seg, const po_query_t& q) {
   std::vector<OpPtr> stack;
   for (int i = 0; i < q.num_filter_nodes; i++) {
     const po_filter_node_t& n = q.filter[i];
+    if (n.type == PO_DOCIDS) {
+      auto o = std::make_unique<FilterOp>();
+      o->kind = FilterOp::DOCIDS; o->num_docs = nd; o->doc_ids = q.doc_ids; o->num_doc_ids = q.num_doc_ids;
+      stack.push_back(std::move(o));
+      continue;
+    }
     if (n.type >= PO_EQ) { stack.push_back(leaf_operator(seg, n, q.literals)); continue; }
     if (n.type == PO_NOT) {
       OpPtr c = std::move(stack.back()); stack.pop_back();
@@ -1001,6 +1009,11 @@ ItPtr make_iterator(const FilterOp& op, ExecCtx& ctx) {
       return it;
     }
     case FilterOp::BITMAP: return std::make_unique<BitmapIterator>(bitmap_from_inverted(op));
+    case FilterOp::DOCIDS: {
+      auto bm = std::make_shared<DenseBitmap>(op.num_docs);
+      for (int64_t i = 0; i < op.num_doc_ids; i++) bm->set((uint32_t)op.doc_ids[i]);
+      return std::make_unique<BitmapIterator>(bm);
+    }
     case FilterOp::SORTED: return std::make_unique<SortedIterator>(sorted_ranges(op));
     case FilterOp::AND: return and_iterator(op, ctx);
     case FilterOp::OR: return or_iterator(op, ctx);
@@ -1403,3 +1416,144 @@ int64_t po_result_distinct(const po_result_t* r, int32_t a, int32_t g, int32_t* 
 void po_result_free(po_result_t* r) { delete r; }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Star-tree: OffHeapStarTree (seglocal/startree/OffHeapStarTree.java:39-82: LITTLE-endian buffer; magic
+// 0xBADDA55B00DAD00D, version 1, header size, dimensions, numNodes; then 7 x int32 per node,
+// seglocal/startree/OffHeapStarTreeNode.java:30-47) and the BFS of
+// core/startree/operator/StarTreeFilterOperator.java:217-370 (traverseStarTree).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kStarAll = -1;  // StarTreeNode.ALL
+struct StarTree {
+  int num_dims = 0, num_nodes = 0;
+  std::vector<std::string> dims;
+  const uint8_t* nodes = nullptr;
+  int field(int node, int f) const { return (int)le32(nodes + 28ll * node + 4 * f); }
+  int dim_id(int n) const { return field(n, 0); }
+  int dim_value(int n) const { return field(n, 1); }
+  int start(int n) const { return field(n, 2); }
+  int end(int n) const { return field(n, 3); }
+  int agg_doc(int n) const { return field(n, 4); }
+  int first_child(int n) const { return field(n, 5); }
+  int last_child(int n) const { return field(n, 6); }
+  bool is_leaf(int n) const { return first_child(n) == -1; }
+  int num_children(int n) const { return is_leaf(n) ? 0 : last_child(n) - first_child(n) + 1; }
+  // getChildForDimensionValue: children are sorted by dimension value (star = -1 first) -> binary search
+  int child_for_value(int n, int value) const {
+    if (is_leaf(n)) return -1;
+    int lo = first_child(n), hi = last_child(n);
+    while (lo <= hi) {
+      int mid = (lo + hi) >> 1, v = dim_value(mid);
+      if (v == value) return mid;
+      if (v < value) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+  }
+};
+bool parse_star_tree(const uint8_t* b, int64_t len, StarTree& t) {
+  if (len < 24 || le64(b) != 0xBADDA55B00DAD00Dull || le32(b + 8) != 1) return false;
+  int64_t root_off = le32(b + 12);
+  t.num_dims = (int)le32(b + 16);
+  int64_t off = 20;
+  t.dims.assign(t.num_dims, "");
+  for (int i = 0; i < t.num_dims; i++) {
+    if (off + 8 > len) return false;
+    int id = (int)le32(b + off), n = (int)le32(b + off + 4);
+    off += 8;
+    if (id < 0 || id >= t.num_dims || off + n > len) return false;
+    t.dims[id] = std::string((const char*)b + off, n);
+    off += n;
+  }
+  t.num_nodes = (int)le32(b + off);
+  off += 4;
+  if (off != root_off || off + 28ll * t.num_nodes != len) return false;
+  t.nodes = b + off;
+  return true;
+}
+}  // namespace
+
+extern "C" int32_t po_startree_info(const uint8_t* tree, int64_t len, int32_t out[2], char* names, int32_t cap) {
+  StarTree t;
+  if (!parse_star_tree(tree, len, t)) return -1;
+  out[0] = t.num_dims; out[1] = t.num_nodes;
+  int pos = 0;
+  for (auto& d : t.dims) for (size_t i = 0; i <= d.size() && pos < cap; i++) names[pos++] = i < d.size() ? d[i] : '\0';
+  return 0;
+}
+
+extern "C" int64_t po_startree_traverse(const uint8_t* tree, int64_t len, int32_t num_predicates,
+                                        const po_star_predicate_t* predicates, int32_t num_group_by,
+                                        const int32_t* group_by_dims, int32_t* out_docs, int64_t cap,
+                                        uint32_t* remaining_predicate_mask) {
+  StarTree t;
+  if (!parse_star_tree(tree, len, t)) return -2;
+  std::vector<const po_star_predicate_t*> pred_of(t.num_dims, nullptr);
+  uint32_t remaining_pred = 0, remaining_gb = 0;
+  for (int i = 0; i < num_predicates; i++) { pred_of[predicates[i].dimension] = &predicates[i]; remaining_pred |= 1u << predicates[i].dimension; }
+  for (int i = 0; i < num_group_by; i++) remaining_gb |= 1u << group_by_dims[i];
+  std::vector<int> docs;
+  auto add_range = [&](long long s, long long e) { for (long long d = s; d < e; d++) docs.push_back((int)d); };
+  bool found_leaf = t.is_leaf(0);
+  bool have_global = false;
+  uint32_t global_remaining = 0;
+  if (found_leaf) { global_remaining = remaining_pred; have_global = true; }
+  std::vector<int> queue{0};
+  size_t head = 0;
+  int current_dim = -1;
+  const po_star_predicate_t* matching = nullptr;
+  while (head < queue.size()) {
+    int node = queue[head++];
+    int dim = t.dim_id(node);
+    if (dim > current_dim) {  // previous level finished
+      remaining_pred &= ~(1u << dim);
+      remaining_gb &= ~(1u << dim);
+      if (found_leaf && !have_global) { global_remaining = remaining_pred; have_global = true; }
+      matching = nullptr;
+      current_dim = dim;
+    }
+    if (remaining_pred == 0 && remaining_gb == 0) { docs.push_back(t.agg_doc(node)); continue; }
+    if (t.is_leaf(node)) { add_range(t.start(node), t.end(node)); continue; }
+    const int child_dim = dim + 1;
+    int star_node = -1;
+    if ((!have_global || !(global_remaining >> child_dim & 1)) && !(remaining_gb >> child_dim & 1))
+      star_node = t.child_for_value(node, kStarAll);
+    const int first = t.first_child(node), nchild = t.num_children(node);
+    if (remaining_pred >> child_dim & 1) {
+      if (!matching) {
+        matching = pred_of[child_dim];
+        if (matching->num_ids == 0) return -1;
+      }
+      auto contains = [&](int v) { return std::binary_search(matching->ids, matching->ids + matching->num_ids, v); };
+      if ((long long)matching->num_ids * 10 > nchild) {  // USE_SCAN_TO_TRAVERSE_NODES_THRESHOLD
+        if (star_node >= 0 && matching->num_ids >= nchild - 1) {
+          std::vector<int> match_children;
+          bool leaf_child = false;
+          for (int c = first; c < first + nchild; c++)
+            if (contains(t.dim_value(c))) { match_children.push_back(c); leaf_child |= t.is_leaf(c); }
+          if ((int)match_children.size() == nchild - 1) { queue.push_back(star_node); found_leaf |= t.is_leaf(star_node); }
+          else { for (int c : match_children) queue.push_back(c); found_leaf |= leaf_child; }
+        } else {
+          for (int c = first; c < first + nchild; c++)
+            if (contains(t.dim_value(c))) { queue.push_back(c); found_leaf |= t.is_leaf(c); }
+        }
+      } else {
+        for (int i = 0; i < matching->num_ids; i++) {
+          int c = t.child_for_value(node, matching->ids[i]);
+          if (c >= 0) { queue.push_back(c); found_leaf |= t.is_leaf(c); }
+        }
+      }
+    } else if (star_node >= 0) {
+      queue.push_back(star_node);
+      found_leaf |= t.is_leaf(star_node);
+    } else {
+      for (int c = first; c < first + nchild; c++)
+        if (t.dim_value(c) != kStarAll) { queue.push_back(c); found_leaf |= t.is_leaf(c); }
+    }
+  }
+  std::sort(docs.begin(), docs.end());
+  docs.erase(std::unique(docs.begin(), docs.end()), docs.end());
+  for (int64_t i = 0; i < (int64_t)docs.size() && i < cap; i++) out_docs[i] = docs[i];
+  if (remaining_predicate_mask) *remaining_predicate_mask = have_global ? global_remaining : 0u;
+  return (int64_t)docs.size();
+}

@@ -52,7 +52,8 @@ typedef struct {
 } po_segment_t;
 
 /* ---- query (value space, like QueryContext) ---- */
-enum { PO_AND = 0, PO_OR = 1, PO_NOT = 2, PO_EQ = 3, PO_NEQ = 4, PO_IN = 5, PO_NOT_IN = 6, PO_RANGE = 7 };
+enum { PO_AND = 0, PO_OR = 1, PO_NOT = 2, PO_EQ = 3, PO_NEQ = 4, PO_IN = 5, PO_NOT_IN = 6, PO_RANGE = 7,
+       PO_DOCIDS = 8 /* BitmapBasedFilterOperator over po_query_t.doc_ids (star-tree traversal result) */ };
 
 typedef struct {
   int64_t i;      /* INT / LONG literal */
@@ -88,6 +89,8 @@ typedef struct {
   int32_t num_groups_limit;                   /* InstancePlanMakerImplV2 default 100000 */
   int32_t max_initial_result_holder_capacity; /* default 10000 (= array based threshold) */
   int32_t and_scan_reordering;                /* query option AndScanReordering, default 0 */
+  int64_t num_doc_ids;                        /* PO_DOCIDS leaf: sorted doc ids */
+  const int32_t* doc_ids;
 } po_query_t;
 
 enum { PO_REGIME_NONE = 0, PO_REGIME_ARRAY = 1, PO_REGIME_INT_MAP = 2, PO_REGIME_LONG_MAP = 3, PO_REGIME_ARRAY_MAP = 4 };
@@ -129,6 +132,21 @@ void po_result_agg_long(const po_result_t* r, int32_t agg, int64_t* out);
 /* DISTINCTCOUNT: sorted dictIds of one group (group = 0 for aggregation only); returns count */
 int64_t po_result_distinct(const po_result_t* r, int32_t agg, int32_t group, int32_t* out, int64_t cap);
 void po_result_free(po_result_t* r);
+
+/* ---- star-tree (OffHeapStarTree / StarTreeFilterOperator.traverseStarTree) ---- */
+typedef struct {
+  int32_t dimension;     /* index into the tree's dimension split order */
+  int32_t num_ids;
+  const int32_t* ids;    /* matching dictIds of the (AND-ed) predicates on that dimension, sorted */
+} po_star_predicate_t;
+/* Header facts: out = {numDimensions, numNodes}; dimension names are copied NUL separated into names (cap bytes). */
+int32_t po_startree_info(const uint8_t* tree, int64_t len, int32_t out[2], char* names, int32_t cap);
+/* BFS traversal exactly as StarTreeFilterOperator: returns the number of matched star-tree docs (sorted ascending in
+ * out_docs, up to cap), -1 when some predicate has no matching dictId (empty result), -2 on a malformed tree.
+ * remaining_predicate_mask: bit d set = predicates on dimension d still have to be applied to the matched docs. */
+int64_t po_startree_traverse(const uint8_t* tree, int64_t len, int32_t num_predicates,
+                             const po_star_predicate_t* predicates, int32_t num_group_by, const int32_t* group_by_dims,
+                             int32_t* out_docs, int64_t cap, uint32_t* remaining_predicate_mask);
 
 /* Matching doc ids of the filter alone (tests). Returns count; writes up to cap. */
 int64_t po_filter_doc_ids(const po_segment_t* segment, const po_query_t* query, int32_t* out, int64_t cap,

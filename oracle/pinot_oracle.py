@@ -53,7 +53,12 @@ class _Query(C.Structure):
     _fields_ = [("num_filter_nodes", C.c_int32), ("filter", C.POINTER(_FilterNode)), ("literals", C.POINTER(_Literal)),
                 ("num_group_by", C.c_int32), ("group_by_columns", C.POINTER(C.c_int32)), ("num_aggs", C.c_int32),
                 ("aggs", C.POINTER(_Agg)), ("num_groups_limit", C.c_int32),
-                ("max_initial_result_holder_capacity", C.c_int32), ("and_scan_reordering", C.c_int32)]
+                ("max_initial_result_holder_capacity", C.c_int32), ("and_scan_reordering", C.c_int32),
+                ("num_doc_ids", C.c_int64), ("doc_ids", C.c_void_p)]
+
+
+class _StarPredicate(C.Structure):
+    _fields_ = [("dimension", C.c_int32), ("num_ids", C.c_int32), ("ids", C.c_void_p)]
 
 
 def build(force: bool = False) -> str:
@@ -117,6 +122,11 @@ class Oracle:
         L.po_roaring_deserialize.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
         L.po_inverted_index_build.restype = C.c_int64
         L.po_inverted_index_build.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+        L.po_startree_info.restype = C.c_int32
+        L.po_startree_info.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_char_p, C.c_int32]
+        L.po_startree_traverse.restype = C.c_int64
+        L.po_startree_traverse.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(_StarPredicate), C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_uint32)]
 
     # ---------------------------------------------------------------- formats
     def bitset_write(self, values: np.ndarray, bits: int) -> np.ndarray:
@@ -178,9 +188,40 @@ class Oracle:
                               0 if c.dict is None else len(c.dict), _ptr(c.inv), 0 if c.inv is None else len(c.inv))
         return _Segment(seg.num_docs, len(seg.columns), cols), cols
 
+    # ---------------------------------------------------------------- star-tree
+    def startree_info(self, tree: np.ndarray):
+        out = (C.c_int32 * 2)()
+        names = C.create_string_buffer(4096)
+        if self.lib.po_startree_info(_ptr(tree), len(tree), out, names, 4096) != 0:
+            raise ValueError("malformed star-tree")
+        dims = names.raw.split(b"\0")[: out[0]]
+        return [d.decode() for d in dims], int(out[1])
+
+    def startree_traverse(self, tree: np.ndarray, predicates: Dict[int, np.ndarray], group_by_dims, max_docs: int):
+        """StarTreeFilterOperator.traverseStarTree: returns (sorted matched star-tree doc ids or None when empty,
+        list of dimensions whose predicates remain to be applied)."""
+        preds = (_StarPredicate * max(1, len(predicates)))()
+        keep = []
+        for i, (dim, ids) in enumerate(sorted(predicates.items())):
+            arr = np.ascontiguousarray(np.sort(np.asarray(ids, dtype=np.int32)))
+            keep.append(arr)
+            preds[i] = _StarPredicate(int(dim), len(arr), _ptr(arr) if len(arr) else None)
+        gb = np.ascontiguousarray(np.asarray(list(group_by_dims), dtype=np.int32))
+        out = np.zeros(max_docs, dtype=np.int32)
+        remaining = C.c_uint32(0)
+        n = self.lib.po_startree_traverse(_ptr(tree), len(tree), len(predicates), preds, len(gb),
+                                          _ptr(gb) if len(gb) else None, _ptr(out), max_docs, C.byref(remaining))
+        if n == -2:
+            raise ValueError("malformed star-tree")
+        if n == -1:
+            return None, []
+        return out[:n].copy(), [d for d in range(32) if remaining.value >> d & 1]
+
     @staticmethod
-    def _c_query(seg: sb.SegmentData, q: QueryContext):
-        nodes = postfix(q.filter)
+    def _c_query(seg: sb.SegmentData, q: QueryContext, doc_ids: Optional[np.ndarray] = None):
+        nodes = list(postfix(q.filter))
+        if doc_ids is not None:  # AND(BitmapBasedFilterOperator(doc_ids), original filter)
+            nodes = ["DOCIDS"] + nodes + ([Filter("AND", [None, None])] if nodes else [])
         lits: List[_Literal] = []
         keep = []  # keep byte strings alive
 
@@ -196,6 +237,9 @@ class Oracle:
 
         c_nodes = (_FilterNode * max(1, len(nodes)))()
         for i, n in enumerate(nodes):
+            if isinstance(n, str):
+                c_nodes[i] = _FilterNode(8, -1, 0, 0, 0, 0, 0, 0, 0)  # PO_DOCIDS
+                continue
             if isinstance(n, Filter):
                 c_nodes[i] = _FilterNode(_TYPE_CODES[n.type], -1, len(n.children), 0, 0, 0, 0, 0, 0)
                 continue
@@ -216,14 +260,17 @@ class Oracle:
         aggs = (_Agg * max(1, len(q.aggregations)))()
         for i, a in enumerate(q.aggregations):
             aggs[i] = _Agg(_FN_CODES[a.function], -1 if a.column is None else seg.column_index(a.column))
+        ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.int32)
         cq = _Query(len(nodes), c_nodes, c_lits, len(q.group_by), gb, len(q.aggregations), aggs, q.num_groups_limit,
-                    q.max_initial_result_holder_capacity, int(q.and_scan_reordering))
-        return cq, (c_nodes, c_lits, gb, aggs, keep)
+                    q.max_initial_result_holder_capacity, int(q.and_scan_reordering),
+                    0 if ids is None else len(ids), _ptr(ids) if ids is not None and len(ids) else None)
+        return cq, (c_nodes, c_lits, gb, aggs, keep, ids)
 
-    def execute(self, seg: sb.SegmentData, q: QueryContext) -> OracleResult:
-        """== getOperator(query).nextBlock() on one segment (BaseQueriesTest.java:97-102)."""
+    def execute(self, seg: sb.SegmentData, q: QueryContext, doc_ids: Optional[np.ndarray] = None) -> OracleResult:
+        """== getOperator(query).nextBlock() on one segment (BaseQueriesTest.java:97-102).  `doc_ids` (star-tree
+        traversal result) is AND-ed to the filter as a BitmapBasedFilterOperator."""
         cseg, _k1 = self._c_segment(seg)
-        cq, _k2 = self._c_query(seg, q)
+        cq, _k2 = self._c_query(seg, q, doc_ids)
         r = self.lib.po_execute(C.byref(cseg), C.byref(cq))
         try:
             err = self.lib.po_result_error(r)
