@@ -118,7 +118,10 @@ enum {
                               :60-96); column must have been registered with an inverted index */
   PB200_F_INV_NOT_IN = 9,  /* ... flipped over [0, numDocs) */
   PB200_F_DOC_RANGES = 10, /* SortedIndexBasedFilterOperator: ids[] holds num_ids/2 inclusive (start,end) docId pairs */
-  PB200_F_RAW_RANGE = 11   /* scan of a raw INT/LONG/FLOAT/DOUBLE column: raw_lo <= v <= raw_hi with the flags below */
+  PB200_F_RAW_RANGE = 11,  /* scan of a raw INT/LONG/FLOAT/DOUBLE column: raw_lo <= v <= raw_hi with the flags below */
+  PB200_F_DOC_MASK = 12    /* BitmapBasedFilterOperator over a caller-computed doc-id set (e.g. the star-tree traversal
+                              result, core/startree/operator/StarTreeFilterOperator.java:168-171): ids points to
+                              num_ids 32-bit words, bit j of word w = doc 32*w + j */
 };
 
 typedef struct {

@@ -65,6 +65,25 @@ int32_t pb200h_segment_column_info(const pb200h_segment* segment, int32_t column
 int32_t pb200h_dictionary_get(const pb200h_segment* segment, int32_t column, int32_t dict_id, double* num, int64_t* lng,
                               char* str, int32_t str_capacity);
 
+/* ---- star-tree (StarTreeV2: seglocal/startree/v2/store/StarTreeLoaderUtils.java:54-88) -------------------------- */
+typedef struct {
+  int32_t function;     /* PB200_AGG_COUNT / SUM / MIN / MAX: the function of the function-column pair */
+  int32_t reserved;
+  const char* column;   /* NULL for count__* */
+  const void* fwd;      /* raw fixed-byte forward index of the pre-aggregated values (PASS_THROUGH chunks; COUNT -> LONG,
+                           others -> DOUBLE: ValueAggregatorFactory.getAggregatedValueType) */
+  uint64_t fwd_bytes;
+} pb200h_star_metric;
+
+/* Attaches one star-tree to a loaded segment: `tree` = the OffHeapStarTree buffer (star_tree_index, LITTLE-endian
+ * nodes), per dimension (split order) the fixed-bit forward index of the star-tree docs, per function-column pair the
+ * raw forward index.  The star-tree docs are uploaded to HBM as a segment of their own; dimensions share the base
+ * columns' dictionaries.  Queries that fit (StarTreeUtils rules) are then answered from it by pb200h_execute. */
+int32_t pb200h_startree_attach(pb200_ctx* ctx, pb200h_segment* segment, const void* tree, uint64_t tree_bytes,
+                               int32_t num_star_docs, int32_t num_dimensions, const char* const* dimension_names,
+                               const void* const* dimension_fwd, const uint64_t* dimension_fwd_bytes,
+                               int32_t num_metrics, const pb200h_star_metric* metrics);
+
 /* ---- QueryContext ---------------------------------------------------------------------------------------------- */
 enum { PB200H_AND = 0, PB200H_OR = 1, PB200H_NOT = 2, PB200H_EQ = 3, PB200H_NEQ = 4, PB200H_IN = 5, PB200H_NOT_IN = 6,
        PB200H_RANGE = 7 };
@@ -100,6 +119,7 @@ typedef struct {
   int32_t num_groups_limit;
   int32_t max_initial_result_holder_capacity;
   int32_t merge_segments; /* device-side combine (requires identical dictionaries across the segments) */
+  int32_t skip_star_tree; /* query option useStarTree=false */
 } pb200h_query;
 
 /* Which operator the plan maker chose per segment (AggregationPlanNode / GroupByPlanNode decisions). */
@@ -107,7 +127,8 @@ enum {
   PB200H_OP_AGGREGATION = 0,          /* AggregationOperator on the device */
   PB200H_OP_GROUP_BY = 1,             /* GroupByOperator on the device */
   PB200H_OP_NON_SCAN_AGGREGATION = 2, /* NonScanBasedAggregationOperator: dictionary / metadata only (host) */
-  PB200H_OP_EMPTY = 3                 /* filter is EmptyFilterOperator: empty results block without any scan */
+  PB200H_OP_EMPTY = 3,                /* filter is EmptyFilterOperator: empty results block without any scan */
+  PB200H_OP_STAR_TREE = 4             /* StarTreeFilterOperator + aggregation over the pre-aggregated star-tree docs */
 };
 
 /* makeSegmentPlanNode(...).run().nextBlock() for every segment; results[] receives num_segments handles (one when

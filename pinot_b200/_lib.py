@@ -19,7 +19,7 @@ FWD_DICT_FIXEDBIT, FWD_DICT_SORTED, FWD_RAW_FIXEDBYTE = 0, 1, 2
 AGG_CODES = {"COUNT": 0, "SUM": 1, "MIN": 2, "MAX": 3, "AVG": 4, "DISTINCTCOUNT": 5}
 FILTER_CODES = {"AND": 0, "OR": 1, "NOT": 2, "EQ": 3, "NEQ": 4, "IN": 5, "NOT_IN": 6, "RANGE": 7}
 REGIMES = {0: "NONE", 1: "ARRAY", 2: "INT_MAP", 3: "LONG_MAP", 4: "ARRAY_MAP"}
-OPERATOR_KINDS = {0: "AGGREGATION", 1: "GROUP_BY", 2: "NON_SCAN_AGGREGATION", 3: "EMPTY"}
+OPERATOR_KINDS = {0: "AGGREGATION", 1: "GROUP_BY", 2: "NON_SCAN_AGGREGATION", 3: "EMPTY", 4: "STAR_TREE"}
 
 
 class Pb200Error(RuntimeError):
@@ -94,7 +94,13 @@ class HQuery(C.Structure):
     _fields_ = [("num_filter_nodes", C.c_int32), ("filter", C.POINTER(HFilterNode)), ("literals", C.POINTER(HLiteral)),
                 ("num_group_by", C.c_int32), ("group_by", C.POINTER(C.c_char_p)), ("num_aggs", C.c_int32),
                 ("aggs", C.POINTER(HAgg)), ("num_groups_limit", C.c_int32),
-                ("max_initial_result_holder_capacity", C.c_int32), ("merge_segments", C.c_int32)]
+                ("max_initial_result_holder_capacity", C.c_int32), ("merge_segments", C.c_int32),
+                ("skip_star_tree", C.c_int32)]
+
+
+class HStarMetric(C.Structure):
+    _fields_ = [("function", C.c_int32), ("reserved", C.c_int32), ("column", C.c_char_p), ("fwd", C.c_void_p),
+                ("fwd_bytes", C.c_uint64)]
 
 
 # every symbol include/pinot_b200.h and include/pinot_b200_host.h declare (checked by tests/test_abi.py)
@@ -107,7 +113,7 @@ EXPORTED_SYMBOLS = [
     "pb200h_segment_create", "pb200h_segment_adopt", "pb200h_segment_load_dir", "pb200h_segment_destroy",
     "pb200h_segment_device", "pb200h_segment_num_docs", "pb200h_segment_num_columns", "pb200h_segment_column_index",
     "pb200h_segment_column_name", "pb200h_segment_column_info", "pb200h_dictionary_get", "pb200h_execute",
-    "pb200h_explain",
+    "pb200h_explain", "pb200h_startree_attach",
 ]
 
 _LIB = None
@@ -159,6 +165,8 @@ def load() -> C.CDLL:
     L.pb200h_dictionary_get.argtypes = [vp, i32, i32, C.POINTER(C.c_double), C.POINTER(i64), C.c_char_p, i32]
     L.pb200h_execute.argtypes = [vp, C.POINTER(HQuery), C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(i32)]
     L.pb200h_explain.argtypes = [vp, C.POINTER(HQuery), vp, C.c_char_p, i32]
+    L.pb200h_startree_attach.argtypes = [vp, vp, vp, C.c_uint64, i32, i32, C.POINTER(C.c_char_p), C.POINTER(vp),
+                                         C.POINTER(C.c_uint64), i32, C.POINTER(HStarMetric)]
     _LIB = L
     return L
 

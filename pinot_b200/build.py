@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libpinot_b200.so")
-SOURCES = ["pb200_api.cu", "pb200_roaring.cu", "pb200_synth.cu", "host/plan_maker.cpp"]
+SOURCES = ["pb200_api.cu", "pb200_roaring.cu", "pb200_synth.cu", "host/plan_maker.cpp", "host/star_tree.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -17,76 +17,14 @@
 #include <string>
 #include <vector>
 
-#include "../../../include/pinot_b200_host.h"
-#include "../pb200_internal.h"
+#include "host_internal.h"
 
 using pb200::set_error;
 
-namespace {
+static inline uint32_t be32(const unsigned char* p) { return pb200h::hbe32(p); }
+static inline uint64_t be64(const unsigned char* p) { return pb200h::hbe64(p); }
 
-inline uint32_t be32(const unsigned char* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
-inline uint64_t be64(const unsigned char* p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
-
-struct HostColumn {
-  std::string name;
-  int data_type = 0, has_dictionary = 0, bits = 0, cardinality = 0, is_sorted = 0, entry_bytes = 0;
-  bool has_inverted = false;
-  std::vector<unsigned char> dict;        // big-endian values or padded strings (host copy)
-  std::vector<unsigned char> sorted_idx;  // (start,end) BE pairs when is_sorted
-
-  int32_t get_int(int id) const { return (int32_t)be32(dict.data() + 4ull * id); }
-  int64_t get_long(int id) const { return (int64_t)be64(dict.data() + 8ull * id); }
-  float get_float(int id) const { uint32_t u = be32(dict.data() + 4ull * id); float f; memcpy(&f, &u, 4); return f; }
-  double get_double(int id) const { uint64_t u = be64(dict.data() + 8ull * id); double d; memcpy(&d, &u, 8); return d; }
-  std::string get_string(int id) const {
-    const char* p = (const char*)dict.data() + (size_t)entry_bytes * id;
-    size_t n = 0;
-    while (n < (size_t)entry_bytes && p[n]) n++;
-    return std::string(p, n);
-  }
-  double as_double(int id) const {
-    switch (data_type) {
-      case PB200_INT: return get_int(id);
-      case PB200_LONG: return (double)get_long(id);
-      case PB200_FLOAT: return get_float(id);
-      case PB200_DOUBLE: return get_double(id);
-      default: return NAN;
-    }
-  }
-  // Dictionary.insertionIndexOf (BaseImmutableDictionary.java:124-139): >= 0 found, else -(insertion point) - 1
-  int insertion_index_of(const pb200h_literal& l) const {
-    int lo = 0, hi = cardinality - 1;
-    while (lo <= hi) {
-      int mid = (lo + hi) >> 1, cmp;
-      switch (data_type) {
-        case PB200_INT: { int64_t v = get_int(mid); cmp = v < l.i ? -1 : v > l.i; break; }
-        case PB200_LONG: { int64_t v = get_long(mid); cmp = v < l.i ? -1 : v > l.i; break; }
-        case PB200_FLOAT: { float v = get_float(mid), t = (float)l.d; cmp = v < t ? -1 : v > t; break; }
-        case PB200_DOUBLE: { double v = get_double(mid); cmp = v < l.d ? -1 : v > l.d; break; }
-        default: { int r = get_string(mid).compare(l.s ? l.s : ""); cmp = r < 0 ? -1 : r > 0; }
-      }
-      if (cmp < 0) lo = mid + 1; else if (cmp > 0) hi = mid - 1; else return mid;
-    }
-    return -(lo + 1);
-  }
-  int sorted_start(int id) const { return (int)be32(sorted_idx.data() + 8ull * id); }
-  int sorted_end(int id) const { return (int)be32(sorted_idx.data() + 8ull * id + 4); }
-};
-
-}  // namespace
-
-struct pb200h_segment {
-  pb200_ctx* ctx = nullptr;
-  pb200_segment* dev = nullptr;
-  std::string name;
-  int num_docs = 0;
-  std::vector<HostColumn> cols;
-  int column_index(const char* n) const {
-    if (!n) return -1;
-    for (size_t i = 0; i < cols.size(); i++) if (cols[i].name == n) return (int)i;
-    return -1;
-  }
-};
+using namespace pb200h;
 
 namespace {
 
@@ -280,6 +218,44 @@ pb200_result* host_result(const pb200h_segment& seg, const pb200h_query& q, bool
 }
 
 }  // namespace
+
+namespace pb200h {
+
+std::vector<int32_t> matching_dict_ids(const HostColumn& c, const pb200h_filter_node& n, const pb200h_literal* lits) {
+  Evaluated e = evaluate(c, n, lits);
+  std::vector<int32_t> ids;
+  if (e.is_range) { for (int i = e.start; i < e.end; i++) ids.push_back(i); return ids; }
+  if (!e.exclusive) return e.ids;
+  size_t k = 0;
+  for (int i = 0; i < c.cardinality; i++) {
+    if (k < e.ids.size() && e.ids[k] == i) { k++; continue; }
+    ids.push_back(i);
+  }
+  return ids;
+}
+
+int leaf_to_device(const pb200h_segment& seg, int column, const pb200h_filter_node& n, const pb200h_literal* lits,
+                   SegmentFilterStore& store, pb200_filter_node& d) {
+  memset(&d, 0, sizeof d);
+  const HostColumn& c = seg.cols[column];
+  if (!c.has_dictionary) { set_error("predicate on raw column '%s' is not accelerated", c.name.c_str()); return PB200_E_UNSUPPORTED; }
+  Evaluated e = evaluate(c, n, lits);
+  d.column = column;
+  if (e.always_false) { d.op = PB200_F_EMPTY; return PB200_OK; }
+  if (e.always_true) { d.op = PB200_F_MATCH_ALL; return PB200_OK; }
+  auto keep = [&](std::vector<int32_t> v) {
+    store.ids.emplace_back(new std::vector<int32_t>(std::move(v)));
+    d.ids = store.ids.back()->data();
+    d.num_ids = (int)store.ids.back()->size();
+  };
+  if (c.is_sorted) { keep(sorted_doc_ranges(c, e, seg.num_docs)); d.op = PB200_F_DOC_RANGES; }
+  else if (n.type == PB200H_RANGE) { d.op = PB200_F_SCAN_RANGE; d.lo = e.start; d.hi = e.end; }
+  else if (c.has_inverted) { keep(e.ids); d.op = e.exclusive ? PB200_F_INV_NOT_IN : PB200_F_INV_IN; }
+  else { keep(e.ids); d.op = e.exclusive ? PB200_F_SCAN_NOT_IN : PB200_F_SCAN_IN; }
+  return PB200_OK;
+}
+
+}  // namespace pb200h
 
 // ------------------------------------------------------------------------------------------------------------------
 // segments
@@ -527,6 +503,18 @@ extern "C" int32_t pb200h_execute(pb200_ctx* ctx, const pb200h_query* q, pb200h_
       else if (filters[s].root_all && non_scan_answerable(*segs[s], *q)) kind[s] = PB200H_OP_NON_SCAN_AGGREGATION;
     }
   }
+  // star-tree substitution (AggregationFunctionUtils.buildAggregationInfo :285-310): first star-tree that fits wins
+  std::vector<pb200_result*> star_results(nseg, nullptr);
+  if (!merge && !q->skip_star_tree) {
+    for (int s = 0; s < nseg; s++) {
+      if (kind[s] != PB200H_OP_AGGREGATION && kind[s] != PB200H_OP_GROUP_BY) continue;
+      for (auto& st : segs[s]->star_trees) {
+        int rc = try_star_tree(ctx, *segs[s], *st, *q, &star_results[s]);
+        if (rc < 0) { for (auto r : star_results) if (r) pb200_result_free(r); return rc; }
+        if (rc == 1) { kind[s] = PB200H_OP_STAR_TREE; break; }
+      }
+    }
+  }
   if (kinds) for (int s = 0; s < nseg; s++) kinds[s] = kind[s];
   // device submission for the segments that need a scan
   std::vector<int> dev_idx;
@@ -548,12 +536,13 @@ extern "C" int32_t pb200h_execute(pb200_ctx* ctx, const pb200h_query* q, pb200h_
     dq.group_by_columns = gb.data();
     dq.aggs = aggs.data();
     int rc = pb200_execute(ctx, &dq, dsegs.data(), (int)dsegs.size(), dev_results.data());
-    if (rc) return rc;
+    if (rc) { for (auto r : star_results) if (r) pb200_result_free(r); return rc; }
   }
   if (merge) { results[0] = dev_results[0]; return PB200_OK; }
   size_t di = 0;
   for (int s = 0; s < nseg; s++) {
-    if (kind[s] == PB200H_OP_EMPTY) results[s] = host_result(*segs[s], *q, true);
+    if (kind[s] == PB200H_OP_STAR_TREE) results[s] = star_results[s];
+    else if (kind[s] == PB200H_OP_EMPTY) results[s] = host_result(*segs[s], *q, true);
     else if (kind[s] == PB200H_OP_NON_SCAN_AGGREGATION) results[s] = host_result(*segs[s], *q, false);
     else results[s] = dev_results[di++];
   }

@@ -739,6 +739,19 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         lf.kind = LEAF_DOCMASK;
         lf.bits = mask;
         lf.negate = n.op == PB200_F_INV_NOT_IN;
+      } else if (n.op == PB200_F_DOC_MASK) {
+        const size_t need = ((size_t)seg->num_docs + 31) / 32;
+        if ((size_t)n.num_ids < need || !n.ids) { set_error("DOC_MASK needs %zu words, got %d", need, n.num_ids); return PB200_E_INVALID; }
+        size_t words = (((size_t)seg->num_docs + kMaxTileRows - 1) / kMaxTileRows + 1) * (kMaxTileRows / 32) + 8;
+        plan.temps.emplace_back(new DevBuf());
+        int rc = plan.temps.back()->alloc(ctx, words * 4);
+        if (rc) return rc;
+        uint32_t* mask = (uint32_t*)plan.temps.back()->p;
+        PB200_CUDA(cudaMemsetAsync(mask + need, 0, (words - need) * 4, st));
+        PB200_CUDA(cudaMemcpyAsync(mask, n.ids, need * 4, cudaMemcpyHostToDevice, st));
+        PB200_CUDA(cudaStreamSynchronize(st));  // caller's buffer may be a temporary
+        lf.kind = LEAF_DOCMASK;
+        lf.bits = mask;
       } else if (n.op == PB200_F_DOC_RANGES) {
         if (n.num_ids % 2) { set_error("DOC_RANGES needs (start,end) pairs"); return PB200_E_INVALID; }
         if (n.num_ids == 0) { lf.kind = LEAF_NONE; continue; }

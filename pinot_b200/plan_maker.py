@@ -103,6 +103,23 @@ class IndexSegment:
         _lib.check(ctx.lib.pb200h_segment_load_dir(ctx.handle, index_dir.encode(), C.byref(h)))
         return cls(ctx, h, index_dir)
 
+    def attach_star_tree(self, tree: np.ndarray, num_star_docs: int, dimensions: Sequence[str],
+                         dimension_fwd: Sequence[np.ndarray], metrics: Sequence[tuple]) -> None:
+        """StarTreeLoaderUtils.loadStarTreeV2 for one tree: `tree` = OffHeapStarTree bytes, per dimension (split order)
+        the fixed-bit forward index of the star-tree docs, `metrics` = [(function, column or None, raw forward index
+        bytes)] for the function-column pairs."""
+        names = (C.c_char_p * len(dimensions))(*[d.encode() for d in dimensions])
+        fwd = (C.c_void_p * len(dimensions))(*[a.ctypes.data for a in dimension_fwd])
+        sizes = (C.c_uint64 * len(dimensions))(*[len(a) for a in dimension_fwd])
+        arr = (_lib.HStarMetric * len(metrics))()
+        keep = []
+        for i, (fn, col, buf) in enumerate(metrics):
+            nm = None if col is None else col.encode()
+            keep.append((nm, buf))
+            arr[i] = _lib.HStarMetric(_lib.AGG_CODES[fn], 0, nm, buf.ctypes.data, len(buf))
+        _lib.check(self.ctx.lib.pb200h_startree_attach(self.ctx.handle, self.handle, _ptr(tree), len(tree), num_star_docs,
+                                                       len(dimensions), names, fwd, sizes, len(metrics), arr))
+
     # ---- accessors ----------------------------------------------------------------------------------------------
     def column_index(self, name: str) -> int:
         return self.ctx.lib.pb200h_segment_column_index(self.handle, name.encode())
@@ -231,7 +248,7 @@ def _marshal_query(q: QueryContext, merge: bool):
         keep.append(nm)
         aggs[i] = _lib.HAgg(_lib.AGG_CODES[a.function], nm)
     hq = _lib.HQuery(len(nodes), c_nodes, c_lits, len(q.group_by), gb, len(q.aggregations), aggs, q.num_groups_limit,
-                     q.max_initial_result_holder_capacity, int(merge))
+                     q.max_initial_result_holder_capacity, int(merge), int(not getattr(q, "use_star_tree", True)))
     return hq, (c_nodes, c_lits, gb, gb_names, aggs, keep)
 
 

@@ -63,6 +63,7 @@ class QueryContext:
     num_groups_limit: int = DEFAULT_NUM_GROUPS_LIMIT
     max_initial_result_holder_capacity: int = DEFAULT_MAX_INITIAL_RESULT_HOLDER_CAPACITY
     and_scan_reordering: bool = False
+    use_star_tree: bool = True  # query option useStarTree
 
     @property
     def is_group_by(self) -> bool:

@@ -2,7 +2,7 @@
 """BASELINE.json configs[2] ("C3"): inverted-index bitmap filter (3 EQ predicates AND-ed) -> GROUP BY dim (card 10 000)
 SUM, 8 segments on 1 GPU.  Also C4-style group-by with a range filter (``--mode range``).
 
-    python tools/run_c3.py --segments 8 --rows 100000000 [--check-rows 2000000]
+    python tests/workloads/run_c3.py --segments 8 --rows 100000000 [--check-rows 2000000]
 
 Prints one JSON line: rows/s, device time of the scan kernel, algorithmic bytes (full-column figure of SURVEY section 8d:
 (bits(g) + bits(m))/8 + 1/8 per doc mask read) and the achieved fraction of the measured HBM peak.
@@ -15,7 +15,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 COLS = [("d1", 10, True), ("d2", 20, True), ("d3", 50, True), ("g", 10_000, False), ("m", 100_000, False),

@@ -3,7 +3,7 @@
 the per-GPU group tables.  Run under torchrun (one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tools/run_c4.py --segments-per-gpu 8 --rows 50000000
+        tests/workloads/run_c4.py --segments-per-gpu 8 --rows 50000000
 
 Every rank generates its own segments (shared dictionaries: same cardinalities / value maps, different seeds), scans
 them with the device-side combine, the dense tables are reduced to rank 0 over NCCL, rank 0 extracts the groups.  The
@@ -18,7 +18,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 COLS = [("f", 10_000), ("g1", 1_000), ("g2", 100), ("m1", 100_000), ("m2", 65_536)]
