@@ -78,7 +78,8 @@ struct StarTree {
   bool is_leaf(int n) const { return first_child(n) == -1; }
   int num_children(int n) const { return is_leaf(n) ? 0 : last_child(n) - first_child(n) + 1; }
   int child_for_value(int n, int value) const;
-  bool traverse(const std::vector<const std::vector<int32_t>*>& preds, uint32_t group_by_mask, std::vector<int32_t>& docs,
+  bool traverse(const std::vector<const std::vector<int32_t>*>& preds, uint32_t group_by_mask,
+                std::vector<std::pair<int32_t, int32_t>>& docs,
                 uint32_t& remaining_out) const;
 };
 

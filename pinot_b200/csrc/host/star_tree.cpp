@@ -65,8 +65,14 @@ int StarTree::child_for_value(int n, int value) const {
 
 // StarTreeFilterOperator.traverseStarTree.  preds[d] == nullptr: no predicate on dimension d.
 // Returns false when some predicate matches no dictId (EmptyFilterOperator).
+// Matching docs come back as [start, end) ranges (adjacent ones coalesced): a star-tree node IS a doc range, and the
+// device consumes them as a doc mask, so single doc ids are never materialised.
 bool StarTree::traverse(const std::vector<const std::vector<int32_t>*>& preds, uint32_t group_by_mask,
-                        std::vector<int32_t>& docs, uint32_t& remaining_out) const {
+                        std::vector<std::pair<int32_t, int32_t>>& docs, uint32_t& remaining_out) const {
+  auto add = [&](int32_t s, int32_t e) {
+    if (!docs.empty() && docs.back().second == s) docs.back().second = e;
+    else docs.emplace_back(s, e);
+  };
   constexpr int kAll = -1;
   uint32_t remaining_pred = 0, remaining_gb = group_by_mask;
   for (size_t d = 0; d < preds.size(); d++) if (preds[d]) remaining_pred |= 1u << d;
@@ -88,8 +94,8 @@ bool StarTree::traverse(const std::vector<const std::vector<int32_t>*>& preds, u
       matching = nullptr;
       current_dim = dim;
     }
-    if (remaining_pred == 0 && remaining_gb == 0) { docs.push_back(agg_doc(node)); continue; }
-    if (is_leaf(node)) { for (int d = start(node); d < end(node); d++) docs.push_back(d); continue; }
+    if (remaining_pred == 0 && remaining_gb == 0) { add(agg_doc(node), agg_doc(node) + 1); continue; }
+    if (is_leaf(node)) { add(start(node), end(node)); continue; }
     const int child_dim = dim + 1;
     int star_node = -1;
     if ((!have_global || !((global_remaining >> child_dim) & 1)) && !((remaining_gb >> child_dim) & 1))
@@ -124,8 +130,6 @@ bool StarTree::traverse(const std::vector<const std::vector<int32_t>*>& preds, u
       for (int c = first; c < first + nchild; c++) if (dim_value(c) != kAll) { queue.push_back(c); found_leaf |= is_leaf(c); }
     }
   }
-  std::sort(docs.begin(), docs.end());
-  docs.erase(std::unique(docs.begin(), docs.end()), docs.end());
   remaining_out = have_global ? global_remaining : 0u;
   return true;
 }
@@ -315,12 +319,21 @@ int try_star_tree(pb200_ctx* ctx, const pb200h_segment& seg, const StarTreeIndex
   if ((int)star_aggs.size() > 6) return 0;
 
   // ---- traversal -> doc mask ----
-  std::vector<int32_t> docs;
+  std::vector<std::pair<int32_t, int32_t>> docs;
   uint32_t remaining = 0;
   const bool non_empty = st.tree.traverse(preds, gb_mask, docs, remaining);
   const int sdocs = st.num_docs;
   std::vector<uint32_t> mask(((size_t)sdocs + 31) / 32 + 1, 0u);
-  if (non_empty) for (int32_t d : docs) if (d >= 0 && d < sdocs) mask[d >> 5] |= 1u << (d & 31);
+  if (non_empty) {
+    for (auto [s, e] : docs) {  // word-wise fill of [s, e)
+      s = std::max(s, 0); e = std::min(e, sdocs);
+      if (s >= e) continue;
+      const int ws = s >> 5, we = (e - 1) >> 5;
+      const uint32_t first = 0xFFFFFFFFu << (s & 31), last = 0xFFFFFFFFu >> (31 - ((e - 1) & 31));
+      if (ws == we) mask[ws] |= first & last;
+      else { mask[ws] |= first; for (int w = ws + 1; w < we; w++) mask[w] = 0xFFFFFFFFu; mask[we] |= last; }
+    }
+  }
 
   // ---- device query on the star-tree segment: DOC_MASK AND remaining predicates ----
   std::vector<pb200_filter_node> nodes;

@@ -87,6 +87,25 @@ void dev_free(pb200_ctx* ctx, void* p) {
   ctx->free_blocks.emplace(it->second, p);
 }
 
+int pinned_alloc(pb200_ctx* ctx, size_t bytes, void** out, size_t* got) {
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    auto it = ctx->free_pinned.lower_bound(bytes);
+    if (it != ctx->free_pinned.end()) { *out = it->second; *got = it->first; ctx->free_pinned.erase(it); return PB200_OK; }
+  }
+  size_t rb = std::max<size_t>(1 << 20, (bytes + (1 << 20) - 1) >> 20 << 20);
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, rb, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); set_error("cudaHostAlloc(%zu) failed", rb); return PB200_E_NOMEM; }
+  *out = p; *got = rb;
+  return PB200_OK;
+}
+void pinned_free(pb200_ctx* ctx, void* p, size_t bytes) {
+  if (!p) return;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (bytes > (256ull << 20) || ctx->free_pinned.size() >= 8) { cudaFreeHost(p); return; }
+  ctx->free_pinned.emplace(bytes, p);
+}
+
 cudaStream_t take_stream(pb200_ctx* ctx) {
   {
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -118,6 +137,24 @@ struct DevBuf {  // RAII pooled device buffer
 
 static inline uint32_t be32(const unsigned char* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
 static inline uint64_t be64(const unsigned char* p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
+
+// HBM layout of forward indexes: file order, every 4-byte big-endian word byte-swapped to native order ONCE at upload
+// (see pb200_unpack.cuh).  In place, grid-stride, 16 bytes per thread.
+__global__ void fwd_words_to_native_kernel(uint4* __restrict__ p, size_t n16) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 x = p[i];
+    x.x = __byte_perm(x.x, 0u, 0x0123u); x.y = __byte_perm(x.y, 0u, 0x0123u);
+    x.z = __byte_perm(x.z, 0u, 0x0123u); x.w = __byte_perm(x.w, 0u, 0x0123u);
+    p[i] = x;
+  }
+}
+static cudaError_t fwd_words_to_native(void* p, size_t bytes) {  // bytes: the padded allocation (multiple of 16)
+  const size_t n16 = bytes / 16;
+  if (!n16) return cudaSuccess;
+  const int blocks = (int)std::min<size_t>((n16 + 255) / 256, 148 * 16);
+  fwd_words_to_native_kernel<<<blocks, 256>>>((uint4*)p, n16);
+  return cudaGetLastError();
+}
 
 static uint64_t padded_fwd_bytes(long long num_docs, int bits) {
   // whole tiles for ANY tile size <= kMaxTileRows: ceil(N/t)*t < N + t <= alloc rows
@@ -152,6 +189,20 @@ __global__ void compact_groups_kernel(const unsigned long long* __restrict__ cou
     if (count[i] != 0ull) {
       unsigned long long pos = atomicAdd(n_out, 1ull);
       if ((long long)pos < cap) idx_out[pos] = (uint32_t)i;
+    }
+  }
+}
+// All per-group columns of one result in one launch: out block = [col 0: n x esz][col 1: ...] (8-byte aligned columns)
+struct GatherCol { const void* src; unsigned long long dst_off; uint32_t esz; uint32_t pad; };
+struct GatherPlan { GatherCol col[2 + kMaxAggs]; int ncols; };
+__global__ void gather_columns_kernel(const GatherPlan gp, const uint32_t* __restrict__ idx, long long n,
+                                      unsigned char* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t g = idx[i];
+    for (int c = 0; c < gp.ncols; ++c) {
+      const GatherCol& k = gp.col[c];
+      if (k.esz == 8) reinterpret_cast<unsigned long long*>(out + k.dst_off)[i] = static_cast<const unsigned long long*>(k.src)[g];
+      else reinterpret_cast<uint32_t*>(out + k.dst_off)[i] = static_cast<const uint32_t*>(k.src)[g];
     }
   }
 }
@@ -203,6 +254,7 @@ extern "C" int32_t pb200_shutdown(pb200_ctx* ctx) {
   cudaDeviceSynchronize();
   for (auto s : ctx->free_streams) cudaStreamDestroy(s);
   for (auto& kv : ctx->block_size) cudaFree(kv.first);
+  for (auto& kv : ctx->free_pinned) cudaFreeHost(kv.second);
   delete ctx;
   return PB200_OK;
 }
@@ -289,6 +341,7 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
         const uint64_t body = need & ~15ull;  // zero only the padding behind the file's bytes
         PB200_CUDA(cudaMemsetAsync((unsigned char*)c.fwd + body, 0, c.fwd_alloc_bytes - body, 0));
         PB200_CUDA(cudaMemcpy(c.fwd, d.fwd, need, cudaMemcpyHostToDevice));
+        PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes));
       }
     } else if (d.fwd_kind == PB200_FWD_DICT_SORTED) {
       // SortedIndexReaderImpl: expand (start,end) pairs into a fixed-bit dictId stream so every kernel sees one format
@@ -310,6 +363,7 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
       }
       PB200_CUDA(cudaMalloc(&c.fwd, c.fwd_alloc_bytes));
       PB200_CUDA(cudaMemcpy(c.fwd, packed.data(), c.fwd_alloc_bytes, cudaMemcpyHostToDevice));
+      PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes));
       c.fwd_kind = PB200_FWD_DICT_FIXEDBIT;
     } else if (d.fwd_kind == PB200_FWD_RAW_FIXEDBYTE) {
       // BaseChunkForwardIndexReader header :60-106; only PASS_THROUGH 4-byte values are accelerated
@@ -329,6 +383,7 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
       PB200_CUDA(cudaMalloc(&c.fwd, c.fwd_alloc_bytes));
       PB200_CUDA(cudaMemset(c.fwd, 0, c.fwd_alloc_bytes));
       PB200_CUDA(cudaMemcpy(c.fwd, p + start, 4ull * num_docs, cudaMemcpyHostToDevice));
+      PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes));
     } else {
       set_error("column %d: unknown forward index kind %d", i, d.fwd_kind);
       return fail(PB200_E_INVALID);
@@ -398,7 +453,11 @@ extern "C" int64_t pb200_segment_read_index(pb200_ctx* ctx, const pb200_segment*
   if (which == 0) {
     if (!out) return (int64_t)c.fwd_file_bytes;
     if (cap < c.fwd_file_bytes) { set_error("buffer too small"); return PB200_E_INVALID; }
-    if (cudaMemcpy(out, c.fwd, c.fwd_file_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); return PB200_E_CUDA; }
+    // back to the file's big-endian words (the HBM copy holds native words)
+    std::vector<uint32_t> words((c.fwd_file_bytes + 3) / 4);
+    if (cudaMemcpy(words.data(), c.fwd, words.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); return PB200_E_CUDA; }
+    for (auto& w : words) w = bswap32(w);
+    memcpy(out, words.data(), c.fwd_file_bytes);
     return (int64_t)c.fwd_file_bytes;
   } else if (which == 1) {
     if (!out) return (int64_t)c.dict_be.size();
@@ -466,15 +525,17 @@ void set_cmp(LeafDesc& lf, const DeviceColumn& c) {
   else lf.cmp = CMP_BOTH;
 }
 
-template <int CW, bool GB>
+template <int CW, bool GB, bool DEFER = !GB>
 cudaError_t launch_scan(const Plan& p, const QueryDesc& q, const TmaTable& tt, const SegDesc* dsegs, int grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(scan_kernel<CW, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(scan_kernel<CW, GB, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
   if (e != cudaSuccess) return e;
-  scan_kernel<CW, GB><<<grid, CW * 32, p.smem_bytes, st>>>(q, tt, dsegs);
+  scan_kernel<CW, GB, DEFER><<<grid, CW * 32, p.smem_bytes, st>>>(q, tt, dsegs);
   return cudaGetLastError();
 }
 
 }  // namespace
+
+static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cudaStream_t st);
 
 extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200_segment* const* segments,
                                  int32_t nseg, pb200_result** results) {
@@ -602,7 +663,9 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   const size_t hdr_bytes = (sizeof(SmemHeader) + 127) / 128 * 128;
   // CTA tile = W warps x 1024 rows; every warp streams its own 1024-row slices through a private TMA ring.
   // Aggregation-only kernels run two CTAs per SM (<= 128 registers at W = 8), group-by one.
-  int cw = 6, stages = 0, ctas_per_sm = 1;  // W = 6: 192-thread CTAs, two per SM, 168 registers (no spills)
+  // W = 6 (aggregation only): 192-thread CTAs, two per SM, 168 registers, no spills.  W = 8 (group-by): one 256-thread
+  // CTA per SM at up to 255 registers; more warps in flight hide the atomics' latency (measured 6.8 -> 5.4 ms on C3/range).
+  int cw = plan.group_by ? 8 : 6, stages = 0, ctas_per_sm = 1;
   if (getenv("PB200_W")) { int w = atoi(getenv("PB200_W")); if (w == 6 || w == 7 || w == 8) cw = w; }  // tuning knob
   q.sparse_max = getenv("PB200_SPARSE_MAX") ? atoi(getenv("PB200_SPARSE_MAX")) : 4;
   ctas_per_sm = plan.group_by ? 1 : 2;
@@ -684,8 +747,9 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       if (n.op == PB200_F_MATCH_ALL) { lf.kind = LEAF_ALL; continue; }
       if (n.op == PB200_F_EMPTY) { lf.kind = LEAF_NONE; continue; }
       (void)n0;
-      if (n.column < 0 || n.column >= ncols) { set_error("filter column out of range"); return PB200_E_INVALID; }
-      const DeviceColumn& c = seg->cols[n.column];
+      const bool needs_col = n.op != PB200_F_DOC_MASK && n.op != PB200_F_DOC_RANGES;
+      if (needs_col && (n.column < 0 || n.column >= ncols)) { set_error("filter column out of range"); return PB200_E_INVALID; }
+      const DeviceColumn& c = seg->cols[needs_col ? n.column : 0];
       if (is_scan_leaf(n.op)) {
         int slot = -1;
         for (int k = 0; k < q.num_slots; k++) if (plan.slot_cols[k] == n.column) slot = k;
@@ -794,6 +858,24 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       };
       std::stable_sort(sd.leaves, sd.leaves + nleaves, [&](const LeafDesc& a, const LeafDesc& b) { return cost(a) < cost(b); });
     }
+  }
+
+  // ---- packed dispatch words (pb200_desc.h): everything the tile loop needs per leaf / aggregation in one word ----
+  for (int s = 0; s < nseg; s++) {
+    SegDesc& sd = plan.segs[s];
+    for (int l = 0; l < nleaves; l++) {
+      LeafDesc& lf = sd.leaves[l];
+      const bool has_slot = lf.slot >= 0;
+      lf.code = leaf_code(lf.kind, lf.cmp, lf.negate, has_slot ? sd.slots[lf.slot].bits : 0, has_slot ? sd.slots[lf.slot].stage_words : 0u);
+    }
+    int n = 0;
+    for (int pass = 0; pass < 2; pass++)  // the software-pipelined aggregation goes last (nothing is waited on after it)
+      for (int a = 0; a < nagg; a++) {
+        if (q.aggs[a].slot < 0 || (a == q.defer_agg) != (pass == 1)) continue;
+        const SlotDesc& sl = sd.slots[q.aggs[a].slot];
+        sd.agg_code[n++] = agg_code(a, q.aggs[a].function, q.aggs[a].val_kind, sl.bits, sl.stage_words);
+      }
+    sd.num_agg_codes = n;
   }
 
   // ---- outputs ----
@@ -958,7 +1040,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     if (getenv("PB200_GRID")) grid = std::max(1, atoi(getenv("PB200_GRID")));
     const SegDesc* dptr = (const SegDesc*)dsegs.p + c0;
     if (plan.group_by) le = cw == 8 ? launch_scan<8, true>(plan, cq, tt, dptr, grid, st) : cw == 7 ? launch_scan<7, true>(plan, cq, tt, dptr, grid, st) : launch_scan<6, true>(plan, cq, tt, dptr, grid, st);
-    else le = cw == 8 ? launch_scan<8, false>(plan, cq, tt, dptr, grid, st) : cw == 7 ? launch_scan<7, false>(plan, cq, tt, dptr, grid, st) : launch_scan<6, false>(plan, cq, tt, dptr, grid, st);
+    else le = cw == 8 ? (getenv("PB200_NO_DEFER") ? launch_scan<8, false, false>(plan, cq, tt, dptr, grid, st) : launch_scan<8, false>(plan, cq, tt, dptr, grid, st)) : cw == 7 ? launch_scan<7, false>(plan, cq, tt, dptr, grid, st) : launch_scan<6, false>(plan, cq, tt, dptr, grid, st);
   }
   if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }
   PB200_CUDA(cudaEventRecord(e1, st));
@@ -1032,10 +1114,16 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     } else {
       std::vector<int> cards = R.dense.cards;
       R.meta.regime = regime_of(cards, query->max_initial_result_holder_capacity);
-      int frc = pb200_result_finalize(ctx, &R);
-      if (frc) return frc;
-      if (!merge) {  // per-segment results do not need the dense state any more
-        pb200_result::Dense& d = R.dense;
+    }
+  }
+  if (plan.group_by) {  // all results of the submission are extracted together (two device round trips in total)
+    std::vector<pb200_result*> rs;
+    for (int r = 0; r < nres; r++) rs.push_back(res[r].get());
+    int frc = finalize_many(ctx, rs.data(), nres, st);
+    if (frc) return frc;
+    if (!merge) {  // per-segment results do not need the dense state any more
+      for (int r = 0; r < nres; r++) {
+        pb200_result::Dense& d = res[r]->dense;
         dev_free(ctx, d.i64_block); dev_free(ctx, d.f64_block); dev_free(ctx, d.u32max_block); dev_free(ctx, d.u32min_block);
         d.i64_block = d.f64_block = d.u32max_block = d.u32min_block = nullptr;
         d.live = false;
@@ -1047,7 +1135,145 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   return PB200_OK;
 }
 
-// Extracts the non-empty groups of the (possibly all-reduced) dense table into the host-side result arrays.
+// Extracts the non-empty groups of the (possibly all-reduced) dense tables into the host-side result arrays, for ALL
+// results of a submission with two device round trips in total: (1) ordered stream compaction of every table
+// (cub::DeviceSelect, raw-key order == ArrayBasedHolder's iteration order: no host sort) + one read-back of the group
+// counts; (2) one gather launch per result writing all its columns into one block + one read-back into pinned memory.
+static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cudaStream_t st) {
+  if (nres <= 0) return PB200_OK;
+  int rc;
+  struct Job { DevBuf idx, block; unsigned long long n = 0; GatherPlan gp; size_t block_bytes = 0, stage_off = 0; std::vector<int> col_of_agg; int count_col = -1; };
+  std::vector<Job> jobs(nres);
+  DevBuf counters, tmp;
+  if ((rc = counters.alloc(ctx, 8ull * nres))) return rc;
+  PB200_CUDA(cudaMemsetAsync(counters.p, 0, 8ull * nres, st));
+  size_t tmp_cap = 0;
+  for (int r = 0; r < nres; r++) {
+    const pb200_result::Dense& d = Rs[r]->dense;
+    size_t tb = 0;
+    cub::CountingInputIterator<uint32_t> first(0u);
+    PB200_CUDA(cub::DeviceSelect::If(nullptr, tb, first, (uint32_t*)nullptr, (unsigned long long*)nullptr, (long long)d.groups, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min}, st));
+    tmp_cap = std::max(tmp_cap, tb);
+  }
+  if ((rc = tmp.alloc(ctx, tmp_cap + 16))) return rc;  // reused by the selects: they are ordered on one stream
+  for (int r = 0; r < nres; r++) {
+    const pb200_result::Dense& d = Rs[r]->dense;
+    if ((rc = jobs[r].idx.alloc(ctx, (size_t)d.groups * 4))) return rc;
+    cub::CountingInputIterator<uint32_t> first(0u);
+    size_t tb = tmp_cap;
+    PB200_CUDA(cub::DeviceSelect::If(tmp.p, tb, first, (uint32_t*)jobs[r].idx.p, (unsigned long long*)counters.p + r, (long long)d.groups, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min}, st));
+  }
+  void* pin = nullptr; size_t pin_bytes = 0;
+  if ((rc = pinned_alloc(ctx, 8ull * nres, &pin, &pin_bytes))) return rc;
+  struct PinReturn { pb200_ctx* c; void** p; size_t* b; ~PinReturn() { pinned_free(c, *p, *b); } } pin_return{ctx, &pin, &pin_bytes};
+  PB200_CUDA(cudaMemcpyAsync(pin, counters.p, 8ull * nres, cudaMemcpyDeviceToHost, st));
+  PB200_CUDA(cudaStreamSynchronize(st));
+  size_t stage_total = 0;
+  for (int r = 0; r < nres; r++) {
+    pb200_result* R = Rs[r];
+    const pb200_result::Dense& d = R->dense;
+    Job& J = jobs[r];
+    J.n = ((const unsigned long long*)pin)[r];
+    R->meta.num_groups = (int32_t)J.n;
+    R->meta.groups_limit_reached = (long long)J.n >= d.num_groups_limit;
+    if ((long long)J.n > d.num_groups_limit) {
+      // the reference admits groups in doc order until the limit binds (IntGroupIdMap.getGroupId :1022-1047); that order
+      // is not reproducible by a parallel scan -> the caller must run the Java operator for this segment
+      set_error("numGroupsLimit %d would bind (%llu groups): fall back to the reference operator", d.num_groups_limit, J.n);
+      return PB200_E_LIMIT;
+    }
+    // column plan: [idx u32][count u64]?[per aggregation one column]
+    const int nagg = (int)d.aggs.size();
+    const size_t n8 = (J.n + 1) / 2 * 8;  // bytes of a 4-byte column, 8-byte aligned
+    size_t off = n8;                       // column "idx" is copied device-to-device below
+    J.gp.ncols = 0;
+    J.col_of_agg.assign(nagg, -1);
+    auto add = [&](const void* src, uint32_t esz) { J.gp.col[J.gp.ncols] = GatherCol{src, off, esz, 0}; off += esz == 8 ? J.n * 8 : n8; return J.gp.ncols++; };
+    if (d.count) J.count_col = add(d.count, 8);
+    for (int a = 0; a < nagg; a++) {
+      const int fn = d.aggs[a].function, vk = d.val_kind[a];
+      if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) J.col_of_agg[a] = (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) ? add(d.dsum[a], 8) : add(d.isum[a], 8);
+      else if (fn == PB200_AGG_MIN) J.col_of_agg[a] = add(d.gmin[a], 4);
+      else if (fn == PB200_AGG_MAX) J.col_of_agg[a] = add(d.gmax[a], 4);
+    }
+    J.block_bytes = off;
+    J.stage_off = stage_total;
+    stage_total += (off + 63) / 64 * 64;
+  }
+  pinned_free(ctx, pin, pin_bytes);
+  pin = nullptr;
+  if ((rc = pinned_alloc(ctx, std::max<size_t>(stage_total, 64), &pin, &pin_bytes))) return rc;
+  for (int r = 0; r < nres; r++) {
+    Job& J = jobs[r];
+    if (!J.n) continue;
+    if ((rc = J.block.alloc(ctx, J.block_bytes))) return rc;
+    PB200_CUDA(cudaMemcpyAsync(J.block.p, J.idx.p, J.n * 4, cudaMemcpyDeviceToDevice, st));
+    if (J.gp.ncols) {
+      const int gb = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((J.n + 255) / 256, 148 * 8));
+      gather_columns_kernel<<<gb, 256, 0, st>>>(J.gp, (const uint32_t*)J.idx.p, (long long)J.n, (unsigned char*)J.block.p);
+    }
+    PB200_CUDA(cudaMemcpyAsync((unsigned char*)pin + J.stage_off, J.block.p, J.block_bytes, cudaMemcpyDeviceToHost, st));
+  }
+  PB200_CUDA(cudaGetLastError());
+  PB200_CUDA(cudaStreamSynchronize(st));
+  // ---- host side: raw columns -> the result's intermediate representation ----
+  for (int r = 0; r < nres; r++) {
+    pb200_result* R = Rs[r];
+    const pb200_result::Dense& d = R->dense;
+    const Job& J = jobs[r];
+    const size_t n = J.n;
+    const int nagg = (int)d.aggs.size(), ngb = (int)d.cards.size();
+    const unsigned char* blk = (const unsigned char*)pin + J.stage_off;
+    const uint32_t* hidx = (const uint32_t*)blk;
+    R->keys.resize(n * ngb);
+    if (ngb == 1) { for (size_t i = 0; i < n; i++) R->keys[i] = (int32_t)hidx[i]; }
+    else for (size_t i = 0; i < n; i++) {
+      uint32_t raw = hidx[i];
+      for (int g = 0; g < ngb; g++) { R->keys[i * ngb + g] = (int32_t)(raw % (uint32_t)d.cards[g]); raw /= (uint32_t)d.cards[g]; }
+    }
+    R->dbl.assign(nagg, {}); R->lng.assign(nagg, {}); R->ids.assign(nagg, {}); R->distinct.assign(nagg, {});
+    const unsigned long long* counts = J.count_col >= 0 && n ? (const unsigned long long*)(blk + J.gp.col[J.count_col].dst_off) : nullptr;
+    for (int a = 0; a < nagg; a++) {
+      const int fn = d.aggs[a].function, vk = d.val_kind[a];
+      std::vector<double>& D = R->dbl[a];
+      std::vector<int64_t>& L = R->lng[a];
+      std::vector<int32_t>& I = R->ids[a];
+      D.resize(n); L.resize(n); I.assign(n, -1);
+      const DeviceColumn* c = d.agg_cols[a];
+      const unsigned char* col = J.col_of_agg[a] >= 0 && n ? blk + J.gp.col[J.col_of_agg[a]].dst_off : nullptr;
+      auto value_of = [&](uint32_t x) -> double {
+        if (vk == VAL_RAW_I32) return (double)(int32_t)(x ^ 0x80000000u);
+        if (c->dict_host.empty()) return (double)x;
+        const unsigned char* h = c->dict_host.data();
+        switch (vk) {
+          case VAL_DICT_I32: { int32_t v; memcpy(&v, h + 4ull * x, 4); return (double)v; }
+          case VAL_DICT_I64: { int64_t v; memcpy(&v, h + 8ull * x, 8); return (double)v; }
+          case VAL_DICT_F32: { float v; memcpy(&v, h + 4ull * x, 4); return (double)v; }
+          default: { double v; memcpy(&v, h + 8ull * x, 8); return v; }
+        }
+      };
+      if (fn == PB200_AGG_COUNT) {
+        for (size_t i = 0; i < n; i++) { L[i] = (int64_t)counts[i]; D[i] = (double)counts[i]; }
+      } else if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
+        if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) { if (n) memcpy(D.data(), col, n * 8); }
+        else { const long long* t = (const long long*)col; for (size_t i = 0; i < n; i++) D[i] = (double)t[i]; }
+        if (counts) for (size_t i = 0; i < n; i++) L[i] = (int64_t)counts[i]; else std::fill(L.begin(), L.end(), 0);
+      } else if (fn == PB200_AGG_MIN || fn == PB200_AGG_MAX) {
+        const uint32_t* t = (const uint32_t*)col;
+        std::fill(L.begin(), L.end(), 0);
+        for (size_t i = 0; i < n; i++) {
+          if (fn == PB200_AGG_MIN) {
+            if (t[i] == 0xFFFFFFFFu) D[i] = INFINITY; else { I[i] = (int32_t)t[i]; D[i] = value_of(t[i]); }
+          } else {
+            if (t[i] == 0) D[i] = -INFINITY; else { I[i] = (int32_t)(t[i] - 1); D[i] = value_of(t[i] - 1); }
+          }
+        }
+      } else { std::fill(D.begin(), D.end(), 0.0); std::fill(L.begin(), L.end(), 0); }
+    }
+  }
+  return PB200_OK;
+}
+
 extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
   if (!ctx || !R) { set_error("null argument"); return PB200_E_INVALID; }
   pb200_result::Dense& d = R->dense;
@@ -1055,106 +1281,8 @@ extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
   PB200_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = take_stream(ctx);
   struct StreamReturn { pb200_ctx* c; cudaStream_t s; ~StreamReturn() { give_stream(c, s); } } stream_return{ctx, st};
-  const int nagg = (int)d.aggs.size(), ngb = (int)d.cards.size();
-  const long long G = d.groups;
-  DevBuf counter, idx;
-  int rc;
-  if ((rc = counter.alloc(ctx, 8))) return rc;
-  if ((rc = idx.alloc(ctx, (size_t)G * 4))) return rc;
-  PB200_CUDA(cudaMemsetAsync(counter.p, 0, 8, st));
-  int blocks = (int)std::min<long long>((G + 255) / 256, 148 * 8);
-  (void)blocks;
-  {  // stream compaction of the non-empty groups IN raw-key order (== ArrayBasedHolder's iteration order): no host sort
-    cub::CountingInputIterator<uint32_t> first(0u);
-    size_t tmp_bytes = 0;
-    PB200_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, first, (uint32_t*)idx.p, (unsigned long long*)counter.p, (long long)G, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min}, st));
-    DevBuf tmp;
-    if ((rc = tmp.alloc(ctx, tmp_bytes + 16))) return rc;
-    PB200_CUDA(cub::DeviceSelect::If(tmp.p, tmp_bytes, first, (uint32_t*)idx.p, (unsigned long long*)counter.p, (long long)G, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min}, st));
-    PB200_CUDA(cudaStreamSynchronize(st));  // tmp is released at scope exit
-  }
-  unsigned long long n = 0;
-  PB200_CUDA(cudaMemcpyAsync(&n, counter.p, 8, cudaMemcpyDeviceToHost, st));
-  PB200_CUDA(cudaStreamSynchronize(st));
-  R->meta.num_groups = (int32_t)n;
-  R->meta.groups_limit_reached = (long long)n >= d.num_groups_limit;
-  if ((long long)n > d.num_groups_limit) {
-    // the reference admits groups in doc order until the limit binds (IntGroupIdMap.getGroupId :1022-1047); that order
-    // is not reproducible by a parallel scan -> the caller must run the Java operator for this segment
-    set_error("numGroupsLimit %d would bind (%llu groups): fall back to the reference operator", d.num_groups_limit, n);
-    return PB200_E_LIMIT;
-  }
-  std::vector<uint32_t> hidx(n);
-  if (n) PB200_CUDA(cudaMemcpy(hidx.data(), idx.p, n * 4, cudaMemcpyDeviceToHost));
-  R->keys.assign((size_t)n * ngb, 0);
-  for (size_t i = 0; i < n; i++) {
-    uint32_t raw = hidx[i];
-    for (int g = 0; g < ngb; g++) { R->keys[i * ngb + g] = (int32_t)(raw % (uint32_t)d.cards[g]); raw /= (uint32_t)d.cards[g]; }
-  }
-  R->dbl.assign(nagg, {}); R->lng.assign(nagg, {}); R->ids.assign(nagg, {}); R->distinct.assign(nagg, {});
-  DevBuf g64, g32;
-  if ((rc = g64.alloc(ctx, std::max<size_t>(n, 1) * 8))) return rc;
-  if ((rc = g32.alloc(ctx, std::max<size_t>(n, 1) * 4))) return rc;
-  const int gb = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n + 255) / 256, 148 * 8));
-  std::vector<unsigned long long> counts(n, 0ull);
-  if (n && d.count) {
-    gather_kernel<unsigned long long><<<gb, 256, 0, st>>>(d.count, (const uint32_t*)idx.p, (long long)n, (unsigned long long*)g64.p);
-    PB200_CUDA(cudaMemcpyAsync(counts.data(), g64.p, n * 8, cudaMemcpyDeviceToHost, st));
-    PB200_CUDA(cudaStreamSynchronize(st));
-  }
-  for (int a = 0; a < nagg; a++) {
-    const int fn = d.aggs[a].function, vk = d.val_kind[a];
-    std::vector<double>& D = R->dbl[a];
-    std::vector<int64_t>& L = R->lng[a];
-    std::vector<int32_t>& I = R->ids[a];
-    D.assign(n, 0.0); L.assign(n, 0); I.assign(n, -1);
-    const DeviceColumn* c = d.agg_cols[a];
-    auto value_of = [&](uint32_t x) -> double {
-      if (vk == VAL_RAW_I32) return (double)(int32_t)(x ^ 0x80000000u);
-      if (c->dict_host.empty()) return (double)x;
-      const unsigned char* h = c->dict_host.data();
-      switch (vk) {
-        case VAL_DICT_I32: { int32_t v; memcpy(&v, h + 4ull * x, 4); return (double)v; }
-        case VAL_DICT_I64: { int64_t v; memcpy(&v, h + 8ull * x, 8); return (double)v; }
-        case VAL_DICT_F32: { float v; memcpy(&v, h + 4ull * x, 4); return (double)v; }
-        default: { double v; memcpy(&v, h + 8ull * x, 8); return v; }
-      }
-    };
-    if (fn == PB200_AGG_COUNT) {
-      for (size_t i = 0; i < n; i++) { L[i] = (int64_t)counts[i]; D[i] = (double)counts[i]; }
-    } else if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
-      if (n) {
-        if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
-          gather_kernel<double><<<gb, 256, 0, st>>>(d.dsum[a], (const uint32_t*)idx.p, (long long)n, (double*)g64.p);
-          PB200_CUDA(cudaMemcpyAsync(D.data(), g64.p, n * 8, cudaMemcpyDeviceToHost, st));
-          PB200_CUDA(cudaStreamSynchronize(st));
-        } else {
-          std::vector<long long> tmp(n);
-          gather_kernel<long long><<<gb, 256, 0, st>>>(d.isum[a], (const uint32_t*)idx.p, (long long)n, (long long*)g64.p);
-          PB200_CUDA(cudaMemcpyAsync(tmp.data(), g64.p, n * 8, cudaMemcpyDeviceToHost, st));
-          PB200_CUDA(cudaStreamSynchronize(st));
-          for (size_t i = 0; i < n; i++) D[i] = (double)tmp[i];
-        }
-      }
-      for (size_t i = 0; i < n; i++) L[i] = (int64_t)counts[i];
-    } else if (fn == PB200_AGG_MIN || fn == PB200_AGG_MAX) {
-      std::vector<uint32_t> tmp(n);
-      if (n) {
-        gather_kernel<uint32_t><<<gb, 256, 0, st>>>(fn == PB200_AGG_MIN ? d.gmin[a] : d.gmax[a], (const uint32_t*)idx.p, (long long)n, (uint32_t*)g32.p);
-        PB200_CUDA(cudaMemcpyAsync(tmp.data(), g32.p, n * 4, cudaMemcpyDeviceToHost, st));
-        PB200_CUDA(cudaStreamSynchronize(st));
-      }
-      for (size_t i = 0; i < n; i++) {
-        if (fn == PB200_AGG_MIN) {
-          if (tmp[i] == 0xFFFFFFFFu) D[i] = INFINITY; else { I[i] = (int32_t)tmp[i]; D[i] = value_of(tmp[i]); }
-        } else {
-          if (tmp[i] == 0) D[i] = -INFINITY; else { I[i] = (int32_t)(tmp[i] - 1); D[i] = value_of(tmp[i] - 1); }
-        }
-      }
-    }
-  }
-  PB200_CUDA(cudaGetLastError());
-  return PB200_OK;
+  pb200_result* one[1] = {R};
+  return finalize_many(ctx, one, 1, st);
 }
 
 extern "C" int32_t pb200_result_device_buffers(pb200_result* R, int32_t kind, void** p, int64_t* n) {

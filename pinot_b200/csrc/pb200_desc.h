@@ -35,8 +35,19 @@ struct SlotDesc {
   uint32_t pad;
 };
 
-struct LeafDesc {
-  int32_t kind;
+// LeafDesc.code packs everything the tile loop needs to dispatch a leaf into ONE word (one LDS.128 then brings code,
+// slot, lo and span): kind [0:3)  cmp [4:6)  negate [8]  bits of the slot [12:18)  stage_words of the slot [18:32)
+__host__ __device__ constexpr uint32_t leaf_code(int kind, int cmp, int negate, int bits, uint32_t stage_words) {
+  return (uint32_t)kind | (uint32_t)cmp << 4 | (uint32_t)(negate ? 1 : 0) << 8 | (uint32_t)bits << 12 | stage_words << 18;
+}
+// SegDesc.agg_code: one word per aggregation that reads a column (COUNT(*) never appears), the software-pipelined one
+// LAST: index [0:3)  function [4:7)  value kind [8:11)  bits [12:18)  stage_words [18:32)
+__host__ __device__ constexpr uint32_t agg_code(int a, int fn, int vk, int bits, uint32_t stage_words) {
+  return (uint32_t)a | (uint32_t)fn << 4 | (uint32_t)vk << 8 | (uint32_t)bits << 12 | stage_words << 18;
+}
+
+struct alignas(16) LeafDesc {
+  uint32_t code;    // leaf_code(...); kind = code & 7
   int32_t slot;
   uint32_t lo;      // RANGE: dictId lower bound
   uint32_t span;    // RANGE: hi - lo  (match iff (v - lo) < span, unsigned)
@@ -45,7 +56,7 @@ struct LeafDesc {
   int32_t num_ranges;
   int32_t negate;
   int32_t cmp;      // LEAF_RANGE: CMP_*
-  int32_t pad;
+  int32_t kind;     // LEAF_* (host side; the kernel reads it from code)
 };
 
 // Per-aggregation outputs of the aggregation-only kernel (one per segment or one merged)
@@ -62,7 +73,9 @@ struct SegDesc {
   long long first_tile;   // index of this segment's first tile in the launch-wide tile sequence
   long long num_tiles;
   uint32_t stage_tx;      // bytes TMA delivers per warp slice for THIS segment (sum of its slots' tile_bytes)
-  uint32_t pad0;
+  int32_t num_agg_codes;
+  uint32_t agg_code[kMaxAggs];
+  uint32_t pad1[2];
   SlotDesc slots[kMaxSlots];
   LeafDesc leaves[kMaxLeaves];
   const void* dict[kMaxAggs];          // native (little-endian) dictionary value array of the aggregation's column

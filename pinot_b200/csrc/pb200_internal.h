@@ -54,6 +54,7 @@ struct pb200_ctx {
   std::multimap<size_t, void*> free_blocks;  // caching allocator: size -> block
   std::map<void*, size_t> block_size;
   size_t pooled_bytes = 0;
+  std::multimap<size_t, void*> free_pinned;  // pinned host staging blocks (result read-back), size -> block
 };
 
 struct pb200_segment {
@@ -102,6 +103,8 @@ namespace pb200 {
 // caching device allocator + stream pool (thread safe)
 int dev_alloc(pb200_ctx* ctx, size_t bytes, void** out);
 void dev_free(pb200_ctx* ctx, void* p);
+int pinned_alloc(pb200_ctx* ctx, size_t bytes, void** out, size_t* got);  // cudaHostAlloc, cached per context
+void pinned_free(pb200_ctx* ctx, void* p, size_t bytes);
 cudaStream_t take_stream(pb200_ctx* ctx);
 void give_stream(pb200_ctx* ctx, cudaStream_t s);
 

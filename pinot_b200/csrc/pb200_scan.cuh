@@ -33,13 +33,15 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+// The ring primitives take 32-bit shared-window addresses computed ONCE per thread (a generic -> shared conversion
+// per call costs an S2UR/ULEA/IMAD chain in the tile loop).
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -48,17 +50,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
-      "}" ::"r"(smem_u32(bar)),
+      "}" ::"r"(bar),
       "r"(parity)
       : "memory");
 }
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`; streaming data: L2 evict-first policy.
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar,
                                             uint64_t policy) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+          dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
@@ -108,8 +110,8 @@ __device__ __forceinline__ uint32_t eval_doc_ranges(uint32_t row0u, const int32_
 __device__ __forceinline__ uint32_t read_one_group(const uint32_t* __restrict__ p, int j, int bits) {
   const int bit = j * bits;
   const int k = bit >> 5, s = bit & 31;
-  const uint32_t hi = bswap32(p[k]);
-  const uint32_t lo = (s + bits > 32) ? bswap32(p[k + 1]) : 0u;
+  const uint32_t hi = fwd_word(p[k]);
+  const uint32_t lo = (s + bits > 32) ? fwd_word(p[k + 1]) : 0u;
   const uint32_t x = __funnelshift_l(lo, hi, s);
   return bits == 32 ? x : (x >> (32 - bits));
 }
@@ -238,6 +240,8 @@ constexpr int kMaxStages = 4;
 
 struct SmemHeader {
   SegDesc seg;                              // CTA-wide copy of the current segment's descriptor
+  AggDesc aggs[kMaxAggs];                   // q.aggs: indexed with a runtime `a` (an indexed LDC costs a long-scoreboard wait)
+  uint32_t slot_roles[kMaxSlots];           // q.slot_roles, same reason
   uint64_t full[kMaxWarps][kMaxStages];     // per-warp ring: "stage filled by TMA"
 };
 
@@ -253,16 +257,21 @@ struct SmemHeader {
 //   [acc64: num_aggs x threads x 8 B][accmm: num_aggs x threads x 8 B]     (aggregation-only kernel)
 // acc64/accmm are the per-thread running aggregates; they live in shared memory (private slot per thread, touched once
 // per tile) instead of registers so that two CTAs fit on an SM.
-template <int W, bool GROUPBY>
+template <int W, bool GROUPBY, bool DEFER = !GROUPBY>
 __global__ void __launch_bounds__(W * 32, GROUPBY ? 1 : 2)
 scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTable tt, const SegDesc* __restrict__ segs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
+  // The shared-window base is made opaque to the compiler once: otherwise every access through hdr-> / the accumulator
+  // pointers rematerialises it as S2R SR_CgaCtaId + LEA (a variable-latency special-register read per access).
+  uint32_t smem_base_s = smem_u32(smem_raw);
+  asm volatile("" : "+r"(smem_base_s));
+  unsigned char* const smem_base = static_cast<unsigned char*>(__cvta_shared_to_generic(smem_base_s));
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_base);
   constexpr int kHdrBytes = (sizeof(SmemHeader) + 127) / 128 * 128;
   constexpr int kConsumers = W * 32;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  uint32_t* stages_all = reinterpret_cast<uint32_t*>(smem_raw + kHdrBytes);
+  uint32_t* stages_all = reinterpret_cast<uint32_t*>(smem_base + kHdrBytes);
   uint32_t* wstages = stages_all + (size_t)warp * q.num_stages * q.stage_words;   // this warp's ring
   uint32_t* fstack = stages_all + (size_t)W * q.num_stages * q.stage_words;       // generic-filter mask stack
   unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(fstack + (q.conj ? 0 : kConsumers * kMaxStack));
@@ -273,6 +282,8 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     for (int s = 0; s < q.num_stages; ++s) mbar_init(&hdr->full[warp][s], 1);
     mbar_fence_init();
   }
+  if (threadIdx.x < kMaxAggs) hdr->aggs[threadIdx.x] = q.aggs[threadIdx.x];
+  if (threadIdx.x < kMaxSlots) hdr->slot_roles[threadIdx.x] = q.slot_roles[threadIdx.x];
   __syncthreads();
 
   const int group = threadIdx.x;  // index of this thread's per-thread accumulators
@@ -282,7 +293,8 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
   // ---- warp-private TMA ring.  Prefetch cursor state lives in registers and advances incrementally (lane k < num_slots
   //      owns slot k's source pointer); the constant-bank table is consulted only when the cursor enters a new segment.
   const uint64_t policy = policy_evict_first();
-  uint64_t* const fullw = &hdr->full[warp][0];
+  const uint32_t fullw = smem_u32(&hdr->full[warp][0]);  // + 8 * stage
+  const uint32_t wstages_s = smem_u32(wstages);
   int pidx = 0, p_end = 0;            // prefetch segment cursor and its exclusive end tile
   int Tp = blockIdx.x;                // next CTA tile to prefetch
   const unsigned char* p_src = nullptr;
@@ -320,15 +332,16 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     }
     if (skip) {
       skipbits |= 1u << stage;
-      if (lane == 0) mbar_arrive(fullw + stage);  // completes the phase without any bytes
+      if (lane == 0) mbar_arrive(fullw + 8u * stage);  // completes the phase without any bytes
     } else {
       skipbits &= ~(1u << stage);
-      if (lane == 0) {
-        fence_proxy_async();  // the buffer was read through the generic proxy; order those reads before the async write
-        mbar_expect_tx(fullw + stage, p_tx);
-      }
+      // WAR on the stage buffer: every lane's generic-proxy reads of it have completed (their values were consumed
+      // before the __syncwarp() that precedes issue()), so the async-proxy write may follow without a proxy fence --
+      // the same consumer-release -> producer-TMA ordering CUTLASS pipelines rely on.  (A fence.proxy.async here
+      // compiles to MEMBAR.ALL.CTA, which also drains the deferred dictionary gathers.)
+      if (lane == 0) mbar_expect_tx(fullw + 8u * stage, p_tx);
       __syncwarp();
-      if (lane < q.num_slots) tma_load_1d(wstages + stage * q.stage_words + p_dst, p_src, p_tb, fullw + stage, policy);
+      if (lane < q.num_slots) tma_load_1d(wstages_s + 4u * (stage * q.stage_words + p_dst), p_src, p_tb, fullw + 8u * stage, policy);
     }
     p_src += p_stride;
     Tp += gridDim.x;
@@ -340,13 +353,13 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 
   // deferred dictionary gathers (software pipelining across tiles): the biased values of tile t's surviving rows are
   // loaded into x[] while tile t+1 is being filtered and are summed afterwards -- one L2 latency hidden per tile
-  uint32_t x[32];
+  uint32_t x[DEFER ? 32 : 1];
   int pend_pc = -1;  // >= 0: x[] holds a tile's gathers (pend_pc surviving rows in this thread)
   auto drain = [&]() {
-    if (pend_pc >= 0) {
+    if (DEFER && pend_pc >= 0) {
       unsigned long long a0 = 0, a1 = 0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < (DEFER ? 32 : 0); j += 4) {
         a0 += (unsigned long long)x[j] + (unsigned long long)x[j + 1];
         a1 += (unsigned long long)x[j + 2] + (unsigned long long)x[j + 3];
       }
@@ -371,11 +384,11 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     cnt = 0;
     if (!GROUPBY) {
       for (int a = 0; a < q.num_aggs; ++a) {
-        if (q.aggs[a].slot < 0) continue;
-        const int fn = q.aggs[a].function;
+        if (hdr->aggs[a].slot < 0) continue;
+        const int fn = hdr->aggs[a].function;
         if (fn == 1 || fn == 4) {  // SUM / AVG
           const unsigned long long raw = acc64[a * kConsumers + group];
-          if (q.aggs[a].val_kind == VAL_DICT_F32 || q.aggs[a].val_kind == VAL_DICT_F64) {
+          if (hdr->aggs[a].val_kind == VAL_DICT_F32 || hdr->aggs[a].val_kind == VAL_DICT_F64) {
             double d = warp_sum(__longlong_as_double((long long)raw));
             if (lane == 0) atomicAdd(&sd.accum->dsum[a], d);
           } else {
@@ -415,7 +428,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     const int left = row0 >= c_docs ? 0 : (c_docs - row0 >= 32u ? 32 : (int)(c_docs - row0));
     uint32_t m = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
 
-    if (use_pipe) mbar_wait(fullw + stage, phase);
+    if (use_pipe) mbar_wait(fullw + 8u * stage, phase);
     if (use_pipe && ((skipbits >> stage) & 1u)) m = 0u;  // slice was never loaded: no doc of it passes the bitmap leaves
     const uint32_t* st = wstages + stage * q.stage_words;
     const int group_in_stage = lane;  // the thread's 32-row group inside the warp's slice
@@ -430,41 +443,46 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 #pragma unroll 1
         for (int l = 0; l < q.num_leaves; ++l) {
           const LeafDesc& lf = sd.leaves[l];
+          const uint4 L = *reinterpret_cast<const uint4*>(&lf);  // code, slot, lo, span in one LDS.128
+          const uint32_t code = L.x, lf_lo = L.z, lf_span = L.w;
+          const int kind = (int)(code & 7u);
           uint32_t lm;
-          if (lf.kind == LEAF_ALL) lm = 0xFFFFFFFFu;
-          else if (lf.kind == LEAF_NONE) lm = 0u;
-          else if (lf.kind == LEAF_DOCMASK) lm = left > 0 ? __ldg(lf.bits + (row0 >> 5)) : 0u;
-          else if (lf.kind == LEAF_DOCRANGES) lm = eval_doc_ranges(row0, lf.ranges, lf.num_ranges);
+          if (kind == LEAF_ALL) lm = 0xFFFFFFFFu;
+          else if (kind == LEAF_NONE) lm = 0u;
+          else if (kind == LEAF_DOCMASK) lm = left > 0 ? __ldg(lf.bits + (row0 >> 5)) : 0u;
+          else if (kind == LEAF_DOCRANGES) lm = eval_doc_ranges(row0, lf.ranges, lf.num_ranges);
           else {
-            const int wmax = __reduce_max_sync(0xFFFFFFFFu, __popc(m));
-            const SlotDesc& sl = sd.slots[lf.slot];
+            const int sbits = (int)((code >> 12) & 63u);
+            const uint32_t* base = st + (code >> 18);
+            // the first leaf sees (almost) full masks: no need to count survivors to pick the dense path
+            const int wmax = l == 0 ? 32 : __reduce_max_sync(0xFFFFFFFFu, __popc(m));
             if (wmax == 0) {
               lm = 0u;  // nothing left to test (m == 0 in every lane)
             } else if (wmax <= q.sparse_max) {
-              const uint32_t* p = st + sl.stage_words + group_in_stage * sl.bits;
+              const uint32_t* p = base + group_in_stage * sbits;
               uint32_t keep = 0, mm = m;
               while (mm) {
                 const int j = 31 - __clz(mm);
                 mm &= ~(1u << j);
-                const uint32_t id = read_one_group(p, j, sl.bits);
-                const bool hit = lf.kind == LEAF_RANGE ? ((id - lf.lo) < lf.span)
-                                                       : (((__ldg(lf.bits + (id >> 5)) >> (id & 31)) & 1u) != 0u);
+                const uint32_t id = read_one_group(p, j, sbits);
+                const bool hit = kind == LEAF_RANGE ? ((id - lf_lo) < lf_span)
+                                                    : (((__ldg(lf.bits + (id >> 5)) >> (id & 31)) & 1u) != 0u);
                 keep |= (hit ? 1u : 0u) << j;
               }
               lm = keep;  // bits outside m are irrelevant (m &= lm below)
-            } else if (lf.kind == LEAF_RANGE) {
-              const int sh = 32 - sl.bits;
-              const uint32_t* base = st + sl.stage_words;
-              if (lf.cmp == CMP_GE) { RangeGE f; f.LO = lf.lo << sh; dispatch_left_aligned(sl.bits, base, group_in_stage, f); lm = f.mask(); }
-              else if (lf.cmp == CMP_LT) { RangeLT f; f.HI = (lf.lo + lf.span) << sh; dispatch_left_aligned(sl.bits, base, group_in_stage, f); lm = f.mask(); }
-              else { RangeBoth f; f.LO = lf.lo << sh; f.SPAN = lf.span << sh; dispatch_left_aligned(sl.bits, base, group_in_stage, f); lm = f.mask(); }
+            } else if (kind == LEAF_RANGE) {
+              const int sh = 32 - sbits;
+              const int cmp = (int)((code >> 4) & 3u);
+              if (cmp == CMP_GE) { RangeGE f; f.LO = lf_lo << sh; dispatch_left_aligned(sbits, base, group_in_stage, f); lm = f.mask(); }
+              else if (cmp == CMP_LT) { RangeLT f; f.HI = (lf_lo + lf_span) << sh; dispatch_left_aligned(sbits, base, group_in_stage, f); lm = f.mask(); }
+              else { RangeBoth f; f.LO = lf_lo << sh; f.SPAN = lf_span << sh; dispatch_left_aligned(sbits, base, group_in_stage, f); lm = f.mask(); }
             } else {
               uint32_t v[32];
-              unpack_group(sl.bits, st + sl.stage_words, group_in_stage, v);
+              unpack_group(sbits, base, group_in_stage, v);
               lm = eval_lut(v, lf.bits);
             }
           }
-          if (lf.negate) lm = ~lm;
+          if ((code >> 8) & 1u) lm = ~lm;
           m &= lm;
         }
       } else {
@@ -474,21 +492,21 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
           lm[l] = 0xFFFFFFFFu;
           if (l < q.num_leaves) {
             const LeafDesc& lf = sd.leaves[l];
-            if (lf.kind == LEAF_NONE) lm[l] = 0u;
-            else if (lf.kind == LEAF_DOCMASK) lm[l] = left > 0 ? __ldg(lf.bits + (row0 >> 5)) : 0u;
-            else if (lf.kind == LEAF_DOCRANGES) lm[l] = eval_doc_ranges(row0, lf.ranges, lf.num_ranges);
+            if ((lf.code & 7u) == LEAF_NONE) lm[l] = 0u;
+            else if ((lf.code & 7u) == LEAF_DOCMASK) lm[l] = left > 0 ? __ldg(lf.bits + (row0 >> 5)) : 0u;
+            else if ((lf.code & 7u) == LEAF_DOCRANGES) lm[l] = eval_doc_ranges(row0, lf.ranges, lf.num_ranges);
           }
         }
         for (int s = 0; s < q.num_slots; ++s) {
-          if (!(q.slot_roles[s] & ROLE_FILTER)) continue;
+          if (!(hdr->slot_roles[s] & ROLE_FILTER)) continue;
           uint32_t v[32];
           unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group_in_stage, v);
 #pragma unroll
           for (int l = 0; l < kMaxLeaves; ++l) {
             if (l < q.num_leaves && sd.leaves[l].slot == s) {
               const LeafDesc& lf = sd.leaves[l];
-              if (lf.kind == LEAF_RANGE) lm[l] = eval_range(v, lf.lo, lf.span);
-              else if (lf.kind == LEAF_LUT) lm[l] = eval_lut(v, lf.bits);
+              if ((lf.code & 7u) == LEAF_RANGE) lm[l] = eval_range(v, lf.lo, lf.span);
+              else if ((lf.code & 7u) == LEAF_LUT) lm[l] = eval_lut(v, lf.bits);
             }
           }
         }
@@ -546,11 +564,12 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
           touch_group(sd, g);
         }
 #pragma unroll 1
-        for (int a = 0; a < q.num_aggs; ++a) {
-          if (q.aggs[a].slot < 0) continue;
-          const SlotDesc& sl = sd.slots[q.aggs[a].slot];
-          const uint32_t id = read_one_group(st + sl.stage_words + group_in_stage * sl.bits, j, sl.bits);
-          const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
+        for (int ai = 0; ai < sd.num_agg_codes; ++ai) {
+          const uint32_t ac = sd.agg_code[ai];  // index | function | value kind | bits | stage_words (pb200_desc.h)
+          const int a = (int)(ac & 7u), fn = (int)((ac >> 4) & 7u), vk = (int)((ac >> 8) & 7u);
+          const int abits = (int)((ac >> 12) & 63u);
+          const uint32_t* base = st + (ac >> 18);
+          const uint32_t id = read_one_group(base + group_in_stage * abits, j, abits);
           if (fn == 1 || fn == 4) {
             if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
               const double x = vk == VAL_DICT_F32 ? (double)__ldg(static_cast<const float*>(sd.dict[a]) + id)
@@ -577,28 +596,30 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
       // ---- dense projection ----
       if (!GROUPBY) {
 #pragma unroll 1
-        for (int a = 0; a < q.num_aggs; ++a) {
-          if (q.aggs[a].slot < 0) continue;
-          const SlotDesc& sl = sd.slots[q.aggs[a].slot];
-          const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
-          const uint32_t* base = st + sl.stage_words;
-          if ((fn == 1 || fn == 4) && vk == VAL_DICT_I32 && a == q.defer_agg) {
+        for (int ai = 0; ai < sd.num_agg_codes; ++ai) {
+          const uint32_t ac = sd.agg_code[ai];  // index | function | value kind | bits | stage_words (pb200_desc.h)
+          const int a = (int)(ac & 7u), fn = (int)((ac >> 4) & 7u), vk = (int)((ac >> 8) & 7u);
+          const int abits = (int)((ac >> 12) & 63u);
+          const uint32_t* base = st + (ac >> 18);
+          if (DEFER && (fn == 1 || fn == 4) && vk == VAL_DICT_I32 && a == q.defer_agg) {
             // gathers of biased INT dictionary values (device copy holds value ^ 0x80000000) are only ISSUED here;
             // they are summed after the next tile's filter phase (drain())
-            GatherBiasedU32 f{static_cast<const uint32_t*>(sd.dict[a]), m, (uint32_t)(32 - sl.bits), x};
-            dispatch_left_aligned(sl.bits, base, group_in_stage, f);
-            pend_pc = pc;
+            if constexpr (DEFER) {
+              GatherBiasedU32 f{static_cast<const uint32_t*>(sd.dict[a]), m, (uint32_t)(32 - abits), x};
+              dispatch_left_aligned(abits, base, group_in_stage, f);
+              pend_pc = pc;
+            }
           } else if ((fn == 1 || fn == 4) && vk == VAL_DICT_I32) {
             SumBiasedU32 f;
-            f.d = static_cast<const uint32_t*>(sd.dict[a]); f.m = m; f.sh = 32 - sl.bits;
-            dispatch_left_aligned(sl.bits, base, group_in_stage, f);
+            f.d = static_cast<const uint32_t*>(sd.dict[a]); f.m = m; f.sh = 32 - abits;
+            dispatch_left_aligned(abits, base, group_in_stage, f);
             acc64[a * kConsumers + group] += (f.a0 + f.a1) - ((unsigned long long)pc << 31);
           } else if ((fn == 2 || fn == 3) && vk != VAL_RAW_I32) {
             MinMaxLeft f;
             f.m = m;
-            dispatch_left_aligned(sl.bits, base, group_in_stage, f);
+            dispatch_left_aligned(abits, base, group_in_stage, f);
             if (pc) {
-              const int sh = 32 - sl.bits;
+              const int sh = 32 - abits;
               uint2 mmx = accmm[a * kConsumers + group];
               mmx.x = min(mmx.x, f.mn >> sh);
               mmx.y = max(mmx.y, (f.mx >> sh) + 1u);
@@ -606,7 +627,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
             }
           } else {
             uint32_t v[32];
-            unpack_group(sl.bits, base, group_in_stage, v);
+            unpack_group(abits, base, group_in_stage, v);
             if (fn == 1 || fn == 4) {
               if (vk == VAL_RAW_I32) {
                 long long acc = 0;
@@ -654,7 +675,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 #pragma unroll
         for (int j = 0; j < 32; ++j) gid[j] = 0;
         for (int s = 0; s < q.num_slots; ++s) {
-          if (!(q.slot_roles[s] & ROLE_GROUP)) continue;
+          if (!(hdr->slot_roles[s] & ROLE_GROUP)) continue;
           unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group_in_stage, v);
 #pragma unroll
           for (int g = 0; g < kMaxGroupBy; ++g) {
@@ -678,11 +699,12 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
             if (cur[j] == 0u) sd.g_seen[gid[j]] = 1u;
         }
 #pragma unroll 1
-        for (int a = 0; a < q.num_aggs; ++a) {
-          if (q.aggs[a].slot < 0) continue;
-          const SlotDesc& sl = sd.slots[q.aggs[a].slot];
-          const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
-          unpack_group(sl.bits, st + sl.stage_words, group_in_stage, v);
+        for (int ai = 0; ai < sd.num_agg_codes; ++ai) {
+          const uint32_t ac = sd.agg_code[ai];  // index | function | value kind | bits | stage_words (pb200_desc.h)
+          const int a = (int)(ac & 7u), fn = (int)((ac >> 4) & 7u), vk = (int)((ac >> 8) & 7u);
+          const int abits = (int)((ac >> 12) & 63u);
+          const uint32_t* base = st + (ac >> 18);
+          unpack_group(abits, base, group_in_stage, v);
           if (fn == 1 || fn == 4) {
             // all gathers of the tile are issued BEFORE the first atomic consumes one: one L2 latency per tile, not
             // one per surviving row

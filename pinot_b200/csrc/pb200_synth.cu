@@ -47,7 +47,7 @@ __global__ void synth_fwd_kernel(uint32_t* __restrict__ out, long long num_group
       acc = (acc << bits) | v;
       have += bits;
       if (have >= 32) {
-        o[k++] = bswap32((uint32_t)(acc >> (have - 32)));
+        o[k++] = (uint32_t)(acc >> (have - 32));  // native word order (the HBM layout; see pb200_unpack.cuh)
         have -= 32;
       }
     }

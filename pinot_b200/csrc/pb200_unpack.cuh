@@ -5,8 +5,12 @@
 // big-endian bit stream.  Consequence used here (same as FixedBitIntReader.read32): 32 consecutive values whose first
 // index is a multiple of 32 occupy exactly B consecutive, 4-byte aligned big-endian words -- no carry between groups.
 //
+// HBM layout: the B-word groups are kept in the file's order, but every 4-byte word is stored in the GPU's native
+// (little-endian) byte order -- the byte swap of the big-endian file words is done ONCE when the segment is uploaded
+// (fwd_words_to_native in pb200_api.cu) instead of once per value group per query (a PRMT per word otherwise).
+//
 // B200 mapping: ONE THREAD owns one such group (32 rows).  Its B words sit contiguously in shared memory (the tile was
-// brought in by a TMA bulk copy, so the layout is the file's own byte order); lane l of a warp reads words
+// brought in by a TMA bulk copy, so the layout is the HBM layout); lane l of a warp reads words
 // [l*B, (l+1)*B).  With the widest naturally aligned load (LDS.128 when B%4==0, LDS.64 when B%2==0, else LDS.32) the
 // lane stride is an odd multiple of the access width for every B except 8, 16 and 24, i.e. bank-conflict free; all
 // shift amounts are compile-time constants after unrolling, so a value costs ~2 ALU ops (SHF/funnel + mask).
@@ -15,7 +19,11 @@
 
 namespace pb200 {
 
-__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0u, 0x0123u); }
+__host__ __device__ __forceinline__ uint32_t bswap32(uint32_t x) {
+  return (x >> 24) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24);
+}
+// a forward-index word as the unpackers want it (MSB-first bit stream): identity on the native HBM layout
+__device__ __forceinline__ uint32_t fwd_word(uint32_t x) { return x; }
 
 template <int B>
 struct Unpack32 {
@@ -28,22 +36,22 @@ struct Unpack32 {
 #pragma unroll
       for (int k = 0; k < B / 4; ++k) {
         uint4 x = p4[k];
-        w[4 * k + 0] = bswap32(x.x);
-        w[4 * k + 1] = bswap32(x.y);
-        w[4 * k + 2] = bswap32(x.z);
-        w[4 * k + 3] = bswap32(x.w);
+        w[4 * k + 0] = fwd_word(x.x);
+        w[4 * k + 1] = fwd_word(x.y);
+        w[4 * k + 2] = fwd_word(x.z);
+        w[4 * k + 3] = fwd_word(x.w);
       }
     } else if constexpr (B % 2 == 0) {
       const uint2* p2 = reinterpret_cast<const uint2*>(p);
 #pragma unroll
       for (int k = 0; k < B / 2; ++k) {
         uint2 x = p2[k];
-        w[2 * k + 0] = bswap32(x.x);
-        w[2 * k + 1] = bswap32(x.y);
+        w[2 * k + 0] = fwd_word(x.x);
+        w[2 * k + 1] = fwd_word(x.y);
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < B; ++k) w[k] = bswap32(p[k]);
+      for (int k = 0; k < B; ++k) w[k] = fwd_word(p[k]);
     }
     constexpr uint32_t kMask = B == 32 ? 0xFFFFFFFFu : ((1u << (B & 31)) - 1u);
 #pragma unroll
@@ -84,22 +92,22 @@ __device__ __forceinline__ void for_each_left_aligned(const uint32_t* __restrict
 #pragma unroll
     for (int k = 0; k < B / 4; ++k) {
       uint4 x = p4[k];
-      w[4 * k + 0] = bswap32(x.x);
-      w[4 * k + 1] = bswap32(x.y);
-      w[4 * k + 2] = bswap32(x.z);
-      w[4 * k + 3] = bswap32(x.w);
+      w[4 * k + 0] = fwd_word(x.x);
+      w[4 * k + 1] = fwd_word(x.y);
+      w[4 * k + 2] = fwd_word(x.z);
+      w[4 * k + 3] = fwd_word(x.w);
     }
   } else if constexpr (B % 2 == 0) {
     const uint2* p2 = reinterpret_cast<const uint2*>(p);
 #pragma unroll
     for (int k = 0; k < B / 2; ++k) {
       uint2 x = p2[k];
-      w[2 * k + 0] = bswap32(x.x);
-      w[2 * k + 1] = bswap32(x.y);
+      w[2 * k + 0] = fwd_word(x.x);
+      w[2 * k + 1] = fwd_word(x.y);
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < B; ++k) w[k] = bswap32(p[k]);
+    for (int k = 0; k < B; ++k) w[k] = fwd_word(p[k]);
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -159,13 +167,13 @@ __device__ __forceinline__ void unpack_group(int bits, const uint32_t* __restric
 }
 
 // Random access to one value (FixedBitIntReader.readUnchecked shape; used by the sparse / post-bitmap paths):
-// two aligned big-endian words cover any value of width <= 32.
+// two aligned words cover any value of width <= 32.
 __device__ __forceinline__ uint32_t read_one(const uint32_t* __restrict__ words, long long index, int bits) {
   const long long bit = index * bits;
   const long long k = bit >> 5;
   const int s = (int)(bit & 31);
-  const uint32_t hi = bswap32(words[k]);
-  const uint32_t lo = (s + bits > 32) ? bswap32(words[k + 1]) : 0u;
+  const uint32_t hi = fwd_word(words[k]);
+  const uint32_t lo = (s + bits > 32) ? fwd_word(words[k + 1]) : 0u;
   const uint32_t x = __funnelshift_l(lo, hi, s);
   return bits == 32 ? x : (x >> (32 - bits));
 }
