@@ -525,11 +525,11 @@ void set_cmp(LeafDesc& lf, const DeviceColumn& c) {
   else lf.cmp = CMP_BOTH;
 }
 
-template <int CW, bool GB, bool DEFER = !GB>
+template <int CW, bool GB, bool DEFER = !GB, int MINB = (GB ? 1 : 2)>
 cudaError_t launch_scan(const Plan& p, const QueryDesc& q, const TmaTable& tt, const SegDesc* dsegs, int grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(scan_kernel<CW, GB, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(scan_kernel<CW, GB, DEFER, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
   if (e != cudaSuccess) return e;
-  scan_kernel<CW, GB, DEFER><<<grid, CW * 32, p.smem_bytes, st>>>(q, tt, dsegs);
+  scan_kernel<CW, GB, DEFER, MINB><<<grid, CW * 32, p.smem_bytes, st>>>(q, tt, dsegs);
   return cudaGetLastError();
 }
 
@@ -670,8 +670,40 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   q.sparse_max = getenv("PB200_SPARSE_MAX") ? atoi(getenv("PB200_SPARSE_MAX")) : 4;
   ctas_per_sm = plan.group_by ? 1 : 2;
   if (getenv("PB200_CTAS")) ctas_per_sm = std::max(1, atoi(getenv("PB200_CTAS")));
+  if (plan.group_by && ctas_per_sm >= 2) { ctas_per_sm = 2; cw = 6; }  // experiment: two 192-thread group-by CTAs per SM
   const size_t warp_stage_bytes = (size_t)128 * max_bits_sum;
-  const size_t extra_bytes = (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4) + (plan.group_by ? 0 : (size_t)nagg * cw * 32 * 16);
+  size_t extra_bytes = (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4) + (plan.group_by ? 0 : (size_t)nagg * cw * 32 * 16);
+  // CTA-private group tables in shared memory when the key space is small and every function is COUNT or an integer SUM
+  q.smem_groups = 0;
+  for (int a = 0; a < kMaxAggs; a++) q.smem_slot[a] = -1;
+  if (plan.group_by && !getenv("PB200_NO_SMEM_GROUPS")) {
+    // Small key spaces only: there the global table's few addresses serialise in L2, while for thousands of groups the
+    // fire-and-forget global REDs beat shared atomics that must return the old low word (measured on C3/range, 10 000
+    // groups: 3.6 ms global vs 4.4 ms shared).
+    const long long smem_groups_max = getenv("PB200_SMEM_GROUPS_MAX") ? atoll(getenv("PB200_SMEM_GROUPS_MAX")) : 2048;
+    long long gmax = 1;
+    for (int s = 0; s < nseg && gmax > 0; s++) {
+      long long g = 1;
+      for (int k = 0; k < ngb; k++) { g *= std::max(segments[s]->cols[query->group_by_columns[k]].cardinality, 1); if (g > smem_groups_max) { g = -1; break; } }
+      gmax = g < 0 ? -1 : std::max(gmax, g);
+    }
+    bool ok = gmax > 0;
+    int nsum = 0;
+    for (int a = 0; a < nagg && ok; a++) {
+      const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
+      if (fn == PB200_AGG_COUNT) continue;
+      if ((fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) && (vk == VAL_DICT_I32 || vk == VAL_RAW_I32)) q.smem_slot[a] = (int8_t)nsum++;
+      else ok = false;
+    }
+    const size_t table_bytes = ok ? (size_t)gmax * 4 * (1 + 2 * nsum) : 0;
+    const long long left = (long long)ctx->max_smem_optin / ctas_per_sm - (long long)hdr_bytes - (long long)extra_bytes - 1024 - 256 - (long long)table_bytes;
+    if (ok && left >= (long long)(2 * warp_stage_bytes * cw)) {  // keep a 2-deep ring
+      q.smem_groups = (int32_t)gmax;
+      extra_bytes += table_bytes;
+    } else {
+      for (int a = 0; a < kMaxAggs; a++) q.smem_slot[a] = -1;
+    }
+  }
   {
     long long budget = (long long)ctx->max_smem_optin / ctas_per_sm - (long long)hdr_bytes - (long long)extra_bytes - 1024 - 256;
     stages = warp_stage_bytes == 0 ? 2 : (budget <= 0 ? 0 : (int)std::min<long long>(kMaxStages, budget / (long long)(warp_stage_bytes * cw)));
@@ -693,6 +725,8 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     for (int a = 0; a < nagg; a++)
       if ((q.aggs[a].function == PB200_AGG_SUM || q.aggs[a].function == PB200_AGG_AVG) && q.aggs[a].val_kind == VAL_DICT_I32) { q.defer_agg = a; break; }
   plan.smem_bytes = hdr_bytes + (size_t)cw * stages * q.stage_words * 4 + extra_bytes;
+  // the group table sits behind the rings and the generic-filter stack
+  q.smem_table_off = (uint32_t)(hdr_bytes + (size_t)cw * stages * q.stage_words * 4 + (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4));
 
   cudaStream_t st = take_stream(ctx);
   struct StreamReturn { pb200_ctx* c; cudaStream_t s; ~StreamReturn() { give_stream(c, s); } } stream_return{ctx, st};
@@ -1039,7 +1073,8 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     if (cq.total_tiles >= (1 << 30)) { set_error("too many tiles in one launch"); return PB200_E_UNSUPPORTED; }
     if (getenv("PB200_GRID")) grid = std::max(1, atoi(getenv("PB200_GRID")));
     const SegDesc* dptr = (const SegDesc*)dsegs.p + c0;
-    if (plan.group_by) le = cw == 8 ? launch_scan<8, true>(plan, cq, tt, dptr, grid, st) : cw == 7 ? launch_scan<7, true>(plan, cq, tt, dptr, grid, st) : launch_scan<6, true>(plan, cq, tt, dptr, grid, st);
+    if (plan.group_by && ctas_per_sm == 2) le = launch_scan<6, true, false, 2>(plan, cq, tt, dptr, grid, st);
+    else if (plan.group_by) le = cw == 8 ? launch_scan<8, true>(plan, cq, tt, dptr, grid, st) : cw == 7 ? launch_scan<7, true>(plan, cq, tt, dptr, grid, st) : launch_scan<6, true>(plan, cq, tt, dptr, grid, st);
     else le = cw == 8 ? (getenv("PB200_NO_DEFER") ? launch_scan<8, false, false>(plan, cq, tt, dptr, grid, st) : launch_scan<8, false>(plan, cq, tt, dptr, grid, st)) : cw == 7 ? launch_scan<7, false>(plan, cq, tt, dptr, grid, st) : launch_scan<6, false>(plan, cq, tt, dptr, grid, st);
   }
   if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }

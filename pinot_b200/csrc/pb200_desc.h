@@ -142,7 +142,13 @@ struct QueryDesc {
   uint8_t prog_arg[kMaxNodes];  // OP_LEAF: leaf index; AND/OR: operand count
   AggDesc aggs[kMaxAggs];
   int32_t total_tiles;     // CTA tiles in this launch
-  int32_t pad_tail;
+  // CTA-private group table in shared memory (group-by with a small key space and COUNT / integer SUM only): rows
+  // update it with native 32-bit shared atomics and it is merged into the global dense table once per segment.
+  // Layout at byte offset smem_table_off: count u32[G], then per summed aggregation lo u32[G], hi u32[G].
+  int32_t smem_groups;     // 0 = off, else the size G of the dense key space (max over the launch's segments)
+  uint32_t smem_table_off;
+  int8_t smem_slot[kMaxAggs];  // aggregation -> index of its (lo, hi) pair, -1: none (COUNT)
+  int8_t pad_tail[2];
 };
 
 }  // namespace pb200

@@ -160,6 +160,47 @@ __device__ __forceinline__ uint32_t ldcg_bit_u32(const uint32_t* p, uint32_t mas
                "@p ld.global.cg.b32 %0, [%1];\n\t}" : "=r"(x) : "l"(p), "r"(mask), "r"(bit), "r"(otherwise) : "memory");
   return x;
 }
+// ---- predicated (branch-free) table updates of the dense group-by path.  One divergent branch per row and table costs
+//      BSSY/BRA/BSYNC plus a branch-resolve stall each (32 rows x tables per tile); a predicated RED/ATOM keeps the 32
+//      updates of a thread straight-line and in flight together.  Predicate = (mask & bit) != 0, bit a constant.
+__device__ __forceinline__ void reds_inc_bit(uint32_t saddr, uint32_t mask, uint32_t bit) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+               "@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(saddr), "r"(mask), "r"(bit) : "memory");
+}
+// 64-bit signed add into a (lo, hi) pair of u32 words in shared memory (see smem_add64 below), predicated
+__device__ __forceinline__ void reds_add64_bit(uint32_t lo_addr, uint32_t hi_addr, uint32_t x, uint32_t mask, uint32_t bit) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b32 t, old, s, c, sx, h;\n\t"
+      "and.b32 t, %3, %4;\n\tsetp.ne.u32 p, t, 0;\n\t"
+      "mov.b32 old, 0;\n\t"
+      "@p atom.shared.add.u32 old, [%0], %2;\n\t"
+      "add.u32 s, old, %2;\n\t"
+      "setp.lt.u32 q, s, %2;\n\t"          // carry out of the low word
+      "selp.u32 c, 1, 0, q;\n\t"
+      "shr.s32 sx, %2, 31;\n\t"            // sign extension: 0 or 0xFFFFFFFF
+      "add.u32 h, sx, c;\n\t"
+      "setp.ne.and.u32 q, h, 0, p;\n\t"
+      "@q red.shared.add.u32 [%1], h;\n\t}" ::"r"(lo_addr), "r"(hi_addr), "r"(x), "r"(mask), "r"(bit)
+      : "memory");
+}
+__device__ __forceinline__ void redg_add_u64_bit(unsigned long long* p, unsigned long long v, uint32_t mask, uint32_t bit) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t"
+               "@p red.global.add.u64 [%0], %1;\n\t}" ::"l"(p), "l"(v), "r"(mask), "r"(bit) : "memory");
+}
+__device__ __forceinline__ void redg_add_f64_bit(double* p, double v, uint32_t mask, uint32_t bit) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t"
+               "@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(mask), "r"(bit) : "memory");
+}
+__device__ __forceinline__ void redg_min_u32_pred(uint32_t* p, uint32_t v, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.min.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void redg_max_u32_pred(uint32_t* p, uint32_t v, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.max.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void stg_u32_pred(uint32_t* p, uint32_t v, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pred) : "memory");
+}
+
 // Group bookkeeping of one surviving row: the exact count when some function needs it (COUNT / AVG), otherwise a
 // test-then-set "seen" flag (benign race: every writer stores 1), or nothing when a MIN/MAX table already marks groups.
 __device__ __forceinline__ void touch_group(const SegDesc& sd, uint32_t g) {
@@ -168,6 +209,15 @@ __device__ __forceinline__ void touch_group(const SegDesc& sd, uint32_t g) {
 }
 // MIN / MAX tables only change for O(log n) of a group's rows: read the current value (L2) and skip the atomic when it
 // cannot win.  A stale read only costs a redundant atomic, never a wrong result.
+// 64-bit signed accumulate into a CTA-private shared-memory table kept as two u32 words: shared 64-bit atomic adds
+// compile to a CAS spin loop (ATOMS.CAST.SPIN.64) while 32-bit ones are native, and the high word only moves on a
+// carry or a negative addend.
+__device__ __forceinline__ void smem_add64(uint32_t* lo, uint32_t* hi, uint32_t g, int x) {
+  const uint32_t xl = (uint32_t)x;
+  const uint32_t old = atomicAdd(lo + g, xl);
+  const int h = (x >> 31) + ((uint32_t)(old + xl) < xl ? 1 : 0);  // sign extension + carry out of the low word
+  if (h) atomicAdd(hi + g, (uint32_t)h);
+}
 __device__ __forceinline__ void group_min(uint32_t* p, uint32_t x) { if (x < __ldcg(p)) atomicMin(p, x); }
 __device__ __forceinline__ void group_max(uint32_t* p, uint32_t x1) { if (x1 > __ldcg(p)) atomicMax(p, x1); }
 
@@ -257,8 +307,8 @@ struct SmemHeader {
 //   [acc64: num_aggs x threads x 8 B][accmm: num_aggs x threads x 8 B]     (aggregation-only kernel)
 // acc64/accmm are the per-thread running aggregates; they live in shared memory (private slot per thread, touched once
 // per tile) instead of registers so that two CTAs fit on an SM.
-template <int W, bool GROUPBY, bool DEFER = !GROUPBY>
-__global__ void __launch_bounds__(W * 32, GROUPBY ? 1 : 2)
+template <int W, bool GROUPBY, bool DEFER = !GROUPBY, int MINB = (GROUPBY ? 1 : 2)>
+__global__ void __launch_bounds__(W * 32, MINB)
 scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTable tt, const SegDesc* __restrict__ segs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // The shared-window base is made opaque to the compiler once: otherwise every access through hdr-> / the accumulator
@@ -281,6 +331,16 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
   if (lane == 0) {
     for (int s = 0; s < q.num_stages; ++s) mbar_init(&hdr->full[warp][s], 1);
     mbar_fence_init();
+  }
+  // CTA-private group table (see QueryDesc.smem_groups)
+  uint32_t* const tcnt = reinterpret_cast<uint32_t*>(smem_base + q.smem_table_off);
+  const uint32_t TG = (uint32_t)q.smem_groups;
+  const uint32_t tcnt_s = smem_base_s + q.smem_table_off;  // shared-window address of the table
+  if (GROUPBY && TG) {
+    int nsl = 0;
+#pragma unroll
+    for (int a = 0; a < kMaxAggs; ++a) nsl = max(nsl, (int)q.smem_slot[a] + 1);
+    for (uint32_t i = threadIdx.x; i < TG * (1u + 2u * nsl); i += W * 32) tcnt[i] = 0u;
   }
   if (threadIdx.x < kMaxAggs) hdr->aggs[threadIdx.x] = q.aggs[threadIdx.x];
   if (threadIdx.x < kMaxSlots) hdr->slot_roles[threadIdx.x] = q.slot_roles[threadIdx.x];
@@ -405,6 +465,25 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     }
   };
   reset_acc();
+  // merges the CTA-private group table into the segment's dense global table and clears it (whole CTA, between barriers)
+  auto table_flush = [&]() {
+    for (uint32_t g = threadIdx.x; g < TG; g += W * 32) {
+      const uint32_t c = tcnt[g];
+      if (c == 0u) continue;
+      tcnt[g] = 0u;
+      if (sd.g_count) atomicAdd(sd.g_count + g, (unsigned long long)c);
+      else if (sd.g_seen) sd.g_seen[g] = 1u;
+#pragma unroll
+      for (int a = 0; a < kMaxAggs; ++a) {
+        const int k = q.smem_slot[a];
+        if (k < 0 || a >= q.num_aggs) continue;
+        uint32_t* lo = tcnt + TG * (1u + 2u * k);
+        const unsigned long long v = (unsigned long long)lo[g] | (unsigned long long)lo[TG + g] << 32;
+        lo[g] = 0u; lo[TG + g] = 0u;
+        atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + g), v);
+      }
+    }
+  };
 
   int sidx = -1, stage = 0, c_first = 0, c_end = 0;
   uint32_t phase = 0, c_docs = 0;
@@ -415,6 +494,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
       while (T >= tt.seg[ns].end_tile) ++ns;
       if (sidx >= 0) flush();
       consumer_bar_sync(kConsumers);  // everyone done reading the old descriptor
+      if (GROUPBY && TG && sidx >= 0) { table_flush(); consumer_bar_sync(kConsumers); }
       const uint32_t* src = reinterpret_cast<const uint32_t*>(segs + ns);
       uint32_t* dstw = reinterpret_cast<uint32_t*>(&hdr->seg);
       for (int i = threadIdx.x; i < (int)(sizeof(SegDesc) / 4); i += kConsumers) dstw[i] = __ldg(src + i);
@@ -561,7 +641,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
               g += read_one_group(st + sl.stage_words + group_in_stage * sl.bits, j, sl.bits) * sd.group_mult[gi];
             }
           }
-          touch_group(sd, g);
+          if (TG) atomicAdd(tcnt + g, 1u); else touch_group(sd, g);
         }
 #pragma unroll 1
         for (int ai = 0; ai < sd.num_agg_codes; ++ai) {
@@ -580,7 +660,8 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
               const long long x = vk == VAL_DICT_I32 ? (long long)(int)(__ldg(static_cast<const uint32_t*>(sd.dict[a]) + id) ^ 0x80000000u)
                                   : vk == VAL_DICT_I64 ? __ldg(static_cast<const long long*>(sd.dict[a]) + id)
                                                        : (long long)(int)id;
-              if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + g), (unsigned long long)x);
+              if (GROUPBY && TG) { uint32_t* lo = tcnt + TG * (1u + 2u * q.smem_slot[a]); smem_add64(lo, lo + TG, g, (int)x); }
+              else if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + g), (unsigned long long)x);
               else acc64[a * kConsumers + group] += (unsigned long long)x;
             }
           } else if (fn == 2 || fn == 3) {
@@ -686,17 +767,20 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
             }
           }
         }
-        if (sd.g_count) {
+        if (TG) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if ((m >> j) & 1u) atomicAdd(sd.g_count + gid[j], 1ull);
+          for (int j = 0; j < 32; ++j) reds_inc_bit(tcnt_s + 4u * gid[j], m, 1u << j);
+        } else if (sd.g_count) {
+          unsigned long long* const gc = sd.g_count;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) redg_add_u64_bit(gc + gid[j], 1ull, m, 1u << j);
         } else if (sd.g_seen) {  // test-then-set flags: all tests first (one L2 latency), then the few stores
+          uint32_t* const gs = sd.g_seen;
           uint32_t cur[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cur[j] = ldcg_bit_u32(sd.g_seen + gid[j], m, 1u << j, 1u);
+          for (int j = 0; j < 32; ++j) cur[j] = ldcg_bit_u32(gs + gid[j], m, 1u << j, 1u);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cur[j] == 0u) sd.g_seen[gid[j]] = 1u;
+          for (int j = 0; j < 32; ++j) stg_u32_pred(gs + gid[j], 1u, cur[j] == 0u ? 1u : 0u);
         }
 #pragma unroll 1
         for (int ai = 0; ai < sd.num_agg_codes; ++ai) {
@@ -713,38 +797,50 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
               uint32_t xv[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) xv[j] = ldg_bit_u32(d + v[j], m, 1u << j);  // straight-line: 32 loads in flight
+              if (TG) {
+                const uint32_t lo_s = tcnt_s + 4u * TG * (1u + 2u * q.smem_slot[a]), hi_s = lo_s + 4u * TG;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if ((m >> j) & 1u)
-                  atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)(long long)(int)(xv[j] ^ 0x80000000u));
+                for (int j = 0; j < 32; ++j) reds_add64_bit(lo_s + 4u * gid[j], hi_s + 4u * gid[j], xv[j] ^ 0x80000000u, m, 1u << j);
+              } else {
+                unsigned long long* const gsum = reinterpret_cast<unsigned long long*>(sd.g_isum[a]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  redg_add_u64_bit(gsum + gid[j], (unsigned long long)(long long)(int)(xv[j] ^ 0x80000000u), m, 1u << j);
+              }
             } else if (vk == VAL_RAW_I32) {
+              if (TG) {
+                const uint32_t lo_s = tcnt_s + 4u * TG * (1u + 2u * q.smem_slot[a]), hi_s = lo_s + 4u * TG;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if ((m >> j) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)(long long)(int)v[j]);
+                for (int j = 0; j < 32; ++j) reds_add64_bit(lo_s + 4u * gid[j], hi_s + 4u * gid[j], v[j], m, 1u << j);
+              } else {
+                unsigned long long* const gsum = reinterpret_cast<unsigned long long*>(sd.g_isum[a]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) redg_add_u64_bit(gsum + gid[j], (unsigned long long)(long long)(int)v[j], m, 1u << j);
+              }
             } else if (vk == VAL_DICT_I64) {
               const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
               long long xv[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) xv[j] = ldg_pred_s64(d + v[j], (m >> j) & 1u);
+              unsigned long long* const gsum = reinterpret_cast<unsigned long long*>(sd.g_isum[a]);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if ((m >> j) & 1u) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + gid[j]), (unsigned long long)xv[j]);
+              for (int j = 0; j < 32; ++j) redg_add_u64_bit(gsum + gid[j], (unsigned long long)xv[j], m, 1u << j);
             } else if (vk == VAL_DICT_F32) {
               const float* __restrict__ d = static_cast<const float*>(sd.dict[a]);
               float xv[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) xv[j] = __int_as_float(ldg_pred_s32(reinterpret_cast<const int*>(d + v[j]), (m >> j) & 1u));
+              double* const gd = sd.g_dsum[a];
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], (double)xv[j]);
+              for (int j = 0; j < 32; ++j) redg_add_f64_bit(gd + gid[j], (double)xv[j], m, 1u << j);
             } else {
               const double* __restrict__ d = static_cast<const double*>(sd.dict[a]);
               double xv[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) xv[j] = __longlong_as_double(ldg_pred_s64(reinterpret_cast<const long long*>(d + v[j]), (m >> j) & 1u));
+              double* const gd = sd.g_dsum[a];
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if ((m >> j) & 1u) atomicAdd(sd.g_dsum[a] + gid[j], xv[j]);
+              for (int j = 0; j < 32; ++j) redg_add_f64_bit(gd + gid[j], xv[j], m, 1u << j);
             }
           } else if (fn == 2 || fn == 3) {
             // MIN / MAX tables change for only O(log n) of a group's rows: read the current entries of the whole tile
@@ -754,11 +850,12 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
             uint32_t cur[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) cur[j] = ldcg_bit_u32(tab + gid[j], m, 1u << j, fn == 2 ? 0u : 0xFFFFFFFFu);
+            if (fn == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const uint32_t x = v[j] ^ bias;
-              if (fn == 2) { if (x < cur[j]) atomicMin(tab + gid[j], x); }
-              else { if (x + 1u > cur[j]) atomicMax(tab + gid[j], x + 1u); }
+              for (int j = 0; j < 32; ++j) { const uint32_t x = v[j] ^ bias; redg_min_u32_pred(tab + gid[j], x, x < cur[j] ? 1u : 0u); }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { const uint32_t x = (v[j] ^ bias) + 1u; redg_max_u32_pred(tab + gid[j], x, x > cur[j] ? 1u : 0u); }
             }
           }
         }
@@ -772,6 +869,10 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     }
   }
   if (sidx >= 0) flush();
+  if (GROUPBY && TG) {
+    consumer_bar_sync(kConsumers);  // every warp's rows are in the table
+    if (sidx >= 0) table_flush();
+  }
 }
 
 }  // namespace pb200

@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--rows", type=int, default=100_000_000)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--mode", default="bitmap", choices=["bitmap", "range", "range2"])
+    ap.add_argument("--mode", default="bitmap", choices=["bitmap", "range", "range2", "range3"])
     ap.add_argument("--check-rows", type=int, default=0, help="also verify against the oracle on a small segment")
     args = ap.parse_args()
 
@@ -49,6 +49,9 @@ def main():
     elif args.mode == "range":
         text = "SELECT SUM(m), COUNT(*) FROM t WHERE f BETWEEN 3002 AND 5999 GROUP BY g"             # 10 %
         bits = 14 + 14 + 17
+    elif args.mode == "range3":
+        text = "SELECT SUM(m), COUNT(*) FROM t WHERE f BETWEEN 3002 AND 5999 GROUP BY g2"                 # 100 groups
+        bits = 14 + 7 + 17
     else:
         text = "SELECT SUM(m), MAX(f), COUNT(*) FROM t WHERE f BETWEEN 3002 AND 5999 GROUP BY g, g2"  # 1M-group key space
         bits = 14 + 14 + 7 + 17
