@@ -668,6 +668,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   int cw = plan.group_by ? 8 : 6, stages = 0, ctas_per_sm = 1;
   if (getenv("PB200_W")) { int w = atoi(getenv("PB200_W")); if (w == 6 || w == 7 || w == 8) cw = w; }  // tuning knob
   q.sparse_max = getenv("PB200_SPARSE_MAX") ? atoi(getenv("PB200_SPARSE_MAX")) : 4;
+  q.sparse_max_agg = getenv("PB200_SPARSE_MAX_AGG") ? atoi(getenv("PB200_SPARSE_MAX_AGG")) : (plan.group_by ? std::min(q.sparse_max, 2) : q.sparse_max);
   ctas_per_sm = plan.group_by ? 1 : 2;
   if (getenv("PB200_CTAS")) ctas_per_sm = std::max(1, atoi(getenv("PB200_CTAS")));
   if (plan.group_by && ctas_per_sm >= 2) { ctas_per_sm = 2; cw = 6; }  // experiment: two 192-thread group-by CTAs per SM

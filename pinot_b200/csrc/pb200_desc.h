@@ -129,6 +129,7 @@ struct QueryDesc {
   int32_t num_nodes;       // program length; 0 = match all
   int32_t conj;            // 1: root is a flat AND (or single leaf) of leaves -> no stack
   int32_t sparse_max;      // per-row probing instead of unpacking when <= this many rows per thread survive
+  int32_t sparse_max_agg;  // same decision for the projection / aggregation phase
   int32_t defer_agg;       // aggregation whose dictionary gathers are software-pipelined across tiles (-1: none)
   int32_t num_aggs;
   int32_t num_group_by;

@@ -225,29 +225,38 @@ __device__ __forceinline__ void group_max(uint32_t* p, uint32_t x1) { if (x1 > _
 // streaming functors for dispatch_left_aligned(): consume one left-aligned value at a time (pb200_unpack.cuh)
 // ------------------------------------------------------------------------------------------------------------------
 // dictId range predicate -> 32-bit row mask.  Four partial masks keep the OR chain short (ILP).
-struct RangeBoth {   // lo <= v < hi   as   (xl - LO) < SPAN,  LO = lo << (32-B), SPAN = (hi-lo) << (32-B)
-  uint32_t LO, SPAN, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-  __device__ __forceinline__ void operator()(int j, uint32_t xl) {
-    const uint32_t bit = ((xl - LO) < SPAN) ? (1u << j) : 0u;
-    if ((j & 3) == 0) m0 |= bit; else if ((j & 3) == 1) m1 |= bit; else if ((j & 3) == 2) m2 |= bit; else m3 |= bit;
+// Mask building through the carry flag: compare = one subtract that leaves the borrow in CC.CF, and `addc m, m, m`
+// shifts it into the mask (m = 2m + CF) -- 2 instructions per value (IADD3 + IADD3.X) instead of ISETP + SEL + OR.
+// Four chains of 8 values (rows 8k .. 8k+7 in chain k, first row in the chain's highest bit) keep the adds independent;
+// the chains are concatenated and bit-reversed once per leaf.
+__device__ __forceinline__ void borrow_into(uint32_t& m, uint32_t a, uint32_t b) {  // m = 2m + (a < b)
+  asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, %0;\n\t}" : "+r"(m) : "r"(a), "r"(b));
+}
+struct CarryMask {
+  uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  __device__ __forceinline__ void push(int j, uint32_t a, uint32_t b) {
+    if (j < 8) borrow_into(c0, a, b); else if (j < 16) borrow_into(c1, a, b); else if (j < 24) borrow_into(c2, a, b); else borrow_into(c3, a, b);
   }
-  __device__ __forceinline__ uint32_t mask() const { return (m0 | m1) | (m2 | m3); }
+  // bit j = (a_j < b_j)
+  __device__ __forceinline__ uint32_t lt_mask() const { return __brev((c0 << 24) | (c1 << 16) | (c2 << 8) | c3); }
+};
+struct RangeBoth {   // lo <= v < hi   as   (xl - LO) < SPAN,  LO = lo << (32-B), SPAN = (hi-lo) << (32-B)
+  uint32_t LO, SPAN;
+  CarryMask cm;
+  __device__ __forceinline__ void operator()(int j, uint32_t xl) { cm.push(j, xl - LO, SPAN); }
+  __device__ __forceinline__ uint32_t mask() const { return cm.lt_mask(); }
 };
 struct RangeGE {     // v >= lo  (upper bound is the whole dictionary: every stored dictId is < cardinality)
-  uint32_t LO, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-  __device__ __forceinline__ void operator()(int j, uint32_t xl) {
-    const uint32_t bit = (xl >= LO) ? (1u << j) : 0u;
-    if ((j & 3) == 0) m0 |= bit; else if ((j & 3) == 1) m1 |= bit; else if ((j & 3) == 2) m2 |= bit; else m3 |= bit;
-  }
-  __device__ __forceinline__ uint32_t mask() const { return (m0 | m1) | (m2 | m3); }
+  uint32_t LO;
+  CarryMask cm;
+  __device__ __forceinline__ void operator()(int j, uint32_t xl) { cm.push(j, xl, LO); }
+  __device__ __forceinline__ uint32_t mask() const { return ~cm.lt_mask(); }
 };
 struct RangeLT {     // v < hi  (lower bound 0)
-  uint32_t HI, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-  __device__ __forceinline__ void operator()(int j, uint32_t xl) {
-    const uint32_t bit = (xl < HI) ? (1u << j) : 0u;
-    if ((j & 3) == 0) m0 |= bit; else if ((j & 3) == 1) m1 |= bit; else if ((j & 3) == 2) m2 |= bit; else m3 |= bit;
-  }
-  __device__ __forceinline__ uint32_t mask() const { return (m0 | m1) | (m2 | m3); }
+  uint32_t HI;
+  CarryMask cm;
+  __device__ __forceinline__ void operator()(int j, uint32_t xl) { cm.push(j, xl, HI); }
+  __device__ __forceinline__ uint32_t mask() const { return cm.lt_mask(); }
 };
 // SUM over an INT dictionary: gather the BIASED value (value ^ 0x80000000, i.e. value + 2^31 as unsigned) of every
 // surviving row and add pairs with one 3-input 64-bit add; the bias is removed once per tile (popc * 2^31).
@@ -625,7 +634,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     const int pc = __popc(m);
     cnt += pc;
     const int wmax2 = __reduce_max_sync(0xFFFFFFFFu, pc);
-    if (wmax2 > 0 && wmax2 <= (GROUPBY ? min(q.sparse_max, 2) : q.sparse_max)) {
+    if (wmax2 > 0 && wmax2 <= q.sparse_max_agg) {
       // ---- sparse projection: per surviving row, read its dictIds from the tile (FixedBitIntReader.readUnchecked
       //      shape; what DataFetcher does with sparse docIds, core/common/DataFetcher.java:335-338) ----
       uint32_t mm = m;
