@@ -365,13 +365,23 @@ def main():
                "sample": f"{cores} work items x {sample_rows} rows (prefixes of this run's segments), {cores} threads, "
                          "C++ restatement of the Java operator chain (oracle/); no JVM in the image"}
 
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the scan kernel, from the committed `ncu --set full`
+    # capture of this same workload (profiles/): only quoted when this run IS that workload
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_c2_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("segments") == args.segments and tj.get("rows_per_segment") == args.rows and abs(tj.get("selectivity", -1) - args.selectivity) < 1e-9:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "pb200::scan_kernel<6,false>", "kernel_ms": k_ms,
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                             "peak_source": peak_src,
+                             "kernel": "pb200::scan_kernel<6,false> (W=6 warps, 2 CTAs/SM)", "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": rows_per_step * bpr},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d,

@@ -696,11 +696,18 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       if ((fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) && (vk == VAL_DICT_I32 || vk == VAL_RAW_I32)) q.smem_slot[a] = (int8_t)nsum++;
       else ok = false;
     }
-    const size_t table_bytes = ok ? (size_t)gmax * 4 * (1 + 2 * nsum) : 0;
-    const long long left = (long long)ctx->max_smem_optin / ctas_per_sm - (long long)hdr_bytes - (long long)extra_bytes - 1024 - 256 - (long long)table_bytes;
-    if (ok && left >= (long long)(2 * warp_stage_bytes * cw)) {  // keep a 2-deep ring
+    const long long gstride = gmax | 1;
+    const size_t copy_bytes = ok ? (size_t)gstride * 4 * (1 + 2 * nsum) : 0;
+    // room left after a 2-deep ring; the table may take at most 64 KB of it
+    const long long room = (long long)ctx->max_smem_optin / ctas_per_sm - (long long)hdr_bytes - (long long)extra_bytes - 1024 - 256 - (long long)(2 * warp_stage_bytes * cw);
+    if (ok && room >= (long long)copy_bytes) {
+      int copies = 1;
+      while (copies < 32 && (long long)copy_bytes * copies * 2 <= std::min<long long>(room, 64 << 10)) copies *= 2;
+      if (getenv("PB200_SMEM_COPIES")) copies = std::max(1, std::min(copies, atoi(getenv("PB200_SMEM_COPIES"))));
       q.smem_groups = (int32_t)gmax;
-      extra_bytes += table_bytes;
+      q.smem_copies = copies;
+      q.smem_gstride = (int32_t)gstride;
+      extra_bytes += copy_bytes * copies;
     } else {
       for (int a = 0; a < kMaxAggs; a++) q.smem_slot[a] = -1;
     }

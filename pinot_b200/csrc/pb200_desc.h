@@ -148,6 +148,11 @@ struct QueryDesc {
   // Layout at byte offset smem_table_off: count u32[G], then per summed aggregation lo u32[G], hi u32[G].
   int32_t smem_groups;     // 0 = off, else the size G of the dense key space (max over the launch's segments)
   uint32_t smem_table_off;
+  // the table is replicated `smem_copies` (power of two) times, lane l updates copy l % copies: same-address conflicts
+  // inside a warp (the norm for a handful of groups) drop by that factor; each array is smem_copies * smem_gstride words,
+  // entry of (copy c, group g) at c * smem_gstride + g; smem_gstride is odd so that the copies start in different banks
+  int32_t smem_copies;
+  int32_t smem_gstride;
   int8_t smem_slot[kMaxAggs];  // aggregation -> index of its (lo, hi) pair, -1: none (COUNT)
   int8_t pad_tail[2];
 };

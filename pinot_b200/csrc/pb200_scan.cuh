@@ -224,39 +224,41 @@ __device__ __forceinline__ void group_max(uint32_t* p, uint32_t x1) { if (x1 > _
 // ------------------------------------------------------------------------------------------------------------------
 // streaming functors for dispatch_left_aligned(): consume one left-aligned value at a time (pb200_unpack.cuh)
 // ------------------------------------------------------------------------------------------------------------------
-// dictId range predicate -> 32-bit row mask.  Four partial masks keep the OR chain short (ILP).
-// Mask building through the carry flag: compare = one subtract that leaves the borrow in CC.CF, and `addc m, m, m`
-// shifts it into the mask (m = 2m + CF) -- 2 instructions per value (IADD3 + IADD3.X) instead of ISETP + SEL + OR.
+// dictId range predicate -> 32-bit row mask.
+// Mask building through the carry flag: compare = one subtract whose carry-out lands in CC.CF, and `addc m, m, m`
+// shifts it into the mask (m = 2m + CF) -- 2 instructions per value (IADD3 + IMAD.X, the second one on the FMA pipe)
+// instead of ISETP + SEL + OR.  After `sub.cc.u32 t, a, b` ptxas / sm_100a leave CF = 1 iff there was NO borrow, i.e.
+// a >= b (the hardware carry of a + ~b + 1; measured by tests/workloads/cc_probe and guarded by every parity test).
 // Four chains of 8 values (rows 8k .. 8k+7 in chain k, first row in the chain's highest bit) keep the adds independent;
 // the chains are concatenated and bit-reversed once per leaf.
-__device__ __forceinline__ void borrow_into(uint32_t& m, uint32_t a, uint32_t b) {  // m = 2m + (a < b)
+__device__ __forceinline__ void ge_into(uint32_t& m, uint32_t a, uint32_t b) {  // m = 2m + (a >= b)
   asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, %0;\n\t}" : "+r"(m) : "r"(a), "r"(b));
 }
 struct CarryMask {
   uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
   __device__ __forceinline__ void push(int j, uint32_t a, uint32_t b) {
-    if (j < 8) borrow_into(c0, a, b); else if (j < 16) borrow_into(c1, a, b); else if (j < 24) borrow_into(c2, a, b); else borrow_into(c3, a, b);
+    if (j < 8) ge_into(c0, a, b); else if (j < 16) ge_into(c1, a, b); else if (j < 24) ge_into(c2, a, b); else ge_into(c3, a, b);
   }
-  // bit j = (a_j < b_j)
-  __device__ __forceinline__ uint32_t lt_mask() const { return __brev((c0 << 24) | (c1 << 16) | (c2 << 8) | c3); }
+  // bit j = (a_j >= b_j)
+  __device__ __forceinline__ uint32_t ge_mask() const { return __brev((c0 << 24) | (c1 << 16) | (c2 << 8) | c3); }
 };
 struct RangeBoth {   // lo <= v < hi   as   (xl - LO) < SPAN,  LO = lo << (32-B), SPAN = (hi-lo) << (32-B)
   uint32_t LO, SPAN;
   CarryMask cm;
   __device__ __forceinline__ void operator()(int j, uint32_t xl) { cm.push(j, xl - LO, SPAN); }
-  __device__ __forceinline__ uint32_t mask() const { return cm.lt_mask(); }
+  __device__ __forceinline__ uint32_t mask() const { return ~cm.ge_mask(); }
 };
 struct RangeGE {     // v >= lo  (upper bound is the whole dictionary: every stored dictId is < cardinality)
   uint32_t LO;
   CarryMask cm;
   __device__ __forceinline__ void operator()(int j, uint32_t xl) { cm.push(j, xl, LO); }
-  __device__ __forceinline__ uint32_t mask() const { return ~cm.lt_mask(); }
+  __device__ __forceinline__ uint32_t mask() const { return cm.ge_mask(); }
 };
 struct RangeLT {     // v < hi  (lower bound 0)
   uint32_t HI;
   CarryMask cm;
   __device__ __forceinline__ void operator()(int j, uint32_t xl) { cm.push(j, xl, HI); }
-  __device__ __forceinline__ uint32_t mask() const { return cm.lt_mask(); }
+  __device__ __forceinline__ uint32_t mask() const { return ~cm.ge_mask(); }
 };
 // SUM over an INT dictionary: gather the BIASED value (value ^ 0x80000000, i.e. value + 2^31 as unsigned) of every
 // surviving row and add pairs with one 3-input 64-bit add; the bias is removed once per tile (popc * 2^31).
@@ -344,12 +346,14 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
   // CTA-private group table (see QueryDesc.smem_groups)
   uint32_t* const tcnt = reinterpret_cast<uint32_t*>(smem_base + q.smem_table_off);
   const uint32_t TG = (uint32_t)q.smem_groups;
-  const uint32_t tcnt_s = smem_base_s + q.smem_table_off;  // shared-window address of the table
+  const uint32_t TA = (uint32_t)(q.smem_copies * q.smem_gstride);                  // words per table array (all copies)
+  const uint32_t tcopy = (uint32_t)((threadIdx.x & (q.smem_copies - 1)) * q.smem_gstride);  // this lane's copy
+  const uint32_t tcnt_s = smem_base_s + q.smem_table_off + 4u * tcopy;             // shared-window address, lane's copy
   if (GROUPBY && TG) {
     int nsl = 0;
 #pragma unroll
     for (int a = 0; a < kMaxAggs; ++a) nsl = max(nsl, (int)q.smem_slot[a] + 1);
-    for (uint32_t i = threadIdx.x; i < TG * (1u + 2u * nsl); i += W * 32) tcnt[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < TA * (1u + 2u * nsl); i += W * 32) tcnt[i] = 0u;
   }
   if (threadIdx.x < kMaxAggs) hdr->aggs[threadIdx.x] = q.aggs[threadIdx.x];
   if (threadIdx.x < kMaxSlots) hdr->slot_roles[threadIdx.x] = q.slot_roles[threadIdx.x];
@@ -477,18 +481,22 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
   // merges the CTA-private group table into the segment's dense global table and clears it (whole CTA, between barriers)
   auto table_flush = [&]() {
     for (uint32_t g = threadIdx.x; g < TG; g += W * 32) {
-      const uint32_t c = tcnt[g];
+      uint32_t c = 0;
+      for (int r = 0; r < q.smem_copies; ++r) { c += tcnt[r * q.smem_gstride + g]; tcnt[r * q.smem_gstride + g] = 0u; }
       if (c == 0u) continue;
-      tcnt[g] = 0u;
       if (sd.g_count) atomicAdd(sd.g_count + g, (unsigned long long)c);
       else if (sd.g_seen) sd.g_seen[g] = 1u;
 #pragma unroll
       for (int a = 0; a < kMaxAggs; ++a) {
         const int k = q.smem_slot[a];
         if (k < 0 || a >= q.num_aggs) continue;
-        uint32_t* lo = tcnt + TG * (1u + 2u * k);
-        const unsigned long long v = (unsigned long long)lo[g] | (unsigned long long)lo[TG + g] << 32;
-        lo[g] = 0u; lo[TG + g] = 0u;
+        uint32_t* lo = tcnt + TA * (1u + 2u * k);
+        unsigned long long v = 0;
+        for (int r = 0; r < q.smem_copies; ++r) {
+          const uint32_t i = r * q.smem_gstride + g;
+          v += (unsigned long long)lo[i] | (unsigned long long)lo[TA + i] << 32;
+          lo[i] = 0u; lo[TA + i] = 0u;
+        }
         atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + g), v);
       }
     }
@@ -650,7 +658,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
               g += read_one_group(st + sl.stage_words + group_in_stage * sl.bits, j, sl.bits) * sd.group_mult[gi];
             }
           }
-          if (TG) atomicAdd(tcnt + g, 1u); else touch_group(sd, g);
+          if (TG) atomicAdd(tcnt + tcopy + g, 1u); else touch_group(sd, g);
         }
 #pragma unroll 1
         for (int ai = 0; ai < sd.num_agg_codes; ++ai) {
@@ -669,7 +677,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
               const long long x = vk == VAL_DICT_I32 ? (long long)(int)(__ldg(static_cast<const uint32_t*>(sd.dict[a]) + id) ^ 0x80000000u)
                                   : vk == VAL_DICT_I64 ? __ldg(static_cast<const long long*>(sd.dict[a]) + id)
                                                        : (long long)(int)id;
-              if (GROUPBY && TG) { uint32_t* lo = tcnt + TG * (1u + 2u * q.smem_slot[a]); smem_add64(lo, lo + TG, g, (int)x); }
+              if (GROUPBY && TG) { uint32_t* lo = tcnt + tcopy + TA * (1u + 2u * q.smem_slot[a]); smem_add64(lo, lo + TA, g, (int)x); }
               else if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + g), (unsigned long long)x);
               else acc64[a * kConsumers + group] += (unsigned long long)x;
             }
@@ -807,7 +815,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 #pragma unroll
               for (int j = 0; j < 32; ++j) xv[j] = ldg_bit_u32(d + v[j], m, 1u << j);  // straight-line: 32 loads in flight
               if (TG) {
-                const uint32_t lo_s = tcnt_s + 4u * TG * (1u + 2u * q.smem_slot[a]), hi_s = lo_s + 4u * TG;
+                const uint32_t lo_s = tcnt_s + 4u * TA * (1u + 2u * q.smem_slot[a]), hi_s = lo_s + 4u * TA;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) reds_add64_bit(lo_s + 4u * gid[j], hi_s + 4u * gid[j], xv[j] ^ 0x80000000u, m, 1u << j);
               } else {
@@ -818,7 +826,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
               }
             } else if (vk == VAL_RAW_I32) {
               if (TG) {
-                const uint32_t lo_s = tcnt_s + 4u * TG * (1u + 2u * q.smem_slot[a]), hi_s = lo_s + 4u * TG;
+                const uint32_t lo_s = tcnt_s + 4u * TA * (1u + 2u * q.smem_slot[a]), hi_s = lo_s + 4u * TA;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) reds_add64_bit(lo_s + 4u * gid[j], hi_s + 4u * gid[j], v[j], m, 1u << j);
               } else {
