@@ -673,7 +673,8 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   if (getenv("PB200_CTAS")) ctas_per_sm = std::max(1, atoi(getenv("PB200_CTAS")));
   if (plan.group_by && ctas_per_sm >= 2) { ctas_per_sm = 2; cw = 6; }  // experiment: two 192-thread group-by CTAs per SM
   const size_t warp_stage_bytes = (size_t)128 * max_bits_sum;
-  size_t extra_bytes = (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4) + (plan.group_by ? 0 : (size_t)nagg * cw * 32 * 16);
+  size_t extra_bytes = (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4) + (plan.group_by ? (size_t)cw * 2048 : (size_t)nagg * cw * 32 * 16);
+  q.queue_max = !plan.group_by ? 0 : getenv("PB200_QUEUE_MAX") ? atoi(getenv("PB200_QUEUE_MAX")) : 512;
   // CTA-private group tables in shared memory when the key space is small and every function is COUNT or an integer SUM
   q.smem_groups = 0;
   for (int a = 0; a < kMaxAggs; a++) q.smem_slot[a] = -1;
@@ -734,7 +735,8 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       if ((q.aggs[a].function == PB200_AGG_SUM || q.aggs[a].function == PB200_AGG_AVG) && q.aggs[a].val_kind == VAL_DICT_I32) { q.defer_agg = a; break; }
   plan.smem_bytes = hdr_bytes + (size_t)cw * stages * q.stage_words * 4 + extra_bytes;
   // the group table sits behind the rings and the generic-filter stack
-  q.smem_table_off = (uint32_t)(hdr_bytes + (size_t)cw * stages * q.stage_words * 4 + (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4));
+  q.queue_off = (uint32_t)(hdr_bytes + (size_t)cw * stages * q.stage_words * 4 + (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4));
+  q.smem_table_off = q.queue_off + (plan.group_by ? (uint32_t)cw * 2048u : 0u);
 
   cudaStream_t st = take_stream(ctx);
   struct StreamReturn { pb200_ctx* c; cudaStream_t s; ~StreamReturn() { give_stream(c, s); } } stream_return{ctx, st};

@@ -153,6 +153,9 @@ struct QueryDesc {
   // entry of (copy c, group g) at c * smem_gstride + g; smem_gstride is odd so that the copies start in different banks
   int32_t smem_copies;
   int32_t smem_gstride;
+  // group-by survivor queue: u16[1024] per warp at byte offset queue_off; used when a warp slice has <= queue_max survivors
+  uint32_t queue_off;
+  int32_t queue_max;
   int8_t smem_slot[kMaxAggs];  // aggregation -> index of its (lo, hi) pair, -1: none (COUNT)
   int8_t pad_tail[2];
 };
