@@ -24,6 +24,11 @@
 
 namespace pb200 {
 
+// The group-by kernel aggregates through the warp survivor queue (see phase 2).  The older "dense" path -- 32 keys, 32
+// gathered values and 32 predicated reductions per thread and tile -- needs ~100 more registers (one CTA per SM) and
+// ptxas turns its predicated RED/ATOM instructions into one branch each; it is kept for experiments only.
+constexpr bool kDenseGroupByPath = false;
+
 // ------------------------------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy primitives (PTX ISA 8.x; SASS: SYNCS.*, UBLKCP)
 // ------------------------------------------------------------------------------------------------------------------
@@ -190,6 +195,12 @@ __device__ __forceinline__ void redg_add_u64_bit(unsigned long long* p, unsigned
 __device__ __forceinline__ void redg_add_f64_bit(double* p, double v, uint32_t mask, uint32_t bit) {
   asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t"
                "@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(mask), "r"(bit) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 __device__ __forceinline__ void redg_min_u32_pred(uint32_t* p, uint32_t v, uint32_t pred) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.min.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pred) : "memory");
@@ -697,7 +708,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
       const int S = __shfl_sync(0xFFFFFFFFu, incl, 31);
       if (S == 0) handled = true;
-      else if (S <= q.queue_max) {
+      else if (S <= q.queue_max || !kDenseGroupByPath) {
         unsigned short* wq = reinterpret_cast<unsigned short*>(smem_base + q.queue_off) + warp * 1024;
         int pos = incl - pc;
         uint32_t mm = m;
@@ -707,9 +718,88 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
           wq[pos++] = (unsigned short)((lane << 5) | j);
         }
         __syncwarp();
-        for (int i = lane; i < S; i += 32) {
-          const uint32_t e = wq[i];
-          process_row((int)(e >> 5), (int)(e & 31u));
+        // kQB queue entries per lane and step: their smem probes, dictionary gathers and table updates are issued as
+        // groups (all keys, all gathers, all reductions) so that kQB latency chains overlap instead of running back to back
+        constexpr int kQB = 4;
+        for (int i0 = lane; i0 < S; i0 += 32 * kQB) {
+          uint32_t e[kQB], g[kQB];
+          bool ok[kQB];
+#pragma unroll
+          for (int u = 0; u < kQB; ++u) { ok[u] = i0 + 32 * u < S; e[u] = ok[u] ? (uint32_t)wq[i0 + 32 * u] : 0u; g[u] = 0u; }
+#pragma unroll
+          for (int gi = 0; gi < kMaxGroupBy; ++gi) {
+            if (gi < q.num_group_by) {
+              const SlotDesc& sl = sd.slots[q.group_slot[gi]];
+              const uint32_t* gb = st + sl.stage_words;
+              const uint32_t mult = sd.group_mult[gi];
+#pragma unroll
+              for (int u = 0; u < kQB; ++u) g[u] += read_one_group(gb + (e[u] >> 5) * sl.bits, (int)(e[u] & 31u), sl.bits) * mult;
+            }
+          }
+          if (TG) {
+#pragma unroll
+            for (int u = 0; u < kQB; ++u) if (ok[u]) atomicAdd(tcnt + tcopy + g[u], 1u);
+          } else if (sd.g_count) {
+#pragma unroll
+            for (int u = 0; u < kQB; ++u) if (ok[u]) red_add_u64(sd.g_count + g[u], 1ull);
+          } else if (sd.g_seen) {
+            uint32_t cur[kQB];
+#pragma unroll
+            for (int u = 0; u < kQB; ++u) cur[u] = ok[u] ? __ldcg(sd.g_seen + g[u]) : 1u;
+#pragma unroll
+            for (int u = 0; u < kQB; ++u) if (cur[u] == 0u) sd.g_seen[g[u]] = 1u;
+          }
+#pragma unroll 1
+          for (int ai = 0; ai < sd.num_agg_codes; ++ai) {
+            const uint32_t ac = sd.agg_code[ai];  // index | function | value kind | bits | stage_words (pb200_desc.h)
+            const int a = (int)(ac & 7u), fn = (int)((ac >> 4) & 7u), vk = (int)((ac >> 8) & 7u);
+            const int abits = (int)((ac >> 12) & 63u);
+            const uint32_t* base = st + (ac >> 18);
+            uint32_t id[kQB];
+#pragma unroll
+            for (int u = 0; u < kQB; ++u) id[u] = read_one_group(base + (e[u] >> 5) * abits, (int)(e[u] & 31u), abits);
+            if (fn == 1 || fn == 4) {
+              if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
+                double x[kQB];
+#pragma unroll
+                for (int u = 0; u < kQB; ++u)
+                  x[u] = vk == VAL_DICT_F32 ? (double)__ldg(static_cast<const float*>(sd.dict[a]) + id[u])
+                                            : __ldg(static_cast<const double*>(sd.dict[a]) + id[u]);
+#pragma unroll
+                for (int u = 0; u < kQB; ++u) if (ok[u]) red_add_f64(sd.g_dsum[a] + g[u], x[u]);
+              } else {
+                long long x[kQB];
+#pragma unroll
+                for (int u = 0; u < kQB; ++u)
+                  x[u] = vk == VAL_DICT_I32 ? (long long)(int)(__ldg(static_cast<const uint32_t*>(sd.dict[a]) + id[u]) ^ 0x80000000u)
+                         : vk == VAL_DICT_I64 ? __ldg(static_cast<const long long*>(sd.dict[a]) + id[u])
+                                              : (long long)(int)id[u];
+                if (TG) {
+                  uint32_t* lo = tcnt + tcopy + TA * (1u + 2u * q.smem_slot[a]);
+#pragma unroll
+                  for (int u = 0; u < kQB; ++u) if (ok[u]) smem_add64(lo, lo + TA, g[u], (int)x[u]);
+                } else {
+                  unsigned long long* gs = reinterpret_cast<unsigned long long*>(sd.g_isum[a]);
+#pragma unroll
+                  for (int u = 0; u < kQB; ++u) if (ok[u]) red_add_u64(gs + g[u], (unsigned long long)x[u]);
+                }
+              }
+            } else if (fn == 2 || fn == 3) {
+              // MIN / MAX tables change for only O(log n) of a group's rows: read the current entries first, then issue
+              // a reduction only where the row can win (a stale read costs a redundant reduction, never a wrong result)
+              const uint32_t bias = vk == VAL_RAW_I32 ? 0x80000000u : 0u;
+              uint32_t* tab = fn == 2 ? sd.g_min[a] : sd.g_max[a];
+              uint32_t cur[kQB];
+#pragma unroll
+              for (int u = 0; u < kQB; ++u) cur[u] = ok[u] ? __ldcg(tab + g[u]) : (fn == 2 ? 0u : 0xFFFFFFFFu);
+#pragma unroll
+              for (int u = 0; u < kQB; ++u) {
+                const uint32_t x = id[u] ^ bias;
+                if (fn == 2) { if (x < cur[u]) atomicMin(tab + g[u], x); }
+                else { if (x + 1u > cur[u]) atomicMax(tab + g[u], x + 1u); }
+              }
+            }
+          }
         }
         handled = true;  // the __syncwarp() before the ring refill also orders the queue reads before the next appends
       }
@@ -800,7 +890,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
             }
           }
         }
-      } else {
+      } else if constexpr (kDenseGroupByPath) {
         uint32_t gid[32], v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) gid[j] = 0;
