@@ -170,12 +170,14 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, long long n) {
   for (; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
-struct NonEmptyGroup {  // a group exists iff any of its (present) markers says so
+struct NonEmptyGroup {  // a group exists iff any of its (present) markers says so; hash tables: iff the slot holds a key
   const unsigned long long* count;
   const uint32_t* seen;
   const uint32_t* maxk;
   const uint32_t* mink;
+  const unsigned long long* hkeys;
   __device__ __forceinline__ bool operator()(const uint32_t& i) const {
+    if (hkeys) return hkeys[i] != ~0ull;
     return (count && count[i] != 0ull) || (seen && seen[i] != 0u) || (maxk && maxk[i] != 0u) || (mink && mink[i] != 0xFFFFFFFFu);
   }
 };
@@ -690,6 +692,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       gmax = g < 0 ? -1 : std::max(gmax, g);
     }
     bool ok = gmax > 0;
+    if (ok && getenv("PB200_DENSE_MAX") && gmax > atoll(getenv("PB200_DENSE_MAX"))) ok = false;  // hashed: slots, not raw keys
     int nsum = 0;
     for (int a = 0; a < nagg && ok; a++) {
       const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
@@ -971,6 +974,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       pb200_result::Dense& d = res[r]->dense;
       d.ctx = ctx;
       long long groups = 1;
+      unsigned __int128 space = 1;  // size of the raw key space
       for (int g = 0; g < ngb; g++) {
         int card = seg->cols[query->group_by_columns[g]].cardinality;
         if (merge) for (int s = 1; s < nseg; s++) if (segments[s]->cols[query->group_by_columns[g]].cardinality != card) {
@@ -979,12 +983,37 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         }
         card = std::max(card, 1);
         // every representable dictId must stay inside the table even for padded / corrupt rows
-        d.mult.push_back((uint32_t)groups);
+        d.mult.push_back((uint32_t)(unsigned long long)space);
+        d.mult64.push_back((unsigned long long)space);
         d.cards.push_back(card);
-        if (groups > (1ll << 31) / card) { set_error("group key space too large for the dense device table"); return PB200_E_UNSUPPORTED; }
-        groups *= card;
+        space *= (unsigned)card;
+        if (space >> 63) {  // the reference's ARRAY_MAP regime (keys wider than a long): not accelerated
+          set_error("group key space does not fit 63 bits (ARRAY_MAP regime): fall back to the reference operator");
+          return PB200_E_UNSUPPORTED;
+        }
       }
-      if (groups > (1ll << 27)) { set_error("group key space of %lld exceeds the dense device table limit", groups); return PB200_E_UNSUPPORTED; }
+      // dense table up to kDenseMax raw keys (ARRAY / INT_MAP regimes of the reference), beyond it a hash table over the
+      // 64-bit raw key (LONG_MAP regime, and INT_MAP key spaces too large to be worth a dense table)
+      const long long dense_max = getenv("PB200_DENSE_MAX") ? atoll(getenv("PB200_DENSE_MAX")) : (1ll << 24);
+      const bool hashed = space > (unsigned __int128)dense_max;
+      if (hashed) {
+        const long long limit = std::max(query->num_groups_limit, 1);
+        long long cap = 1 << 16;
+        while (cap < 2 * (limit + 1) && cap < (1ll << 27)) cap <<= 1;
+        if (cap < 2 * (limit + 1)) { set_error("numGroupsLimit %lld too large for the device hash table", limit); return PB200_E_UNSUPPORTED; }
+        groups = cap;
+        void* hk = nullptr; void* hc = nullptr;
+        int rc = dev_alloc(ctx, (size_t)cap * 8, &hk);
+        if (rc) return rc;
+        d.hkeys = (unsigned long long*)hk;
+        PB200_CUDA(cudaMemsetAsync(hk, 0xFF, (size_t)cap * 8, st));
+        rc = dev_alloc(ctx, 8, &hc);
+        if (rc) return rc;
+        d.hctl = (uint32_t*)hc;
+        PB200_CUDA(cudaMemsetAsync(hc, 0, 8, st));
+      } else {
+        groups = (long long)space;
+      }
       d.groups = groups;
       d.live = true;
       d.num_groups_limit = query->num_groups_limit;
@@ -998,7 +1027,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         need_count |= q.aggs[a].function == PB200_AGG_COUNT || q.aggs[a].function == PB200_AGG_AVG;
         has_minmax |= q.aggs[a].function == PB200_AGG_MIN || q.aggs[a].function == PB200_AGG_MAX;
       }
-      const bool need_seen = !need_count && !has_minmax;
+      const bool need_seen = !need_count && !has_minmax && !hashed;  // a hash table's keys mark the groups that exist
       long long n_i64 = need_count ? 1 : 0, n_f64 = 0, n_max = need_seen ? 1 : 0, n_min = 0;
       for (int a = 0; a < nagg; a++) {
         const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
@@ -1037,7 +1066,11 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       sd.g_count = d.count;
       sd.g_seen = d.seen;
       for (int a = 0; a < nagg; a++) { sd.g_isum[a] = d.isum[a]; sd.g_dsum[a] = d.dsum[a]; sd.g_min[a] = d.gmin[a]; sd.g_max[a] = d.gmax[a]; }
-      for (int g = 0; g < ngb; g++) sd.group_mult[g] = d.mult[g];
+      for (int g = 0; g < ngb; g++) { sd.group_mult[g] = d.mult[g]; sd.group_mult64[g] = d.mult64[g]; }
+      sd.h_keys = d.hkeys;
+      sd.h_ctl = d.hctl;
+      sd.h_mask = d.hkeys ? (uint32_t)(d.groups - 1) : 0u;
+      sd.h_limit = query->num_groups_limit;
     }
   }
 
@@ -1170,6 +1203,8 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       for (int r = 0; r < nres; r++) {
         pb200_result::Dense& d = res[r]->dense;
         dev_free(ctx, d.i64_block); dev_free(ctx, d.f64_block); dev_free(ctx, d.u32max_block); dev_free(ctx, d.u32min_block);
+        dev_free(ctx, d.hkeys); dev_free(ctx, d.hctl);
+        d.hkeys = nullptr; d.hctl = nullptr;
         d.i64_block = d.f64_block = d.u32max_block = d.u32min_block = nullptr;
         d.live = false;
       }
@@ -1187,7 +1222,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
 static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cudaStream_t st) {
   if (nres <= 0) return PB200_OK;
   int rc;
-  struct Job { DevBuf idx, block; unsigned long long n = 0; GatherPlan gp; size_t block_bytes = 0, stage_off = 0; std::vector<int> col_of_agg; int count_col = -1; };
+  struct Job { DevBuf idx, block; unsigned long long n = 0; GatherPlan gp; size_t block_bytes = 0, stage_off = 0; std::vector<int> col_of_agg; int count_col = -1, key_col = -1; };
   std::vector<Job> jobs(nres);
   DevBuf counters, tmp;
   if ((rc = counters.alloc(ctx, 8ull * nres))) return rc;
@@ -1197,7 +1232,7 @@ static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cuda
     const pb200_result::Dense& d = Rs[r]->dense;
     size_t tb = 0;
     cub::CountingInputIterator<uint32_t> first(0u);
-    PB200_CUDA(cub::DeviceSelect::If(nullptr, tb, first, (uint32_t*)nullptr, (unsigned long long*)nullptr, (long long)d.groups, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min}, st));
+    PB200_CUDA(cub::DeviceSelect::If(nullptr, tb, first, (uint32_t*)nullptr, (unsigned long long*)nullptr, (long long)d.groups, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min, d.hkeys}, st));
     tmp_cap = std::max(tmp_cap, tb);
   }
   if ((rc = tmp.alloc(ctx, tmp_cap + 16))) return rc;  // reused by the selects: they are ordered on one stream
@@ -1206,13 +1241,23 @@ static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cuda
     if ((rc = jobs[r].idx.alloc(ctx, (size_t)d.groups * 4))) return rc;
     cub::CountingInputIterator<uint32_t> first(0u);
     size_t tb = tmp_cap;
-    PB200_CUDA(cub::DeviceSelect::If(tmp.p, tb, first, (uint32_t*)jobs[r].idx.p, (unsigned long long*)counters.p + r, (long long)d.groups, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min}, st));
+    PB200_CUDA(cub::DeviceSelect::If(tmp.p, tb, first, (uint32_t*)jobs[r].idx.p, (unsigned long long*)counters.p + r, (long long)d.groups, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min, d.hkeys}, st));
   }
   void* pin = nullptr; size_t pin_bytes = 0;
   if ((rc = pinned_alloc(ctx, 8ull * nres, &pin, &pin_bytes))) return rc;
   struct PinReturn { pb200_ctx* c; void** p; size_t* b; ~PinReturn() { pinned_free(c, *p, *b); } } pin_return{ctx, &pin, &pin_bytes};
   PB200_CUDA(cudaMemcpyAsync(pin, counters.p, 8ull * nres, cudaMemcpyDeviceToHost, st));
   PB200_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < nres; r++) {  // hash tables: more groups than numGroupsLimit (or a full table) -> the result is unusable
+    const pb200_result::Dense& d = Rs[r]->dense;
+    if (!d.hctl) continue;
+    uint32_t ctl[2] = {0, 0};
+    PB200_CUDA(cudaMemcpy(ctl, d.hctl, 8, cudaMemcpyDeviceToHost));
+    if (ctl[1]) {
+      set_error("numGroupsLimit %d would bind (hash table saw more groups): fall back to the reference operator", d.num_groups_limit);
+      return PB200_E_LIMIT;
+    }
+  }
   size_t stage_total = 0;
   for (int r = 0; r < nres; r++) {
     pb200_result* R = Rs[r];
@@ -1234,6 +1279,7 @@ static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cuda
     J.gp.ncols = 0;
     J.col_of_agg.assign(nagg, -1);
     auto add = [&](const void* src, uint32_t esz) { J.gp.col[J.gp.ncols] = GatherCol{src, off, esz, 0}; off += esz == 8 ? J.n * 8 : n8; return J.gp.ncols++; };
+    if (d.hkeys) J.key_col = add(d.hkeys, 8);
     if (d.count) J.count_col = add(d.count, 8);
     for (int a = 0; a < nagg; a++) {
       const int fn = d.aggs[a].function, vk = d.val_kind[a];
@@ -1271,7 +1317,13 @@ static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cuda
     const unsigned char* blk = (const unsigned char*)pin + J.stage_off;
     const uint32_t* hidx = (const uint32_t*)blk;
     R->keys.resize(n * ngb);
-    if (ngb == 1) { for (size_t i = 0; i < n; i++) R->keys[i] = (int32_t)hidx[i]; }
+    if (J.key_col >= 0) {  // hash table: the slot's 64-bit raw key, column 0 least significant
+      const unsigned long long* hk = n ? (const unsigned long long*)(blk + J.gp.col[J.key_col].dst_off) : nullptr;
+      for (size_t i = 0; i < n; i++) {
+        unsigned long long raw = hk[i];
+        for (int g = 0; g < ngb; g++) { R->keys[i * ngb + g] = (int32_t)(raw % (unsigned long long)d.cards[g]); raw /= (unsigned long long)d.cards[g]; }
+      }
+    } else if (ngb == 1) { for (size_t i = 0; i < n; i++) R->keys[i] = (int32_t)hidx[i]; }
     else for (size_t i = 0; i < n; i++) {
       uint32_t raw = hidx[i];
       for (int g = 0; g < ngb; g++) { R->keys[i * ngb + g] = (int32_t)(raw % (uint32_t)d.cards[g]); raw /= (uint32_t)d.cards[g]; }
@@ -1333,6 +1385,7 @@ extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
 extern "C" int32_t pb200_result_device_buffers(pb200_result* R, int32_t kind, void** p, int64_t* n) {
   if (!R || !p || !n) { set_error("null argument"); return PB200_E_INVALID; }
   pb200_result::Dense& d = R->dense;
+  if (d.hkeys) { set_error("hash group tables of different GPUs are not element-wise reducible"); return PB200_E_UNSUPPORTED; }
   switch (kind) {
     case 0: *p = d.i64_block; *n = d.i64_elems; break;
     case 1: *p = d.f64_block; *n = d.f64_elems; break;
@@ -1373,7 +1426,7 @@ extern "C" int64_t pb200_result_distinct(const pb200_result* R, int32_t a, int32
 extern "C" int32_t pb200_result_free(pb200_result* R) {
   if (!R) return PB200_OK;
   pb200_result::Dense& d = R->dense;
-  if (d.ctx) { dev_free(d.ctx, d.i64_block); dev_free(d.ctx, d.f64_block); dev_free(d.ctx, d.u32max_block); dev_free(d.ctx, d.u32min_block); }
+  if (d.ctx) { dev_free(d.ctx, d.i64_block); dev_free(d.ctx, d.f64_block); dev_free(d.ctx, d.u32max_block); dev_free(d.ctx, d.u32min_block); dev_free(d.ctx, d.hkeys); dev_free(d.ctx, d.hctl); }
   delete R;
   return PB200_OK;
 }

@@ -4,11 +4,11 @@
 
 namespace pb200 {
 
-constexpr int kMaxSlots = 8;     // distinct columns one query may touch on the device
+constexpr int kMaxSlots = 12;    // distinct columns one query may touch on the device
 constexpr int kMaxLeaves = 8;    // filter leaves
 constexpr int kMaxNodes = 16;    // filter tree nodes (postfix program length)
 constexpr int kMaxAggs = 6;      // aggregation functions per query
-constexpr int kMaxGroupBy = 4;   // group-by columns (dense key space)
+constexpr int kMaxGroupBy = 8;   // group-by columns (dense table or 64-bit-key hash table)
 constexpr int kRowsPerThread = 32;
 constexpr int kMaxStack = 8;
 
@@ -89,6 +89,13 @@ struct SegDesc {
   uint32_t* g_min[kMaxAggs];
   uint32_t* g_max[kMaxAggs];
   uint32_t group_mult[kMaxGroupBy];
+  // hash group table (key spaces beyond the dense limit, the reference's LONG_MAP regime): open addressing over the
+  // 64-bit raw key; the accumulator tables above are then indexed by SLOT instead of by raw key
+  unsigned long long* h_keys;          // NULL = dense table; else capacity (h_mask + 1) keys, empty = ~0
+  uint32_t* h_ctl;                     // [0] = inserted keys, [1] = overflow flag (more groups than h_limit, or table full)
+  uint32_t h_mask;
+  int32_t h_limit;
+  unsigned long long group_mult64[kMaxGroupBy];
 };
 
 // Everything lane 0 needs to refill a warp's TMA ring, for every segment of the launch, passed BY VALUE as a kernel

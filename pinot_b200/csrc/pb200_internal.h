@@ -86,6 +86,9 @@ struct pb200_result {
     uint32_t* gmin[pb200::kMaxAggs] = {};
     uint32_t* gmax[pb200::kMaxAggs] = {};
     std::vector<uint32_t> mult;
+    std::vector<unsigned long long> mult64;
+    unsigned long long* hkeys = nullptr;        // hash table keys (NULL: dense table indexed by raw key)
+    uint32_t* hctl = nullptr;                   // [0] inserted, [1] overflow
     std::vector<int> cards;
     std::vector<pb200_agg> aggs;
     std::vector<int> val_kind;

@@ -212,6 +212,35 @@ __device__ __forceinline__ void stg_u32_pred(uint32_t* p, uint32_t v, uint32_t p
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pred) : "memory");
 }
 
+// Hash group table: slot of `key` in the open-addressing table (linear probing, 64-bit CAS on the key itself -- exact,
+// no fingerprints).  Returns false once the table holds more than h_limit groups (the caller's result is then discarded:
+// numGroupsLimit would bind, PB200_E_LIMIT) or is full.
+__device__ __forceinline__ uint32_t mix64_32(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (uint32_t)(z ^ (z >> 31));
+}
+__device__ __forceinline__ bool hash_slot(const SegDesc& sd, unsigned long long key, uint32_t& slot) {
+  constexpr unsigned long long kEmpty = ~0ull;
+  if (*reinterpret_cast<volatile uint32_t*>(sd.h_ctl + 1)) return false;
+  uint32_t h = mix64_32(key) & sd.h_mask;
+  for (uint32_t probe = 0; probe <= sd.h_mask; ++probe) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(sd.h_keys + h);
+    if (cur == kEmpty) {
+      cur = atomicCAS(sd.h_keys + h, kEmpty, key);
+      if (cur == kEmpty) {
+        if (atomicAdd(sd.h_ctl, 1u) >= (uint32_t)sd.h_limit) { sd.h_ctl[1] = 1u; return false; }
+        slot = h;
+        return true;
+      }
+    }
+    if (cur == key) { slot = h; return true; }
+    h = (h + 1u) & sd.h_mask;
+  }
+  sd.h_ctl[1] = 1u;
+  return false;
+}
+
 // Group bookkeeping of one surviving row: the exact count when some function needs it (COUNT / AVG), otherwise a
 // test-then-set "seen" flag (benign race: every writer stores 1), or nothing when a MIN/MAX table already marks groups.
 __device__ __forceinline__ void touch_group(const SegDesc& sd, uint32_t g) {
@@ -314,6 +343,7 @@ struct SmemHeader {
   SegDesc seg;                              // CTA-wide copy of the current segment's descriptor
   AggDesc aggs[kMaxAggs];                   // q.aggs: indexed with a runtime `a` (an indexed LDC costs a long-scoreboard wait)
   uint32_t slot_roles[kMaxSlots];           // q.slot_roles, same reason
+  int32_t group_slot[kMaxGroupBy];          // q.group_slot, same reason
   uint64_t full[kMaxWarps][kMaxStages];     // per-warp ring: "stage filled by TMA"
 };
 
@@ -368,6 +398,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
   }
   if (threadIdx.x < kMaxAggs) hdr->aggs[threadIdx.x] = q.aggs[threadIdx.x];
   if (threadIdx.x < kMaxSlots) hdr->slot_roles[threadIdx.x] = q.slot_roles[threadIdx.x];
+  if (threadIdx.x < kMaxGroupBy) hdr->group_slot[threadIdx.x] = q.group_slot[threadIdx.x];
   __syncthreads();
 
   const int group = threadIdx.x;  // index of this thread's per-thread accumulators
@@ -726,10 +757,24 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
           bool ok[kQB];
 #pragma unroll
           for (int u = 0; u < kQB; ++u) { ok[u] = i0 + 32 * u < S; e[u] = ok[u] ? (uint32_t)wq[i0 + 32 * u] : 0u; g[u] = 0u; }
+          if (sd.h_keys) {  // hash table: 64-bit raw key -> slot
+            unsigned long long key[kQB];
 #pragma unroll
-          for (int gi = 0; gi < kMaxGroupBy; ++gi) {
-            if (gi < q.num_group_by) {
-              const SlotDesc& sl = sd.slots[q.group_slot[gi]];
+            for (int u = 0; u < kQB; ++u) key[u] = 0ull;
+#pragma unroll 1
+            for (int gi = 0; gi < q.num_group_by; ++gi) {
+              const SlotDesc& sl = sd.slots[hdr->group_slot[gi]];
+              const uint32_t* gb = st + sl.stage_words;
+              const unsigned long long mult = sd.group_mult64[gi];
+#pragma unroll
+              for (int u = 0; u < kQB; ++u) key[u] += read_one_group(gb + (e[u] >> 5) * sl.bits, (int)(e[u] & 31u), sl.bits) * mult;
+            }
+#pragma unroll
+            for (int u = 0; u < kQB; ++u) if (ok[u]) ok[u] = hash_slot(sd, key[u], g[u]);
+          } else {
+#pragma unroll 1
+            for (int gi = 0; gi < q.num_group_by; ++gi) {
+              const SlotDesc& sl = sd.slots[hdr->group_slot[gi]];
               const uint32_t* gb = st + sl.stage_words;
               const uint32_t mult = sd.group_mult[gi];
 #pragma unroll

@@ -45,8 +45,8 @@ def test_golden_inner_segment_aggregation(pm, sv_segment, sv_dev, query, stats, 
 @pytest.mark.parametrize("query,regime,stats,key,expected", G.INNER_SEGMENT_GROUP_BY)
 def test_golden_inner_segment_group_by(pm, sv_segment, sv_dev, query, regime, stats, key, expected):
     q = sql.parse(query)
-    if regime in ("LONG_MAP", "ARRAY_MAP"):
-        # key space beyond the dense device table: the plan maker must refuse (-> Java operator), never guess
+    if regime == "ARRAY_MAP":
+        # keys wider than 63 bits are not accelerated: the plan maker must refuse (-> Java operator), never guess
         with pytest.raises(UnsupportedQueryError):
             pm.make_segment_plan_node(sv_dev, q).run().next_block()
         return
@@ -250,6 +250,55 @@ def test_num_groups_limit_forces_fallback(oracle, ctx, pm):
         q = sql.parse("SELECT SUM(v) FROM t GROUP BY k", num_groups_limit=100, max_initial_result_holder_capacity=100)
         with pytest.raises(UnsupportedQueryError):
             pm.make_segment_plan_node(dev, q).run().next_block()
+    finally:
+        dev.destroy()
+
+
+GROUP_BY_QUERIES = [t for t in QUERIES if "GROUP BY" in t] + [
+    "SELECT COUNT(*), SUM(b), MIN(c), MAX(e), AVG(f) FROM t WHERE b < 700 GROUP BY a, d, s, t, g",   # 5 keys
+    "SELECT SUM(c) FROM t GROUP BY c, b",                                                              # many groups
+]
+
+
+@pytest.mark.parametrize("n", [1, 33, 8193, 100_003])
+def test_hash_group_table_parity(oracle, ctx, pm, n, monkeypatch):
+    """Key spaces beyond the dense limit (the reference's LONG_MAP regime) go through the device hash table; forcing the
+    limit down to 1 sends every group-by shape through it."""
+    monkeypatch.setenv("PB200_DENSE_MAX", "1")
+    rng = np.random.default_rng(2000 + n)
+    seg = _random_segment(oracle, rng, n)
+    dev = to_device(ctx, seg)
+    try:
+        for text in GROUP_BY_QUERIES:
+            check_query(oracle, pm, seg, dev, sql.parse(text, num_groups_limit=200_000), what=f"hash n={n}: {text}")
+        # device-side merge of several segments into ONE hash table
+        q = sql.parse("SELECT COUNT(*), SUM(b), MAX(c) FROM t WHERE b > 100 GROUP BY d, a", num_groups_limit=200_000)
+        merged = pm.execute_segments([dev, dev, dev], q, merge=True)[0]
+        single = gpu_table(seg, q, pm.execute_segments([dev], q)[0])
+        got = gpu_table(seg, q, merged)
+        assert set(got) == set(single)
+        for k, v in single.items():
+            assert got[k] == [3 * v[0], 3 * v[1], v[2]], (k, got[k], v)
+        # more groups than numGroupsLimit: explicit fallback, never a truncated table
+        if n >= 8193:
+            with pytest.raises(UnsupportedQueryError):
+                pm.execute_segments([dev], sql.parse("SELECT SUM(c) FROM t GROUP BY c, b", num_groups_limit=1000))
+    finally:
+        dev.destroy()
+
+
+def test_hash_group_table_natural_long_map(oracle, ctx, pm):
+    """A key space that really needs 64-bit raw keys (product of cardinalities > 2^31)."""
+    rng = np.random.default_rng(77)
+    n = 60_000
+    seg = oracle.build_segment("lm", {
+        "k1": rng.integers(0, 50_000, size=n).astype(np.int32), "k2": rng.integers(0, 40_000, size=n).astype(np.int32),
+        "k3": rng.integers(0, 300, size=n).astype(np.int32), "v": rng.integers(-1000, 1000, size=n).astype(np.int32)})
+    dev = to_device(ctx, seg)
+    try:
+        q = sql.parse("SELECT COUNT(*), SUM(v), MIN(v), MAX(v) FROM t WHERE v > -900 GROUP BY k1, k2, k3")
+        r, block = check_query(oracle, pm, seg, dev, q, "natural LONG_MAP")
+        assert block.regime == "LONG_MAP" and block.num_groups > 50_000
     finally:
         dev.destroy()
 
