@@ -208,6 +208,11 @@ __global__ void gather_columns_kernel(const GatherPlan gp, const uint32_t* __res
     }
   }
 }
+__global__ void gather_rows_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, long long n, int words,
+                                   uint32_t* __restrict__ dst) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * words; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[(size_t)idx[i / words] * words + (i % words)];
+}
 template <typename T>
 __global__ void gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, long long n, T* __restrict__ dst) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -276,17 +281,21 @@ extern "C" int32_t pb200_device_info(pb200_ctx* ctx, int64_t out[5]) {
 // ------------------------------------------------------------------------------------------------------------------
 // segments
 // ------------------------------------------------------------------------------------------------------------------
+// Blocks of the caching allocator go back to it (load / evict cycles then cost no cudaMalloc / cudaFree, both of which
+// synchronise the device); buffers the generator allocated with cudaMalloc are freed directly.
+static void free_any(pb200_ctx* ctx, void* p) {
+  if (!p) return;
+  bool pooled;
+  { std::lock_guard<std::mutex> g(ctx->mu); pooled = ctx->block_size.count(p) != 0; }
+  if (pooled) dev_free(ctx, p); else cudaFree(p);
+}
 static void free_column(pb200_ctx* ctx, DeviceColumn& c) {
-  if (c.owns) {
-    if (c.fwd && c.pooled) dev_free(ctx, c.fwd);
-    else if (c.fwd) cudaFree(c.fwd);
-    if (c.inv) cudaFree(c.inv);
-  }
-  if (c.dict_native) cudaFree(c.dict_native);
+  if (c.owns) { free_any(ctx, c.fwd); free_any(ctx, c.inv); }
+  free_any(ctx, c.dict_native);
   c.fwd = nullptr; c.inv = nullptr; c.dict_native = nullptr;
 }
 
-static int convert_dictionary(const pb200_col_desc& d, DeviceColumn& c, const unsigned char* be) {
+static int convert_dictionary(pb200_ctx* ctx, const pb200_col_desc& d, DeviceColumn& c, const unsigned char* be) {
   // BIG-endian fixed-width values (SegmentDictionaryCreator.java:117-177) -> native little-endian arrays
   const int w = c.dict_width();
   if (d.dict_bytes < (uint64_t)w * c.cardinality) { set_error("dictionary too short: %llu bytes for %d x %d", (unsigned long long)d.dict_bytes, c.cardinality, w); return PB200_E_INVALID; }
@@ -296,7 +305,7 @@ static int convert_dictionary(const pb200_col_desc& d, DeviceColumn& c, const un
     if (w == 4) { uint32_t v = be32(be + 4ll * i); memcpy(&c.dict_host[4ull * i], &v, 4); }
     else { uint64_t v = be64(be + 8ll * i); memcpy(&c.dict_host[8ull * i], &v, 8); }
   }
-  PB200_CUDA(cudaMalloc(&c.dict_native, std::max<size_t>(c.dict_host.size(), 16)));
+  { int rc = dev_alloc(ctx, std::max<size_t>(c.dict_host.size(), 16), &c.dict_native); if (rc) return rc; }
   if (c.stored_type == PB200_INT) {
     // the DEVICE copy of an INT dictionary is biased (value ^ 0x80000000 == value + 2^31 as unsigned): the scan kernel
     // sums unsigned words with 3-input adds and removes count * 2^31 once per tile (SumBiasedU32)
@@ -363,7 +372,7 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
             if ((id >> b) & 1) packed[bit >> 3] |= (unsigned char)(0x80 >> (bit & 7));
         }
       }
-      PB200_CUDA(cudaMalloc(&c.fwd, c.fwd_alloc_bytes));
+      { void* fp = nullptr; int rc = dev_alloc(ctx, c.fwd_alloc_bytes, &fp); if (rc) return fail(rc); c.fwd = (uint32_t*)fp; }
       PB200_CUDA(cudaMemcpy(c.fwd, packed.data(), c.fwd_alloc_bytes, cudaMemcpyHostToDevice));
       PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes));
       c.fwd_kind = PB200_FWD_DICT_FIXEDBIT;
@@ -382,7 +391,7 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
       c.bits = 32;
       c.fwd_file_bytes = 4ull * num_docs;
       c.fwd_alloc_bytes = padded_fwd_bytes(num_docs, 32);
-      PB200_CUDA(cudaMalloc(&c.fwd, c.fwd_alloc_bytes));
+      { void* fp = nullptr; int rc = dev_alloc(ctx, c.fwd_alloc_bytes, &fp); if (rc) return fail(rc); c.fwd = (uint32_t*)fp; }
       PB200_CUDA(cudaMemset(c.fwd, 0, c.fwd_alloc_bytes));
       PB200_CUDA(cudaMemcpy(c.fwd, p + start, 4ull * num_docs, cudaMemcpyHostToDevice));
       PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes));
@@ -399,7 +408,7 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
         PB200_CUDA(cudaMemcpy(tmp.data(), d.dict, d.dict_bytes, cudaMemcpyDeviceToHost));
         be = tmp.data();
       }
-      int rc = convert_dictionary(d, c, be);
+      int rc = convert_dictionary(ctx, d, c, be);
       if (rc) return fail(rc);
       seg->device_bytes += (int64_t)c.dict_host.size();
     }
@@ -412,7 +421,7 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
         c.inv = (unsigned char*)d.inv;
         PB200_CUDA(cudaMemcpy(hdr.data(), d.inv, hdr.size(), cudaMemcpyDeviceToHost));
       } else {
-        PB200_CUDA(cudaMalloc(&c.inv, d.inv_bytes + 16));
+        { void* ip = nullptr; int rc = dev_alloc(ctx, d.inv_bytes + 16, &ip); if (rc) return fail(rc); c.inv = (unsigned char*)ip; }
         PB200_CUDA(cudaMemcpy(c.inv, d.inv, d.inv_bytes, cudaMemcpyHostToDevice));
         memcpy(hdr.data(), d.inv, hdr.size());
       }
@@ -593,7 +602,6 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     if (ag.function == PB200_AGG_COUNT) continue;
     if (ag.function < 0 || ag.function > PB200_AGG_DISTINCTCOUNT) { set_error("unknown aggregation function %d", ag.function); return PB200_E_INVALID; }
     if (ag.column < 0 || ag.column >= ncols) { set_error("aggregation column %d out of range", ag.column); return PB200_E_INVALID; }
-    if (ag.function == PB200_AGG_DISTINCTCOUNT && ngb > 0) { set_error("DISTINCTCOUNT with GROUP BY is not accelerated"); return PB200_E_UNSUPPORTED; }
     int s = slot_of(plan, ag.column, ROLE_AGG);
     if (s < 0) { set_error("too many distinct columns (max %d)", kMaxSlots); return PB200_E_UNSUPPORTED; }
     q.aggs[a].slot = s;
@@ -1058,6 +1066,19 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
           else d.isum[a] = (long long*)d.i64_block + (ii++) * groups;
         } else if (fn == PB200_AGG_MIN) { d.gmin[a] = (uint32_t*)d.u32min_block + (ni++) * groups; if (!need_count && !d.exists_max && !d.exists_min) d.exists_min = d.gmin[a]; }
         else if (fn == PB200_AGG_MAX) { d.gmax[a] = (uint32_t*)d.u32max_block + (xi++) * groups; if (!need_count && !d.exists_max && !d.exists_min) d.exists_max = d.gmax[a]; }
+        else if (fn == PB200_AGG_DISTINCTCOUNT) {  // one dictId bitset per group / slot
+          const DeviceColumn& c = seg->cols[query->aggs[a].column];
+          const unsigned long long words = ((unsigned long long)c.cardinality + 31) / 32;
+          if (words * (unsigned long long)groups > (1ull << 28)) {
+            set_error("DISTINCTCOUNT with GROUP BY: %lld groups x %d dictIds exceed the device bitset budget", groups, c.cardinality);
+            return PB200_E_UNSUPPORTED;
+          }
+          void* bp = nullptr;
+          if ((rc = dev_alloc(ctx, (size_t)(words * groups) * 4, &bp))) return rc;
+          PB200_CUDA(cudaMemsetAsync(bp, 0, (size_t)(words * groups) * 4, st));
+          d.dbits[a] = (uint32_t*)bp;
+          d.dwords[a] = (uint32_t)words;
+        }
       }
     }
     for (int s = 0; s < nseg; s++) {
@@ -1065,7 +1086,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       pb200_result::Dense& d = res[merge ? 0 : s]->dense;
       sd.g_count = d.count;
       sd.g_seen = d.seen;
-      for (int a = 0; a < nagg; a++) { sd.g_isum[a] = d.isum[a]; sd.g_dsum[a] = d.dsum[a]; sd.g_min[a] = d.gmin[a]; sd.g_max[a] = d.gmax[a]; }
+      for (int a = 0; a < nagg; a++) { sd.g_isum[a] = d.isum[a]; sd.g_dsum[a] = d.dsum[a]; sd.g_min[a] = d.gmin[a]; sd.g_max[a] = d.gmax[a]; sd.distinct_bits[a] = d.dbits[a]; sd.distinct_words[a] = d.dwords[a]; }
       for (int g = 0; g < ngb; g++) { sd.group_mult[g] = d.mult[g]; sd.group_mult64[g] = d.mult64[g]; }
       sd.h_keys = d.hkeys;
       sd.h_ctl = d.hctl;
@@ -1205,6 +1226,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         dev_free(ctx, d.i64_block); dev_free(ctx, d.f64_block); dev_free(ctx, d.u32max_block); dev_free(ctx, d.u32min_block);
         dev_free(ctx, d.hkeys); dev_free(ctx, d.hctl);
         d.hkeys = nullptr; d.hctl = nullptr;
+        for (int a = 0; a < kMaxAggs; a++) { dev_free(ctx, d.dbits[a]); d.dbits[a] = nullptr; }
         d.i64_block = d.f64_block = d.u32max_block = d.u32min_block = nullptr;
         d.live = false;
       }
@@ -1365,6 +1387,25 @@ static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cuda
             if (t[i] == 0) D[i] = -INFINITY; else { I[i] = (int32_t)(t[i] - 1); D[i] = value_of(t[i] - 1); }
           }
         }
+      } else if (fn == PB200_AGG_DISTINCTCOUNT && d.dbits[a]) {
+        // the groups' bitset rows: gathered on the device, decoded here into dictId lists (what extractGroupByResult's
+        // value-set conversion starts from, BaseDistinctAggregateAggregationFunction :306-321)
+        const size_t wpg = d.dwords[a];
+        std::vector<uint32_t> rows(n * wpg);
+        if (n) {
+          DevBuf g;
+          if ((rc = g.alloc(ctx, n * wpg * 4))) return rc;
+          const int gb2 = (int)std::max<size_t>(1, std::min<size_t>((n * wpg + 255) / 256, 148 * 8));
+          gather_rows_kernel<<<gb2, 256, 0, st>>>(d.dbits[a], (const uint32_t*)J.idx.p, (long long)n, (int)wpg, (uint32_t*)g.p);
+          PB200_CUDA(cudaMemcpyAsync(rows.data(), g.p, n * wpg * 4, cudaMemcpyDeviceToHost, st));
+          PB200_CUDA(cudaStreamSynchronize(st));
+        }
+        R->distinct[a].resize(n);
+        for (size_t i = 0; i < n; i++) {
+          std::vector<int32_t>& ids = R->distinct[a][i];
+          for (size_t w = 0; w < wpg; w++) { uint32_t x = rows[i * wpg + w]; while (x) { ids.push_back((int32_t)(w * 32 + __builtin_ctz(x))); x &= x - 1; } }
+          L[i] = (int64_t)ids.size(); D[i] = (double)ids.size();
+        }
       } else { std::fill(D.begin(), D.end(), 0.0); std::fill(L.begin(), L.end(), 0); }
     }
   }
@@ -1426,7 +1467,7 @@ extern "C" int64_t pb200_result_distinct(const pb200_result* R, int32_t a, int32
 extern "C" int32_t pb200_result_free(pb200_result* R) {
   if (!R) return PB200_OK;
   pb200_result::Dense& d = R->dense;
-  if (d.ctx) { dev_free(d.ctx, d.i64_block); dev_free(d.ctx, d.f64_block); dev_free(d.ctx, d.u32max_block); dev_free(d.ctx, d.u32min_block); dev_free(d.ctx, d.hkeys); dev_free(d.ctx, d.hctl); }
+  if (d.ctx) { dev_free(d.ctx, d.i64_block); dev_free(d.ctx, d.f64_block); dev_free(d.ctx, d.u32max_block); dev_free(d.ctx, d.u32min_block); dev_free(d.ctx, d.hkeys); dev_free(d.ctx, d.hctl); for (int a = 0; a < kMaxAggs; a++) dev_free(d.ctx, d.dbits[a]); }
   delete R;
   return PB200_OK;
 }

@@ -79,7 +79,8 @@ struct SegDesc {
   SlotDesc slots[kMaxSlots];
   LeafDesc leaves[kMaxLeaves];
   const void* dict[kMaxAggs];          // native (little-endian) dictionary value array of the aggregation's column
-  uint32_t* distinct_bits[kMaxAggs];   // DISTINCTCOUNT (aggregation only): bitset over dictIds
+  uint32_t* distinct_bits[kMaxAggs];   // DISTINCTCOUNT: bitset over dictIds (group-by: one of distinct_words[a] words per group / slot)
+  uint32_t distinct_words[kMaxAggs];
   AggAccum* accum;                     // aggregation-only output
   // dense group table (group-by): indexed by raw key = sum_j dictId_j * mult_j
   unsigned long long* g_count;   // per-group row count; NULL when no COUNT / AVG needs it

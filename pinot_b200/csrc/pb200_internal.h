@@ -87,6 +87,8 @@ struct pb200_result {
     uint32_t* gmax[pb200::kMaxAggs] = {};
     std::vector<uint32_t> mult;
     std::vector<unsigned long long> mult64;
+    uint32_t* dbits[pb200::kMaxAggs] = {};      // DISTINCTCOUNT with GROUP BY: per-group dictId bitsets, dwords[a] words each
+    uint32_t dwords[pb200::kMaxAggs] = {};
     unsigned long long* hkeys = nullptr;        // hash table keys (NULL: dense table indexed by raw key)
     uint32_t* hctl = nullptr;                   // [0] inserted, [1] overflow
     std::vector<int> cards;

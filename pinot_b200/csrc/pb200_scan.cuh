@@ -829,6 +829,11 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
                   for (int u = 0; u < kQB; ++u) if (ok[u]) red_add_u64(gs + g[u], (unsigned long long)x[u]);
                 }
               }
+            } else if (fn == 5) {  // DISTINCTCOUNT: the group's dictId bitset (RoaringBitmap per group in the reference)
+              uint32_t* bits = sd.distinct_bits[a];
+              const size_t wpg = sd.distinct_words[a];
+#pragma unroll
+              for (int u = 0; u < kQB; ++u) if (ok[u]) atomicOr(bits + (size_t)g[u] * wpg + (id[u] >> 5), 1u << (id[u] & 31u));
             } else if (fn == 2 || fn == 3) {
               // MIN / MAX tables change for only O(log n) of a group's rows: read the current entries first, then issue
               // a reduction only where the row can win (a stale read costs a redundant reduction, never a wrong result)

@@ -62,10 +62,6 @@ def test_golden_inner_segment_group_by(pm, sv_segment, sv_dev, query, regime, st
 def test_golden_inter_segment(pm, sv_segment, sv_dev, select, ascending, expected):
     base = f"SELECT {select} FROM testTable"
     for i, (flt, gb) in enumerate([("", ""), (G.FILTER, ""), ("", G.INTER_GROUP_BY), (G.FILTER, G.INTER_GROUP_BY)]):
-        if gb and "DISTINCTCOUNT" in select:
-            with pytest.raises(UnsupportedQueryError):  # group-by DISTINCTCOUNT is not accelerated: explicit fallback
-                pm.execute_segments([sv_dev], sql.parse(base + flt + gb))
-            continue
         q = sql.parse(base + flt + gb)
         fns = [a.function for a in q.aggregations]
         blocks = pm.execute_segments([sv_dev] * 4, q)  # 2 segments x 2 servers in the reference's harness
@@ -135,6 +131,8 @@ QUERIES = [
     "SELECT COUNT(*), SUM(b) FROM t WHERE a = 1 AND d < 50 GROUP BY b",
     "SELECT MAX(g), MIN(f) FROM t WHERE s != 'x' GROUP BY t, a",
     "SELECT COUNT(*) FROM t WHERE b > 5000 GROUP BY a",                   # no groups
+    "SELECT DISTINCTCOUNT(b), DISTINCTCOUNT(s), COUNT(*) FROM t WHERE c > 100000 GROUP BY a",
+    "SELECT DISTINCTCOUNT(d) FROM t GROUP BY s, t",
 ]
 
 
