@@ -677,14 +677,14 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   // for a 3-deep ring (measured on C3/range: 2.26 ms vs 2.95 ms at W = 8); falls back to one CTA when the rows are too wide
   // for two 2-deep rings.
   int cw = 6, stages = 0, ctas_per_sm = 1;
-  if (getenv("PB200_W")) { int w = atoi(getenv("PB200_W")); if (w == 6 || w == 7 || w == 8) cw = w; }  // tuning knob
+  if (getenv("PB200_W")) { int w = atoi(getenv("PB200_W")); if (w == 6 || w == 8) cw = w; }  // tuning knob
   q.sparse_max = getenv("PB200_SPARSE_MAX") ? atoi(getenv("PB200_SPARSE_MAX")) : 4;
   q.sparse_max_agg = getenv("PB200_SPARSE_MAX_AGG") ? atoi(getenv("PB200_SPARSE_MAX_AGG")) : (plan.group_by ? std::min(q.sparse_max, 2) : q.sparse_max);
   ctas_per_sm = 2;  // group-by through the survivor queue needs < 128 registers: two 256-thread CTAs per SM
   if (getenv("PB200_CTAS")) ctas_per_sm = std::max(1, std::min(2, atoi(getenv("PB200_CTAS"))));
   const size_t warp_stage_bytes = (size_t)128 * max_bits_sum;
   size_t extra_bytes = (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4) + (plan.group_by ? (size_t)cw * 2048 : (size_t)nagg * cw * 32 * 16);
-  q.queue_max = !plan.group_by ? 0 : getenv("PB200_QUEUE_MAX") ? atoi(getenv("PB200_QUEUE_MAX")) : 1024;
+  q.queue_max = plan.group_by ? 1024 : 0;  // every group-by slice goes through the survivor queue
   // CTA-private group tables in shared memory when the key space is small and every function is COUNT or an integer SUM
   q.smem_groups = 0;
   for (int a = 0; a < kMaxAggs; a++) q.smem_slot[a] = -1;
@@ -1137,9 +1137,11 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     if (cq.total_tiles >= (1 << 30)) { set_error("too many tiles in one launch"); return PB200_E_UNSUPPORTED; }
     if (getenv("PB200_GRID")) grid = std::max(1, atoi(getenv("PB200_GRID")));
     const SegDesc* dptr = (const SegDesc*)dsegs.p + c0;
+    // instantiations: W in {6, 8} x {aggregation only (2 CTAs/SM), group-by with 2 or 1 CTAs/SM}
     if (plan.group_by && ctas_per_sm == 2) le = cw == 8 ? launch_scan<8, true, false, 2>(plan, cq, tt, dptr, grid, st) : launch_scan<6, true, false, 2>(plan, cq, tt, dptr, grid, st);
-    else if (plan.group_by) le = cw == 8 ? launch_scan<8, true>(plan, cq, tt, dptr, grid, st) : cw == 7 ? launch_scan<7, true>(plan, cq, tt, dptr, grid, st) : launch_scan<6, true>(plan, cq, tt, dptr, grid, st);
-    else le = cw == 8 ? (getenv("PB200_NO_DEFER") ? launch_scan<8, false, false>(plan, cq, tt, dptr, grid, st) : launch_scan<8, false>(plan, cq, tt, dptr, grid, st)) : cw == 7 ? launch_scan<7, false>(plan, cq, tt, dptr, grid, st) : launch_scan<6, false>(plan, cq, tt, dptr, grid, st);
+    else if (plan.group_by) le = cw == 8 ? launch_scan<8, true>(plan, cq, tt, dptr, grid, st) : launch_scan<6, true>(plan, cq, tt, dptr, grid, st);
+    else if (cw == 8) le = getenv("PB200_NO_DEFER") ? launch_scan<8, false, false>(plan, cq, tt, dptr, grid, st) : launch_scan<8, false>(plan, cq, tt, dptr, grid, st);
+    else le = launch_scan<6, false>(plan, cq, tt, dptr, grid, st);
   }
   if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }
   PB200_CUDA(cudaEventRecord(e1, st));

@@ -6,13 +6,16 @@
 //    query/AggregationOperator.java:64-80; bit unpack in seglocal/io/reader/impl/FixedBitIntReader.java)
 // is done here for ALL segments of a query by one persistent kernel:
 //
-//   * tile = consumer_warps x 1024 rows of every touched column; a producer thread streams tiles HBM -> shared memory
-//     with TMA 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) through an N-stage full/empty mbarrier ring;
-//   * each consumer thread owns 32 consecutive rows: unpacks its B big-endian words per column (pb200_unpack.cuh),
-//     evaluates every filter leaf into a 32-bit row mask, combines masks with the filter's boolean program,
-//     then aggregates the surviving rows: register accumulators + warp reduction + one atomic per warp for
-//     aggregation-only queries, atomics into a dense group table (raw key = sum dictId_j * mult_j, the same key
-//     DictionaryBasedGroupKeyGenerator computes, :311-346) for group-by;
+//   * every WARP streams its own 1024-row slices of every touched column HBM -> shared memory with TMA 1-D bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx) through a private ring of stage buffers -- no producer warp;
+//   * each thread owns 32 consecutive rows: unpacks its B words per column (pb200_unpack.cuh; native word order in HBM),
+//     evaluates every filter leaf into a 32-bit row mask (compare through the carry flag), combines masks with the
+//     filter's boolean program, then aggregates the surviving rows:
+//       aggregation only: per-thread accumulators in shared memory + warp reduction + one atomic per warp and segment,
+//                         dictionary gathers software-pipelined across tiles;
+//       group-by:         survivors compacted into a per-warp queue, then dense gathers / reductions over the queue into a
+//                         dense table indexed by the raw key (sum dictId_j * mult_j, DictionaryBasedGroupKeyGenerator
+//                         :311-346), a CTA-private shared-memory table (small key spaces) or a hash table (LONG_MAP);
 //   * integer work only: no tensor cores; the bound is HBM bandwidth (algorithmic bytes = sum of bits/8 per row).
 #pragma once
 #include <cuda_runtime.h>
@@ -23,11 +26,6 @@
 #include "pb200_unpack.cuh"
 
 namespace pb200 {
-
-// The group-by kernel aggregates through the warp survivor queue (see phase 2).  The older "dense" path -- 32 keys, 32
-// gathered values and 32 predicated reductions per thread and tile -- needs ~100 more registers (one CTA per SM) and
-// ptxas turns its predicated RED/ATOM instructions into one branch each; it is kept for experiments only.
-constexpr bool kDenseGroupByPath = false;
 
 // ------------------------------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy primitives (PTX ISA 8.x; SASS: SYNCS.*, UBLKCP)
@@ -158,58 +156,12 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t x) {
 
 
 
-// L2-coherent (.cg) predicated load; masked rows get `otherwise`, chosen so that they never trigger an update
-__device__ __forceinline__ uint32_t ldcg_bit_u32(const uint32_t* p, uint32_t mask, uint32_t bit, uint32_t otherwise) {
-  uint32_t x;
-  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\tmov.b32 %0, %4;\n\t"
-               "@p ld.global.cg.b32 %0, [%1];\n\t}" : "=r"(x) : "l"(p), "r"(mask), "r"(bit), "r"(otherwise) : "memory");
-  return x;
-}
-// ---- predicated (branch-free) table updates of the dense group-by path.  One divergent branch per row and table costs
-//      BSSY/BRA/BSYNC plus a branch-resolve stall each (32 rows x tables per tile); a predicated RED/ATOM keeps the 32
-//      updates of a thread straight-line and in flight together.  Predicate = (mask & bit) != 0, bit a constant.
-__device__ __forceinline__ void reds_inc_bit(uint32_t saddr, uint32_t mask, uint32_t bit) {
-  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
-               "@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(saddr), "r"(mask), "r"(bit) : "memory");
-}
-// 64-bit signed add into a (lo, hi) pair of u32 words in shared memory (see smem_add64 below), predicated
-__device__ __forceinline__ void reds_add64_bit(uint32_t lo_addr, uint32_t hi_addr, uint32_t x, uint32_t mask, uint32_t bit) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b32 t, old, s, c, sx, h;\n\t"
-      "and.b32 t, %3, %4;\n\tsetp.ne.u32 p, t, 0;\n\t"
-      "mov.b32 old, 0;\n\t"
-      "@p atom.shared.add.u32 old, [%0], %2;\n\t"
-      "add.u32 s, old, %2;\n\t"
-      "setp.lt.u32 q, s, %2;\n\t"          // carry out of the low word
-      "selp.u32 c, 1, 0, q;\n\t"
-      "shr.s32 sx, %2, 31;\n\t"            // sign extension: 0 or 0xFFFFFFFF
-      "add.u32 h, sx, c;\n\t"
-      "setp.ne.and.u32 q, h, 0, p;\n\t"
-      "@q red.shared.add.u32 [%1], h;\n\t}" ::"r"(lo_addr), "r"(hi_addr), "r"(x), "r"(mask), "r"(bit)
-      : "memory");
-}
-__device__ __forceinline__ void redg_add_u64_bit(unsigned long long* p, unsigned long long v, uint32_t mask, uint32_t bit) {
-  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t"
-               "@p red.global.add.u64 [%0], %1;\n\t}" ::"l"(p), "l"(v), "r"(mask), "r"(bit) : "memory");
-}
-__device__ __forceinline__ void redg_add_f64_bit(double* p, double v, uint32_t mask, uint32_t bit) {
-  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t"
-               "@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(mask), "r"(bit) : "memory");
-}
+// fire-and-forget global reductions (the result is never needed: RED, not ATOM)
 __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void red_add_f64(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ void redg_min_u32_pred(uint32_t* p, uint32_t v, uint32_t pred) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.min.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pred) : "memory");
-}
-__device__ __forceinline__ void redg_max_u32_pred(uint32_t* p, uint32_t v, uint32_t pred) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.max.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pred) : "memory");
-}
-__device__ __forceinline__ void stg_u32_pred(uint32_t* p, uint32_t v, uint32_t pred) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pred) : "memory");
 }
 
 // Hash group table: slot of `key` in the open-addressing table (linear probing, 64-bit CAS on the key itself -- exact,
@@ -241,14 +193,6 @@ __device__ __forceinline__ bool hash_slot(const SegDesc& sd, unsigned long long 
   return false;
 }
 
-// Group bookkeeping of one surviving row: the exact count when some function needs it (COUNT / AVG), otherwise a
-// test-then-set "seen" flag (benign race: every writer stores 1), or nothing when a MIN/MAX table already marks groups.
-__device__ __forceinline__ void touch_group(const SegDesc& sd, uint32_t g) {
-  if (sd.g_count) atomicAdd(sd.g_count + g, 1ull);
-  else if (sd.g_seen) { if (__ldcg(sd.g_seen + g) == 0u) sd.g_seen[g] = 1u; }
-}
-// MIN / MAX tables only change for O(log n) of a group's rows: read the current value (L2) and skip the atomic when it
-// cannot win.  A stale read only costs a redundant atomic, never a wrong result.
 // 64-bit signed accumulate into a CTA-private shared-memory table kept as two u32 words: shared 64-bit atomic adds
 // compile to a CAS spin loop (ATOMS.CAST.SPIN.64) while 32-bit ones are native, and the high word only moves on a
 // carry or a negative addend.
@@ -258,8 +202,6 @@ __device__ __forceinline__ void smem_add64(uint32_t* lo, uint32_t* hi, uint32_t 
   const int h = (x >> 31) + ((uint32_t)(old + xl) < xl ? 1 : 0);  // sign extension + carry out of the low word
   if (h) atomicAdd(hi + g, (uint32_t)h);
 }
-__device__ __forceinline__ void group_min(uint32_t* p, uint32_t x) { if (x < __ldcg(p)) atomicMin(p, x); }
-__device__ __forceinline__ void group_max(uint32_t* p, uint32_t x1) { if (x1 > __ldcg(p)) atomicMax(p, x1); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // streaming functors for dispatch_left_aligned(): consume one left-aligned value at a time (pb200_unpack.cuh)
@@ -356,7 +298,8 @@ struct SmemHeader {
 //   * a THREAD owns 32 consecutive rows (one FixedBitIntReader.read32 group): B words per column.
 // Shared-memory layout (dynamic):
 //   [SmemHeader][W x num_stages x stage_words][filter stack (generic filters only)]
-//   [acc64: num_aggs x threads x 8 B][accmm: num_aggs x threads x 8 B]     (aggregation-only kernel)
+//   [acc64: num_aggs x threads x 8 B][accmm: num_aggs x threads x 8 B]                        (aggregation-only kernel)
+//   [survivor queue: W x 1024 u16][group table copies: count, (lo, hi) per sum -- optional]     (group-by kernel)
 // acc64/accmm are the per-thread running aggregates; they live in shared memory (private slot per thread, touched once
 // per tile) instead of registers so that two CTAs fit on an SM.
 template <int W, bool GROUPBY, bool DEFER = !GROUPBY, int MINB = (GROUPBY ? 1 : 2)>
@@ -684,46 +627,33 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     const int pc = __popc(m);
     cnt += pc;
     const int wmax2 = __reduce_max_sync(0xFFFFFFFFu, pc);
-    // One surviving row (thread group `gl` of this warp's slice, row j of it): read its dictIds from the tile
-    // (FixedBitIntReader.readUnchecked shape; what DataFetcher does with sparse docIds, core/common/DataFetcher.java:335-338)
-    auto process_row = [&](const int gl, const int j) {
-      uint32_t g = 0;
-      if (GROUPBY) {
-#pragma unroll
-        for (int gi = 0; gi < kMaxGroupBy; ++gi) {
-          if (gi < q.num_group_by) {
-            const SlotDesc& sl = sd.slots[q.group_slot[gi]];
-            g += read_one_group(st + sl.stage_words + gl * sl.bits, j, sl.bits) * sd.group_mult[gi];
-          }
-        }
-        if (TG) atomicAdd(tcnt + tcopy + g, 1u); else touch_group(sd, g);
-      }
+    // Aggregation-only kernels, few survivors: one surviving row (row j of this thread's group) is read straight from the
+    // tile (FixedBitIntReader.readUnchecked shape; what DataFetcher does with sparse docIds, core/common/DataFetcher.java:335-338)
+    auto process_row = [&](const int j) {
 #pragma unroll 1
       for (int ai = 0; ai < sd.num_agg_codes; ++ai) {
         const uint32_t ac = sd.agg_code[ai];  // index | function | value kind | bits | stage_words (pb200_desc.h)
         const int a = (int)(ac & 7u), fn = (int)((ac >> 4) & 7u), vk = (int)((ac >> 8) & 7u);
         const int abits = (int)((ac >> 12) & 63u);
-        const uint32_t* base = st + (ac >> 18);
-        const uint32_t id = read_one_group(base + gl * abits, j, abits);
+        const uint32_t id = read_one_group(st + (ac >> 18) + group_in_stage * abits, j, abits);
         if (fn == 1 || fn == 4) {
           if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
             const double x = vk == VAL_DICT_F32 ? (double)__ldg(static_cast<const float*>(sd.dict[a]) + id)
                                                 : __ldg(static_cast<const double*>(sd.dict[a]) + id);
-            if (GROUPBY) atomicAdd(sd.g_dsum[a] + g, x);
-            else { double* slot = reinterpret_cast<double*>(acc64 + a * kConsumers + group); *slot += x; }
+            double* slot = reinterpret_cast<double*>(acc64 + a * kConsumers + group);
+            *slot += x;
           } else {
             const long long x = vk == VAL_DICT_I32 ? (long long)(int)(__ldg(static_cast<const uint32_t*>(sd.dict[a]) + id) ^ 0x80000000u)
                                 : vk == VAL_DICT_I64 ? __ldg(static_cast<const long long*>(sd.dict[a]) + id)
                                                      : (long long)(int)id;
-            if (GROUPBY && TG) { uint32_t* lo = tcnt + tcopy + TA * (1u + 2u * q.smem_slot[a]); smem_add64(lo, lo + TA, g, (int)x); }
-            else if (GROUPBY) atomicAdd(reinterpret_cast<unsigned long long*>(sd.g_isum[a] + g), (unsigned long long)x);
-            else acc64[a * kConsumers + group] += (unsigned long long)x;
+            acc64[a * kConsumers + group] += (unsigned long long)x;
           }
         } else if (fn == 2 || fn == 3) {
           const uint32_t x = id ^ (vk == VAL_RAW_I32 ? 0x80000000u : 0u);
-          if (GROUPBY) { if (fn == 2) group_min(sd.g_min[a] + g, x); else group_max(sd.g_max[a] + g, x + 1u); }
-          else { uint2 mmx = accmm[a * kConsumers + group]; mmx.x = min(mmx.x, x); mmx.y = max(mmx.y, x + 1u); accmm[a * kConsumers + group] = mmx; }
-        } else if (fn == 5 && !GROUPBY) {
+          uint2 mmx = accmm[a * kConsumers + group];
+          mmx.x = min(mmx.x, x); mmx.y = max(mmx.y, x + 1u);
+          accmm[a * kConsumers + group] = mmx;
+        } else if (fn == 5) {
           atomicOr(sd.distinct_bits[a] + (id >> 5), 1u << (id & 31));
         }
       }
@@ -739,7 +669,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
       const int S = __shfl_sync(0xFFFFFFFFu, incl, 31);
       if (S == 0) handled = true;
-      else if (S <= q.queue_max || !kDenseGroupByPath) {
+      else {
         unsigned short* wq = reinterpret_cast<unsigned short*>(smem_base + q.queue_off) + warp * 1024;
         int pos = incl - pc;
         uint32_t mm = m;
@@ -860,7 +790,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
       while (mm) {
         const int j = 31 - __clz(mm);
         mm &= ~(1u << j);
-        process_row(group_in_stage, j);
+        process_row(j);
       }
     } else if (wmax2 > 0) {
       // ---- dense projection ----
@@ -937,114 +867,6 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if ((m >> j) & 1u) atomicOr(bits + (v[j] >> 5), 1u << (v[j] & 31));
-            }
-          }
-        }
-      } else if constexpr (kDenseGroupByPath) {
-        uint32_t gid[32], v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) gid[j] = 0;
-        for (int s = 0; s < q.num_slots; ++s) {
-          if (!(hdr->slot_roles[s] & ROLE_GROUP)) continue;
-          unpack_group(sd.slots[s].bits, st + sd.slots[s].stage_words, group_in_stage, v);
-#pragma unroll
-          for (int g = 0; g < kMaxGroupBy; ++g) {
-            if (g < q.num_group_by && q.group_slot[g] == s) {
-              const uint32_t mult = sd.group_mult[g];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) gid[j] += v[j] * mult;
-            }
-          }
-        }
-        if (TG) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) reds_inc_bit(tcnt_s + 4u * gid[j], m, 1u << j);
-        } else if (sd.g_count) {
-          unsigned long long* const gc = sd.g_count;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) redg_add_u64_bit(gc + gid[j], 1ull, m, 1u << j);
-        } else if (sd.g_seen) {  // test-then-set flags: all tests first (one L2 latency), then the few stores
-          uint32_t* const gs = sd.g_seen;
-          uint32_t cur[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) cur[j] = ldcg_bit_u32(gs + gid[j], m, 1u << j, 1u);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg_u32_pred(gs + gid[j], 1u, cur[j] == 0u ? 1u : 0u);
-        }
-#pragma unroll 1
-        for (int ai = 0; ai < sd.num_agg_codes; ++ai) {
-          const uint32_t ac = sd.agg_code[ai];  // index | function | value kind | bits | stage_words (pb200_desc.h)
-          const int a = (int)(ac & 7u), fn = (int)((ac >> 4) & 7u), vk = (int)((ac >> 8) & 7u);
-          const int abits = (int)((ac >> 12) & 63u);
-          const uint32_t* base = st + (ac >> 18);
-          unpack_group(abits, base, group_in_stage, v);
-          if (fn == 1 || fn == 4) {
-            // all gathers of the tile are issued BEFORE the first atomic consumes one: one L2 latency per tile, not
-            // one per surviving row
-            if (vk == VAL_DICT_I32) {
-              const uint32_t* __restrict__ d = static_cast<const uint32_t*>(sd.dict[a]);
-              uint32_t xv[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) xv[j] = ldg_bit_u32(d + v[j], m, 1u << j);  // straight-line: 32 loads in flight
-              if (TG) {
-                const uint32_t lo_s = tcnt_s + 4u * TA * (1u + 2u * q.smem_slot[a]), hi_s = lo_s + 4u * TA;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) reds_add64_bit(lo_s + 4u * gid[j], hi_s + 4u * gid[j], xv[j] ^ 0x80000000u, m, 1u << j);
-              } else {
-                unsigned long long* const gsum = reinterpret_cast<unsigned long long*>(sd.g_isum[a]);
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  redg_add_u64_bit(gsum + gid[j], (unsigned long long)(long long)(int)(xv[j] ^ 0x80000000u), m, 1u << j);
-              }
-            } else if (vk == VAL_RAW_I32) {
-              if (TG) {
-                const uint32_t lo_s = tcnt_s + 4u * TA * (1u + 2u * q.smem_slot[a]), hi_s = lo_s + 4u * TA;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) reds_add64_bit(lo_s + 4u * gid[j], hi_s + 4u * gid[j], v[j], m, 1u << j);
-              } else {
-                unsigned long long* const gsum = reinterpret_cast<unsigned long long*>(sd.g_isum[a]);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) redg_add_u64_bit(gsum + gid[j], (unsigned long long)(long long)(int)v[j], m, 1u << j);
-              }
-            } else if (vk == VAL_DICT_I64) {
-              const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
-              long long xv[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) xv[j] = ldg_pred_s64(d + v[j], (m >> j) & 1u);
-              unsigned long long* const gsum = reinterpret_cast<unsigned long long*>(sd.g_isum[a]);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) redg_add_u64_bit(gsum + gid[j], (unsigned long long)xv[j], m, 1u << j);
-            } else if (vk == VAL_DICT_F32) {
-              const float* __restrict__ d = static_cast<const float*>(sd.dict[a]);
-              float xv[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) xv[j] = __int_as_float(ldg_pred_s32(reinterpret_cast<const int*>(d + v[j]), (m >> j) & 1u));
-              double* const gd = sd.g_dsum[a];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) redg_add_f64_bit(gd + gid[j], (double)xv[j], m, 1u << j);
-            } else {
-              const double* __restrict__ d = static_cast<const double*>(sd.dict[a]);
-              double xv[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) xv[j] = __longlong_as_double(ldg_pred_s64(reinterpret_cast<const long long*>(d + v[j]), (m >> j) & 1u));
-              double* const gd = sd.g_dsum[a];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) redg_add_f64_bit(gd + gid[j], xv[j], m, 1u << j);
-            }
-          } else if (fn == 2 || fn == 3) {
-            // MIN / MAX tables change for only O(log n) of a group's rows: read the current entries of the whole tile
-            // first (straight-line predicated loads, one L2 latency), then issue an atomic only where the row can win
-            const uint32_t bias = vk == VAL_RAW_I32 ? 0x80000000u : 0u;
-            uint32_t* tab = fn == 2 ? sd.g_min[a] : sd.g_max[a];
-            uint32_t cur[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) cur[j] = ldcg_bit_u32(tab + gid[j], m, 1u << j, fn == 2 ? 0u : 0xFFFFFFFFu);
-            if (fn == 2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { const uint32_t x = v[j] ^ bias; redg_min_u32_pred(tab + gid[j], x, x < cur[j] ? 1u : 0u); }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { const uint32_t x = (v[j] ^ bias) + 1u; redg_max_u32_pred(tab + gid[j], x, x > cur[j] ? 1u : 0u); }
             }
           }
         }

@@ -12,4 +12,3 @@ b PB200_W=8
 b PB200_W=8 PB200_NO_DEFER=1 PB200_STAGES=2
 b PB200_W=8 PB200_NO_DEFER=1 PB200_SPARSE_MAX=0
 b PB200_SPARSE_MAX=0
-b PB200_W=7
