@@ -163,6 +163,9 @@ typedef struct {
 #define PB200_Q_PER_SEGMENT_FILTER 1 /* filter[] holds one tree per segment (segment-local dictIds) */
 #define PB200_Q_MERGE_SEGMENTS 2     /* all segments share dictionaries: accumulate into ONE result (device-side
                                         combine, the GroupByCombineOperator/AggregationCombineOperator analogue) */
+#define PB200_Q_DEFER_FINALIZE 4     /* group-by with PB200_Q_MERGE_SEGMENTS: leave the groups in the dense device tables
+                                        (pb200_result_device_buffers) and extract them later with pb200_result_finalize --
+                                        for a cross-GPU reduce of the tables in between; only the reduce root extracts */
 
 /* Runs the operator chain DocIdSet -> Projection -> Aggregation/GroupBy for `num_segments` segments in one device
  * submission (one persistent kernel over all segments' tiles).  Writes num_segments result handles (or exactly one

@@ -118,7 +118,8 @@ typedef struct {
   const pb200h_agg* aggs;
   int32_t num_groups_limit;
   int32_t max_initial_result_holder_capacity;
-  int32_t merge_segments; /* device-side combine (requires identical dictionaries across the segments) */
+  int32_t merge_segments; /* 1: device-side combine (requires identical dictionaries across the segments);
+                             2: combine and defer the group extraction (PB200_Q_DEFER_FINALIZE) */
   int32_t skip_star_tree; /* query option useStarTree=false */
 } pb200h_query;
 

@@ -531,7 +531,7 @@ extern "C" int32_t pb200h_execute(pb200_ctx* ctx, const pb200h_query* q, pb200h_
     dq.num_aggs = q->num_aggs;
     dq.num_groups_limit = q->num_groups_limit > 0 ? q->num_groups_limit : 100000;
     dq.max_initial_result_holder_capacity = q->max_initial_result_holder_capacity > 0 ? q->max_initial_result_holder_capacity : 10000;
-    dq.flags = PB200_Q_PER_SEGMENT_FILTER | (merge ? PB200_Q_MERGE_SEGMENTS : 0);
+    dq.flags = PB200_Q_PER_SEGMENT_FILTER | (merge ? PB200_Q_MERGE_SEGMENTS : 0) | (q->merge_segments == 2 ? PB200_Q_DEFER_FINALIZE : 0);
     dq.filter = flat.data();
     dq.group_by_columns = gb.data();
     dq.aggs = aggs.data();

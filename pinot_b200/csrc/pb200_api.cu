@@ -1217,7 +1217,10 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       R.meta.regime = regime_of(cards, query->max_initial_result_holder_capacity);
     }
   }
-  if (plan.group_by) {  // all results of the submission are extracted together (two device round trips in total)
+  const bool defer_finalize = merge && (query->flags & PB200_Q_DEFER_FINALIZE);
+  if (plan.group_by && defer_finalize) {
+    for (int r = 0; r < nres; r++) { res[r]->meta.num_groups = 0; res[r]->dbl.assign(nagg, {}); res[r]->lng.assign(nagg, {}); res[r]->ids.assign(nagg, {}); res[r]->distinct.assign(nagg, {}); }
+  } else if (plan.group_by) {  // all results of the submission are extracted together (two device round trips in total)
     std::vector<pb200_result*> rs;
     for (int r = 0; r < nres; r++) rs.push_back(res[r].get());
     int frc = finalize_many(ctx, rs.data(), nres, st);

@@ -39,8 +39,8 @@ def shard_segments(num_segments: int, world_size: int, rank: int) -> List[int]:
 def reduce_buffers(buffers: Dict[str, "torch.Tensor"], dist, dst: int = 0) -> None:
     """In-place reduce of the four table kinds to rank `dst` (works on CPU tensors with gloo and CUDA with nccl).
 
-    The two u32 tables are carried by int32 tensors (torch has no uint32 collectives); they are widened to int64 with
-    the unsigned value for the MAX / MIN reduce and written back -- they are O(groups) small.
+    The two u32 tables are carried by int32 tensors (torch has no uint32 collectives): the top bit is flipped before and
+    after the MAX / MIN reduce so that the signed order equals the unsigned one.
     """
     import torch
     for kind, t in buffers.items():
@@ -49,9 +49,10 @@ def reduce_buffers(buffers: Dict[str, "torch.Tensor"], dist, dst: int = 0) -> No
         if kind in ("i64", "f64"):
             dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM)
         elif kind in ("u32max", "u32min"):
-            wide = t.to(torch.int64) & 0xFFFFFFFF
-            dist.reduce(wide, dst=dst, op=dist.ReduceOp.MAX if kind == "u32max" else dist.ReduceOp.MIN)
-            t.copy_(wide.to(torch.int32))
+            # unsigned order == signed order after flipping the top bit: reduce in place, no widened copy
+            t.bitwise_xor_(-2147483648)
+            dist.reduce(t, dst=dst, op=dist.ReduceOp.MAX if kind == "u32max" else dist.ReduceOp.MIN)
+            t.bitwise_xor_(-2147483648)
         else:
             raise KeyError(kind)
 
@@ -88,10 +89,9 @@ def combine_across_ranks(plan_maker, block, query, dist, dst: int = 0):
     import torch
     from .plan_maker import _read_result
     ctx = plan_maker.ctx
-    bufs = device_buffers(ctx, block)
-    torch.cuda.synchronize(ctx.device)
+    bufs = device_buffers(ctx, block)  # pb200_execute returned after its stream finished: the tables are complete
     reduce_buffers(bufs, dist, dst)
-    torch.cuda.synchronize(ctx.device)
+    torch.cuda.synchronize(ctx.device)  # the extraction below runs on the library's own stream
     out = None
     if dist.get_rank() == dst:
         from . import _lib

@@ -341,8 +341,11 @@ class B200PlanMaker:
     def execute_segments(self, segments: Sequence[IndexSegment], query: QueryContext, merge: bool = False,
                          keep_handle: bool = False) -> List[ResultsBlock]:
         """All segments of one query in ONE device submission (makeInstancePlan-level batching).  With merge=True the
-        segments (sharing dictionaries) are combined on the device and one block is returned."""
-        hq, _keep = _marshal_query(query, merge)
+        segments (sharing dictionaries) are combined on the device and one block is returned; with keep_handle=True as
+        well, a group-by block comes back WITHOUT its groups extracted (PB200_Q_DEFER_FINALIZE): its dense device tables
+        are meant to be reduced across GPUs (pinot_b200.distributed.combine_across_ranks), which extracts on the root."""
+        # merge + keep_handle: the caller reduces the dense tables across GPUs first; groups are extracted afterwards
+        hq, _keep = _marshal_query(query, 2 if (merge and keep_handle and query.is_group_by) else merge)
         n = len(segments)
         segs = (C.c_void_p * n)(*[s.handle for s in segments])
         nres = 1 if merge else n

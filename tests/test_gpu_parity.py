@@ -234,6 +234,15 @@ def test_multi_segment_single_submission_and_device_merge(oracle, ctx, pm):
             merged = pm.execute_segments(devs, q, merge=True)
             assert len(merged) == 1
             assert_tables_equal(q, gpu_table(segs[0], q, merged[0]), combine(fns, want_blocks), "merged " + text)
+            if q.is_group_by:
+                # deferred extraction (what a cross-GPU reduce of the dense tables sits between): tables first, groups later
+                from pinot_b200 import _lib
+                from pinot_b200.plan_maker import _read_result
+                late = pm.execute_segments(devs, q, merge=True, keep_handle=True)[0]
+                assert late.num_groups == 0 and late.handle is not None
+                _lib.check(ctx.lib.pb200_result_finalize(ctx.handle, late.handle))
+                late = _read_result(ctx, late.handle, q, 1, keep_handle=False)
+                assert gpu_table(segs[0], q, late) == gpu_table(segs[0], q, merged[0]), "deferred " + text
     finally:
         for d in devs:
             d.destroy()
