@@ -133,6 +133,8 @@ QUERIES = [
     "SELECT COUNT(*) FROM t WHERE b > 5000 GROUP BY a",                   # no groups
     "SELECT DISTINCTCOUNT(b), DISTINCTCOUNT(s), COUNT(*) FROM t WHERE c > 100000 GROUP BY a",
     "SELECT DISTINCTCOUNT(d) FROM t GROUP BY s, t",
+    "SELECT SUM(c), SUM(a), COUNT(*) FROM t GROUP BY a",                  # shared-memory tables: carries and negative addends
+    "SELECT SUM(a), AVG(c) FROM t WHERE b < 990 GROUP BY t, a",
 ]
 
 
