@@ -389,7 +389,9 @@ def main():
                         "note": "every step re-uploads the touched columns from pinned host memory (PCIe bound); "
                                 "`value` is the same plugin call with the segments resident in HBM"},
                 "gpu_launches": args.steps * 1, "clocks": clocks, "segment_generation_s": gen_s,
-                "result": {"sum_c5": s, "count": c}}
+                "result": {"sum_c5": s, "count": c, "scope": "rank 0's segments",
+                           "all_ranks": None if result_dev is None else {"sum_c5": float(result_dev[0].item()),
+                                                                         "count": int(result_dev[1].item())}}}
         print(json.dumps(line))
     for sgm in segs:
         sgm.destroy()

@@ -1099,9 +1099,13 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   DevBuf dsegs;
   int rc = dsegs.alloc(ctx, sizeof(SegDesc) * nseg);
   if (rc) return rc;
-  cudaEvent_t e0, e1;
-  PB200_CUDA(cudaEventCreate(&e0));
-  PB200_CUDA(cudaEventCreate(&e1));
+  struct Events {  // RAII: every early return below releases them
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
+  PB200_CUDA(cudaEventCreate(&ev.a));
+  PB200_CUDA(cudaEventCreate(&ev.b));
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   cudaError_t le = cudaSuccess;
   int grid = 0;
   std::vector<SegDesc> launch_segs = plan.segs;
@@ -1143,15 +1147,13 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     else if (cw == 8) le = getenv("PB200_NO_DEFER") ? launch_scan<8, false, false>(plan, cq, tt, dptr, grid, st) : launch_scan<8, false>(plan, cq, tt, dptr, grid, st);
     else le = launch_scan<6, false>(plan, cq, tt, dptr, grid, st);
   }
-  if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }
+  if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); return PB200_E_CUDA; }
   PB200_CUDA(cudaEventRecord(e1, st));
   cudaError_t se = cudaStreamSynchronize(st);
-  if (se != cudaSuccess) { set_error("scan kernel failed: %s", cudaGetErrorString(se)); cudaEventDestroy(e0); cudaEventDestroy(e1); return PB200_E_CUDA; }
+  if (se != cudaSuccess) { set_error("scan kernel failed: %s", cudaGetErrorString(se)); return PB200_E_CUDA; }
   PB200_CUDA(cudaMemcpy(host_acc.data(), accum_buf.p, sizeof(AggAccum) * nres, cudaMemcpyDeviceToHost));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
 
   // ---- results ----
   int projected = 0;
