@@ -204,6 +204,10 @@ int32_t pb200_result_agg(const pb200_result* result, int32_t agg, double* out_do
 int32_t pb200_result_agg_dict_ids(const pb200_result* result, int32_t agg, int32_t* out);
 /* DISTINCTCOUNT: the dictId set of row `row` (ascending); returns the count (or < 0 on error), writes <= capacity */
 int64_t pb200_result_distinct(const pb200_result* result, int32_t agg, int32_t row, int32_t* out, int64_t capacity);
+/* Everything of a result in ONE call (a JNI / ctypes round trip per accessor adds up when many small per-segment results
+ * are read): keys [rows x num_group_by] (may be NULL), doubles / longs / dict_ids [num_aggs x rows] each (row-major by
+ * aggregation; any may be NULL).  rows = num_groups, or 1 for an aggregation-only result. */
+int32_t pb200_result_fetch(const pb200_result* result, int32_t* keys, double* doubles, int64_t* longs, int32_t* dict_ids);
 int32_t pb200_result_free(pb200_result* result);
 
 /* ---- multi-GPU combine support (dense group tables with shared dictionaries) ----------------------------------- */

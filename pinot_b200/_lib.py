@@ -108,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "pb200_init", "pb200_shutdown", "pb200_last_error", "pb200_abi_version", "pb200_device_info",
     "pb200_segment_register", "pb200_segment_release", "pb200_segment_device_bytes", "pb200_execute",
     "pb200_result_meta_get", "pb200_result_group_keys", "pb200_result_agg", "pb200_result_agg_dict_ids",
-    "pb200_result_distinct", "pb200_result_free", "pb200_result_device_buffers", "pb200_result_finalize",
+    "pb200_result_distinct", "pb200_result_fetch", "pb200_result_free", "pb200_result_device_buffers", "pb200_result_finalize",
     "pb200_synth_segment", "pb200_segment_read_index", "pb200_segment_column_info",
     "pb200h_segment_create", "pb200h_segment_adopt", "pb200h_segment_load_dir", "pb200h_segment_destroy",
     "pb200h_segment_device", "pb200h_segment_num_docs", "pb200h_segment_num_columns", "pb200h_segment_column_index",
@@ -143,6 +143,7 @@ def load() -> C.CDLL:
     L.pb200_result_agg_dict_ids.argtypes = [vp, i32, vp]
     L.pb200_result_distinct.restype = i64
     L.pb200_result_distinct.argtypes = [vp, i32, i32, vp, i64]
+    L.pb200_result_fetch.argtypes = [vp, vp, vp, vp, vp]
     L.pb200_result_free.argtypes = [vp]
     L.pb200_result_device_buffers.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
     L.pb200_result_finalize.argtypes = [vp, vp]

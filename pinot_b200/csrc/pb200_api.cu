@@ -1465,6 +1465,17 @@ extern "C" int32_t pb200_result_agg_dict_ids(const pb200_result* R, int32_t a, i
   if (!R->ids[a].empty()) memcpy(out, R->ids[a].data(), R->ids[a].size() * 4);
   return PB200_OK;
 }
+extern "C" int32_t pb200_result_fetch(const pb200_result* R, int32_t* keys, double* dbl, int64_t* lng, int32_t* ids) {
+  if (!R) { set_error("null result"); return PB200_E_INVALID; }
+  const size_t rows = R->meta.num_groups < 0 ? 1 : (size_t)R->meta.num_groups;
+  if (keys && !R->keys.empty()) memcpy(keys, R->keys.data(), R->keys.size() * 4);
+  for (size_t a = 0; a < R->dbl.size(); a++) {
+    if (dbl && R->dbl[a].size() == rows && rows) memcpy(dbl + a * rows, R->dbl[a].data(), rows * 8);
+    if (lng && R->lng[a].size() == rows && rows) memcpy(lng + a * rows, R->lng[a].data(), rows * 8);
+    if (ids && R->ids[a].size() == rows && rows) memcpy(ids + a * rows, R->ids[a].data(), rows * 4);
+  }
+  return PB200_OK;
+}
 extern "C" int64_t pb200_result_distinct(const pb200_result* R, int32_t a, int32_t row, int32_t* out, int64_t cap) {
   if (!R || a < 0 || a >= (int)R->distinct.size() || row < 0 || row >= (int)R->distinct[a].size()) { set_error("bad distinct index"); return PB200_E_INVALID; }
   const auto& v = R->distinct[a][row];

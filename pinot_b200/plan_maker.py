@@ -260,22 +260,17 @@ def _read_result(ctx: B200Context, handle, q: QueryContext, kind: int, keep_hand
     rows = 1 if g < 0 else g
     k = len(q.group_by)
     keys = np.zeros((max(g, 0), k), dtype=np.int32)
-    if g > 0 and k > 0:
-        _lib.check(L.pb200_result_group_keys(handle, _ptr(keys)))
-    doubles, longs, ids, distinct = [], [], [], {}
+    na = len(q.aggregations)
+    d_all = np.zeros((na, rows), dtype=np.float64)
+    l_all = np.zeros((na, rows), dtype=np.int64)
+    i_all = np.full((na, rows), -1, dtype=np.int32)
+    if rows:  # one ABI round trip for keys and all intermediates
+        _lib.check(L.pb200_result_fetch(handle, _ptr(keys) if (g > 0 and k > 0) else None, _ptr(d_all), _ptr(l_all), _ptr(i_all)))
+    doubles, longs, ids, distinct = list(d_all), list(l_all), list(i_all), {}
     for a, agg in enumerate(q.aggregations):
-        d = np.zeros(rows, dtype=np.float64)
-        l = np.zeros(rows, dtype=np.int64)
-        di = np.full(rows, -1, dtype=np.int32)
-        if rows:
-            _lib.check(L.pb200_result_agg(handle, a, _ptr(d), _ptr(l)))
-            _lib.check(L.pb200_result_agg_dict_ids(handle, a, _ptr(di)))
-        doubles.append(d)
-        longs.append(l)
-        ids.append(di)
         if agg.function == "DISTINCTCOUNT":
             for row in range(rows):
-                buf = np.zeros(int(l[row]), dtype=np.int32)
+                buf = np.zeros(int(l_all[a][row]), dtype=np.int32)
                 n = L.pb200_result_distinct(handle, a, row, _ptr(buf), len(buf))
                 if n < 0:
                     _lib.check(int(n))
