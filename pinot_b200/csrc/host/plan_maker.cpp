@@ -358,7 +358,13 @@ bool read_file(const std::string& p, std::vector<unsigned char>& out) {
   if (n) f.read((char*)out.data(), n);
   return (bool)f;
 }
-std::map<std::string, std::string> read_properties(const std::string& p) {
+std::string trim(const std::string& s) {
+  size_t a = s.find_first_not_of(" \t\r"), b = s.find_last_not_of(" \t\r");
+  return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+// commons-configuration properties: list values are written either as repeated keys or comma separated; `lists` (optional)
+// collects every value of a key in file order, the plain map keeps the last one
+std::map<std::string, std::string> read_properties(const std::string& p, std::map<std::string, std::vector<std::string>>* lists = nullptr) {
   std::map<std::string, std::string> m;
   std::ifstream f(p);
   std::string line;
@@ -366,10 +372,83 @@ std::map<std::string, std::string> read_properties(const std::string& p) {
     if (line.empty() || line[0] == '#') continue;
     size_t eq = line.find('=');
     if (eq == std::string::npos) continue;
-    auto trim = [](std::string s) { size_t a = s.find_first_not_of(" \t\r"), b = s.find_last_not_of(" \t\r"); return a == std::string::npos ? std::string() : s.substr(a, b - a + 1); };
-    m[trim(line.substr(0, eq))] = trim(line.substr(eq + 1));
+    const std::string k = trim(line.substr(0, eq)), v = trim(line.substr(eq + 1));
+    m[k] = v;
+    if (lists) {
+      size_t start = 0;
+      while (start <= v.size()) {
+        size_t comma = v.find(',', start);
+        std::string item = trim(v.substr(start, comma == std::string::npos ? std::string::npos : comma - start));
+        if (!item.empty()) (*lists)[k].push_back(item);
+        if (comma == std::string::npos) break;
+        start = comma + 1;
+      }
+    }
   }
   return m;
+}
+
+// StarTreeV2 files of a segment directory (seglocal/startree/v2/store/StarTreeIndexMapUtils.java: `star_tree_index_map`
+// lines "<tree>.<column>.<FORWARD_INDEX|STAR_TREE>.<OFFSET|SIZE> = n", the tree itself under column "null";
+// metadata.properties keys startree.v2.count / .<t>.total.docs / .split.order / .function.column.pairs): every tree whose
+// dimensions are loaded columns is attached; function-column pairs other than COUNT / SUM / MIN / MAX are skipped.
+void attach_star_trees_from_dir(pb200_ctx* ctx, const std::string& dir, pb200h_segment* seg) {
+  std::map<std::string, std::vector<std::string>> lists;
+  std::map<std::string, std::string> meta = read_properties(dir + "/metadata.properties", &lists);
+  const int ntrees = meta.count("startree.v2.count") ? atoi(meta["startree.v2.count"].c_str()) : 0;
+  if (ntrees <= 0) return;
+  std::vector<unsigned char> file;
+  if (!read_file(dir + "/star_tree_index", file)) return;
+  std::map<std::string, std::string> imap = read_properties(dir + "/star_tree_index_map");
+  for (int t = 0; t < ntrees; t++) {
+    const std::string pre = "startree.v2." + std::to_string(t) + ".";
+    const int total = meta.count(pre + "total.docs") ? atoi(meta[pre + "total.docs"].c_str()) : 0;
+    const std::vector<std::string>& dims = lists[pre + "split.order"];
+    const std::vector<std::string>& pairs = lists[pre + "function.column.pairs"];
+    if (total <= 0 || dims.empty() || pairs.empty()) continue;
+    auto slice = [&](const std::string& col, const char* kind, const unsigned char*& p, uint64_t& n) -> bool {
+      const std::string k = std::to_string(t) + "." + col + "." + kind;
+      auto o = imap.find(k + ".OFFSET"), z = imap.find(k + ".SIZE");
+      if (o == imap.end() || z == imap.end()) return false;
+      const unsigned long long off = strtoull(o->second.c_str(), nullptr, 10), size = strtoull(z->second.c_str(), nullptr, 10);
+      if (off + size > file.size()) return false;
+      p = file.data() + off; n = size;
+      return true;
+    };
+    const unsigned char* tree = nullptr; uint64_t tree_bytes = 0;
+    if (!slice("null", "STAR_TREE", tree, tree_bytes)) continue;
+    std::vector<const char*> dim_names;
+    std::vector<const void*> dim_fwd;
+    std::vector<uint64_t> dim_bytes;
+    bool ok = true;
+    for (const std::string& d : dims) {
+      const unsigned char* p = nullptr; uint64_t n = 0;
+      if (seg->column_index(d.c_str()) < 0 || !slice(d, "FORWARD_INDEX", p, n)) { ok = false; break; }
+      dim_names.push_back(d.c_str()); dim_fwd.push_back(p); dim_bytes.push_back(n);
+    }
+    if (!ok) continue;
+    std::vector<pb200h_star_metric> metrics;
+    std::vector<std::string> metric_cols(pairs.size());
+    for (size_t i = 0; i < pairs.size(); i++) {
+      const size_t sep = pairs[i].find("__");
+      if (sep == std::string::npos) continue;
+      std::string fn = pairs[i].substr(0, sep);
+      for (auto& ch : fn) ch = (char)toupper((unsigned char)ch);
+      const int code = fn == "COUNT" ? PB200_AGG_COUNT : fn == "SUM" ? PB200_AGG_SUM : fn == "MIN" ? PB200_AGG_MIN : fn == "MAX" ? PB200_AGG_MAX : -1;
+      const unsigned char* p = nullptr; uint64_t n = 0;
+      if (code < 0 || !slice(pairs[i], "FORWARD_INDEX", p, n)) continue;
+      metric_cols[i] = pairs[i].substr(sep + 2);
+      if (code != PB200_AGG_COUNT && seg->column_index(metric_cols[i].c_str()) < 0) continue;
+      pb200h_star_metric m;
+      memset(&m, 0, sizeof m);
+      m.function = code; m.column = code == PB200_AGG_COUNT ? nullptr : metric_cols[i].c_str(); m.fwd = p; m.fwd_bytes = n;
+      metrics.push_back(m);
+    }
+    if (metrics.empty()) continue;
+    // a tree that cannot be attached (unsupported layout) is simply not used: queries then scan the base columns
+    pb200h_startree_attach(ctx, seg, tree, tree_bytes, total, (int)dims.size(), dim_names.data(), dim_fwd.data(), dim_bytes.data(),
+                           (int)metrics.size(), metrics.data());
+  }
 }
 }  // namespace
 
@@ -446,7 +525,10 @@ extern "C" int32_t pb200h_segment_load_dir(pb200_ctx* ctx, const char* path, pb2
     cols[i].inv = bufs[i].inv.empty() ? nullptr : bufs[i].inv.data(); cols[i].inv_bytes = bufs[i].inv.size();
   }
   const std::string seg_name = meta.count("segment.name") ? meta["segment.name"] : dir;
-  return pb200h_segment_create(ctx, seg_name.c_str(), num_docs, (int)cols.size(), cols.data(), out);
+  int rc = pb200h_segment_create(ctx, seg_name.c_str(), num_docs, (int)cols.size(), cols.data(), out);
+  if (rc) return rc;
+  attach_star_trees_from_dir(ctx, dir, *out);
+  return PB200_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
