@@ -1,0 +1,65 @@
+"""-m gpu: the native segment-directory loader (pb200h_segment_load_dir = ImmutableSegmentLoader.load without a JVM):
+v1 file-per-index and v3 columns.psf + index_map layouts, and StarTreeV2 files picked up from the directory."""
+import numpy as np
+import pytest
+
+from gpu_util import assert_tables_equal, check_query, gpu_table, oracle_table
+from oracle import startree_builder as stb
+from pinot_b200 import sql
+from pinot_b200.plan_maker import B200Context, B200PlanMaker, IndexSegment
+from segment_dir_util import write_segment_dir
+from test_gpu_parity import QUERIES, _random_segment
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = B200Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("version", ["v1", "v3"])
+def test_load_segment_directory(oracle, ctx, tmp_path, version):
+    rng = np.random.default_rng(11)
+    seg = _random_segment(oracle, rng, 20_011, name="disk")
+    root = write_segment_dir(str(tmp_path / version), seg, version)
+    dev = IndexSegment.load(ctx, root)
+    pm = B200PlanMaker(ctx)
+    try:
+        assert dev.num_docs == seg.num_docs and sorted(dev.column_names) == sorted(c.name for c in seg.columns)
+        for c in seg.columns:  # the loader reproduces what from_columns gets directly
+            info = dev.column_info(c.name)
+            assert (info["bits"], info["cardinality"], bool(info["is_sorted"])) == (c.bits, c.cardinality, c.is_sorted), c.name
+            assert bool(info["has_inverted"]) == (c.inv is not None and not c.is_sorted), c.name
+        for text in QUERIES:
+            check_query(oracle, pm, seg, dev, sql.parse(text), what=f"{version}: {text}")
+    finally:
+        dev.destroy()
+
+
+def test_load_directory_with_star_tree(oracle, ctx, tmp_path):
+    rng = np.random.default_rng(12)
+    n = 40_000
+    seg = oracle.build_segment("st_disk", {
+        "d1": rng.integers(0, 60, size=n).astype(np.int32), "d2": rng.integers(0, 40, size=n).astype(np.int32) * 3,
+        "d3": rng.integers(0, 5, size=n).astype(np.int32), "m": rng.integers(0, 500, size=n).astype(np.int32)})
+    st = stb.build_star_tree(seg, ["d1", "d2", "d3"], [("COUNT", None), ("SUM", "m"), ("MAX", "m")], max_leaf_records=100)
+    root = write_segment_dir(str(tmp_path / "seg"), seg, "v3", star_tree=st)
+    dev = IndexSegment.load(ctx, root)
+    pm = B200PlanMaker(ctx)
+    try:
+        for text in ("SELECT COUNT(*), SUM(m), MAX(m), AVG(m) FROM t WHERE d1 < 20 GROUP BY d2",
+                     "SELECT SUM(m) FROM t WHERE d1 = 7 AND d3 IN (1, 2)",
+                     "SELECT COUNT(*) FROM t GROUP BY d3, d1"):
+            q = sql.parse(text)
+            star = pm.execute_segments([dev], q)[0]
+            assert star.operator_kind == "STAR_TREE", text          # the tree came from the directory
+            scan = pm.execute_segments([dev], sql.parse(text, use_star_tree=False))[0]
+            want = oracle_table(seg, q, oracle.execute(seg, q))
+            assert_tables_equal(q, gpu_table(seg, q, scan), want, "scan " + text)
+            assert_tables_equal(q, gpu_table(seg, q, star), want, "star " + text)
+            assert star.stats.num_docs_scanned <= scan.stats.num_docs_scanned
+    finally:
+        dev.destroy()
