@@ -966,7 +966,9 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         if (q.aggs[a].function != PB200_AGG_DISTINCTCOUNT) continue;
         const DeviceColumn& c = segments[s]->cols[query->aggs[a].column];
         if (!distinct_bufs[r][a]) {
-          size_t words = ((size_t)1 << c.bits) / 32 + 1;
+          int maxbits = c.bits;  // a merged result's bitset must hold the dictIds of every segment that writes into it
+          if (merge) for (int t = 0; t < nseg; t++) maxbits = std::max(maxbits, segments[t]->cols[query->aggs[a].column].bits);
+          size_t words = ((size_t)1 << maxbits) / 32 + 1;
           distinct_bufs[r][a].reset(new DevBuf());
           int rc = distinct_bufs[r][a]->alloc(ctx, words * 4);
           if (rc) return rc;
@@ -1068,6 +1070,10 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         else if (fn == PB200_AGG_MAX) { d.gmax[a] = (uint32_t*)d.u32max_block + (xi++) * groups; if (!need_count && !d.exists_max && !d.exists_min) d.exists_max = d.gmax[a]; }
         else if (fn == PB200_AGG_DISTINCTCOUNT) {  // one dictId bitset per group / slot
           const DeviceColumn& c = seg->cols[query->aggs[a].column];
+          if (merge) for (int s = 1; s < nseg; s++) if (segments[s]->cols[query->aggs[a].column].cardinality != c.cardinality) {
+            set_error("PB200_Q_MERGE_SEGMENTS needs identical dictionaries (cardinality of DISTINCTCOUNT column %d differs)", query->aggs[a].column);
+            return PB200_E_INVALID;
+          }
           const unsigned long long words = ((unsigned long long)c.cardinality + 31) / 32;
           if (words * (unsigned long long)groups > (1ull << 28)) {
             set_error("DISTINCTCOUNT with GROUP BY: %lld groups x %d dictIds exceed the device bitset budget", groups, c.cardinality);
@@ -1204,7 +1210,9 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         } else if (fn == PB200_AGG_MAX) {
           if (acc.max_id_plus1[a] == 0) d = -INFINITY; else { id = (int32_t)(acc.max_id_plus1[a] - 1); d = c->dict_host.empty() && vk != VAL_RAW_I32 ? (double)id : value_of(acc.max_id_plus1[a] - 1); }
         } else if (fn == PB200_AGG_DISTINCTCOUNT) {
-          size_t words = ((size_t)1 << c->bits) / 32 + 1;
+          int maxbits = c->bits;
+          if (merge) for (int t = 0; t < nseg; t++) maxbits = std::max(maxbits, segments[t]->cols[query->aggs[a].column].bits);
+          size_t words = ((size_t)1 << maxbits) / 32 + 1;
           std::vector<uint32_t> bits(words);
           PB200_CUDA(cudaMemcpy(bits.data(), distinct_bufs[r][a]->p, words * 4, cudaMemcpyDeviceToHost));
           std::vector<int32_t> idsv;
