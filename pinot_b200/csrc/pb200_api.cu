@@ -182,18 +182,6 @@ struct NonEmptyGroup {  // a group exists iff any of its (present) markers says 
   }
 };
 
-// compaction of a dense group table: indices of non-empty groups (any order)
-__global__ void compact_groups_kernel(const unsigned long long* __restrict__ count, long long groups,
-                                      unsigned long long* __restrict__ n_out, uint32_t* __restrict__ idx_out,
-                                      long long cap) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  for (; i < groups; i += (long long)gridDim.x * blockDim.x) {
-    if (count[i] != 0ull) {
-      unsigned long long pos = atomicAdd(n_out, 1ull);
-      if ((long long)pos < cap) idx_out[pos] = (uint32_t)i;
-    }
-  }
-}
 // All per-group columns of one result in one launch: out block = [col 0: n x esz][col 1: ...] (8-byte aligned columns)
 struct GatherCol { const void* src; unsigned long long dst_off; uint32_t esz; uint32_t pad; };
 struct GatherPlan { GatherCol col[2 + kMaxAggs]; int ncols; };
@@ -213,12 +201,6 @@ __global__ void gather_rows_kernel(const uint32_t* __restrict__ src, const uint3
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * words; i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[(size_t)idx[i / words] * words + (i % words)];
 }
-template <typename T>
-__global__ void gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, long long n, T* __restrict__ dst) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  for (; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
-}
-
 }  // namespace pb200
 
 using namespace pb200;
