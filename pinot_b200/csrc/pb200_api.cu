@@ -304,6 +304,9 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
                                           const pb200_col_desc* cols, pb200_segment** out) {
   if (!ctx || !cols || !out || num_docs < 0 || ncols <= 0) { set_error("invalid argument to pb200_segment_register"); return PB200_E_INVALID; }
   PB200_CUDA(cudaSetDevice(ctx->device));
+  // uploads below are asynchronous on the default stream; whatever way this function returns, they are finished first
+  // (the caller's buffers must not be read after the return)
+  struct DrainDefaultStream { ~DrainDefaultStream() { cudaStreamSynchronize(0); } } drain_default_stream;
   std::unique_ptr<pb200_segment> seg(new pb200_segment());
   seg->ctx = ctx;
   seg->name = name ? name : "";
@@ -333,7 +336,10 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
         c.pooled = true;
         const uint64_t body = need & ~15ull;  // zero only the padding behind the file's bytes
         PB200_CUDA(cudaMemsetAsync((unsigned char*)c.fwd + body, 0, c.fwd_alloc_bytes - body, 0));
-        PB200_CUDA(cudaMemcpy(c.fwd, d.fwd, need, cudaMemcpyHostToDevice));
+        // asynchronous on the default stream: with pinned caller buffers the DMA of this column overlaps the host-side
+        // dictionary conversion below and the next column's set-up (pageable buffers are staged synchronously by the
+        // runtime); the stream is drained once at the end of the registration
+        PB200_CUDA(cudaMemcpyAsync(c.fwd, d.fwd, need, cudaMemcpyHostToDevice, 0));
         PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes));
       }
     } else if (d.fwd_kind == PB200_FWD_DICT_SORTED) {
@@ -416,6 +422,10 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
     }
   }
   for (auto& c : seg->cols) c.owns = true;  // adopted device buffers belong to the segment from here on
+  {  // every upload / re-layout kernel above ran on the default stream: the caller's buffers may go away after this
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) { set_error("segment upload failed: %s", cudaGetErrorString(e)); return fail(PB200_E_CUDA); }
+  }
   *out = seg.release();
   return PB200_OK;
 }
