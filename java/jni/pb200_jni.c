@@ -145,6 +145,20 @@ JNIEXPORT jint JNICALL CLS(resultAggDictIds)(JNIEnv* env, jclass cls, jlong resu
   return rc;
 }
 
+JNIEXPORT jint JNICALL CLS(resultFetch)(JNIEnv* env, jclass cls, jlong result, jintArray keys, jdoubleArray dbl,
+                                        jlongArray lng, jintArray ids) {
+  jint* k = keys ? (*env)->GetIntArrayElements(env, keys, NULL) : NULL;
+  jdouble* d = dbl ? (*env)->GetDoubleArrayElements(env, dbl, NULL) : NULL;
+  jlong* l = lng ? (*env)->GetLongArrayElements(env, lng, NULL) : NULL;
+  jint* i = ids ? (*env)->GetIntArrayElements(env, ids, NULL) : NULL;
+  int rc = pb200_result_fetch((const pb200_result*)(intptr_t)result, (int32_t*)k, (double*)d, (int64_t*)l, (int32_t*)i);
+  if (k) (*env)->ReleaseIntArrayElements(env, keys, k, 0);
+  if (d) (*env)->ReleaseDoubleArrayElements(env, dbl, d, 0);
+  if (l) (*env)->ReleaseLongArrayElements(env, lng, l, 0);
+  if (i) (*env)->ReleaseIntArrayElements(env, ids, i, 0);
+  return rc;
+}
+
 JNIEXPORT jintArray JNICALL CLS(resultDistinct)(JNIEnv* env, jclass cls, jlong result, jint agg, jint row) {
   int64_t n = pb200_result_distinct((const pb200_result*)(intptr_t)result, agg, row, NULL, 0);
   if (n < 0) return NULL;

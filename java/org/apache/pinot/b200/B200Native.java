@@ -54,5 +54,7 @@ public final class B200Native {
   public static native int resultAgg(long result, int agg, double[] doublesOut, long[] longsOut);
   public static native int resultAggDictIds(long result, int agg, int[] dictIdsOut);
   public static native int[] resultDistinct(long result, int agg, int row);
+  /** pb200_result_fetch: keys [rows x groupBy], doubles / longs / dictIds [aggs x rows] in ONE JNI call (any may be null). */
+  public static native int resultFetch(long result, int[] keysOut, double[] doublesOut, long[] longsOut, int[] dictIdsOut);
   public static native int resultFree(long result);
 }
