@@ -121,3 +121,42 @@ def test_inverted_index_layout(oracle):
     for d in range(card):
         docs = oracle.roaring_deserialize(inv[offs[d]:offs[d + 1]])
         assert np.array_equal(docs, np.nonzero(ids == d)[0])
+
+
+def test_segment_directory_writer_follows_the_reference_layouts(oracle, tmp_path):
+    """tests/segment_dir_util.py (the helper the loader tests use) against what the reference wrote: the star-tree index
+    map grammar of the reference-built fixture, the metadata key names, the v3 magic marker."""
+    import os
+    import re
+    import struct
+
+    import numpy as np
+
+    from oracle import startree_builder as stb
+    from segment_dir_util import write_segment_dir
+
+    rng = np.random.default_rng(3)
+    seg = oracle.build_segment("w", {"d1": rng.integers(0, 9, size=700).astype(np.int32),
+                                     "m": rng.integers(0, 90, size=700).astype(np.int32)}, inverted=["d1"])
+    st = stb.build_star_tree(seg, ["d1"], [("COUNT", None), ("MAX", "m")], max_leaf_records=10)
+    root = write_segment_dir(str(tmp_path / "s"), seg, "v3", star_tree=st)
+    here = os.path.dirname(os.path.abspath(__file__))
+    grammar = re.compile(r"^(\d+)\.(.+)\.(STAR_TREE|FORWARD_INDEX)\.(OFFSET|SIZE) = (\d+)$")
+    ref_lines = [l.strip() for l in open(os.path.join(here, "golden", "star_tree_index_map.txt")) if l.strip()]
+    our_lines = [l.strip() for l in open(os.path.join(root, "v3", "star_tree_index_map")) if l.strip()]
+    assert all(grammar.match(l) for l in ref_lines) and all(grammar.match(l) for l in our_lines)
+    assert {grammar.match(l).group(2) for l in ref_lines} >= {"null", "count__*"}       # tree under "null", pair names
+    assert {grammar.match(l).group(2) for l in our_lines} == {"null", "d1", "count__*", "max__m"}
+    sizes = {grammar.match(l).group(2): int(grammar.match(l).group(5)) for l in our_lines if l.split(".")[-1].startswith("SIZE")}
+    assert sum(sizes.values()) == os.path.getsize(os.path.join(root, "v3", "star_tree_index"))
+    ref_meta = open(os.path.join(here, "golden", "star_tree_metadata.txt")).read()
+    our_meta = open(os.path.join(root, "v3", "metadata.properties")).read()
+    for key in ("startree.v2.count", "startree.v2.0.total.docs", "startree.v2.0.split.order", "startree.v2.0.function.column.pairs",
+                "column.d1.cardinality", "column.d1.bitsPerElement", "column.d1.hasDictionary", "column.d1.isSorted"):
+        assert key.replace("d1", "AirlineID") in ref_meta and key in our_meta, key
+    psf = open(os.path.join(root, "v3", "columns.psf"), "rb").read()
+    imap = dict(l.strip().split(" = ") for l in open(os.path.join(root, "v3", "index_map")) if " = " in l)
+    for col in ("d1", "m"):
+        off = int(imap[f"{col}.forward_index.startOffset"])
+        assert struct.unpack(">Q", psf[off:off + 8])[0] == 0xDEADBEEFDEAFBEAD
+    assert "d1.inverted_index.startOffset" in imap
