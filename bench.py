@@ -31,7 +31,6 @@ import sys
 import threading
 import time
 
-import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:

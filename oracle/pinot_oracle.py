@@ -12,7 +12,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from pinot_b200.query import Filter, Predicate, QueryContext, postfix
+from pinot_b200.query import Filter, QueryContext, postfix
 
 from . import segment_builder as sb
 

@@ -11,7 +11,7 @@ the same aggregation operators, which read the pre-aggregated metric columns:
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List
 
 import numpy as np
 

@@ -21,9 +21,8 @@ exchange is latency-bound (C4: 100 000 groups x (8+8+4) B = 2 MB per rank).
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Sequence
+from typing import Dict, List
 
-import numpy as np
 
 KINDS = {"i64": 0, "f64": 1, "u32max": 2, "u32min": 3}
 _TORCH_DTYPES = {"i64": "int64", "f64": "float64", "u32max": "int32", "u32min": "int32"}

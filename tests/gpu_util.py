@@ -1,8 +1,6 @@
 """Helpers shared by the -m gpu tests: run one query through the product (C-ABI) and through the oracle, compare."""
 from __future__ import annotations
 
-import numpy as np
-
 from pinot_b200.plan_maker import IndexSegment
 from reduce_util import normalise
 

@@ -1,9 +1,7 @@
 """world_size-2 gloo tests (CPU) of the multi-GPU host logic: segment sharding and the table reduce semantics."""
 import os
-import sys
 
 import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

@@ -60,7 +60,6 @@ def main():
     if args.check_rows:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from gpu_util import assert_tables_equal, gpu_table, oracle_table
-        from test_gpu_synth import synth_dict_ids
         from oracle import segment_builder as sb
         from oracle.pinot_oracle import oracle as get_oracle
         o = get_oracle()
