@@ -250,6 +250,33 @@ def test_multi_segment_single_submission_and_device_merge(oracle, ctx, pm):
             d.destroy()
 
 
+def test_more_segments_than_one_launch_holds(oracle, ctx, pm):
+    """A submission of more than 16 segments is split into several launches (the TMA table of a launch holds 16): per-segment
+    results and the device-side merge must not depend on where the chunk boundaries fall."""
+    rng = np.random.default_rng(21)
+    n = 9_000
+    seg = oracle.build_segment("many", {"a": rng.integers(0, 6, size=n).astype(np.int32),
+                                        "b": rng.integers(0, 300, size=n).astype(np.int32),
+                                        "c": rng.integers(-50, 50, size=n).astype(np.int32)})
+    dev = to_device(ctx, seg)
+    try:
+        for text in ("SELECT COUNT(*), SUM(c), MIN(b), MAX(b) FROM t WHERE b > 100",
+                     "SELECT COUNT(*), SUM(c) FROM t WHERE b < 250 GROUP BY a",            # shared-memory tables
+                     "SELECT SUM(b), MAX(c), AVG(c) FROM t WHERE c > -40 GROUP BY b, a"):   # global tables
+            q = sql.parse(text)
+            want = oracle_table(seg, q, oracle.execute(seg, q))
+            k = 37  # 16 + 16 + 5
+            blocks = pm.execute_segments([dev] * k, q)
+            assert len(blocks) == k
+            for b in blocks:
+                assert_tables_equal(q, gpu_table(seg, q, b), want, text)
+            merged = gpu_table(seg, q, pm.execute_segments([dev] * k, q, merge=True)[0])
+            fns = [a.function for a in q.aggregations]
+            assert_tables_equal(q, merged, combine(fns, [want] * k), "merged x37 " + text)
+    finally:
+        dev.destroy()
+
+
 def test_num_groups_limit_forces_fallback(oracle, ctx, pm):
     rng = np.random.default_rng(5)
     seg = oracle.build_segment("lim", {"k": rng.integers(0, 5000, size=40_000).astype(np.int32),
