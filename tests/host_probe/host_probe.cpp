@@ -1,0 +1,53 @@
+// host_probe.cpp -- TEST shim: calls the product's host-side logic (inside libpinot_b200.so) without a GPU, so that the
+// CPU test suite can compare it with the oracle:
+//   * pb200h::StarTree::parse / traverse   (StarTreeFilterOperator's traversal as the product runs it)
+//   * pb200h::matching_dict_ids             (PredicateEvaluator resolution: value-space predicate -> dictIds)
+// Built by tests/test_host_logic_cpu.py with g++ against the in-tree library; nothing here ships.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../pinot_b200/csrc/host/host_internal.h"
+
+extern "C" {
+
+// preds: npreds entries (dimension, count, ids...) flattened as dims[i], offsets[i]..offsets[i+1] into ids[].
+// Returns the number of [start, end) ranges written (pairs), -1 when a predicate matches nothing, -2 malformed tree.
+int64_t probe_startree_traverse(const unsigned char* tree, uint64_t len, int32_t num_dims, int32_t npreds, const int32_t* dims,
+                                const int32_t* offsets, const int32_t* ids, uint32_t group_by_mask, int32_t* out_pairs,
+                                int64_t cap_pairs, uint32_t* remaining) {
+  pb200h::StarTree t;
+  if (!t.parse(tree, len) || (int)t.dim_names.size() != num_dims) return -2;
+  std::vector<std::vector<int32_t>> store(num_dims);
+  std::vector<const std::vector<int32_t>*> preds(num_dims, nullptr);
+  for (int i = 0; i < npreds; i++) {
+    if (dims[i] < 0 || dims[i] >= num_dims) return -2;
+    store[dims[i]].assign(ids + offsets[i], ids + offsets[i + 1]);
+    preds[dims[i]] = &store[dims[i]];
+  }
+  std::vector<std::pair<int32_t, int32_t>> docs;
+  uint32_t rem = 0;
+  if (!t.traverse(preds, group_by_mask, docs, rem)) return -1;
+  if (remaining) *remaining = rem;
+  int64_t n = 0;
+  for (auto& r : docs) {
+    if (n < cap_pairs) { out_pairs[2 * n] = r.first; out_pairs[2 * n + 1] = r.second; }
+    n++;
+  }
+  return n;
+}
+
+// One predicate against one dictionary column described like pb200h_segment_create's input.
+int64_t probe_matching_dict_ids(const pb200h_column* col, const pb200h_filter_node* node, const pb200h_literal* literals,
+                                int32_t* out, int64_t cap) {
+  pb200h::HostColumn h;
+  h.name = col->name ? col->name : "";
+  h.data_type = col->data_type; h.has_dictionary = col->has_dictionary; h.bits = col->bits_per_value;
+  h.cardinality = col->cardinality; h.is_sorted = col->is_sorted; h.entry_bytes = col->dict_entry_bytes;
+  if (col->dict && col->dict_bytes) h.dict.assign((const unsigned char*)col->dict, (const unsigned char*)col->dict + col->dict_bytes);
+  std::vector<int32_t> ids = pb200h::matching_dict_ids(h, *node, literals);
+  for (size_t i = 0; i < ids.size() && (int64_t)i < cap; i++) out[i] = ids[i];
+  return (int64_t)ids.size();
+}
+
+}  // extern "C"

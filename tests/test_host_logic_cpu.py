@@ -1,0 +1,163 @@
+"""CPU tests of the PRODUCT's host-side logic (inside libpinot_b200.so, no GPU needed) against the oracle:
+star-tree traversal (pb200h::StarTree) and predicate -> dictId resolution (pb200h::matching_dict_ids).
+
+The product functions are reached through a tiny test shim (tests/host_probe/host_probe.cpp) that is compiled with g++ and
+linked against the in-tree library; the library loads without a GPU (only pb200_init needs one)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import segment_builder as sb
+from oracle import startree_builder as stb
+from oracle.startree_query import matching_dict_ids as oracle_matching_dict_ids
+from pinot_b200 import _lib
+from pinot_b200.plan_maker import _marshal_query
+from pinot_b200.query import Aggregation, Predicate, QueryContext
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def probe():
+    from pinot_b200.build import build
+    build()
+    src = os.path.join(HERE, "host_probe", "host_probe.cpp")
+    out = os.path.join(HERE, "host_probe", "libhost_probe.so")
+    libdir = os.path.join(ROOT, "pinot_b200")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(_lib.LIB_PATH)):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", f"-I{cuda_inc}", "-o", out, src, f"-L{libdir}",
+                        "-lpinot_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    lib = C.CDLL(out)
+    lib.probe_startree_traverse.restype = C.c_int64
+    lib.probe_startree_traverse.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_uint32, C.c_void_p, C.c_int64, C.POINTER(C.c_uint32)]
+    lib.probe_matching_dict_ids.restype = C.c_int64
+    lib.probe_matching_dict_ids.argtypes = [C.POINTER(_lib.HColumn), C.POINTER(_lib.HFilterNode), C.POINTER(_lib.HLiteral),
+                                            C.c_void_p, C.c_int64]
+    return lib
+
+
+def _product_traverse(probe, tree, num_dims, preds, gb_dims, max_docs):
+    dims = np.asarray(sorted(preds), dtype=np.int32)
+    arrays = [np.sort(np.asarray(preds[d], dtype=np.int32)) for d in dims]
+    offsets = np.concatenate([[0], np.cumsum([len(a) for a in arrays])]).astype(np.int32)
+    ids = np.concatenate(arrays).astype(np.int32) if arrays else np.zeros(0, dtype=np.int32)
+    ids = np.ascontiguousarray(np.concatenate([ids, [0]]).astype(np.int32))  # never a NULL pointer
+    mask = 0
+    for d in gb_dims:
+        mask |= 1 << d
+    out = np.zeros(2 * (max_docs + 1), dtype=np.int32)
+    rem = C.c_uint32(0)
+    n = probe.probe_startree_traverse(tree.ctypes.data, len(tree), num_dims, len(dims), dims.ctypes.data if len(dims) else None,
+                                      offsets.ctypes.data, ids.ctypes.data, mask, out.ctypes.data, max_docs + 1, C.byref(rem))
+    assert n != -2, "product rejected the tree"
+    if n == -1:
+        return None, []
+    docs = set()
+    for s, e in out[: 2 * n].reshape(-1, 2):
+        docs.update(range(int(s), int(e)))
+    return docs, [d for d in range(32) if rem.value >> d & 1]
+
+
+def _compare_traversals(oracle, probe, tree, num_dims, num_docs, cases):
+    for preds, gb in cases:
+        want_docs, want_rem = oracle.startree_traverse(tree, preds, gb, num_docs)
+        got_docs, got_rem = _product_traverse(probe, tree, num_dims, preds, gb, num_docs)
+        if want_docs is None:
+            assert got_docs is None, (preds, gb)
+            continue
+        assert got_docs == set(int(d) for d in want_docs), (preds, gb)
+        assert sorted(got_rem) == sorted(want_rem), (preds, gb)
+
+
+def test_product_traversal_on_the_reference_built_star_tree(oracle, probe):
+    blob = np.fromfile(os.path.join(HERE, "golden", "star_tree_index.bin"), dtype=np.uint8)
+    tree = np.ascontiguousarray(blob[:18715])  # star_tree_index_map: 0.null.STAR_TREE.OFFSET = 0, SIZE = 18715
+    dims, _ = oracle.startree_info(tree)
+    assert dims == ["AirlineID", "Origin", "Dest"]
+    cases = [({}, []), ({}, [0]), ({}, [1]), ({}, [0, 2]), ({0: [3]}, []), ({0: [3, 5, 9]}, [1]), ({1: [10, 11, 12]}, []),
+             ({0: [1], 2: [50, 51]}, []), ({2: list(range(0, 104, 2))}, [0]), ({0: list(range(14)), 1: [7]}, [2]),
+             ({0: []}, []), ({1: [96], 2: [103]}, [0, 1, 2])]
+    _compare_traversals(oracle, probe, tree, 3, 1004, cases)
+
+
+@pytest.mark.parametrize("max_leaf", [1, 7, 100, 100000])
+def test_product_traversal_on_built_trees(oracle, probe, max_leaf):
+    rng = np.random.default_rng(max_leaf)
+    n = 6000
+    seg = oracle.build_segment("t", {"d1": rng.integers(0, 40, size=n).astype(np.int32),
+                                     "d2": rng.integers(0, 25, size=n).astype(np.int32),
+                                     "d3": rng.integers(0, 4, size=n).astype(np.int32),
+                                     "m": rng.integers(0, 99, size=n).astype(np.int32)})
+    st = stb.build_star_tree(seg, ["d1", "d2", "d3"], [("COUNT", None), ("SUM", "m")], max_leaf_records=max_leaf)
+    cases = []
+    for _ in range(40):
+        preds = {}
+        for d, card in ((0, 40), (1, 25), (2, 4)):
+            r = rng.random()
+            if r < 0.35:
+                preds[d] = rng.choice(card, size=int(rng.integers(1, max(2, card // 2))), replace=False).tolist()
+            elif r < 0.42:
+                preds[d] = list(range(card))           # matches every value: the star node may stand in
+            elif r < 0.45:
+                preds[d] = []                          # matches nothing
+        gb = [d for d in range(3) if rng.random() < 0.3]
+        cases.append((preds, gb))
+    _compare_traversals(oracle, probe, st.tree, 3, st.num_docs, cases)
+
+
+def _column_struct(col):
+    nm = col.name.encode()
+    return _lib.HColumn(nm, col.data_type, 1, col.bits, col.cardinality, int(col.is_sorted), col.dict_entry_bytes,
+                        col.fwd.ctypes.data, len(col.fwd), col.dict.ctypes.data, len(col.dict), None, 0), nm
+
+
+def test_product_predicate_resolution_matches_the_oracle(oracle, probe):
+    rng = np.random.default_rng(5)
+    n = 3000
+    seg = oracle.build_segment("p", {
+        "i": rng.integers(-500, 500, size=n).astype(np.int32) * 3,
+        "l": rng.integers(0, 400, size=n).astype(np.int64) * 10_000_000_019,
+        "f": (rng.integers(0, 300, size=n) / 8.0).astype(np.float32),
+        "d": (rng.integers(-200, 200, size=n) / 3.0).astype(np.float64),
+        "s": np.array([b"aa", b"ab", b"b", b"ba", b"zz", b"m", b"mm"])[rng.integers(0, 7, size=n)],
+    })
+    checked = 0
+    for col in seg.columns:
+        vals = col.dict_values
+        present = [v.decode() if isinstance(v, bytes) else v.item() for v in vals]
+        if col.data_type == sb.STRING:
+            absent = ["", "a", "abc", "zzz", "n"]
+        elif col.data_type in (sb.INT, sb.LONG):
+            absent = [int(present[0]) - 1, int(present[-1]) + 1, int(present[3]) + 1]
+        else:
+            absent = [float(present[0]) - 0.5, float(present[-1]) + 0.5, float(present[3]) + 1e-3]
+        pool = present[:: max(1, len(present) // 12)] + absent
+        preds = []
+        for v in pool:
+            preds += [Predicate("EQ", col.name, [v]), Predicate("NEQ", col.name, [v])]
+        for _ in range(12):
+            k = int(rng.integers(1, 6))
+            vs = [pool[int(j)] for j in rng.integers(0, len(pool), size=k)]
+            preds += [Predicate("IN", col.name, vs), Predicate("NOT_IN", col.name, vs)]
+        for lo in pool[:8] + [None]:
+            for hi in pool[-8:] + [None]:
+                for li in (True, False):
+                    for ui in (True, False):
+                        preds.append(Predicate("RANGE", col.name, [], lo, hi, li, ui))
+        cstruct, _keep = _column_struct(col)
+        for p in preds:
+            if p.type == "RANGE" and p.lower is not None and p.upper is not None and p.lower > p.upper:
+                continue
+            hq, keep = _marshal_query(QueryContext([Aggregation("COUNT", None)], filter=p), False)
+            out = np.zeros(col.cardinality + 1, dtype=np.int32)
+            m = probe.probe_matching_dict_ids(C.byref(cstruct), hq.filter, hq.literals, out.ctypes.data, len(out))
+            want = oracle_matching_dict_ids(col, p)
+            assert m == len(want) and np.array_equal(out[:m], want), (col.name, p)
+            checked += 1
+    assert checked > 1500
