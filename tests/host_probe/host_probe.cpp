@@ -50,4 +50,28 @@ int64_t probe_matching_dict_ids(const pb200h_column* col, const pb200h_filter_no
   return (int64_t)ids.size();
 }
 
+// FilterOperatorUtils.getLeafFilterOperator as the product runs it: one predicate on one column of a (host-only) segment ->
+// the device leaf.  out4 = {op, column, lo, hi}; ids (<= cap) receives the node's id / doc-range payload; returns num_ids
+// or a negative pb200 status.
+int64_t probe_leaf_to_device(const pb200h_column* col, int32_t num_docs, const pb200h_filter_node* node,
+                             const pb200h_literal* literals, int32_t* out4, int32_t* ids, int64_t cap) {
+  pb200h_segment seg;
+  seg.num_docs = num_docs;
+  pb200h::HostColumn h;
+  h.name = col->name ? col->name : "";
+  h.data_type = col->data_type; h.has_dictionary = col->has_dictionary; h.bits = col->bits_per_value;
+  h.cardinality = col->cardinality; h.is_sorted = col->is_sorted; h.entry_bytes = col->dict_entry_bytes;
+  h.has_inverted = col->inv != nullptr && col->inv_bytes > 0 && !col->is_sorted;
+  if (col->dict && col->dict_bytes) h.dict.assign((const unsigned char*)col->dict, (const unsigned char*)col->dict + col->dict_bytes);
+  if (col->is_sorted && col->fwd) h.sorted_idx.assign((const unsigned char*)col->fwd, (const unsigned char*)col->fwd + col->fwd_bytes);
+  seg.cols.push_back(std::move(h));
+  pb200h::SegmentFilterStore store;
+  pb200_filter_node d;
+  int rc = pb200h::leaf_to_device(seg, 0, *node, literals, store, d);
+  if (rc) return rc;
+  out4[0] = d.op; out4[1] = d.column; out4[2] = d.lo; out4[3] = d.hi;
+  for (int i = 0; i < d.num_ids && i < cap; i++) ids[i] = d.ids[i];
+  return d.num_ids;
+}
+
 }  // extern "C"

@@ -161,3 +161,84 @@ def test_product_predicate_resolution_matches_the_oracle(oracle, probe):
             assert m == len(want) and np.array_equal(out[:m], want), (col.name, p)
             checked += 1
     assert checked > 1500
+
+
+F_MATCH_ALL, F_EMPTY, F_SCAN_RANGE, F_SCAN_IN, F_SCAN_NOT_IN, F_INV_IN, F_INV_NOT_IN, F_DOC_RANGES = 3, 4, 5, 6, 7, 8, 9, 10
+
+
+def _leaf_docs(op, lo, hi, ids, dict_ids, num_docs):
+    """What the device leaf the product built would match, evaluated with numpy on the column's dictIds."""
+    if op == F_MATCH_ALL:
+        return np.arange(num_docs)
+    if op == F_EMPTY:
+        return np.zeros(0, dtype=np.int64)
+    if op == F_SCAN_RANGE:
+        return np.nonzero((dict_ids >= lo) & (dict_ids < hi))[0]
+    if op in (F_SCAN_IN, F_INV_IN):
+        return np.nonzero(np.isin(dict_ids, ids))[0]
+    if op in (F_SCAN_NOT_IN, F_INV_NOT_IN):
+        return np.nonzero(~np.isin(dict_ids, ids))[0]
+    assert op == F_DOC_RANGES, op
+    m = np.zeros(num_docs, dtype=bool)
+    for s, e in np.asarray(ids).reshape(-1, 2):
+        m[s:e + 1] = True  # inclusive pairs
+    return np.nonzero(m)[0]
+
+
+def test_product_leaf_choice_and_matches(oracle, probe):
+    """pb200h::leaf_to_device = PredicateEvaluator resolution + FilterOperatorUtils.getLeafFilterOperator: the leaf kind follows
+    the reference's priorities (sorted index, then inverted index for EQ/IN-like predicates, else scan) and the docs it would
+    match are exactly the oracle's docs for that predicate."""
+    probe.probe_leaf_to_device.restype = C.c_int64
+    probe.probe_leaf_to_device.argtypes = [C.POINTER(_lib.HColumn), C.c_int32, C.POINTER(_lib.HFilterNode),
+                                           C.POINTER(_lib.HLiteral), C.c_void_p, C.c_void_p, C.c_int64]
+    rng = np.random.default_rng(9)
+    n = 5000
+    seg = oracle.build_segment("lf", {
+        "plain": rng.integers(0, 200, size=n).astype(np.int32) * 5,
+        "inv": rng.integers(0, 60, size=n).astype(np.int32),
+        "srt": np.sort(rng.integers(0, 30, size=n)).astype(np.int32) * 2,
+        "str": np.array([b"k1", b"k2", b"k3", b"k9"])[rng.integers(0, 4, size=n)],
+    }, inverted=["inv", "str"])
+    checked = 0
+    for col in seg.columns:
+        present = [v.decode() if isinstance(v, bytes) else v.item() for v in col.dict_values]
+        absent = ["k0", "k5", "zz"] if col.data_type == sb.STRING else [present[0] - 1, present[-1] + 7, present[2] + 1]
+        pool = present[:: max(1, len(present) // 10)] + absent
+        preds = [Predicate(t, col.name, [v]) for v in pool for t in ("EQ", "NEQ")]
+        for _ in range(10):
+            vs = [pool[int(j)] for j in rng.integers(0, len(pool), size=int(rng.integers(1, 5)))]
+            preds += [Predicate("IN", col.name, vs), Predicate("NOT_IN", col.name, vs)]
+        for lo in pool[:5] + [None]:
+            for hi in pool[-5:] + [None]:
+                for li, ui in ((True, True), (False, True), (True, False), (False, False)):
+                    if lo is None or hi is None or lo <= hi:
+                        preds.append(Predicate("RANGE", col.name, [], lo, hi, li, ui))
+        nm = col.name.encode()
+        has_inv = col.inv is not None and not col.is_sorted
+        cstruct = _lib.HColumn(nm, col.data_type, 1, col.bits, col.cardinality, int(col.is_sorted), col.dict_entry_bytes,
+                               col.fwd.ctypes.data, len(col.fwd), col.dict.ctypes.data, len(col.dict),
+                               col.inv.ctypes.data if has_inv else None, len(col.inv) if has_inv else 0)
+        for p in preds:
+            q = QueryContext([Aggregation("COUNT", None)], filter=p)
+            hq, keep = _marshal_query(q, False)
+            out4 = np.zeros(4, dtype=np.int32)
+            ids = np.zeros(2 * col.cardinality + 8, dtype=np.int32)
+            m = probe.probe_leaf_to_device(C.byref(cstruct), seg.num_docs, hq.filter, hq.literals, out4.ctypes.data,
+                                           ids.ctypes.data, len(ids))
+            assert m >= 0, (col.name, p, m)
+            op, lo, hi = int(out4[0]), int(out4[2]), int(out4[3])
+            if op not in (F_MATCH_ALL, F_EMPTY):  # FilterOperatorUtils.getLeafFilterOperator :74-133
+                if col.is_sorted:
+                    assert op == F_DOC_RANGES, (col.name, p, op)
+                elif p.type == "RANGE":
+                    assert op == F_SCAN_RANGE, (col.name, p, op)
+                elif has_inv:
+                    assert op in (F_INV_IN, F_INV_NOT_IN), (col.name, p, op)
+                else:
+                    assert op in (F_SCAN_IN, F_SCAN_NOT_IN), (col.name, p, op)
+            got = _leaf_docs(op, lo, hi, ids[:m], col.dict_ids, seg.num_docs)
+            want, _ = oracle.filter_doc_ids(seg, q)
+            assert np.array_equal(got, want), (col.name, p, op)
+            checked += 1
+    assert checked > 600
