@@ -74,4 +74,24 @@ int64_t probe_leaf_to_device(const pb200h_column* col, int32_t num_docs, const p
   return d.num_ids;
 }
 
+// pb200h_explain over a HOST-ONLY segment (no device registration): the filter tree after predicate resolution and
+// constant folding (FilterPlanNode / AndFilterOperator / OrFilterOperator always-true / always-false rules) plus the
+// operator the plan maker would choose.  Returns the text length or a negative status.
+int32_t probe_explain(const pb200h_column* cols, int32_t ncols, int32_t num_docs, const pb200h_query* q, char* out, int32_t cap) {
+  pb200h_segment seg;
+  seg.num_docs = num_docs;
+  for (int i = 0; i < ncols; i++) {
+    const pb200h_column& c = cols[i];
+    pb200h::HostColumn h;
+    h.name = c.name ? c.name : "";
+    h.data_type = c.data_type; h.has_dictionary = c.has_dictionary; h.bits = c.bits_per_value;
+    h.cardinality = c.cardinality; h.is_sorted = c.is_sorted; h.entry_bytes = c.dict_entry_bytes;
+    h.has_inverted = c.inv != nullptr && c.inv_bytes > 0 && !c.is_sorted;
+    if (c.dict && c.dict_bytes) h.dict.assign((const unsigned char*)c.dict, (const unsigned char*)c.dict + c.dict_bytes);
+    if (c.is_sorted && c.fwd) h.sorted_idx.assign((const unsigned char*)c.fwd, (const unsigned char*)c.fwd + c.fwd_bytes);
+    seg.cols.push_back(std::move(h));
+  }
+  return pb200h_explain(nullptr, q, &seg, out, cap);
+}
+
 }  // extern "C"

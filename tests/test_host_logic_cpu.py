@@ -242,3 +242,45 @@ def test_product_leaf_choice_and_matches(oracle, probe):
             assert np.array_equal(got, want), (col.name, p, op)
             checked += 1
     assert checked > 600
+
+
+def test_product_plan_constant_folding_and_operator_choice(oracle, probe):
+    """pb200h_explain on a host-only segment: predicates that resolve to always-true / always-false are folded through
+    AND / OR / NOT exactly like FilterPlanNode + FilterOperatorUtils do, and the operator choice follows AggregationPlanNode
+    (empty filter -> EMPTY, match-all + dictionary-answerable functions -> NonScanBasedAggregationOperator)."""
+    from pinot_b200 import sql
+    probe.probe_explain.restype = C.c_int32
+    probe.probe_explain.argtypes = [C.POINTER(_lib.HColumn), C.c_int32, C.c_int32, C.POINTER(_lib.HQuery), C.c_char_p, C.c_int32]
+    rng = np.random.default_rng(2)
+    n = 2000
+    seg = oracle.build_segment("pl", {"a": rng.integers(0, 50, size=n).astype(np.int32),
+                                      "b": rng.integers(0, 10, size=n).astype(np.int32),
+                                      "s": np.sort(rng.integers(0, 8, size=n)).astype(np.int32)}, inverted=["b"])
+    arr = (_lib.HColumn * len(seg.columns))()
+    keep = []
+    for i, c in enumerate(seg.columns):
+        nm = c.name.encode()
+        keep.append(nm)
+        has_inv = c.inv is not None and not c.is_sorted
+        arr[i] = _lib.HColumn(nm, c.data_type, 1, c.bits, c.cardinality, int(c.is_sorted), c.dict_entry_bytes, c.fwd.ctypes.data,
+                              len(c.fwd), c.dict.ctypes.data, len(c.dict), c.inv.ctypes.data if has_inv else None,
+                              len(c.inv) if has_inv else 0)
+
+    def explain(text):
+        hq, k = _marshal_query(sql.parse(text), False)
+        buf = C.create_string_buffer(4096)
+        m = probe.probe_explain(arr, len(seg.columns), seg.num_docs, C.byref(hq), buf, 4096)
+        assert m >= 0, text
+        return buf.value.decode()
+
+    assert explain("SELECT SUM(a) FROM t WHERE a > 1000") == "EMPTY(FILTER_EMPTY)"                       # beyond the dictionary
+    assert explain("SELECT SUM(a) FROM t WHERE a > 1000 AND b = 3") == "EMPTY(FILTER_EMPTY)"             # AND with always-false
+    assert explain("SELECT SUM(a) FROM t WHERE a >= 0") == "AGGREGATE(FILTER_MATCH_ENTIRE_SEGMENT)"      # always-true
+    assert explain("SELECT MAX(a), MIN(b) FROM t WHERE a >= 0 OR b = 3") == "AGGREGATE_NO_SCAN(FILTER_MATCH_ENTIRE_SEGMENT)"
+    assert explain("SELECT COUNT(*) FROM t") == "AGGREGATE_NO_SCAN(FILTER_MATCH_ENTIRE_SEGMENT)"
+    # partial constants stay in the tree: every segment of a submission must keep the same tree SHAPE (one launch for all
+    # segments), so an always-false operand becomes an EMPTY leaf instead of being dropped as FilterOperatorUtils would
+    assert explain("SELECT SUM(a) FROM t WHERE a > 1000 OR b = 3") == "AGGREGATE(FILTER_OR(FILTER_INVERTED_INDEX(EQ,b),FILTER_EMPTY))"
+    assert explain("SELECT SUM(a) FROM t WHERE NOT (a > 1000)") == "AGGREGATE(FILTER_MATCH_ENTIRE_SEGMENT)"
+    g = explain("SELECT SUM(a) FROM t WHERE b != 3 AND s = 2 AND a < 10 GROUP BY b")
+    assert g.startswith("GROUP_BY(FILTER_AND(") and "FILTER_SORTED_INDEX" in g and "FILTER_INVERTED_INDEX" in g and "FILTER_FULL_SCAN(RANGE,a,[0,10))" in g
