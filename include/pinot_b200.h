@@ -59,6 +59,12 @@ int32_t pb200_abi_version(void);
 /* Device facts for the caller's bookkeeping: {sm_count, major, minor, total_mem_mb, free_mem_mb}. */
 int32_t pb200_device_info(pb200_ctx* ctx, int64_t out[5]);
 
+/* Launch-tuning knobs of the scan kernel ("warps", "ctas_per_sm", "stages", "grid", "sparse_max", "sparse_max_agg",
+ * "smem_groups", "smem_groups_max", "smem_copies", "dense_max", "defer", "gb_defer", "skip", "always_count"; DESIGN.md
+ * section 3.1).  Their defaults are read from the environment (PB200_W, PB200_CTAS, ...) once, in pb200_init;
+ * pb200_execute never reads the environment.  Not meant to be changed while queries are in flight on the context. */
+int32_t pb200_tuning_set(pb200_ctx* ctx, const char* name, int64_t value);
+
 /* ---- segments ------------------------------------------------------------------------------------------------ */
 /* Stored types (FieldSpec.DataType.getStoredType()). */
 enum { PB200_INT = 0, PB200_LONG = 1, PB200_FLOAT = 2, PB200_DOUBLE = 3, PB200_STRING = 4 };
@@ -80,11 +86,12 @@ typedef struct {
   int32_t bits_per_value; /* column.<c>.bitsPerElement (V1Constants.MetadataKeys.Column.BITS_PER_ELEMENT) */
   int32_t cardinality;    /* column.<c>.cardinality == Dictionary.length() */
   int32_t flags;
-  int32_t reserved;
+  int32_t reserved;       /* STRING dictionaries: width of one padded entry (column.<c>.lengthOfEachEntry); else 0 */
   const void* fwd;        /* forward index bytes exactly as in columns.psf / <col>.sv.unsorted.fwd */
   uint64_t fwd_bytes;
   const void* dict;       /* fixed-width BIG-endian sorted dictionary (<col>.dict without its 8-byte-less header: the
-                             raw value array, cardinality * width bytes); NULL for STRING or no dictionary */
+                             raw value array, cardinality * width bytes); NULL = no dictionary.  STRING dictionaries
+                             (padded entries) stay on the host: they are only hashed / unioned (pb200_domain_*) */
   uint64_t dict_bytes;
   const void* inv;        /* bitmap inverted index file (<col>.bitmap.inv) or NULL:
                              BitmapInvertedIndexWriter layout, seglocal/.../inv/BitmapInvertedIndexWriter.java:33-50 */
@@ -99,6 +106,41 @@ int32_t pb200_segment_register(pb200_ctx* ctx, const char* segment_name, int32_t
 int32_t pb200_segment_release(pb200_ctx* ctx, pb200_segment* segment);
 /* Bytes of HBM held by the segment. */
 int64_t pb200_segment_device_bytes(const pb200_segment* segment);
+
+/* ---- table-wide dictionaries ("domains") ------------------------------------------------------------------------- */
+/* dictIds are segment local in Pinot; the reference merges per-segment results BY VALUE
+ * (GroupByCombineOperator.java:130-146 -> IndexedTable.upsert, AggregationFunction.merge).  A device-side or cross-GPU
+ * merge of dictId-indexed tables needs ONE id space per column instead: a domain = the sorted union of the per-segment
+ * dictionaries.  Binding a segment re-encodes the listed columns' forward indexes into the domain's ids (one streaming
+ * pass at load time, no per-row work at query time) and lets the column adopt the shared table-wide dictionary; from
+ * then on every id the library takes or returns for that column (filter leaves, group keys, MIN / MAX ids, DISTINCTCOUNT
+ * sets, pb200_segment_read_index bytes) is a DOMAIN id.  PB200_Q_MERGE_SEGMENTS requires, for every group-by, MIN / MAX
+ * and DISTINCTCOUNT column, identical dictionaries in all segments -- which bound segments have by construction. */
+typedef struct pb200_domain pb200_domain;
+typedef struct {
+  int32_t column;               /* column id (registration order) */
+  int32_t stored_type;          /* PB200_INT ... PB200_STRING */
+  int32_t num_parts;            /* sorted dictionaries to union (one per segment, or per rank, ...) */
+  int32_t reserved;
+  const void* const* parts;     /* each: BIG-endian sorted values (or padded strings), cardinalities[i] entries */
+  const int32_t* cardinalities;
+  const int32_t* entry_bytes;   /* STRING: padded width of each part's entries; NULL for numeric types */
+} pb200_domain_col;
+int32_t pb200_domain_create(pb200_ctx* ctx, int32_t num_columns, const pb200_domain_col* columns, pb200_domain** domain);
+/* Union over the given (unbound) segments' own dictionaries. */
+int32_t pb200_domain_from_segments(pb200_ctx* ctx, pb200_segment* const* segments, int32_t num_segments,
+                                   int32_t num_columns, const int32_t* columns, pb200_domain** domain);
+/* {stored_type, cardinality, bits, entry_bytes} of one domain column. */
+int32_t pb200_domain_column_info(const pb200_domain* domain, int32_t column, int64_t out[4]);
+/* The domain dictionary's bytes (big-endian sorted values / padded strings); returns the size, or the needed size if
+ * out == NULL.  Used to decode ids of bound columns and to exchange rank-local unions between GPUs. */
+int64_t pb200_domain_dictionary(const pb200_domain* domain, int32_t column, void* out, uint64_t capacity);
+/* Drops the caller's reference; bound segments keep the domain alive. */
+int32_t pb200_domain_release(pb200_ctx* ctx, pb200_domain* domain);
+/* Fails with PB200_E_INVALID (segment untouched) if a dictionary value of the segment is missing from the domain. */
+int32_t pb200_segment_bind_domain(pb200_ctx* ctx, pb200_segment* segment, pb200_domain* domain);
+/* The ids of `column` that occur in this segment, ascending (unbound: 0 .. cardinality-1).  Returns their number. */
+int64_t pb200_segment_local_ids(const pb200_segment* segment, int32_t column, int32_t* out, int64_t capacity);
 
 /* ---- query (dictId space) ------------------------------------------------------------------------------------ */
 /* Filter tree in POSTFIX order (children before parent, root last), per SEGMENT because dictIds are segment local.
@@ -161,8 +203,10 @@ typedef struct {
 } pb200_query;
 
 #define PB200_Q_PER_SEGMENT_FILTER 1 /* filter[] holds one tree per segment (segment-local dictIds) */
-#define PB200_Q_MERGE_SEGMENTS 2     /* all segments share dictionaries: accumulate into ONE result (device-side
-                                        combine, the GroupByCombineOperator/AggregationCombineOperator analogue) */
+#define PB200_Q_MERGE_SEGMENTS 2     /* accumulate into ONE result (device-side combine, the GroupByCombineOperator /
+                                        AggregationCombineOperator analogue).  Every group-by, MIN / MAX and DISTINCTCOUNT
+                                        column must have the SAME dictionary in all segments (bind them to a domain);
+                                        otherwise PB200_E_UNSUPPORTED -- never a merge of unrelated dictIds */
 #define PB200_Q_DEFER_FINALIZE 4     /* group-by with PB200_Q_MERGE_SEGMENTS: leave the groups in the dense device tables
                                         (pb200_result_device_buffers) and extract them later with pb200_result_finalize --
                                         for a cross-GPU reduce of the tables in between; only the reduce root extracts */

@@ -65,6 +65,15 @@ int32_t pb200h_segment_column_info(const pb200h_segment* segment, int32_t column
 int32_t pb200h_dictionary_get(const pb200h_segment* segment, int32_t column, int32_t dict_id, double* num, int64_t* lng,
                               char* str, int32_t str_capacity);
 
+/* ---- table-wide dictionaries (include/pinot_b200.h "domains") by column NAME ------------------------------------- */
+/* Union of the given segments' dictionaries for the named columns (every segment must hold them at the same position). */
+int32_t pb200h_domain_build(pb200_ctx* ctx, pb200h_segment* const* segments, int32_t num_segments, int32_t num_columns,
+                            const char* const* column_names, pb200_domain** domain);
+/* pb200_segment_bind_domain + host bookkeeping: predicates keep being resolved against the segment's OWN dictionary
+ * (identical alwaysTrue / alwaysFalse / index-choice decisions), ids are translated on the way to the device, and
+ * pb200h_dictionary_get / pb200h_segment_column_info describe the domain dictionary (the id space of the results). */
+int32_t pb200h_segment_bind_domain(pb200_ctx* ctx, pb200h_segment* segment, pb200_domain* domain);
+
 /* ---- star-tree (StarTreeV2: seglocal/startree/v2/store/StarTreeLoaderUtils.java:54-88) -------------------------- */
 typedef struct {
   int32_t function;     /* PB200_AGG_COUNT / SUM / MIN / MAX: the function of the function-column pair */
@@ -118,7 +127,8 @@ typedef struct {
   const pb200h_agg* aggs;
   int32_t num_groups_limit;
   int32_t max_initial_result_holder_capacity;
-  int32_t merge_segments; /* 1: device-side combine (requires identical dictionaries across the segments);
+  int32_t merge_segments; /* 1: device-side combine (group-by / MIN / MAX / DISTINCTCOUNT columns must have identical
+                             dictionaries in all segments -- bind them to a domain -- else PB200_E_UNSUPPORTED);
                              2: combine and defer the group extraction (PB200_Q_DEFER_FINALIZE) */
   int32_t skip_star_tree; /* query option useStarTree=false */
 } pb200h_query;

@@ -76,6 +76,12 @@ class HColumn(C.Structure):
                 ("dict_bytes", C.c_uint64), ("inv", C.c_void_p), ("inv_bytes", C.c_uint64)]
 
 
+class DomainCol(C.Structure):
+    _fields_ = [("column", C.c_int32), ("stored_type", C.c_int32), ("num_parts", C.c_int32), ("reserved", C.c_int32),
+                ("parts", C.POINTER(C.c_void_p)), ("cardinalities", C.POINTER(C.c_int32)),
+                ("entry_bytes", C.POINTER(C.c_int32))]
+
+
 class HLiteral(C.Structure):
     _fields_ = [("i", C.c_int64), ("d", C.c_double), ("s", C.c_char_p)]
 
@@ -105,7 +111,7 @@ class HStarMetric(C.Structure):
 
 # every symbol include/pinot_b200.h and include/pinot_b200_host.h declare (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
-    "pb200_init", "pb200_shutdown", "pb200_last_error", "pb200_abi_version", "pb200_device_info",
+    "pb200_init", "pb200_shutdown", "pb200_last_error", "pb200_abi_version", "pb200_device_info", "pb200_tuning_set",
     "pb200_segment_register", "pb200_segment_release", "pb200_segment_device_bytes", "pb200_execute",
     "pb200_result_meta_get", "pb200_result_group_keys", "pb200_result_agg", "pb200_result_agg_dict_ids",
     "pb200_result_distinct", "pb200_result_fetch", "pb200_result_free", "pb200_result_device_buffers", "pb200_result_finalize",
@@ -113,7 +119,9 @@ EXPORTED_SYMBOLS = [
     "pb200h_segment_create", "pb200h_segment_adopt", "pb200h_segment_load_dir", "pb200h_segment_destroy",
     "pb200h_segment_device", "pb200h_segment_num_docs", "pb200h_segment_num_columns", "pb200h_segment_column_index",
     "pb200h_segment_column_name", "pb200h_segment_column_info", "pb200h_dictionary_get", "pb200h_execute",
-    "pb200h_explain", "pb200h_startree_attach",
+    "pb200h_explain", "pb200h_startree_attach", "pb200h_domain_build", "pb200h_segment_bind_domain",
+    "pb200_domain_create", "pb200_domain_from_segments", "pb200_domain_column_info", "pb200_domain_dictionary",
+    "pb200_domain_release", "pb200_segment_bind_domain", "pb200_segment_local_ids",
 ]
 
 _LIB = None
@@ -132,6 +140,7 @@ def load() -> C.CDLL:
     L.pb200_init.argtypes = [i32, C.POINTER(vp)]
     L.pb200_shutdown.argtypes = [vp]
     L.pb200_device_info.argtypes = [vp, C.POINTER(i64)]
+    L.pb200_tuning_set.argtypes = [vp, C.c_char_p, i64]
     L.pb200_segment_register.argtypes = [vp, C.c_char_p, i32, i32, C.POINTER(ColDesc), C.POINTER(vp)]
     L.pb200_segment_release.argtypes = [vp, vp]
     L.pb200_segment_device_bytes.restype = i64
@@ -168,6 +177,17 @@ def load() -> C.CDLL:
     L.pb200h_explain.argtypes = [vp, C.POINTER(HQuery), vp, C.c_char_p, i32]
     L.pb200h_startree_attach.argtypes = [vp, vp, vp, C.c_uint64, i32, i32, C.POINTER(C.c_char_p), C.POINTER(vp),
                                          C.POINTER(C.c_uint64), i32, C.POINTER(HStarMetric)]
+    L.pb200h_domain_build.argtypes = [vp, C.POINTER(vp), i32, i32, C.POINTER(C.c_char_p), C.POINTER(vp)]
+    L.pb200h_segment_bind_domain.argtypes = [vp, vp, vp]
+    L.pb200_domain_create.argtypes = [vp, i32, C.POINTER(DomainCol), C.POINTER(vp)]
+    L.pb200_domain_from_segments.argtypes = [vp, C.POINTER(vp), i32, i32, C.POINTER(i32), C.POINTER(vp)]
+    L.pb200_domain_column_info.argtypes = [vp, i32, C.POINTER(i64)]
+    L.pb200_domain_dictionary.restype = i64
+    L.pb200_domain_dictionary.argtypes = [vp, i32, vp, C.c_uint64]
+    L.pb200_domain_release.argtypes = [vp, vp]
+    L.pb200_segment_bind_domain.argtypes = [vp, vp, vp]
+    L.pb200_segment_local_ids.restype = i64
+    L.pb200_segment_local_ids.argtypes = [vp, i32, vp, i64]
     _LIB = L
     return L
 

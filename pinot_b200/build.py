@@ -14,7 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libpinot_b200.so")
-SOURCES = ["pb200_api.cu", "pb200_roaring.cu", "pb200_synth.cu", "host/plan_maker.cpp", "host/star_tree.cpp"]
+SCAN_KERNELS = ["w6_agg", "w8_agg", "w8_agg_nodefer", "w6_gb1", "w8_gb1", "w6_gb2", "w8_gb2"]  # one instantiation per TU
+SOURCES = [f"pb200_scan_k_{k}.cu" for k in SCAN_KERNELS] + ["pb200_api.cu", "pb200_domain.cu", "pb200_roaring.cu", "pb200_synth.cu",
+                                                             "host/plan_maker.cpp", "host/star_tree.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -24,7 +26,7 @@ def _deps():
     out = []
     for root in (CSRC, os.path.join(CSRC, "host"), os.path.join(os.path.dirname(HERE), "include")):
         for f in os.listdir(root):
-            if f.endswith((".cu", ".cuh", ".h", ".cpp")):
+            if f.endswith((".cu", ".cuh", ".h", ".cpp", ".inc")):
                 out.append(os.path.join(root, f))
     return out
 
@@ -48,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     tmp = LIB + ".tmp"  # link beside the target, then rename: a reader (or a repo snapshot) never sees a half-written .so
     cmd = [NVCC, "-shared", "-o", tmp, *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]

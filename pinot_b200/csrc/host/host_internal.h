@@ -18,8 +18,15 @@ struct HostColumn {
   std::string name;
   int data_type = 0, has_dictionary = 0, bits = 0, cardinality = 0, is_sorted = 0, entry_bytes = 0;
   bool has_inverted = false;
-  std::vector<unsigned char> dict;        // big-endian values or padded strings (host copy)
+  std::vector<unsigned char> dict;        // big-endian values or padded strings (host copy): the SEGMENT's own dictionary
   std::vector<unsigned char> sorted_idx;  // (start,end) BE pairs when is_sorted
+  // Bound to a table-wide dictionary domain (pb200h_segment_bind_domain): predicates are still resolved against the
+  // segment's own dictionary above (same alwaysTrue / alwaysFalse / index decisions as the reference), then ids are
+  // translated with local_ids; everything the device returns for this column is a DOMAIN id, decoded through `global`.
+  std::vector<int32_t> local_ids;               // local dictId -> domain id (ascending); empty = unbound
+  std::shared_ptr<const HostColumn> global;     // the domain's dictionary as a column (dict, cardinality, bits, entry_bytes)
+  int to_device_id(int local) const { return local_ids.empty() ? local : local_ids[local]; }
+  const HostColumn& decode_column() const { return global ? *global : *this; }
 
   int32_t get_int(int id) const { return (int32_t)hbe32(dict.data() + 4ull * id); }
   int64_t get_long(int id) const { return (int64_t)hbe64(dict.data() + 8ull * id); }

@@ -151,13 +151,16 @@ int build_segment_filter(const pb200h_segment& seg, const pb200h_query& q, Segme
       d.op = PB200_F_DOC_RANGES;
       text.push_back(std::string("FILTER_SORTED_INDEX(") + pname + "," + c.name + ")");
     } else if (n.type == PB200H_RANGE) {
-      d.op = PB200_F_SCAN_RANGE; d.lo = e.start; d.hi = e.end;
+      // bound column: the local range [start, end) is the domain range [id(start), id(end-1)] for this segment's rows
+      d.op = PB200_F_SCAN_RANGE; d.lo = c.to_device_id(e.start); d.hi = c.to_device_id(e.end - 1) + 1;
       text.push_back(std::string("FILTER_FULL_SCAN(RANGE,") + c.name + ",[" + std::to_string(e.start) + "," + std::to_string(e.end) + "))");
     } else if (c.has_inverted) {  // :121-124
+      for (auto& id : e.ids) id = c.to_device_id(id);
       store(e.ids);
       d.op = e.exclusive ? PB200_F_INV_NOT_IN : PB200_F_INV_IN;
       text.push_back(std::string("FILTER_INVERTED_INDEX(") + pname + "," + c.name + ")");
     } else {
+      for (auto& id : e.ids) id = c.to_device_id(id);
       store(e.ids);
       d.op = e.exclusive ? PB200_F_SCAN_NOT_IN : PB200_F_SCAN_IN;
       text.push_back(std::string("FILTER_FULL_SCAN(") + pname + "," + c.name + ")");
@@ -202,11 +205,11 @@ pb200_result* host_result(const pb200h_segment& seg, const pb200h_query& q, bool
     switch (ag.function) {
       case PB200_AGG_COUNT: l = empty ? 0 : seg.num_docs; d = (double)l; break;
       case PB200_AGG_SUM: case PB200_AGG_AVG: d = 0; l = 0; break;
-      case PB200_AGG_MIN: if (empty) d = INFINITY; else { id = 0; d = c->as_double(0); } break;
-      case PB200_AGG_MAX: if (empty) d = -INFINITY; else { id = c->cardinality - 1; d = c->as_double(id); } break;
+      case PB200_AGG_MIN: if (empty) d = INFINITY; else { id = c->to_device_id(0); d = c->as_double(0); } break;
+      case PB200_AGG_MAX: if (empty) d = -INFINITY; else { id = c->to_device_id(c->cardinality - 1); d = c->as_double(c->cardinality - 1); } break;
       case PB200_AGG_DISTINCTCOUNT: {
         std::vector<int32_t> ids;
-        if (!empty) for (int i = 0; i < c->cardinality; i++) ids.push_back(i);
+        if (!empty) for (int i = 0; i < c->cardinality; i++) ids.push_back(c->to_device_id(i));
         l = (int64_t)ids.size(); d = (double)l;
         R->distinct[a].push_back(std::move(ids));
         break;
@@ -248,9 +251,10 @@ int leaf_to_device(const pb200h_segment& seg, int column, const pb200h_filter_no
     d.ids = store.ids.back()->data();
     d.num_ids = (int)store.ids.back()->size();
   };
-  if (c.is_sorted) { keep(sorted_doc_ranges(c, e, seg.num_docs)); d.op = PB200_F_DOC_RANGES; }
-  else if (n.type == PB200H_RANGE) { d.op = PB200_F_SCAN_RANGE; d.lo = e.start; d.hi = e.end; }
-  else if (c.has_inverted) { keep(e.ids); d.op = e.exclusive ? PB200_F_INV_NOT_IN : PB200_F_INV_IN; }
+  if (c.is_sorted) { keep(sorted_doc_ranges(c, e, seg.num_docs)); d.op = PB200_F_DOC_RANGES; return PB200_OK; }
+  if (n.type == PB200H_RANGE) { d.op = PB200_F_SCAN_RANGE; d.lo = c.to_device_id(e.start); d.hi = c.to_device_id(e.end - 1) + 1; return PB200_OK; }
+  for (auto& id : e.ids) id = c.to_device_id(id);
+  if (c.has_inverted) { keep(e.ids); d.op = e.exclusive ? PB200_F_INV_NOT_IN : PB200_F_INV_IN; }
   else { keep(e.ids); d.op = e.exclusive ? PB200_F_SCAN_NOT_IN : PB200_F_SCAN_IN; }
   return PB200_OK;
 }
@@ -280,7 +284,8 @@ extern "C" int32_t pb200h_segment_create(pb200_ctx* ctx, const char* name, int32
     d.fwd_kind = !c.has_dictionary ? PB200_FWD_RAW_FIXEDBYTE : c.is_sorted ? PB200_FWD_DICT_SORTED : PB200_FWD_DICT_FIXEDBIT;
     d.stored_type = c.data_type; d.bits_per_value = c.bits_per_value; d.cardinality = c.cardinality;
     d.fwd = c.fwd; d.fwd_bytes = c.fwd_bytes;
-    d.dict = c.data_type == PB200_STRING ? nullptr : c.dict; d.dict_bytes = c.data_type == PB200_STRING ? 0 : c.dict_bytes;
+    d.dict = c.dict; d.dict_bytes = c.dict_bytes;  // STRING: kept on the host by the device layer too (hashing / domains)
+    d.reserved = c.data_type == PB200_STRING ? c.dict_entry_bytes : 0;
     d.inv = h.has_inverted ? c.inv : nullptr; d.inv_bytes = h.has_inverted ? c.inv_bytes : 0;
     seg->cols.push_back(std::move(h));
   }
@@ -328,13 +333,14 @@ extern "C" const char* pb200h_segment_column_name(const pb200h_segment* seg, int
 extern "C" int32_t pb200h_segment_column_info(const pb200h_segment* seg, int32_t c, int32_t out[6]) {
   if (!seg || c < 0 || c >= (int)seg->cols.size()) { set_error("bad column"); return PB200_E_INVALID; }
   const HostColumn& h = seg->cols[c];
-  out[0] = h.data_type; out[1] = h.has_dictionary; out[2] = h.bits; out[3] = h.cardinality; out[4] = h.is_sorted; out[5] = h.has_inverted;
+  const HostColumn& g = h.decode_column();  // bound column: the id space results come back in is the domain's
+  out[0] = h.data_type; out[1] = h.has_dictionary; out[2] = g.bits; out[3] = g.cardinality; out[4] = h.is_sorted; out[5] = h.has_inverted;
   return PB200_OK;
 }
 extern "C" int32_t pb200h_dictionary_get(const pb200h_segment* seg, int32_t c, int32_t id, double* num, int64_t* lng,
                                          char* str, int32_t cap) {
   if (!seg || c < 0 || c >= (int)seg->cols.size()) { set_error("bad column"); return PB200_E_INVALID; }
-  const HostColumn& h = seg->cols[c];
+  const HostColumn& h = seg->cols[c].decode_column();
   if (id < 0 || id >= h.cardinality || h.dict.empty()) { set_error("dictId %d out of range", id); return PB200_E_INVALID; }
   if (h.data_type == PB200_STRING) {
     std::string s = h.get_string(id);
@@ -343,6 +349,41 @@ extern "C" int32_t pb200h_dictionary_get(const pb200h_segment* seg, int32_t c, i
   }
   if (num) *num = h.as_double(id);
   if (lng) *lng = h.data_type == PB200_INT ? h.get_int(id) : h.data_type == PB200_LONG ? h.get_long(id) : (int64_t)h.as_double(id);
+  return PB200_OK;
+}
+
+// ---- table-wide dictionaries (value space face of pb200_domain_*) --------------------------------------------------
+extern "C" int32_t pb200h_domain_build(pb200_ctx* ctx, pb200h_segment* const* segs, int32_t nseg, int32_t ncols,
+                                       const char* const* names, pb200_domain** out) {
+  if (!ctx || !segs || !names || !out || nseg <= 0 || ncols <= 0) { set_error("invalid argument to pb200h_domain_build"); return PB200_E_INVALID; }
+  std::vector<int32_t> cols(ncols);
+  std::vector<pb200_segment*> dev(nseg);
+  for (int k = 0; k < ncols; k++) {
+    cols[k] = segs[0]->column_index(names[k]);
+    if (cols[k] < 0) { set_error("unknown column '%s'", names[k] ? names[k] : "(null)"); return PB200_E_INVALID; }
+    for (int s = 0; s < nseg; s++) {
+      if (segs[s]->column_index(names[k]) != cols[k]) { set_error("column '%s' is not at the same position in every segment", names[k]); return PB200_E_INVALID; }
+      if (!segs[s]->cols[cols[k]].has_dictionary) { set_error("column '%s' has no dictionary", names[k]); return PB200_E_INVALID; }
+    }
+  }
+  for (int s = 0; s < nseg; s++) dev[s] = segs[s]->dev;
+  return pb200_domain_from_segments(ctx, dev.data(), nseg, ncols, cols.data(), out);
+}
+
+extern "C" int32_t pb200h_segment_bind_domain(pb200_ctx* ctx, pb200h_segment* seg, pb200_domain* dom) {
+  if (!ctx || !seg || !dom) { set_error("invalid argument to pb200h_segment_bind_domain"); return PB200_E_INVALID; }
+  if (!seg->star_trees.empty()) { set_error("segment '%s' has star-trees (their dimension columns share the base dictionaries): not bindable", seg->name.c_str()); return PB200_E_UNSUPPORTED; }
+  int rc = pb200_segment_bind_domain(ctx, seg->dev, dom);
+  if (rc) return rc;
+  for (const auto& dc : dom->cols) {
+    HostColumn& h = seg->cols[dc.column];
+    auto g = std::make_shared<HostColumn>();
+    g->name = h.name; g->data_type = dc.stored_type; g->has_dictionary = 1; g->bits = dc.bits;
+    g->cardinality = dc.cardinality; g->entry_bytes = dc.entry_bytes; g->dict = dc.dict_be;
+    h.global = g;
+    const auto& ids = seg->dev->cols[dc.column].local_ids;
+    h.local_ids.assign(ids.begin(), ids.end());
+  }
   return PB200_OK;
 }
 
@@ -578,6 +619,14 @@ extern "C" int32_t pb200h_execute(pb200_ctx* ctx, const pb200h_query* q, pb200h_
   std::vector<int> kind(nseg, q->num_group_by > 0 ? PB200H_OP_GROUP_BY : PB200H_OP_AGGREGATION);
   for (int s = 0; s < nseg; s++) {
     if (segs[s]->cols.size() != s0.cols.size()) { set_error("segments do not share a schema"); return PB200_E_INVALID; }
+    // group-by / aggregation columns were resolved by name against segment 0: every segment must hold the same column
+    // (name, type, dictionary-encoded or not) at that position
+    auto same_column = [&](int idx) {
+      const HostColumn &a = s0.cols[idx], &b = segs[s]->cols[idx];
+      return a.name == b.name && a.data_type == b.data_type && a.has_dictionary == b.has_dictionary;
+    };
+    for (int g = 0; g < q->num_group_by; g++) if (!same_column(gb[g])) { set_error("segment %d: column '%s' is not at the position it has in segment 0", s, q->group_by[g]); return PB200_E_INVALID; }
+    for (int a = 0; a < q->num_aggs; a++) if (aggs[a].column >= 0 && !same_column(aggs[a].column)) { set_error("segment %d: column '%s' is not at the position it has in segment 0", s, q->aggs[a].column); return PB200_E_INVALID; }
     int rc = build_segment_filter(*segs[s], *q, filters[s], nullptr);
     if (rc) return rc;
     if (!merge) {

@@ -164,6 +164,7 @@ extern "C" int32_t pb200h_startree_attach(pb200_ctx* ctx, pb200h_segment* seg, c
                                           const void* const* dim_fwd, const uint64_t* dim_fwd_bytes, int32_t nmetrics,
                                           const pb200h_star_metric* metrics) {
   if (!ctx || !seg || !tree || ndims <= 0 || ndims > 30 || nmetrics <= 0 || num_star_docs <= 0) { set_error("invalid argument to pb200h_startree_attach"); return PB200_E_INVALID; }
+  if (seg->dev && seg->dev->domain) { set_error("segment is bound to a dictionary domain: star-tree dimension ids would not match"); return PB200_E_UNSUPPORTED; }
   std::unique_ptr<StarTreeIndex> st(new StarTreeIndex());
   if (!st->tree.parse((const unsigned char*)tree, tree_bytes)) { set_error("malformed star-tree buffer (magic / version / size)"); return PB200_E_INVALID; }
   if ((int)st->tree.dim_names.size() != ndims) { set_error("star-tree has %zu dimensions, %d given", st->tree.dim_names.size(), ndims); return PB200_E_INVALID; }

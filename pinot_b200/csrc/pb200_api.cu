@@ -18,7 +18,8 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 
 #include "pb200_internal.h"
-#include "pb200_scan.cuh"
+#include "pb200_scan_launch.h"
+#include "pb200_unpack.cuh"
 
 namespace pb200 {
 
@@ -233,7 +234,49 @@ extern "C" int32_t pb200_init(int32_t device, pb200_ctx** out) {
     delete ctx;
     return PB200_E_UNSUPPORTED;
   }
+  {  // tuning knobs: environment read once here
+    Tuning& t = ctx->tune;
+    auto env_i = [](const char* n, long long dflt) -> long long { const char* v = getenv(n); return v ? atoll(v) : dflt; };
+    const int w = (int)env_i("PB200_W", t.warps);
+    if (w == 6 || w == 8) t.warps = w;
+    t.sparse_max = (int)env_i("PB200_SPARSE_MAX", t.sparse_max);
+    t.sparse_max_agg = (int)env_i("PB200_SPARSE_MAX_AGG", t.sparse_max_agg);
+    t.ctas_per_sm = (int)std::max<long long>(1, std::min<long long>(2, env_i("PB200_CTAS", t.ctas_per_sm)));
+    t.stages = (int)env_i("PB200_STAGES", 0);
+    t.grid = (int)env_i("PB200_GRID", 0);
+    t.smem_groups = getenv("PB200_NO_SMEM_GROUPS") ? 0 : 1;
+    t.smem_groups_max = env_i("PB200_SMEM_GROUPS_MAX", t.smem_groups_max);
+    t.smem_copies = (int)env_i("PB200_SMEM_COPIES", 0);
+    t.dense_max = env_i("PB200_DENSE_MAX", t.dense_max);
+    t.defer = getenv("PB200_NO_DEFER") ? 0 : 1;
+    t.gb_defer = getenv("PB200_NO_GB_DEFER") ? 0 : 1;
+    t.skip = getenv("PB200_NO_SKIP") ? 0 : 1;
+    t.always_count = getenv("PB200_ALWAYS_COUNT") ? 1 : 0;
+  }
   *out = ctx;
+  return PB200_OK;
+}
+
+extern "C" int32_t pb200_tuning_set(pb200_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) { set_error("null argument"); return PB200_E_INVALID; }
+  Tuning& t = ctx->tune;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  const std::string n(name);
+  if (n == "warps") { if (value != 6 && value != 8) { set_error("warps must be 6 or 8"); return PB200_E_INVALID; } t.warps = (int)value; }
+  else if (n == "sparse_max") t.sparse_max = (int)value;
+  else if (n == "sparse_max_agg") t.sparse_max_agg = (int)value;
+  else if (n == "ctas_per_sm") t.ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(2, value));
+  else if (n == "stages") t.stages = (int)value;
+  else if (n == "grid") t.grid = (int)value;
+  else if (n == "smem_groups") t.smem_groups = value != 0;
+  else if (n == "smem_groups_max") t.smem_groups_max = value;
+  else if (n == "smem_copies") t.smem_copies = (int)value;
+  else if (n == "dense_max") t.dense_max = value;
+  else if (n == "defer") t.defer = value != 0;
+  else if (n == "gb_defer") t.gb_defer = value != 0;
+  else if (n == "skip") t.skip = value != 0;
+  else if (n == "always_count") t.always_count = value != 0;
+  else { set_error("unknown tuning knob '%s'", name); return PB200_E_INVALID; }
   return PB200_OK;
 }
 
@@ -273,7 +316,7 @@ static void free_any(pb200_ctx* ctx, void* p) {
 }
 static void free_column(pb200_ctx* ctx, DeviceColumn& c) {
   if (c.owns) { free_any(ctx, c.fwd); free_any(ctx, c.inv); }
-  free_any(ctx, c.dict_native);
+  if (!c.dict_shared) free_any(ctx, c.dict_native);
   c.fwd = nullptr; c.inv = nullptr; c.dict_native = nullptr;
 }
 
@@ -282,6 +325,8 @@ static int convert_dictionary(pb200_ctx* ctx, const pb200_col_desc& d, DeviceCol
   const int w = c.dict_width();
   if (d.dict_bytes < (uint64_t)w * c.cardinality) { set_error("dictionary too short: %llu bytes for %d x %d", (unsigned long long)d.dict_bytes, c.cardinality, w); return PB200_E_INVALID; }
   c.dict_be.assign(be, be + (size_t)w * c.cardinality);
+  c.dict_entry_bytes = w;
+  c.dict_hash = dictionary_hash(c.stored_type, w, c.cardinality, be);
   c.dict_host.resize((size_t)w * c.cardinality);
   for (int i = 0; i < c.cardinality; i++) {
     if (w == 4) { uint32_t v = be32(be + 4ll * i); memcpy(&c.dict_host[4ull * i], &v, 4); }
@@ -400,6 +445,15 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
       if (rc) return fail(rc);
       seg->device_bytes += (int64_t)c.dict_host.size();
     }
+    if (d.dict && d.stored_type == PB200_STRING && d.fwd_kind != PB200_FWD_RAW_FIXEDBYTE && !on_device && c.cardinality > 0) {
+      // STRING dictionaries never go to the device (keys are dictIds there); the padded entries are kept on the host so
+      // that merges can verify / build a common id space (pb200_domain.cu).  Entry width: `reserved`, else bytes / cardinality.
+      const int w = d.reserved > 0 ? d.reserved : (int)(d.dict_bytes / (uint64_t)c.cardinality);
+      if (w <= 0 || d.dict_bytes < (uint64_t)w * c.cardinality) { set_error("column %d: STRING dictionary too short", i); return fail(PB200_E_INVALID); }
+      c.dict_be.assign((const unsigned char*)d.dict, (const unsigned char*)d.dict + (size_t)w * c.cardinality);
+      c.dict_entry_bytes = w;
+      c.dict_hash = dictionary_hash(PB200_STRING, w, c.cardinality, c.dict_be.data());
+    }
     if (d.inv && d.inv_bytes) {
       if (d.inv_bytes < 4ull * (c.cardinality + 1)) { set_error("column %d: inverted index too short", i); return fail(PB200_E_INVALID); }
       c.inv_bytes = d.inv_bytes;
@@ -434,6 +488,7 @@ extern "C" int32_t pb200_segment_release(pb200_ctx* ctx, pb200_segment* seg) {
   if (!seg) return PB200_OK;
   cudaSetDevice(seg->ctx->device);
   for (auto& c : seg->cols) free_column(seg->ctx, c);
+  if (seg->domain) pb200_domain_release(seg->ctx, seg->domain);
   delete seg;
   return PB200_OK;
 }
@@ -528,15 +583,19 @@ void set_cmp(LeafDesc& lf, const DeviceColumn& c) {
   else lf.cmp = CMP_BOTH;
 }
 
-template <int CW, bool GB, bool DEFER = !GB, int MINB = (GB ? 1 : 2)>
-cudaError_t launch_scan(const Plan& p, const QueryDesc& q, const TmaTable& tt, const SegDesc* dsegs, int grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(scan_kernel<CW, GB, DEFER, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
-  if (e != cudaSuccess) return e;
-  scan_kernel<CW, GB, DEFER, MINB><<<grid, CW * 32, p.smem_bytes, st>>>(q, tt, dsegs);
-  return cudaGetLastError();
-}
-
 }  // namespace
+
+namespace pb200 {
+cudaError_t launch_scan_variant(const ScanVariant& v, size_t smem_bytes, int grid, const QueryDesc& q, const TmaTable& tt,
+                                const SegDesc* dsegs, cudaStream_t st) {
+  if (v.group_by) {
+    if (v.min_blocks >= 2) return v.warps == 8 ? launch_scan_w8_gb2(smem_bytes, grid, q, tt, dsegs, st) : launch_scan_w6_gb2(smem_bytes, grid, q, tt, dsegs, st);
+    return v.warps == 8 ? launch_scan_w8_gb1(smem_bytes, grid, q, tt, dsegs, st) : launch_scan_w6_gb1(smem_bytes, grid, q, tt, dsegs, st);
+  }
+  if (v.warps == 8) return v.defer ? launch_scan_w8_agg(smem_bytes, grid, q, tt, dsegs, st) : launch_scan_w8_agg_nodefer(smem_bytes, grid, q, tt, dsegs, st);
+  return launch_scan_w6_agg(smem_bytes, grid, q, tt, dsegs, st);
+}
+}  // namespace pb200
 
 static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cudaStream_t st);
 
@@ -555,6 +614,36 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   const int ncols = (int)segments[0]->cols.size();
   for (int s = 0; s < nseg; s++) {
     if (!segments[s] || segments[s]->ctx != ctx || (int)segments[s]->cols.size() != ncols) { set_error("segment %d does not belong to this context / schema", s); return PB200_E_INVALID; }
+  }
+
+  if (merge && nseg > 1) {
+    // One result for all segments == a merge of dictId-indexed state (group tables, MIN / MAX ids, DISTINCTCOUNT bitsets).
+    // That is only a merge BY VALUE (GroupByCombineOperator.java:130-146, AggregationFunction.merge) when the column has
+    // the same dictionary everywhere: compare content hashes, not cardinalities.  Bound segments (pb200_domain_*) pass by
+    // construction; anything else is refused so that the caller combines per-segment results itself.
+    auto same_dictionary = [&](int col, const char* what) -> bool {
+      const DeviceColumn& c0 = segments[0]->cols[col];
+      for (int s = 1; s < nseg; s++) {
+        const DeviceColumn& c = segments[s]->cols[col];
+        if (c.dict_hash != c0.dict_hash || c.cardinality != c0.cardinality || c.stored_type != c0.stored_type) {
+          set_error("PB200_Q_MERGE_SEGMENTS: %s column %d has a different dictionary in segment %d than in segment 0 "
+                    "(bind the segments to a pb200_domain first)", what, col, s);
+          return false;
+        }
+      }
+      return true;
+    };
+    for (int g = 0; g < ngb; g++) {
+      const int c = query->group_by_columns[g];
+      if (c >= 0 && c < ncols && !same_dictionary(c, "group-by")) return PB200_E_UNSUPPORTED;
+    }
+    for (int a = 0; a < nagg; a++) {
+      const pb200_agg& ag = query->aggs[a];
+      if (ag.function != PB200_AGG_MIN && ag.function != PB200_AGG_MAX && ag.function != PB200_AGG_DISTINCTCOUNT) continue;
+      if (ag.column < 0 || ag.column >= ncols) continue;
+      if (segments[0]->cols[ag.column].bits == 32 && !segments[0]->cols[ag.column].dict_native) continue;  // raw values, no ids
+      if (!same_dictionary(ag.column, ag.function == PB200_AGG_DISTINCTCOUNT ? "DISTINCTCOUNT" : "MIN/MAX")) return PB200_E_UNSUPPORTED;
+    }
   }
 
   Plan plan;
@@ -582,6 +671,13 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   for (int g = 0; g < ngb; g++) {
     int c = query->group_by_columns[g];
     if (c < 0 || c >= ncols) { set_error("group-by column %d out of range", c); return PB200_E_INVALID; }
+    for (int t = 0; t < nseg; t++) {
+      const DeviceColumn& gc = segments[t]->cols[c];
+      if (gc.bits > 31 || gc.cardinality <= 0 || gc.fwd_kind != PB200_FWD_DICT_FIXEDBIT) {
+        set_error("group-by column %d is not dictionary-encoded in segment %d: not accelerated", c, t);
+        return PB200_E_UNSUPPORTED;
+      }
+    }
     int s = slot_of(plan, c, ROLE_GROUP);
     if (s < 0) { set_error("too many distinct columns (max %d)", kMaxSlots); return PB200_E_UNSUPPORTED; }
     q.group_slot[g] = s;
@@ -668,23 +764,22 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   // dictionary gathers).  Group-by: the survivor-queue path needs ~120 registers; W = 6 with two CTAs per SM leaves room
   // for a 3-deep ring (measured on C3/range: 2.26 ms vs 2.95 ms at W = 8); falls back to one CTA when the rows are too wide
   // for two 2-deep rings.
-  int cw = 6, stages = 0, ctas_per_sm = 1;
-  if (getenv("PB200_W")) { int w = atoi(getenv("PB200_W")); if (w == 6 || w == 8) cw = w; }  // tuning knob
-  q.sparse_max = getenv("PB200_SPARSE_MAX") ? atoi(getenv("PB200_SPARSE_MAX")) : 4;
-  q.sparse_max_agg = getenv("PB200_SPARSE_MAX_AGG") ? atoi(getenv("PB200_SPARSE_MAX_AGG")) : (plan.group_by ? std::min(q.sparse_max, 2) : q.sparse_max);
-  ctas_per_sm = 2;  // group-by through the survivor queue needs < 128 registers: two 256-thread CTAs per SM
-  if (getenv("PB200_CTAS")) ctas_per_sm = std::max(1, std::min(2, atoi(getenv("PB200_CTAS"))));
+  const Tuning tune = [&]() { std::lock_guard<std::mutex> g(ctx->mu); return ctx->tune; }();
+  int cw = tune.warps, stages = 0, ctas_per_sm = 1;
+  q.sparse_max = tune.sparse_max;
+  q.sparse_max_agg = tune.sparse_max_agg >= 0 ? tune.sparse_max_agg : (plan.group_by ? std::min(q.sparse_max, 2) : q.sparse_max);
+  ctas_per_sm = tune.ctas_per_sm;  // default 2: the group-by kernel needs < 168 registers, two 192-thread CTAs per SM
   const size_t warp_stage_bytes = (size_t)128 * max_bits_sum;
   size_t extra_bytes = (q.conj ? 0 : (size_t)cw * 32 * kMaxStack * 4) + (plan.group_by ? (size_t)cw * 2048 : (size_t)nagg * cw * 32 * 16);
   q.queue_max = plan.group_by ? 1024 : 0;  // every group-by slice goes through the survivor queue
   // CTA-private group tables in shared memory when the key space is small and every function is COUNT or an integer SUM
   q.smem_groups = 0;
   for (int a = 0; a < kMaxAggs; a++) q.smem_slot[a] = -1;
-  if (plan.group_by && !getenv("PB200_NO_SMEM_GROUPS")) {
+  if (plan.group_by && tune.smem_groups) {
     // Small key spaces only: there the global table's few addresses serialise in L2, while for thousands of groups the
     // fire-and-forget global REDs beat shared atomics that must return the old low word (measured on C3/range, 10 000
     // groups: 3.6 ms global vs 4.4 ms shared).
-    const long long smem_groups_max = getenv("PB200_SMEM_GROUPS_MAX") ? atoll(getenv("PB200_SMEM_GROUPS_MAX")) : 2048;
+    const long long smem_groups_max = tune.smem_groups_max;
     long long gmax = 1;
     for (int s = 0; s < nseg && gmax > 0; s++) {
       long long g = 1;
@@ -692,7 +787,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       gmax = g < 0 ? -1 : std::max(gmax, g);
     }
     bool ok = gmax > 0;
-    if (ok && getenv("PB200_DENSE_MAX") && gmax > atoll(getenv("PB200_DENSE_MAX"))) ok = false;  // hashed: slots, not raw keys
+    if (ok && gmax > tune.dense_max) ok = false;  // hashed: slots, not raw keys
     int nsum = 0;
     for (int a = 0; a < nagg && ok; a++) {
       const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
@@ -707,7 +802,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     if (ok && room >= (long long)copy_bytes) {
       int copies = 1;
       while (copies < 32 && (long long)copy_bytes * copies * 2 <= std::min<long long>(room, 64 << 10)) copies *= 2;
-      if (getenv("PB200_SMEM_COPIES")) copies = std::max(1, std::min(copies, atoi(getenv("PB200_SMEM_COPIES"))));
+      if (tune.smem_copies > 0) copies = std::max(1, std::min(copies, tune.smem_copies));
       q.smem_groups = (int32_t)gmax;
       q.smem_copies = copies;
       q.smem_gstride = (int32_t)gstride;
@@ -726,14 +821,14 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     }
   }
   if (stages < 2) { set_error("touched columns too wide for the shared-memory pipeline (%d bits per row)", max_bits_sum); return PB200_E_UNSUPPORTED; }
-  if (getenv("PB200_STAGES")) stages = std::max(2, std::min(stages, atoi(getenv("PB200_STAGES"))));
+  if (tune.stages > 0) stages = std::max(2, std::min(stages, tune.stages));
   plan.cw = cw;
   q.tile_rows = cw * 1024;
   q.num_stages = stages;
   q.stage_words = (uint32_t)(32 * max_bits_sum);
   q.use_pipe = q.num_slots > 0;
   q.defer_agg = -1;
-  if (!plan.group_by && !getenv("PB200_NO_DEFER"))
+  if (!plan.group_by && tune.defer)
     for (int a = 0; a < nagg; a++)
       if ((q.aggs[a].function == PB200_AGG_SUM || q.aggs[a].function == PB200_AGG_AVG) && q.aggs[a].val_kind == VAL_DICT_I32) { q.defer_agg = a; break; }
   plan.smem_bytes = hdr_bytes + (size_t)cw * stages * q.stage_words * 4 + extra_bytes;
@@ -845,6 +940,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         for (int k = 0; k < n.num_ids; k++) {  // InvertedIndexFilterOperator: OR of the bitmaps of the dictIds
           const int id = n.ids[k];
           if (id < 0 || id >= c.cardinality) { set_error("dictId %d out of range for inverted index (card %d)", id, c.cardinality); return PB200_E_INVALID; }
+          if (c.inv_offsets[id + 1] == c.inv_offsets[id]) continue;  // bound column: this domain id does not occur in the segment
           decode_jobs.push_back(DecodeJob{c.inv, c.inv_offsets[id], (unsigned long long)c.inv_offsets[id + 1] - c.inv_offsets[id], mask, seg->num_docs});
         }
         lf.kind = LEAF_DOCMASK;
@@ -915,13 +1011,29 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       const bool has_slot = lf.slot >= 0;
       lf.code = leaf_code(lf.kind, lf.cmp, lf.negate, has_slot ? sd.slots[lf.slot].bits : 0, has_slot ? sd.slots[lf.slot].stage_words : 0u);
     }
+    // software-pipelined aggregations go LAST (nothing is waited on after them).  Aggregation only: q.defer_agg.
+    // Group-by (dense / hash tables, not the CTA-private shared tables): up to two of {SUM / AVG over a 4-byte
+    // dictionary, MIN, MAX} -- the kernel issues their loads for the last queue batch and reduces one tile later.
+    bool pipelined[kMaxAggs] = {};
+    int npipe = 0;
+    if (!plan.group_by) {
+      if (q.defer_agg >= 0) pipelined[q.defer_agg] = true;
+    } else if (tune.gb_defer && q.smem_groups == 0) {
+      for (int a = 0; a < nagg && npipe < 2; a++) {
+        if (q.aggs[a].slot < 0) continue;
+        const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
+        const bool sum4 = (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) && (vk == VAL_DICT_I32 || vk == VAL_DICT_F32);
+        if (sum4 || fn == PB200_AGG_MIN || fn == PB200_AGG_MAX) { pipelined[a] = true; npipe++; }
+      }
+    }
     int n = 0;
-    for (int pass = 0; pass < 2; pass++)  // the software-pipelined aggregation goes last (nothing is waited on after it)
+    for (int pass = 0; pass < 2; pass++)
       for (int a = 0; a < nagg; a++) {
-        if (q.aggs[a].slot < 0 || (a == q.defer_agg) != (pass == 1)) continue;
+        if (q.aggs[a].slot < 0 || pipelined[a] != (pass == 1)) continue;
         const SlotDesc& sl = sd.slots[q.aggs[a].slot];
         sd.agg_code[n++] = agg_code(a, q.aggs[a].function, q.aggs[a].val_kind, sl.bits, sl.stage_words);
       }
+    sd.num_defer_codes = plan.group_by ? npipe : 0;
     sd.num_agg_codes = n;
   }
 
@@ -979,10 +1091,6 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       unsigned __int128 space = 1;  // size of the raw key space
       for (int g = 0; g < ngb; g++) {
         int card = seg->cols[query->group_by_columns[g]].cardinality;
-        if (merge) for (int s = 1; s < nseg; s++) if (segments[s]->cols[query->group_by_columns[g]].cardinality != card) {
-          set_error("PB200_Q_MERGE_SEGMENTS needs identical dictionaries (cardinality of group-by column %d differs)", g);
-          return PB200_E_INVALID;
-        }
         card = std::max(card, 1);
         // every representable dictId must stay inside the table even for padded / corrupt rows
         d.mult.push_back((uint32_t)(unsigned long long)space);
@@ -996,7 +1104,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       }
       // dense table up to kDenseMax raw keys (ARRAY / INT_MAP regimes of the reference), beyond it a hash table over the
       // 64-bit raw key (LONG_MAP regime, and INT_MAP key spaces too large to be worth a dense table)
-      const long long dense_max = getenv("PB200_DENSE_MAX") ? atoll(getenv("PB200_DENSE_MAX")) : (1ll << 24);
+      const long long dense_max = tune.dense_max;
       const bool hashed = space > (unsigned __int128)dense_max;
       if (hashed) {
         const long long limit = std::max(query->num_groups_limit, 1);
@@ -1023,7 +1131,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       // one block per element kind
       // the exact per-group count is kept only when a function needs it; otherwise a MIN/MAX table (or a flag table)
       // marks the groups that exist -- one atomic less per surviving row
-      bool need_count = getenv("PB200_ALWAYS_COUNT") != nullptr;
+      bool need_count = tune.always_count != 0;
       bool has_minmax = false;
       for (int a = 0; a < nagg; a++) {
         need_count |= q.aggs[a].function == PB200_AGG_COUNT || q.aggs[a].function == PB200_AGG_AVG;
@@ -1062,10 +1170,6 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         else if (fn == PB200_AGG_MAX) { d.gmax[a] = (uint32_t*)d.u32max_block + (xi++) * groups; if (!need_count && !d.exists_max && !d.exists_min) d.exists_max = d.gmax[a]; }
         else if (fn == PB200_AGG_DISTINCTCOUNT) {  // one dictId bitset per group / slot
           const DeviceColumn& c = seg->cols[query->aggs[a].column];
-          if (merge) for (int s = 1; s < nseg; s++) if (segments[s]->cols[query->aggs[a].column].cardinality != c.cardinality) {
-            set_error("PB200_Q_MERGE_SEGMENTS needs identical dictionaries (cardinality of DISTINCTCOUNT column %d differs)", query->aggs[a].column);
-            return PB200_E_INVALID;
-          }
           const unsigned long long words = ((unsigned long long)c.cardinality + 31) / 32;
           if (words * (unsigned long long)groups > (1ull << 28)) {
             set_error("DISTINCTCOUNT with GROUP BY: %lld groups x %d dictIds exceed the device bitset budget", groups, c.cardinality);
@@ -1127,7 +1231,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       tt.seg[s].stage_tx = sd.stage_tx;
       tt.seg[s].num_docs = (uint32_t)sd.num_docs;
       for (int k = 0; k < q.num_slots; k++) tt.seg[s].slot[k] = TmaSlot{sd.slots[k].data, sd.slots[k].tile_bytes, sd.slots[k].stage_words};
-      if (q.conj && q.num_slots > 0 && !getenv("PB200_NO_SKIP")) {
+      if (q.conj && q.num_slots > 0 && tune.skip) {
         int nm = 0;
         for (int l = 0; l < nleaves && nm < kMaxSkipMasks; l++)
           if (sd.leaves[l].kind == LEAF_DOCMASK && !sd.leaves[l].negate) tt.seg[s].skip_mask[nm++] = sd.leaves[l].bits;
@@ -1137,13 +1241,11 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     for (int s = cn; s < kMaxLaunchSegs; s++) { tt.seg[s].first_tile = cq.total_tiles; tt.seg[s].end_tile = 0x7FFFFFFF; }  // sentinel
     grid = (int)std::min<long long>((long long)ctx->sm_count * ctas_per_sm, std::max<long long>(cq.total_tiles, 1));
     if (cq.total_tiles >= (1 << 30)) { set_error("too many tiles in one launch"); return PB200_E_UNSUPPORTED; }
-    if (getenv("PB200_GRID")) grid = std::max(1, atoi(getenv("PB200_GRID")));
+    if (tune.grid > 0) grid = tune.grid;
     const SegDesc* dptr = (const SegDesc*)dsegs.p + c0;
     // instantiations: W in {6, 8} x {aggregation only (2 CTAs/SM), group-by with 2 or 1 CTAs/SM}
-    if (plan.group_by && ctas_per_sm == 2) le = cw == 8 ? launch_scan<8, true, false, 2>(plan, cq, tt, dptr, grid, st) : launch_scan<6, true, false, 2>(plan, cq, tt, dptr, grid, st);
-    else if (plan.group_by) le = cw == 8 ? launch_scan<8, true>(plan, cq, tt, dptr, grid, st) : launch_scan<6, true>(plan, cq, tt, dptr, grid, st);
-    else if (cw == 8) le = getenv("PB200_NO_DEFER") ? launch_scan<8, false, false>(plan, cq, tt, dptr, grid, st) : launch_scan<8, false>(plan, cq, tt, dptr, grid, st);
-    else le = launch_scan<6, false>(plan, cq, tt, dptr, grid, st);
+    const ScanVariant variant{cw, plan.group_by, !plan.group_by && !(cw == 8 && !tune.defer), plan.group_by ? ctas_per_sm : 2};
+    le = launch_scan_variant(variant, plan.smem_bytes, grid, cq, tt, dptr, st);
   }
   if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); return PB200_E_CUDA; }
   PB200_CUDA(cudaEventRecord(e1, st));

@@ -75,7 +75,8 @@ struct SegDesc {
   uint32_t stage_tx;      // bytes TMA delivers per warp slice for THIS segment (sum of its slots' tile_bytes)
   int32_t num_agg_codes;
   uint32_t agg_code[kMaxAggs];
-  uint32_t pad1[2];
+  int32_t num_defer_codes;  // group-by: the LAST num_defer_codes entries of agg_code are software-pipelined (pb200_scan.cuh drain_gb)
+  uint32_t pad1;
   SlotDesc slots[kMaxSlots];
   LeafDesc leaves[kMaxLeaves];
   const void* dict[kMaxAggs];          // native (little-endian) dictionary value array of the aggregation's column
@@ -166,6 +167,18 @@ struct QueryDesc {
   int32_t queue_max;
   int8_t smem_slot[kMaxAggs];  // aggregation -> index of its (lo, hi) pair, -1: none (COUNT)
   int8_t pad_tail[2];
+};
+
+// ---- shared-memory header of the scan kernel (the host sizes the dynamic shared memory with it) ----
+constexpr int kMaxWarps = 8;    // warps per CTA (all of them consume; there is no producer warp)
+constexpr int kMaxStages = 4;
+
+struct SmemHeader {
+  SegDesc seg;                              // CTA-wide copy of the current segment's descriptor
+  AggDesc aggs[kMaxAggs];                   // q.aggs: indexed with a runtime `a` (an indexed LDC costs a long-scoreboard wait)
+  uint32_t slot_roles[kMaxSlots];           // q.slot_roles, same reason
+  int32_t group_slot[kMaxGroupBy];          // q.group_slot, same reason
+  uint64_t full[kMaxWarps][kMaxStages];     // per-warp ring: "stage filled by TMA"
 };
 
 }  // namespace pb200

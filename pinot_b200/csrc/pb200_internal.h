@@ -40,12 +40,38 @@ struct DeviceColumn {
   std::vector<uint32_t> inv_offsets;  // host: (card+1) offsets into inv (file-relative)
   bool owns = true;
   bool pooled = false;            // fwd came from the context's caching allocator
+  int dict_entry_bytes = 0;       // width of one dict_be entry (4 / 8, STRING: lengthOfEachEntry)
+  uint64_t dict_hash = 0;         // content hash of the dictionary (pb200_domain.cu dictionary_hash); 0 = no dictionary known
+  bool dict_shared = false;       // dict_native belongs to the bound domain, not to this column
+  std::vector<uint32_t> local_ids;  // bound to a domain: the (global) ids that occur in THIS segment, ascending
   int dict_width() const { return (stored_type == PB200_LONG || stored_type == PB200_DOUBLE) ? 8 : 4; }
 };
 
 }  // namespace pb200
 
+namespace pb200 {
+// Tuning knobs of the scan kernel launch.  Read from the environment ONCE, at pb200_init (PB200_W, PB200_CTAS, ... --
+// DESIGN.md section 3.1), changeable afterwards with pb200_tuning_set(); pb200_execute itself never calls getenv.
+struct Tuning {
+  int warps = 6;                 // PB200_W: 6 | 8 warps per CTA
+  int sparse_max = 4;            // PB200_SPARSE_MAX
+  int sparse_max_agg = -1;       // PB200_SPARSE_MAX_AGG (-1: rule in pb200_execute)
+  int ctas_per_sm = 2;           // PB200_CTAS
+  int stages = 0;                // PB200_STAGES (0: as many as fit)
+  int grid = 0;                  // PB200_GRID (0: SMs x CTAs per SM)
+  int smem_groups = 1;           // !PB200_NO_SMEM_GROUPS
+  long long smem_groups_max = 2048;  // PB200_SMEM_GROUPS_MAX
+  int smem_copies = 0;           // PB200_SMEM_COPIES (0: as many as fit)
+  long long dense_max = 1ll << 24;   // PB200_DENSE_MAX: dense group table up to this many raw keys, hash table beyond
+  int defer = 1;                 // !PB200_NO_DEFER: software-pipelined gathers, aggregation-only kernel
+  int gb_defer = 1;              // !PB200_NO_GB_DEFER: software-pipelined last queue batch, group-by kernel
+  int skip = 1;                  // !PB200_NO_SKIP: bitmap-driven slice skipping
+  int always_count = 0;          // PB200_ALWAYS_COUNT
+};
+}  // namespace pb200
+
 struct pb200_ctx {
+  pb200::Tuning tune;
   int device = 0;
   int sm_count = 0;
   int max_smem_optin = 0;
@@ -57,12 +83,27 @@ struct pb200_ctx {
   std::multimap<size_t, void*> free_pinned;  // pinned host staging blocks (result read-back), size -> block
 };
 
+// Table-wide dictionaries (pb200_domain.cu)
+struct pb200_domain {
+  pb200_ctx* ctx = nullptr;
+  struct Col {
+    int column = 0, stored_type = 0, entry_bytes = 0, cardinality = 0, bits = 0;
+    std::vector<unsigned char> dict_be;    // big-endian sorted values / padded strings
+    std::vector<unsigned char> dict_host;  // native little-endian values (numeric types)
+    void* dict_native = nullptr;           // device copy (INT: biased), shared by every bound segment
+    uint64_t hash = 0;
+  };
+  std::vector<Col> cols;
+  int refs = 1;  // the creator + one per bound segment (guarded by ctx->mu)
+};
+
 struct pb200_segment {
   pb200_ctx* ctx = nullptr;
   std::string name;
   int num_docs = 0;
   std::vector<pb200::DeviceColumn> cols;
   int64_t device_bytes = 0;
+  pb200_domain* domain = nullptr;  // holds one reference
 };
 
 struct pb200_result {
@@ -124,6 +165,9 @@ struct DecodeJob {
   long long num_docs;
 };
 int roaring_decode_batch(pb200_ctx* ctx, cudaStream_t stream, const std::vector<DecodeJob>& jobs, void* jobs_dev);
+// pb200_domain.cu
+uint64_t dictionary_hash(int stored_type, int entry_bytes, int cardinality, const unsigned char* be);
+int bits_for_cardinality(int card);
 // pb200_synth.cu
 int synth_build_inverted(pb200_ctx* ctx, cudaStream_t stream, DeviceColumn& col, long long num_docs);
 }  // namespace pb200

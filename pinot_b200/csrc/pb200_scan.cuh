@@ -277,17 +277,6 @@ struct MinMaxLeft {
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kMaxWarps = 8;    // warps per CTA (all of them consume; there is no producer warp)
-constexpr int kMaxStages = 4;
-
-struct SmemHeader {
-  SegDesc seg;                              // CTA-wide copy of the current segment's descriptor
-  AggDesc aggs[kMaxAggs];                   // q.aggs: indexed with a runtime `a` (an indexed LDC costs a long-scoreboard wait)
-  uint32_t slot_roles[kMaxSlots];           // q.slot_roles, same reason
-  int32_t group_slot[kMaxGroupBy];          // q.group_slot, same reason
-  uint64_t full[kMaxWarps][kMaxStages];     // per-warp ring: "stage filled by TMA"
-};
-
 // Execution model
 //   * a CTA tile is W x 1024 consecutive rows of ONE segment; CTA c takes CTA tiles c, c + grid, ...;
 //   * inside it every WARP owns a private slice of 1024 rows and a private TMA ring: lane 0 arms the warp's mbarrier
@@ -425,6 +414,53 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     }
   };
 
+  // Group-by: the LAST batch of a slice's survivor queue (all of it when <= 32 * kQB rows survive) is software-pipelined
+  // too.  Its table indices and the loads its reductions wait for -- the dictionary value of a SUM / AVG argument, the
+  // current table entry of a MIN / MAX -- are issued in this tile and consumed after the NEXT tile's filter phase, so the
+  // L2 round trip of the gathers is hidden behind ~1000 cycles of independent work instead of stalling the warp.
+  // Up to kGD aggregations are pipelined (the host lists them last in SegDesc.agg_code, num_defer_codes of them).
+  constexpr int kQB = 4;   // queue entries per lane and step
+  constexpr int kGD = 2;
+  uint32_t pg[GROUPBY ? kQB : 1];            // table index (raw key or hash slot) of the pending entries
+  uint32_t px[GROUPBY ? kGD : 1][GROUPBY ? kQB : 1];  // loaded word: biased / float dictionary value, or current MIN / MAX entry
+  uint32_t pq[GROUPBY ? kGD : 1][GROUPBY ? kQB : 1];  // MIN / MAX: the row's order-preserving encoding
+  uint32_t pend_ok = 0;                      // bit u: entry u is pending
+  auto drain_gb = [&]() {
+    if constexpr (GROUPBY) {
+      if (pend_ok) {
+        const int n = sd.num_agg_codes, nd = sd.num_defer_codes;
+#pragma unroll
+        for (int k = 0; k < kGD; ++k) {
+          if (k < nd) {
+            const uint32_t ac = sd.agg_code[n - nd + k];
+            const int a = (int)(ac & 7u), fn = (int)((ac >> 4) & 7u), vk = (int)((ac >> 8) & 7u);
+            if (fn == 1 || fn == 4) {
+              if (vk == VAL_DICT_F32) {
+                double* t = sd.g_dsum[a];
+#pragma unroll
+                for (int u = 0; u < kQB; ++u) if ((pend_ok >> u) & 1u) red_add_f64(t + pg[u], (double)__uint_as_float(px[k][u]));
+              } else {
+                unsigned long long* t = reinterpret_cast<unsigned long long*>(sd.g_isum[a]);
+#pragma unroll
+                for (int u = 0; u < kQB; ++u)
+                  if ((pend_ok >> u) & 1u) red_add_u64(t + pg[u], (unsigned long long)(long long)(int)(px[k][u] ^ 0x80000000u));
+              }
+            } else if (fn == 2) {
+              uint32_t* t = sd.g_min[a];
+#pragma unroll
+              for (int u = 0; u < kQB; ++u) if (((pend_ok >> u) & 1u) && pq[k][u] < px[k][u]) atomicMin(t + pg[u], pq[k][u]);
+            } else {
+              uint32_t* t = sd.g_max[a];
+#pragma unroll
+              for (int u = 0; u < kQB; ++u) if (((pend_ok >> u) & 1u) && pq[k][u] + 1u > px[k][u]) atomicMax(t + pg[u], pq[k][u] + 1u);
+            }
+          }
+        }
+        pend_ok = 0;
+      }
+    }
+  };
+
   auto reset_acc = [&]() {
     if (!GROUPBY) {
       for (int a = 0; a < q.num_aggs; ++a) {
@@ -436,6 +472,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
   auto flush = [&]() {
     // one atomic per warp per accumulator into the segment's AggAccum
     drain();
+    drain_gb();
     unsigned long long c = warp_sum(cnt);
     if (lane == 0 && c) atomicAdd(&sd.accum->count, c);
     cnt = 0;
@@ -621,6 +658,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     }
 
     drain();  // the previous tile's gathers have had this tile's whole filter phase to arrive
+    drain_gb();
 
     // ---------------- phase 2: aggregate the surviving rows ----------------
     const int pc = __popc(m);
@@ -679,9 +717,13 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
         }
         __syncwarp();
         // kQB queue entries per lane and step: their smem probes, dictionary gathers and table updates are issued as
-        // groups (all keys, all gathers, all reductions) so that kQB latency chains overlap instead of running back to back
-        constexpr int kQB = 4;
-        for (int i0 = lane; i0 < S; i0 += 32 * kQB) {
+        // groups (all keys, all gathers, all reductions) so that kQB latency chains overlap instead of running back to back.
+        // The loop is warp-uniform (validity is per entry) so that "last batch" is a uniform decision.
+        const int ncodes = sd.num_agg_codes;
+        const int ndefer = sd.num_defer_codes;
+        for (int b0 = 0; b0 < S; b0 += 32 * kQB) {
+          const int i0 = b0 + lane;
+          const bool last = b0 + 32 * kQB >= S;
           uint32_t e[kQB], g[kQB];
           bool ok[kQB];
 #pragma unroll
@@ -723,8 +765,41 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 #pragma unroll
             for (int u = 0; u < kQB; ++u) if (cur[u] == 0u) sd.g_seen[g[u]] = 1u;
           }
+          // ---- software-pipelined aggregations of the last batch: issue the loads, reduce one tile later (drain_gb) ----
+          const int nimm = last ? ncodes - ndefer : ncodes;
+          if (last && ndefer > 0) {
+            uint32_t okm = 0;
+#pragma unroll
+            for (int u = 0; u < kQB; ++u) { okm |= (ok[u] ? 1u : 0u) << u; pg[u] = g[u]; }
+#pragma unroll
+            for (int k = 0; k < kGD; ++k) {
+              if (k < ndefer) {
+                const uint32_t ac = sd.agg_code[ncodes - ndefer + k];
+                const int a = (int)(ac & 7u), fn = (int)((ac >> 4) & 7u), vk = (int)((ac >> 8) & 7u);
+                const int abits = (int)((ac >> 12) & 63u);
+                const uint32_t* base = st + (ac >> 18);
+                uint32_t id[kQB];
+#pragma unroll
+                for (int u = 0; u < kQB; ++u) id[u] = read_one_group(base + (e[u] >> 5) * abits, (int)(e[u] & 31u), abits);
+                if (fn == 1 || fn == 4) {   // 4-byte dictionaries only (host rule): biased INT or FLOAT bits
+                  const uint32_t* d = static_cast<const uint32_t*>(sd.dict[a]);
+#pragma unroll
+                  for (int u = 0; u < kQB; ++u) px[k][u] = (uint32_t)ldg_pred_s32(reinterpret_cast<const int*>(d + id[u]), ok[u] ? 1u : 0u);
+                } else {
+                  const uint32_t bias = vk == VAL_RAW_I32 ? 0x80000000u : 0u;
+                  const uint32_t* tab = fn == 2 ? sd.g_min[a] : sd.g_max[a];
+#pragma unroll
+                  for (int u = 0; u < kQB; ++u) {
+                    pq[k][u] = id[u] ^ bias;
+                    px[k][u] = ok[u] ? __ldcg(tab + g[u]) : (fn == 2 ? 0u : 0xFFFFFFFFu);
+                  }
+                }
+              }
+            }
+            pend_ok = okm;
+          }
 #pragma unroll 1
-          for (int ai = 0; ai < sd.num_agg_codes; ++ai) {
+          for (int ai = 0; ai < nimm; ++ai) {
             const uint32_t ac = sd.agg_code[ai];  // index | function | value kind | bits | stage_words (pb200_desc.h)
             const int a = (int)(ac & 7u), fn = (int)((ac >> 4) & 7u), vk = (int)((ac >> 8) & 7u);
             const int abits = (int)((ac >> 12) & 63u);

@@ -41,6 +41,10 @@ class B200Context:
         _lib.check(self.lib.pb200_device_info(self.handle, out))
         return {"sm_count": out[0], "major": out[1], "minor": out[2], "total_mem_mb": out[3], "free_mem_mb": out[4]}
 
+    def set_tuning(self, name: str, value: int) -> None:
+        """pb200_tuning_set: launch knobs of the scan kernel (defaults come from PB200_* environment variables at init)."""
+        _lib.check(self.lib.pb200_tuning_set(self.handle, name.encode(), int(value)))
+
     def close(self):
         if self.handle:
             self.lib.pb200_shutdown(self.handle)
@@ -156,12 +160,86 @@ class IndexSegment:
                 _lib.check(int(r))
         return out
 
+    def bind_domain(self, domain: "DictionaryDomain") -> None:
+        """Re-encodes the domain's columns into table-wide ids (pb200h_segment_bind_domain): afterwards this segment can
+        be merged with the other bound segments on the device and across GPUs, by value."""
+        _lib.check(self.ctx.lib.pb200h_segment_bind_domain(self.ctx.handle, self.handle, domain.handle))
+
+    def local_ids(self, column: str) -> np.ndarray:
+        """Ids of `column` that occur in this segment (bound: domain ids; unbound: 0..cardinality-1)."""
+        L = self.ctx.lib
+        dev, ci = L.pb200h_segment_device(self.handle), self.column_index(column)
+        n = L.pb200_segment_local_ids(dev, ci, None, 0)
+        out = np.zeros(int(n), dtype=np.int32)
+        L.pb200_segment_local_ids(dev, ci, _ptr(out), int(n))
+        return out
+
     def device_bytes(self) -> int:
         return int(self.ctx.lib.pb200_segment_device_bytes(self.ctx.lib.pb200h_segment_device(self.handle)))
 
     def destroy(self):
         if self.handle:
             self.ctx.lib.pb200h_segment_destroy(self.handle)
+            self.handle = None
+
+
+class DictionaryDomain:
+    """Table-wide dictionaries (include/pinot_b200.h "domains"): the sorted union of per-segment dictionaries, the common
+    id space that makes device-side and cross-GPU merges merges BY VALUE (GroupByCombineOperator.java:130-146)."""
+
+    def __init__(self, ctx: B200Context, handle, columns: Sequence[str], column_ids: Sequence[int]):
+        self.ctx, self.handle, self.columns, self.column_ids = ctx, handle, list(columns), list(column_ids)
+
+    @classmethod
+    def build(cls, ctx: B200Context, segments: Sequence[IndexSegment], columns: Sequence[str]) -> "DictionaryDomain":
+        """Union over the given (still unbound) segments' own dictionaries."""
+        names = (C.c_char_p * len(columns))(*[c.encode() for c in columns])
+        segs = (C.c_void_p * len(segments))(*[s.handle for s in segments])
+        h = C.c_void_p()
+        _lib.check(ctx.lib.pb200h_domain_build(ctx.handle, segs, len(segments), len(columns), names, C.byref(h)))
+        return cls(ctx, h, columns, [segments[0].column_index(c) for c in columns])
+
+    @classmethod
+    def from_dictionaries(cls, ctx: B200Context, columns: Sequence[str], column_ids: Sequence[int],
+                          stored_types: Sequence[int], parts: Sequence[Sequence[np.ndarray]],
+                          entry_bytes: Optional[Sequence[Sequence[int]]] = None) -> "DictionaryDomain":
+        """parts[k] = the sorted dictionaries (Pinot's big-endian bytes, uint8 arrays) to union for column k -- e.g. the
+        rank-local unions gathered from all GPUs."""
+        arr = (_lib.DomainCol * len(columns))()
+        keep = []
+        for k in range(len(columns)):
+            width = 8 if stored_types[k] in (_lib.LONG, _lib.DOUBLE) else 4
+            ptrs = (C.c_void_p * len(parts[k]))(*[p.ctypes.data for p in parts[k]])
+            if stored_types[k] == _lib.STRING:
+                eb = (C.c_int32 * len(parts[k]))(*entry_bytes[k])
+                cards = (C.c_int32 * len(parts[k]))(*[len(p) // w for p, w in zip(parts[k], entry_bytes[k])])
+            else:
+                eb = None
+                cards = (C.c_int32 * len(parts[k]))(*[len(p) // width for p in parts[k]])
+            keep.append((ptrs, cards, eb))
+            arr[k] = _lib.DomainCol(column_ids[k], stored_types[k], len(parts[k]), 0, ptrs, cards, eb)
+        h = C.c_void_p()
+        _lib.check(ctx.lib.pb200_domain_create(ctx.handle, len(columns), arr, C.byref(h)))
+        return cls(ctx, h, columns, column_ids)
+
+    def info(self, column: str) -> Dict[str, int]:
+        out = (C.c_int64 * 4)()
+        _lib.check(self.ctx.lib.pb200_domain_column_info(self.handle, self.column_ids[self.columns.index(column)], out))
+        return dict(zip(("stored_type", "cardinality", "bits", "entry_bytes"), [int(x) for x in out]))
+
+    def dictionary_bytes(self, column: str) -> np.ndarray:
+        """The domain dictionary in Pinot's dictionary-file encoding (big-endian sorted values / padded strings)."""
+        ci = self.column_ids[self.columns.index(column)]
+        n = self.ctx.lib.pb200_domain_dictionary(self.handle, ci, None, 0)
+        if n < 0:
+            _lib.check(int(n))
+        out = np.zeros(int(n), dtype=np.uint8)
+        self.ctx.lib.pb200_domain_dictionary(self.handle, ci, _ptr(out), int(n))
+        return out
+
+    def release(self):
+        if self.handle:
+            self.ctx.lib.pb200_domain_release(self.ctx.handle, self.handle)
             self.handle = None
 
 

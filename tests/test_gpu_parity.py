@@ -297,10 +297,10 @@ GROUP_BY_QUERIES = [t for t in QUERIES if "GROUP BY" in t] + [
 
 
 @pytest.mark.parametrize("n", [1, 33, 8193, 100_003])
-def test_hash_group_table_parity(oracle, ctx, pm, n, monkeypatch):
+def test_hash_group_table_parity(oracle, ctx, pm, n):
     """Key spaces beyond the dense limit (the reference's LONG_MAP regime) go through the device hash table; forcing the
     limit down to 1 sends every group-by shape through it."""
-    monkeypatch.setenv("PB200_DENSE_MAX", "1")
+    ctx.set_tuning("dense_max", 1)
     rng = np.random.default_rng(2000 + n)
     seg = _random_segment(oracle, rng, n)
     dev = to_device(ctx, seg)
@@ -320,6 +320,7 @@ def test_hash_group_table_parity(oracle, ctx, pm, n, monkeypatch):
             with pytest.raises(UnsupportedQueryError):
                 pm.execute_segments([dev], sql.parse("SELECT SUM(c) FROM t GROUP BY c, b", num_groups_limit=1000))
     finally:
+        ctx.set_tuning("dense_max", 1 << 24)
         dev.destroy()
 
 

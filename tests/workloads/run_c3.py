@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mode", default="bitmap", choices=["bitmap", "range", "range2", "range3"])
     ap.add_argument("--check-rows", type=int, default=0, help="also verify against the oracle on a small segment")
+    ap.add_argument("--variants", default="", help="space separated name:knob=value,knob=value tuning variants "
+                    "(pb200_tuning_set) timed on the same resident segments, one JSON line each")
     args = ap.parse_args()
 
     import numpy as np
@@ -80,23 +82,37 @@ def main():
     t0 = time.perf_counter()
     segs = [IndexSegment.synthetic(ctx, f"s{s}", args.rows, specs(s, inverted=args.mode == "bitmap")) for s in range(args.segments)]
     gen_s = time.perf_counter() - t0
-    for _ in range(args.warmup):
-        blocks = pm.execute_segments(segs, q)
-    t0 = time.perf_counter()
-    kms = []
-    for _ in range(args.steps):
-        blocks = pm.execute_segments(segs, q)
-        kms.append(blocks[0].device_ms)
-    el = time.perf_counter() - t0
+    defaults = {"warps": 6, "ctas_per_sm": 2, "stages": 0, "grid": 0, "sparse_max": 4, "sparse_max_agg": -1, "smem_groups": 1,
+                "smem_groups_max": 2048, "smem_copies": 0, "gb_defer": 1, "skip": 1, "always_count": 0}
     rows = args.segments * args.rows
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    k = sum(kms) / len(kms)
-    print(json.dumps({"workload": f"C3/{args.mode}", "query": text, "segments": args.segments, "rows_per_segment": args.rows,
-                      "ms_per_step": el / args.steps * 1e3, "rows_per_s": rows / (el / args.steps), "scan_kernel_ms": k,
-                      "algorithmic_bits_per_row": bits, "achieved_gbs": rows * bits / 8 / (k * 1e-3) / 1e9,
-                      "frac_of_peak": rows * bits / 8 / (k * 1e-3) / 1e9 / peak, "groups": [b.num_groups for b in blocks][:3],
-                      "matched": sum(b.stats.num_docs_scanned for b in blocks), "generation_s": gen_s,
-                      "checked": bool(args.check_rows)}))
+    reference_result = None
+    for variant in (args.variants.split() or ["default:"]):
+        vname, _, knobs = variant.partition(":")
+        for k, v in defaults.items():
+            ctx.set_tuning(k, v)
+        for kv in filter(None, knobs.split(",")):
+            k, _, v = kv.partition("=")
+            ctx.set_tuning(k, int(v))
+        for _ in range(args.warmup):
+            blocks = pm.execute_segments(segs, q)
+        t0 = time.perf_counter()
+        kms = []
+        for _ in range(args.steps):
+            blocks = pm.execute_segments(segs, q)
+            kms.append(blocks[0].device_ms)
+        el = time.perf_counter() - t0
+        # every variant must return the same tables
+        digest = [(b.num_groups, float(b.doubles[0].sum()), int(b.longs[-1].sum()), b.stats.num_docs_scanned) for b in blocks]
+        if reference_result is None:
+            reference_result = digest
+        k = sum(kms) / len(kms)
+        print(json.dumps({"workload": f"C3/{args.mode}", "variant": vname, "knobs": knobs, "query": text, "segments": args.segments,
+                          "rows_per_segment": args.rows, "ms_per_step": el / args.steps * 1e3, "rows_per_s": rows / (el / args.steps),
+                          "scan_kernel_ms": k, "algorithmic_bits_per_row": bits, "achieved_gbs": rows * bits / 8 / (k * 1e-3) / 1e9,
+                          "frac_of_peak": rows * bits / 8 / (k * 1e-3) / 1e9 / peak, "groups": [b.num_groups for b in blocks][:3],
+                          "matched": sum(b.stats.num_docs_scanned for b in blocks), "generation_s": gen_s,
+                          "same_as_first_variant": digest == reference_result, "checked": bool(args.check_rows)}), flush=True)
     for s in segs:
         s.destroy()
     ctx.close()
