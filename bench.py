@@ -1,24 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- rows scanned/sec for Pinot's filter -> project -> aggregate path on B200 (BASELINE.json metric).
+"""bench.py -- rows scanned/sec for Pinot's filter -> project -> GROUP BY aggregate path on B200 (BASELINE.json metric:
+"rows scanned/sec per box, filter+groupby on 100M-row segments, 1/2/4/8 GPU").
 
-Workload (BASELINE.json configs[1], concretised in SURVEY.md section 8d "C2"): 8 segments x 100 M rows per GPU, 8
-dict-encoded fixed-bit INT columns (cardinalities 10 .. 1 000 000 -> 4..20 bits), query
+Table (per GPU): 8 segments x 100 M rows, 8 dict-encoded fixed-bit INT columns c0..c7 (cardinalities 10 .. 1 000 000 ->
+4,7,10,14,16,17,20,20 bits), synthetic, resident in HBM in Pinot's index formats.
 
-    SELECT SUM(c5), COUNT(*) FROM t WHERE c3 BETWEEN lo AND hi AND c6 > K        (2-predicate range filter, ~25 %)
+  headline (the metric: filter + GROUP BY, BASELINE configs[2]/[3] shape on the configs[1] table)
+      SELECT SUM(c5), COUNT(*) FROM benchTable WHERE c6 > K GROUP BY c3          -- 10 % of the rows, 10 000 groups
+  a "step" = ONE pass of that query over all of the rank's segments through the reference-facing plugin call
+  (B200PlanMaker.execute_segments -> pb200h_execute -> one persistent scan kernel), delivered as the server-level results
+  block: the rank's segments are combined on the device (GroupByCombineOperator's job), with N > 1 GPUs the per-GPU group
+  tables are reduced ONCE to rank 0 (NCCL over NVLink), rank 0 extracts the groups.
 
-A "step" is ONE pass of that query over all of the rank's segments through the reference-facing plugin call
-(B200PlanMaker.execute_segments -> pb200h_execute -> one persistent scan kernel).
+  c2 (BASELINE configs[1], the aggregation-only scan of round 1, reported beside the headline)
+      SELECT SUM(c5), COUNT(*) FROM benchTable WHERE c3 BETWEEN lo AND hi AND c6 > K    -- 2-predicate range filter, 25 %
 
     value        rows/s with the segments resident in HBM (Pinot loads a segment once, then serves queries from it)
-    roofline     algorithmic bytes of the scan kernel (sum of bitsPerElement/8 of the touched columns x rows) / its
-                 CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
-    e2e          the same call with HOST-resident index buffers: every step uploads the touched columns from pinned
-                 host memory (H2D inside the timed region), scans, and reads the results back
-    cpu_baseline the CPU oracle (a restatement of the Java operator chain, kind "port") on a bounded sample
-    --impl reference   the CPU restatement alone, all host threads (there is no JVM in this image: SURVEY.md section 0)
+    roofline     algorithmic bytes of the scan kernel (sum of bitsPerElement/8 of the touched columns x rows: both queries
+                 touch c3, c5, c6 = 51 bits/row) / its CUDA-event duration, against MEASURED_PEAKS.json's HBM bandwidth
+    e2e          the headline through the same call with HOST-resident index buffers: every step uploads the touched
+                 columns from pinned host memory (H2D inside the timed region), scans, reads the result block back
+    cpu_baseline the CPU oracle (C++ restatement of the Java operator chain, kind "port") on the SAME full-size table,
+                 generated independently on the CPU; its per-segment group tables are compared with the device's
+    --impl reference   the CPU restatement alone (no device library loaded), all host threads; there is no JVM in the
+                 image, so the reference's own Java path cannot run here
 
-Multi-GPU (torchrun, one rank per GPU): segments shard one set per GPU with no data-path collective except the final
-reduce of the (tiny) result -- weak scaling, value = total rows of all ranks / max-over-ranks time.
+Multi-GPU (torchrun, one rank per GPU): segments shard whole per GPU, no data-path collective; weak scaling:
+value = total rows of all ranks / max-over-ranks time.
 """
 from __future__ import annotations
 
@@ -39,7 +47,7 @@ if ROOT not in sys.path:
 CARDS = [10, 100, 1_000, 10_000, 65_536, 100_000, 1_000_000, 1_000_000]  # c0..c7 -> 4,7,10,14,16,17,20,20 bits
 VALUE_STEP = [1, 1, 1, 3, 1, 7, 2, 2]
 VALUE_BASE = [0, 0, 0, 5, 0, 11, 1, 1]
-TOUCHED = ["c3", "c5", "c6"]
+TOUCHED = ["c3", "c5", "c6"]   # both queries
 METRIC = "rows scanned/sec per box, filter+groupby on 100M-row segments, 1/2/4/8 GPU"
 
 
@@ -47,12 +55,18 @@ def bits_of(card: int) -> int:
     return 1 if card <= 2 else int(card - 1).bit_length()
 
 
-def column_specs(rank: int, seg: int):
+def column_specs(rank: int, seg: int, names=None):
     return [{"name": f"c{c}", "cardinality": CARDS[c], "value_base": VALUE_BASE[c], "value_step": VALUE_STEP[c],
-             "seed": 1000 + 104729 * rank + 131 * seg + c} for c in range(8)]
+             "seed": 1000 + 104729 * rank + 131 * seg + c} for c in range(8) if names is None or f"c{c}" in names]
 
 
-def query_text(selectivity: float) -> str:
+def groupby_query_text(selectivity: float) -> str:
+    k_id = int(round(CARDS[6] * (1 - selectivity))) - 1   # c6 > value(k_id): the upper `selectivity` of the dictionary
+    return (f"SELECT SUM(c5), COUNT(*) FROM benchTable WHERE c6 > {VALUE_BASE[6] + VALUE_STEP[6] * k_id} "
+            f"GROUP BY c3 LIMIT 100000")
+
+
+def c2_query_text(selectivity: float) -> str:
     # each predicate keeps sqrt(selectivity) of the dictionary (uniform dictIds): c3 a centred range, c6 the upper tail
     f = selectivity ** 0.5
     n3 = CARDS[3]
@@ -127,53 +141,106 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def host_segment_for_oracle(sb, dev_seg, rows: int, name: str):
-    """First `rows` docs of the touched columns of a device segment as oracle-readable Pinot buffers."""
-    cols = []
-    for cname in TOUCHED:
-        info = dev_seg.column_info(cname)
-        fwd = dev_seg.read_index(cname, "fwd")[: rows * info["bits"] // 8].copy()
-        dct = dev_seg.read_index(cname, "dict")
-        cols.append(sb.ColumnData(cname, sb.INT, True, info["bits"], info["cardinality"], False, 4, fwd, dct, None))
-    return sb.SegmentData(name, rows, cols)
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
-def time_oracle(oracle, segs, q, threads: int):
-    """Runs the oracle on `segs` with `threads` worker threads (ctypes releases the GIL). Returns (seconds, results)."""
-    results = [None] * len(segs)
-    nxt = [0]
-    lock = threading.Lock()
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle only)
+class CpuTable:
+    """The benchmark table's touched columns, generated on the CPU by the oracle's twin of the device generator
+    (byte-identical: tests/test_gpu_synth.py), split into row ranges so that the single-threaded operator chain of the
+    oracle runs on every host core.  Nothing here touches libpinot_b200.so."""
 
-    def work():
-        while True:
-            with lock:
-                i = nxt[0]
-                nxt[0] += 1
-            if i >= len(segs):
-                return
-            results[i] = oracle.execute(segs[i], q)
+    def __init__(self, segments: int, rows: int, rank: int = 0, threads: int = 0):
+        from oracle.pinot_oracle import oracle as get_oracle
+        self.o = get_oracle()
+        self.threads = threads or (os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        self.segments = [self.o.synth_segment(f"r{rank}s{s}", rows, column_specs(rank, s, TOUCHED), self.threads)
+                         for s in range(segments)]
+        self.generation_s = time.perf_counter() - t0
+        parts = max(1, (self.threads + segments - 1) // segments)
+        self.work = [(s, part) for s, seg in enumerate(self.segments) for part in self.o.row_ranges(seg, parts)]
+        self.rows = segments * rows
 
-    ts = [threading.Thread(target=work) for _ in range(min(threads, len(segs)))]
-    t0 = time.perf_counter()
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    return time.perf_counter() - t0, results
+    def run(self, q):
+        """One pass of `q` over the whole table.  Returns (seconds, [per-segment {dictId key: [sum, count]}])."""
+        import numpy as np
+        results = [None] * len(self.work)
+        nxt = [0]
+        lock = threading.Lock()
+
+        def worker():
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= len(self.work):
+                    return
+                results[i] = self.o.execute(self.work[i][1], q)   # ctypes releases the GIL
+
+        ts = [threading.Thread(target=worker) for _ in range(min(self.threads, len(self.work)))]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        sec = time.perf_counter() - t0
+        # merge the row ranges of a segment (same dictionaries: by dictId) -- outside the timed region, as the
+        # reference's combine is outside its per-segment operators
+        tables = [dict() for _ in self.segments]
+        for (s, _), r in zip(self.work, results):
+            t = tables[s]
+            if r.num_groups < 0:
+                cur = t.setdefault((), [0.0, 0])
+                cur[0] += float(r.doubles[0][0]); cur[1] += int(r.longs[1][0])
+                continue
+            keys = r.keys[:, 0].astype(np.int64)
+            for k, sm, c in zip(keys.tolist(), r.doubles[0].tolist(), r.longs[1].tolist()):
+                cur = t.get(k)
+                if cur is None:
+                    t[k] = [sm, c]
+                else:
+                    cur[0] += sm; cur[1] += c
+        return sec, tables
+
+
+def block_table(block):
+    """{dictId key: [sum, count]} of a device results block of the bench queries (SUM, COUNT)."""
+    if block.num_groups < 0:
+        return {(): [float(block.doubles[0][0]), int(block.longs[1][0])]}
+    return {int(k): [float(s), int(c)] for k, s, c in
+            zip(block.keys[:, 0].tolist(), block.doubles[0].tolist(), block.longs[1].tolist())}
+
+
+def assert_same_table(got, want, what):
+    assert set(got) == set(want), f"{what}: group keys differ ({len(got)} vs {len(want)})"
+    for k, (ws, wc) in want.items():
+        gs, gc = got[k]
+        assert gc == wc, (what, k, "count", gc, wc)
+        assert gs == ws or abs(gs - ws) <= 1e-6 * abs(ws), (what, k, "sum", gs, ws)   # north_star: SUM within 1e-6 relative
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--segments", type=int, default=8)
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows per segment")
-    ap.add_argument("--selectivity", type=float, default=0.25)
+    ap.add_argument("--selectivity", type=float, default=0.10, help="headline filter selectivity")
+    ap.add_argument("--c2-selectivity", type=float, default=0.25)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000, help="rows per oracle work item")
-    ap.add_argument("--quick", action="store_true", help="tuning runs: skip the e2e and cpu_baseline legs")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host cores")
+    ap.add_argument("--reference-seconds", type=float, default=120.0, help="time budget of the --impl reference steps")
+    ap.add_argument("--quick", action="store_true", help="tuning runs: skip the c2, e2e and cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -183,60 +250,56 @@ def main():
     if args.impl == "reference" and rank != 0:
         return 0  # the CPU arm runs on rank 0 only
 
-    import torch
-    from pinot_b200 import sql
-    from pinot_b200.plan_maker import B200Context, B200PlanMaker, IndexSegment
+    from pinot_b200 import sql   # pure Python (the SQL front end of the tests); loads no native code
 
-    dist = None
-    if world > 1 and args.impl == "b200":
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    q = sql.parse(query_text(args.selectivity))
+    q_gb = sql.parse(groupby_query_text(args.selectivity))
+    q_c2 = sql.parse(c2_query_text(args.c2_selectivity))
     bpr = bytes_per_row()
-    config = {"workload": f"C2: {args.segments} segments x {args.rows} rows per GPU, 8 dict-encoded fixed-bit INT columns "
-                          f"(bits 4,7,10,14,16,17,20,20); {query_text(args.selectivity)}",
+    config = {"workload": f"filter+GROUP BY on the C2 table: {args.segments} segments x {args.rows} rows per GPU, 8 dict-encoded "
+                          f"fixed-bit INT columns (bits 4,7,10,14,16,17,20,20); {groupby_query_text(args.selectivity)} "
+                          f"(10 000 groups); per-GPU device-side combine, N>1: one reduce of the group tables to rank 0",
               "segments_per_gpu": args.segments, "rows_per_segment": args.rows, "selectivity": args.selectivity,
-              "touched_bits_per_row": int(bpr * 8), "l2_policy": "inputs larger than L2 (touched columns = "
-              f"{args.segments * args.rows * bpr / 1e9:.2f} GB per step per GPU vs 126 MB L2)",
-              "parallelism": f"segments sharded {args.segments}/GPU x {world} GPU, result reduced once"}
+              "groups": CARDS[3], "touched_bits_per_row": int(bpr * 8),
+              "l2_policy": f"inputs larger than L2 (touched columns = {args.segments * args.rows * bpr / 1e9:.2f} GB per step "
+                           "per GPU vs 126 MB L2)",
+              "parallelism": f"segments sharded {args.segments}/GPU x {world} GPU, group tables reduced once"}
 
     # ---------------------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
-        from oracle import segment_builder as sb
-        from oracle.pinot_oracle import oracle as get_oracle
-        o = get_oracle()
-        cores = os.cpu_count() or 1
-        ctx = B200Context(local_rank)  # only to GENERATE the synthetic segment bytes (device generator), not to scan
-        sample_rows = min(args.rows, args.cpu_sample_rows)
-        items = max(cores, 1)
-        dev_segs = [IndexSegment.synthetic(ctx, f"seg{s}", sample_rows, column_specs(0, s))
-                    for s in range(min(args.segments, items))]
-        base = [host_segment_for_oracle(sb, d, sample_rows, d.name) for d in dev_segs]
-        for d in dev_segs:
-            d.destroy()
-        ctx.close()
-        work = [base[i % len(base)] for i in range(items)]
-        for _ in range(max(1, min(args.warmup, 1))):
-            time_oracle(o, work[:cores], q, cores)
-        steps = max(1, min(args.steps, 3))
-        times = [time_oracle(o, work, q, cores)[0] for _ in range(steps)]
+        cores = args.cpu_threads or (os.cpu_count() or 1)
+        table = CpuTable(args.segments, args.rows, 0, cores)
+        table.run(q_gb)  # warm-up / page-in
+        times = []
+        t_start = time.perf_counter()
+        while len(times) < max(1, args.steps) and (not times or time.perf_counter() - t_start < args.reference_seconds):
+            times.append(table.run(q_gb)[0])
         sec = statistics.mean(times)
-        rows = items * sample_rows
-        val = rows / sec
+        val = table.rows / sec
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rows/s", "n_gpus": args.gpus,
-                "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "steps": len(times), "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": "rows/s", "cores": cores, "kind": "port",
-                                 "sample": f"{items} work items x {sample_rows} rows (prefixes of the C2 segments), "
-                                           f"{cores} threads, C++ restatement of the Java operator chain (no JVM in image)"},
+                "cpu_baseline": {"value": val, "unit": "rows/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
+                                 "nproc": os.cpu_count(),
+                                 "sample": f"the whole table every step: {args.segments} segments x {args.rows} rows generated on the "
+                                           f"CPU, each segment split into {len(table.work) // args.segments} row ranges "
+                                           f"({len(table.work)} work items on {cores} threads); C++ restatement of the Java "
+                                           f"operator chain (oracle/), no JVM in the image; generation {table.generation_s:.1f} s"},
                 "e2e": {"value": val, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
         return 0
 
     # ---------------------------------------------------------------------------------------------- B200 arm
+    import torch
+    from pinot_b200.plan_maker import B200Context, B200PlanMaker, IndexSegment
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from pinot_b200.distributed import combine_across_ranks
+
     ctx = B200Context(local_rank)
     pm = B200PlanMaker(ctx)
     t_gen = time.perf_counter()
@@ -249,58 +312,79 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    result_dev = torch.zeros(2, dtype=torch.float64, device=f"cuda:{local_rank}") if dist is not None else None
+    def gb_step():
+        """The headline step: the whole table's results block on rank 0."""
+        if dist is not None:
+            block = pm.execute_segments(segs, q_gb, merge=True, keep_handle=True)[0]
+            return combine_across_ranks(pm, block, q_gb, dist, dst=0), block.device_ms
+        block = pm.execute_segments(segs, q_gb, merge=True)[0]
+        return block, block.device_ms
 
-    def step():
-        blocks = pm.execute_segments(segs, q)
-        s = sum(float(b.doubles[0][0]) for b in blocks)
-        c = sum(int(b.longs[1][0]) for b in blocks)
-        if dist is not None:  # the one exchange step of the path: reduce the per-rank result to rank 0
-            result_dev.copy_(torch.tensor([s, float(c)], dtype=torch.float64))
-            dist.reduce(result_dev, dst=0)
-        return s, c, blocks[0].device_ms
+    def c2_step():
+        blocks = pm.execute_segments(segs, q_c2)
+        return (sum(float(b.doubles[0][0]) for b in blocks), sum(int(b.longs[1][0]) for b in blocks)), blocks[0].device_ms
 
-    for _ in range(args.warmup):
-        first = step()
+    def timed(step, steps):
+        for _ in range(args.warmup):
+            first = step()
+        barrier()
+        w0 = time.time()
+        t0 = time.perf_counter()
+        kms = []
+        for _ in range(steps):
+            out, dms = step()
+            kms.append(dms)
+        barrier()
+        elapsed = time.perf_counter() - t0
+        w1 = time.time()
+        if dist is not None:
+            t = torch.tensor([elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed = float(t.item())
+        return out, first[0], elapsed, statistics.mean(kms), (w0, w1)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    barrier()
-    w0 = time.time()
-    t0 = time.perf_counter()
-    kernel_ms = []
-    for _ in range(args.steps):
-        s, c, dms = step()
-        kernel_ms.append(dms)
-    barrier()
-    elapsed = time.perf_counter() - t0
-    w1 = time.time()
+    gb_out, gb_first, gb_elapsed, gb_kms, (w0, w1) = timed(gb_step, args.steps)
     clocks = sampler.stop(w0, w1)
-    assert (s, c) == first[:2], "non-deterministic result across steps"
-    expect = rows_per_step * args.selectivity
-    assert abs(c - expect) < 0.02 * expect + 10, (c, expect)
-    if dist is not None:
-        t = torch.tensor([elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
-    ms_per_step = elapsed / args.steps * 1e3
-    value = rows_per_step * world / (elapsed / args.steps)
-    k_ms = statistics.mean(kernel_ms)
     peak, peak_src = measured_peak_gbs()
-    achieved = rows_per_step * bpr / (k_ms * 1e-3) / 1e9
+    gb_ms = gb_elapsed / args.steps * 1e3
+    value = rows_per_step * world / (gb_elapsed / args.steps)
+    gb_achieved = rows_per_step * bpr / (gb_kms * 1e-3) / 1e9
+    gb_table = None
+    if rank == 0:
+        gb_table = block_table(gb_out)
+        assert gb_table == block_table(gb_first), "non-deterministic result across steps"
+        matched = sum(c for _, c in gb_table.values())
+        expect = rows_per_step * world * args.selectivity
+        assert abs(matched - expect) < 0.02 * expect + 10, (matched, expect)
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_per_step, "kernel_ms": k_ms,
-                              "achieved_gbs": achieved, "frac": achieved / peak, "clocks": clocks,
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": gb_ms, "kernel_ms": gb_kms,
+                              "achieved_gbs": gb_achieved, "frac": gb_achieved / peak, "clocks": clocks,
                               "env": {k: v for k, v in os.environ.items() if k.startswith("PB200_")},
-                              "selectivity": args.selectivity, "count": c}))
+                              "selectivity": args.selectivity, "groups": len(gb_table)}))
         for sgm in segs:
             sgm.destroy()
         ctx.close()
         if dist is not None:
             dist.destroy_process_group()
         return 0
+
+    # ---- the same query delivered as PER-SEGMENT results blocks (what the per-segment Operator.nextBlock() seam returns) ----
+    def gb_blocks_step():
+        blocks = pm.execute_segments(segs, q_gb)
+        return blocks, blocks[0].device_ms
+    seg_blocks, _, sb_elapsed, sb_kms, _ = timed(gb_blocks_step, max(20, args.steps // 10))
+    sb_steps = max(20, args.steps // 10)
+
+    # ---- c2: the aggregation-only scan ----
+    c2_steps = max(20, args.steps // 3)
+    c2_out, c2_first, c2_elapsed, c2_kms, _ = timed(c2_step, c2_steps)
+    assert c2_out == c2_first, "non-deterministic c2 result"
+    c2_achieved = rows_per_step * bpr / (c2_kms * 1e-3) / 1e9
 
     # ---- e2e: host-resident index buffers, H2D inside the timed region (rank-local; N>1: max over ranks) ----
     pinned = []
@@ -323,23 +407,26 @@ def main():
             self.bits, self.cardinality, self.is_sorted, self.dict_entry_bytes = info["bits"], info["cardinality"], False, 4
             self.fwd, self.dict, self.inv = fwd, dct, None
 
+    d2h = [0]
+
     def e2e_step():
         loaded = [IndexSegment.from_columns(ctx, f"e2e{i}", args.rows, [_Col(n, inf, pt.numpy(), d) for n, inf, pt, d in cols])
                   for i, cols in enumerate(pinned)]
-        blocks = pm.execute_segments(loaded, q)
-        out = (sum(float(b.doubles[0][0]) for b in blocks), sum(int(b.longs[1][0]) for b in blocks))
+        block = pm.execute_segments(loaded, q_gb, merge=True)[0]
+        d2h[0] = block.keys.nbytes + sum(a.nbytes for a in block.doubles) + sum(a.nbytes for a in block.longs)
         for l in loaded:
             l.destroy()
-        return out
+        return block
 
     e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        es = e2e_step()
+        eb = e2e_step()
     barrier()
     e2e_elapsed = time.perf_counter() - t0
-    assert es == (s, c), "e2e result differs from the resident result"
+    if world == 1:
+        assert block_table(eb) == gb_table, "e2e result differs from the resident result"
     if dist is not None:
         t = torch.tensor([e2e_elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -347,50 +434,74 @@ def main():
     e2e_value = rows_per_step * world / (e2e_elapsed / args.e2e_steps)
     del pinned
 
-    # ---- cpu_baseline: the oracle on a bounded sample, rank 0, N == 1 only ----
+    # ---- cpu_baseline + FULL-SIZE parity: the oracle on the same table, generated independently on the CPU ----
     cpu = None
     if rank == 0 and world == 1:
-        from oracle import segment_builder as sb
-        from oracle.pinot_oracle import oracle as get_oracle
-        o = get_oracle()
-        cores = os.cpu_count() or 1
-        sample_rows = min(args.rows, args.cpu_sample_rows)
-        base = [host_segment_for_oracle(sb, sgm, sample_rows, sgm.name) for sgm in segs[: min(len(segs), cores)]]
-        work = [base[i % len(base)] for i in range(cores)]
-        time_oracle(o, work[: min(4, cores)], q, cores)  # page-in
-        sec, res = time_oracle(o, work, q, cores)
-        # parity of the sample: the GPU path on the same prefix rows must agree with the oracle
-        cpu = {"value": cores * sample_rows / sec, "unit": "rows/s", "cores": cores, "kind": "port",
-               "sample": f"{cores} work items x {sample_rows} rows (prefixes of this run's segments), {cores} threads, "
-                         "C++ restatement of the Java operator chain (oracle/); no JVM in the image"}
+        cores = args.cpu_threads or (os.cpu_count() or 1)
+        table = CpuTable(args.segments, args.rows, 0, cores)
+        table.run(q_gb)  # page-in
+        sec, cpu_tables = table.run(q_gb)
+        for s, (blk, want) in enumerate(zip(seg_blocks, cpu_tables)):
+            assert_same_table(block_table(blk), want, f"segment {s}: device vs CPU oracle, {args.rows} rows")
+        merged = {}
+        for t in cpu_tables:
+            for k, (sm, c) in t.items():
+                cur = merged.setdefault(k, [0.0, 0])
+                cur[0] += sm; cur[1] += c
+        assert_same_table(gb_table, merged, "device-side combine vs merged CPU oracle tables")
+        _, c2_tables = table.run(q_c2)
+        want_c2 = (sum(t[()][0] for t in c2_tables), sum(t[()][1] for t in c2_tables))
+        assert c2_out[1] == want_c2[1] and abs(c2_out[0] - want_c2[0]) <= 1e-6 * abs(want_c2[0]), ("c2 vs CPU oracle", c2_out, want_c2)
+        cpu = {"value": table.rows / sec, "unit": "rows/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
+               "sample": f"the whole table, one pass: {args.segments} segments x {args.rows} rows generated on the CPU (same bytes as "
+                         f"the device generator), {len(table.work)} row-range work items on {cores} threads; C++ restatement of the "
+                         "Java operator chain (oracle/); no JVM in the image",
+               "parity": f"per-segment and combined group tables of the device == the oracle's on all {table.rows} rows "
+                         "(COUNT exact, SUM within 1e-6 relative); c2 result == oracle"}
 
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the scan kernel, from the committed `ncu --set full`
-    # capture of this same workload (profiles/): only quoted when this run IS that workload
-    traffic, traffic_src = None, None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_c2_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        if tj.get("segments") == args.segments and tj.get("rows_per_segment") == args.rows and abs(tj.get("selectivity", -1) - args.selectivity) < 1e-9:
-            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    # captures of these same workloads (profiles/): only quoted when this run IS that workload
+    def traffic_of(name, sel):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("segments") == args.segments and tj.get("rows_per_segment") == args.rows and abs(tj.get("selectivity", -1) - sel) < 1e-9:
+                return tj["dram_bytes_per_launch"], tj["source"]
+        return None, None
+    gb_traffic, gb_traffic_src = traffic_of("r2_gb_traffic.json", args.selectivity)
+    c2_traffic, c2_traffic_src = traffic_of("r2_c2_traffic.json", args.c2_selectivity)
 
     if rank == 0:
+        alg = rows_per_step * bpr
         line = {"metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": gb_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "roofline": {"bound": "hbm", "achieved": gb_achieved, "peak": peak, "unit": "GB/s",
+                             "frac": gb_achieved / peak, "traffic": gb_traffic, "traffic_source": gb_traffic_src,
                              "peak_source": peak_src,
-                             "kernel": "pb200::scan_kernel<6,false> (W=6 warps, 2 CTAs/SM)", "kernel_ms": k_ms,
-                             "algorithmic_bytes_per_launch": rows_per_step * bpr},
+                             "kernel": "pb200::scan_kernel<6,true> (group-by, W=6 warps, 2 CTAs/SM)", "kernel_ms": gb_kms,
+                             "algorithmic_bytes_per_launch": alg},
                 "cpu_baseline": cpu,
-                "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": 152 * args.segments, "steps": args.e2e_steps,
-                        "note": "every step re-uploads the touched columns from pinned host memory (PCIe bound); "
-                                "`value` is the same plugin call with the segments resident in HBM"},
-                "gpu_launches": args.steps * 1, "clocks": clocks, "segment_generation_s": gen_s,
-                "result": {"sum_c5": s, "count": c, "scope": "rank 0's segments",
-                           "all_ranks": None if result_dev is None else {"sum_c5": float(result_dev[0].item()),
-                                                                         "count": int(result_dev[1].item())}}}
+                "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h[0],
+                        "steps": args.e2e_steps,
+                        "note": "every step re-uploads the touched columns from pinned host memory (PCIe bound) and reads the "
+                                "results block back; `value` is the same plugin call with the segments resident in HBM"},
+                "gpu_launches": args.steps * 4,
+                "gpu_launches_note": "per step: 1 scan_kernel + 3 extraction kernels (count, scan, write); memsets and NCCL not counted",
+                "per_segment_blocks": {"ms_per_step": sb_elapsed / sb_steps * 1e3, "kernel_ms": sb_kms, "steps": sb_steps,
+                                       "value": rows_per_step * world / (sb_elapsed / sb_steps),
+                                       "note": "same query, one results block per segment (8 x 10 000 groups extracted) "
+                                               "instead of the device-side combine"},
+                "c2": {"query": c2_query_text(args.c2_selectivity), "value": rows_per_step * world / (c2_elapsed / c2_steps),
+                       "ms_per_step": c2_elapsed / c2_steps * 1e3, "steps": c2_steps,
+                       "roofline": {"bound": "hbm", "achieved": c2_achieved, "peak": peak, "unit": "GB/s",
+                                    "frac": c2_achieved / peak, "traffic": c2_traffic, "traffic_source": c2_traffic_src,
+                                    "kernel": "pb200::scan_kernel<6,false> (aggregation only)", "kernel_ms": c2_kms,
+                                    "algorithmic_bytes_per_launch": alg},
+                       "result": {"sum_c5": c2_out[0], "count": c2_out[1], "scope": "rank 0's segments"}},
+                "clocks": clocks, "segment_generation_s": gen_s,
+                "result": {"groups": len(gb_table), "matched": sum(c for _, c in gb_table.values()),
+                           "sum_c5": sum(s for s, _ in gb_table.values()), "scope": "all ranks (reduced to rank 0)"}}
         print(json.dumps(line))
     for sgm in segs:
         sgm.destroy()

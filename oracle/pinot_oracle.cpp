@@ -1557,3 +1557,55 @@ extern "C" int64_t po_startree_traverse(const uint8_t* tree, int64_t len, int32_
   if (remaining_predicate_mask) *remaining_predicate_mask = have_global ? global_remaining : 0u;
   return (int64_t)docs.size();
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Benchmark table generator (CPU twin of pinot_b200/csrc/pb200_synth.cu; tests/test_gpu_synth.py compares the bytes).
+// NOT part of the reference: it only lets bench.py's CPU arm (--impl reference) create the SAME synthetic segments
+// without touching the device library.  dictId(doc) = mix64(seed + doc * 0x9E3779B97F4A7C15) % cardinality (SplitMix64
+// finaliser), written as FixedBitSVForwardIndexWriter would (MSB-first big-endian bit stream); dictionary =
+// { base + step * i } as sorted big-endian INT values (SegmentDictionaryCreator).
+// ------------------------------------------------------------------------------------------------------------------
+#include <thread>
+
+namespace {
+inline uint64_t synth_mix64(uint64_t z) {
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+}  // namespace
+
+extern "C" void po_synth_fwd(uint64_t seed, int32_t cardinality, int64_t num_docs, int32_t bits, uint8_t* out, int32_t threads) {
+  const int64_t groups = (num_docs + 31) / 32;          // 32 docs = `bits` whole 4-byte words
+  const int64_t out_bytes = (num_docs * bits + 7) / 8;  // the last group may be cut short
+  auto work = [&](int64_t g0, int64_t g1) {
+    for (int64_t g = g0; g < g1; g++) {
+      uint64_t acc = 0;
+      int have = 0;
+      int64_t o = g * bits * 4;
+      for (int i = 0; i < 32; i++) {
+        const int64_t doc = g * 32 + i;
+        const uint32_t v = doc < num_docs ? (uint32_t)(synth_mix64(seed + (uint64_t)doc * 0x9E3779B97F4A7C15ull) % (uint32_t)cardinality) : 0u;
+        acc = (acc << bits) | v;
+        have += bits;
+        while (have >= 8) {
+          if (o < out_bytes) out[o] = (uint8_t)(acc >> (have - 8));
+          o++;
+          have -= 8;
+        }
+      }
+    }
+  };
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(threads, groups / 4096 + 1));
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; t++) pool.emplace_back(work, groups * t / nt, groups * (t + 1) / nt);
+  for (auto& th : pool) th.join();
+}
+
+extern "C" void po_synth_dict(int32_t cardinality, int32_t base, int32_t step, uint8_t* out) {
+  for (int32_t i = 0; i < cardinality; i++) {
+    const uint32_t v = (uint32_t)(base + step * i);
+    out[4 * i + 0] = (uint8_t)(v >> 24); out[4 * i + 1] = (uint8_t)(v >> 16); out[4 * i + 2] = (uint8_t)(v >> 8); out[4 * i + 3] = (uint8_t)v;
+  }
+}

@@ -152,6 +152,13 @@ int64_t po_startree_traverse(const uint8_t* tree, int64_t len, int32_t num_predi
 int64_t po_filter_doc_ids(const po_segment_t* segment, const po_query_t* query, int32_t* out, int64_t cap,
                           int64_t* entries_scanned_in_filter);
 
+/* ---- benchmark table generator (CPU twin of pinot_b200/csrc/pb200_synth.cu; not part of the reference) ---- */
+/* Forward index bytes of one synthetic dict-encoded INT column: dictId(doc) = mix64(seed + doc * golden) % cardinality,
+ * written as an MSB-first big-endian bit stream of ceil(num_docs * bits / 8) bytes, by `threads` threads. */
+void po_synth_fwd(uint64_t seed, int32_t cardinality, int64_t num_docs, int32_t bits, uint8_t* out, int32_t threads);
+/* Dictionary { base + step * i }: cardinality big-endian INT values. */
+void po_synth_dict(int32_t cardinality, int32_t base, int32_t step, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

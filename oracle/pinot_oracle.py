@@ -128,6 +128,46 @@ class Oracle:
         L.po_startree_traverse.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(_StarPredicate), C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_uint32)]
 
+        L.po_synth_fwd.argtypes = [C.c_uint64, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]
+        L.po_synth_dict.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+
+    # ---------------------------------------------------------------- benchmark table (twin of pb200_synth.cu)
+    def synth_segment(self, name: str, num_docs: int, specs, threads: int = 0) -> sb.SegmentData:
+        """The synthetic segment IndexSegment.synthetic(ctx, name, num_docs, specs) creates on the device, built on the
+        CPU (same dictIds, same Pinot bytes; no inverted indexes).  specs: dicts with name, cardinality, seed,
+        value_base=0, value_step=1."""
+        threads = threads or (os.cpu_count() or 1)
+        cols = []
+        for s in specs:
+            card = int(s["cardinality"])
+            bits = sb.num_bits_per_value(card - 1)
+            fwd = np.zeros((num_docs * bits + 7) // 8, dtype=np.uint8)
+            self.lib.po_synth_fwd(int(s["seed"]), card, num_docs, bits, _ptr(fwd), threads)
+            dct = np.zeros(4 * card, dtype=np.uint8)
+            self.lib.po_synth_dict(card, int(s.get("value_base", 0)), int(s.get("value_step", 1)), _ptr(dct))
+            vals = (int(s.get("value_base", 0)) + int(s.get("value_step", 1)) * np.arange(card, dtype=np.int64)).astype(np.int32)
+            cols.append(sb.ColumnData(s["name"], sb.INT, True, bits, card, False, 4, fwd, dct, None, dict_values=vals))
+        return sb.SegmentData(name, num_docs, cols)
+
+    @staticmethod
+    def row_ranges(seg: sb.SegmentData, parts: int):
+        """Splits a segment of unsorted dict-encoded columns into `parts` consecutive row ranges WITHOUT copying: range
+        starts are multiples of 32 rows, where every fixed-bit stream is word aligned (FixedBitIntReader.read32 groups).
+        Used to run the single-threaded operator chain of the oracle on all host cores over one big segment; the
+        sub-results share the dictionaries and are merged by dictId."""
+        per = max(32, ((seg.num_docs + parts - 1) // parts + 31) // 32 * 32)
+        out = []
+        for start in range(0, seg.num_docs, per):
+            n = min(per, seg.num_docs - start)
+            cols = []
+            for c in seg.columns:
+                assert c.has_dictionary and not c.is_sorted and c.inv is None, "row_ranges: plain dict-encoded columns only"
+                b0 = start * c.bits // 8
+                cols.append(sb.ColumnData(c.name, c.data_type, True, c.bits, c.cardinality, False, c.dict_entry_bytes,
+                                          c.fwd[b0: b0 + (n * c.bits + 7) // 8], c.dict, None, dict_values=c.dict_values))
+            out.append(sb.SegmentData(f"{seg.name}[{start}:{start + n}]", n, cols))
+        return out
+
     # ---------------------------------------------------------------- formats
     def bitset_write(self, values: np.ndarray, bits: int) -> np.ndarray:
         v = np.ascontiguousarray(values, dtype=np.int32)

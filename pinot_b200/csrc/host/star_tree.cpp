@@ -367,6 +367,7 @@ int try_star_tree(pb200_ctx* ctx, const pb200h_segment& seg, const StarTreeIndex
   pb200_result* sr = nullptr;
   int rc = pb200_execute(ctx, &dq, &dev, 1, &sr);
   if (rc) return rc;
+  pb200::result_materialize(sr);  // extracted groups sit in a pinned block: this path re-maps them column by column
   // ---- back to the query's own aggregation list ----
   std::unique_ptr<pb200_result> R(new pb200_result());
   R->meta = sr->meta;

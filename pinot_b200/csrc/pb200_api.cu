@@ -14,9 +14,6 @@
 #include <limits>
 #include <memory>
 
-#include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-
 #include "pb200_internal.h"
 #include "pb200_scan_launch.h"
 #include "pb200_unpack.cuh"
@@ -96,7 +93,7 @@ int pinned_alloc(pb200_ctx* ctx, size_t bytes, void** out, size_t* got) {
   }
   size_t rb = std::max<size_t>(1 << 20, (bytes + (1 << 20) - 1) >> 20 << 20);
   void* p = nullptr;
-  if (cudaHostAlloc(&p, rb, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); set_error("cudaHostAlloc(%zu) failed", rb); return PB200_E_NOMEM; }
+  if (cudaHostAlloc(&p, rb, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); set_error("cudaHostAlloc(%zu) failed", rb); return PB200_E_NOMEM; }
   *out = p; *got = rb;
   return PB200_OK;
 }
@@ -124,6 +121,20 @@ void give_stream(pb200_ctx* ctx, cudaStream_t s) {
   std::lock_guard<std::mutex> g(ctx->mu);
   ctx->free_streams.push_back(s);
 }
+cudaEvent_t take_event(pb200_ctx* ctx) {
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->free_events.empty()) { cudaEvent_t e = ctx->free_events.back(); ctx->free_events.pop_back(); return e; }
+  }
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return e;
+}
+void give_event(pb200_ctx* ctx, cudaEvent_t e) {
+  if (!e) return;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->free_events.push_back(e);
+}
 
 struct DevBuf {  // RAII pooled device buffer
   pb200_ctx* ctx = nullptr;
@@ -149,11 +160,11 @@ __global__ void fwd_words_to_native_kernel(uint4* __restrict__ p, size_t n16) {
     p[i] = x;
   }
 }
-static cudaError_t fwd_words_to_native(void* p, size_t bytes) {  // bytes: the padded allocation (multiple of 16)
+static cudaError_t fwd_words_to_native(void* p, size_t bytes, cudaStream_t st) {  // bytes: the padded allocation (multiple of 16)
   const size_t n16 = bytes / 16;
   if (!n16) return cudaSuccess;
   const int blocks = (int)std::min<size_t>((n16 + 255) / 256, 148 * 16);
-  fwd_words_to_native_kernel<<<blocks, 256>>>((uint4*)p, n16);
+  fwd_words_to_native_kernel<<<blocks, 256, 0, st>>>((uint4*)p, n16);
   return cudaGetLastError();
 }
 
@@ -171,37 +182,6 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, long long n) {
   for (; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
-struct NonEmptyGroup {  // a group exists iff any of its (present) markers says so; hash tables: iff the slot holds a key
-  const unsigned long long* count;
-  const uint32_t* seen;
-  const uint32_t* maxk;
-  const uint32_t* mink;
-  const unsigned long long* hkeys;
-  __device__ __forceinline__ bool operator()(const uint32_t& i) const {
-    if (hkeys) return hkeys[i] != ~0ull;
-    return (count && count[i] != 0ull) || (seen && seen[i] != 0u) || (maxk && maxk[i] != 0u) || (mink && mink[i] != 0xFFFFFFFFu);
-  }
-};
-
-// All per-group columns of one result in one launch: out block = [col 0: n x esz][col 1: ...] (8-byte aligned columns)
-struct GatherCol { const void* src; unsigned long long dst_off; uint32_t esz; uint32_t pad; };
-struct GatherPlan { GatherCol col[2 + kMaxAggs]; int ncols; };
-__global__ void gather_columns_kernel(const GatherPlan gp, const uint32_t* __restrict__ idx, long long n,
-                                      unsigned char* __restrict__ out) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const uint32_t g = idx[i];
-    for (int c = 0; c < gp.ncols; ++c) {
-      const GatherCol& k = gp.col[c];
-      if (k.esz == 8) reinterpret_cast<unsigned long long*>(out + k.dst_off)[i] = static_cast<const unsigned long long*>(k.src)[g];
-      else reinterpret_cast<uint32_t*>(out + k.dst_off)[i] = static_cast<const uint32_t*>(k.src)[g];
-    }
-  }
-}
-__global__ void gather_rows_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, long long n, int words,
-                                   uint32_t* __restrict__ dst) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * words; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = src[(size_t)idx[i / words] * words + (i % words)];
-}
 }  // namespace pb200
 
 using namespace pb200;
@@ -250,6 +230,7 @@ extern "C" int32_t pb200_init(int32_t device, pb200_ctx** out) {
     t.dense_max = env_i("PB200_DENSE_MAX", t.dense_max);
     t.defer = getenv("PB200_NO_DEFER") ? 0 : 1;
     t.gb_defer = getenv("PB200_NO_GB_DEFER") ? 0 : 1;
+    t.sparse_max_gb = (int)env_i("PB200_SPARSE_MAX_GB", t.sparse_max_gb);
     t.skip = getenv("PB200_NO_SKIP") ? 0 : 1;
     t.always_count = getenv("PB200_ALWAYS_COUNT") ? 1 : 0;
   }
@@ -274,6 +255,7 @@ extern "C" int32_t pb200_tuning_set(pb200_ctx* ctx, const char* name, int64_t va
   else if (n == "dense_max") t.dense_max = value;
   else if (n == "defer") t.defer = value != 0;
   else if (n == "gb_defer") t.gb_defer = value != 0;
+  else if (n == "sparse_max_gb") t.sparse_max_gb = (int)value;
   else if (n == "skip") t.skip = value != 0;
   else if (n == "always_count") t.always_count = value != 0;
   else { set_error("unknown tuning knob '%s'", name); return PB200_E_INVALID; }
@@ -285,6 +267,7 @@ extern "C" int32_t pb200_shutdown(pb200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (auto s : ctx->free_streams) cudaStreamDestroy(s);
+  for (auto e : ctx->free_events) cudaEventDestroy(e);
   for (auto& kv : ctx->block_size) cudaFree(kv.first);
   for (auto& kv : ctx->free_pinned) cudaFreeHost(kv.second);
   delete ctx;
@@ -349,9 +332,11 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
                                           const pb200_col_desc* cols, pb200_segment** out) {
   if (!ctx || !cols || !out || num_docs < 0 || ncols <= 0) { set_error("invalid argument to pb200_segment_register"); return PB200_E_INVALID; }
   PB200_CUDA(cudaSetDevice(ctx->device));
-  // uploads below are asynchronous on the default stream; whatever way this function returns, they are finished first
-  // (the caller's buffers must not be read after the return)
-  struct DrainDefaultStream { ~DrainDefaultStream() { cudaStreamSynchronize(0); } } drain_default_stream;
+  // uploads below are asynchronous on a stream of the context's pool (NOT the legacy default stream: concurrent segment
+  // loads and queries of other threads must not serialise against each other); whatever way this function returns, they
+  // are finished first (the caller's buffers must not be read after the return)
+  cudaStream_t up = take_stream(ctx);
+  struct DrainUploadStream { pb200_ctx* c; cudaStream_t s; ~DrainUploadStream() { cudaStreamSynchronize(s); give_stream(c, s); } } drain_upload_stream{ctx, up};
   std::unique_ptr<pb200_segment> seg(new pb200_segment());
   seg->ctx = ctx;
   seg->name = name ? name : "";
@@ -380,12 +365,12 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
         c.fwd = (uint32_t*)p;
         c.pooled = true;
         const uint64_t body = need & ~15ull;  // zero only the padding behind the file's bytes
-        PB200_CUDA(cudaMemsetAsync((unsigned char*)c.fwd + body, 0, c.fwd_alloc_bytes - body, 0));
-        // asynchronous on the default stream: with pinned caller buffers the DMA of this column overlaps the host-side
+        PB200_CUDA(cudaMemsetAsync((unsigned char*)c.fwd + body, 0, c.fwd_alloc_bytes - body, up));
+        // asynchronous on the upload stream: with pinned caller buffers the DMA of this column overlaps the host-side
         // dictionary conversion below and the next column's set-up (pageable buffers are staged synchronously by the
         // runtime); the stream is drained once at the end of the registration
-        PB200_CUDA(cudaMemcpyAsync(c.fwd, d.fwd, need, cudaMemcpyHostToDevice, 0));
-        PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes));
+        PB200_CUDA(cudaMemcpyAsync(c.fwd, d.fwd, need, cudaMemcpyHostToDevice, up));
+        PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes, up));
       }
     } else if (d.fwd_kind == PB200_FWD_DICT_SORTED) {
       // SortedIndexReaderImpl: expand (start,end) pairs into a fixed-bit dictId stream so every kernel sees one format
@@ -406,8 +391,8 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
         }
       }
       { void* fp = nullptr; int rc = dev_alloc(ctx, c.fwd_alloc_bytes, &fp); if (rc) return fail(rc); c.fwd = (uint32_t*)fp; }
-      PB200_CUDA(cudaMemcpy(c.fwd, packed.data(), c.fwd_alloc_bytes, cudaMemcpyHostToDevice));
-      PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes));
+      PB200_CUDA(cudaMemcpyAsync(c.fwd, packed.data(), c.fwd_alloc_bytes, cudaMemcpyHostToDevice, up));  // pageable source: staged before the call returns
+      PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes, up));
       c.fwd_kind = PB200_FWD_DICT_FIXEDBIT;
     } else if (d.fwd_kind == PB200_FWD_RAW_FIXEDBYTE) {
       // BaseChunkForwardIndexReader header :60-106; only PASS_THROUGH 4-byte values are accelerated
@@ -425,9 +410,9 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
       c.fwd_file_bytes = 4ull * num_docs;
       c.fwd_alloc_bytes = padded_fwd_bytes(num_docs, 32);
       { void* fp = nullptr; int rc = dev_alloc(ctx, c.fwd_alloc_bytes, &fp); if (rc) return fail(rc); c.fwd = (uint32_t*)fp; }
-      PB200_CUDA(cudaMemset(c.fwd, 0, c.fwd_alloc_bytes));
-      PB200_CUDA(cudaMemcpy(c.fwd, p + start, 4ull * num_docs, cudaMemcpyHostToDevice));
-      PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes));
+      PB200_CUDA(cudaMemsetAsync(c.fwd, 0, c.fwd_alloc_bytes, up));
+      PB200_CUDA(cudaMemcpyAsync(c.fwd, p + start, 4ull * num_docs, cudaMemcpyHostToDevice, up));
+      PB200_CUDA(fwd_words_to_native(c.fwd, c.fwd_alloc_bytes, up));
     } else {
       set_error("column %d: unknown forward index kind %d", i, d.fwd_kind);
       return fail(PB200_E_INVALID);
@@ -477,7 +462,7 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
   }
   for (auto& c : seg->cols) c.owns = true;  // adopted device buffers belong to the segment from here on
   {  // every upload / re-layout kernel above ran on the default stream: the caller's buffers may go away after this
-    cudaError_t e = cudaStreamSynchronize(0);
+    cudaError_t e = cudaStreamSynchronize(up);
     if (e != cudaSuccess) { set_error("segment upload failed: %s", cudaGetErrorString(e)); return fail(PB200_E_CUDA); }
   }
   *out = seg.release();
@@ -597,7 +582,6 @@ cudaError_t launch_scan_variant(const ScanVariant& v, size_t smem_bytes, int gri
 }
 }  // namespace pb200
 
-static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cudaStream_t st);
 
 extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200_segment* const* segments,
                                  int32_t nseg, pb200_result** results) {
@@ -1034,6 +1018,10 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         sd.agg_code[n++] = agg_code(a, q.aggs[a].function, q.aggs[a].val_kind, sl.bits, sl.stage_words);
       }
     sd.num_defer_codes = plan.group_by ? npipe : 0;
+    if (plan.group_by && s == 0) {  // every aggregation that reads a column is pipelined: the per-thread sparse path applies
+      q.gb_simple = (npipe == n && tune.gb_defer && q.smem_groups == 0) ? 1 : 0;
+      q.sparse_max_gb = tune.sparse_max_gb;
+    }
     sd.num_agg_codes = n;
   }
 
@@ -1041,11 +1029,23 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   AggAccum init_acc;
   memset(&init_acc, 0, sizeof init_acc);
   for (int a = 0; a < kMaxAggs; a++) init_acc.min_id[a] = 0xFFFFFFFFu;
-  std::vector<AggAccum> host_acc(nres, init_acc);
+  // initial values go up and results come back through ONE pooled pinned block, both asynchronously on the query's stream
+  // (a pageable cudaMemcpy would synchronise the device twice per query)
+  struct PinnedScratch {
+    pb200_ctx* c; void* p = nullptr; size_t bytes = 0;
+    ~PinnedScratch() { pinned_free(c, p, bytes); }
+  } pacc{ctx};
   {
+    int rc = pinned_alloc(ctx, 2 * sizeof(AggAccum) * nres, &pacc.p, &pacc.bytes);
+    if (rc) return rc;
+  }
+  AggAccum* host_acc = static_cast<AggAccum*>(pacc.p) + nres;  // [0, nres): initial values, [nres, 2 nres): read-back
+  {
+    AggAccum* init = static_cast<AggAccum*>(pacc.p);
+    for (int r = 0; r < nres; r++) init[r] = init_acc;
     int rc = accum_buf.alloc(ctx, sizeof(AggAccum) * nres);
     if (rc) return rc;
-    PB200_CUDA(cudaMemcpyAsync(accum_buf.p, host_acc.data(), sizeof(AggAccum) * nres, cudaMemcpyHostToDevice, st));
+    PB200_CUDA(cudaMemcpyAsync(accum_buf.p, init, sizeof(AggAccum) * nres, cudaMemcpyHostToDevice, st));
   }
   for (int s = 0; s < nseg; s++) {
     const pb200_segment* seg = segments[s];
@@ -1141,7 +1141,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       long long n_i64 = need_count ? 1 : 0, n_f64 = 0, n_max = need_seen ? 1 : 0, n_min = 0;
       for (int a = 0; a < nagg; a++) {
         const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
-        if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) { if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) n_f64++; else n_i64++; }
+        if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) { if (sum_in_double(vk)) n_f64++; else n_i64++; }
         else if (fn == PB200_AGG_MIN) n_min++;
         else if (fn == PB200_AGG_MAX) n_max++;
       }
@@ -1164,7 +1164,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       for (int a = 0; a < nagg; a++) {
         const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
         if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
-          if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) d.dsum[a] = (double*)d.f64_block + (fi++) * groups;
+          if (sum_in_double(vk)) d.dsum[a] = (double*)d.f64_block + (fi++) * groups;
           else d.isum[a] = (long long*)d.i64_block + (ii++) * groups;
         } else if (fn == PB200_AGG_MIN) { d.gmin[a] = (uint32_t*)d.u32min_block + (ni++) * groups; if (!need_count && !d.exists_max && !d.exists_min) d.exists_min = d.gmin[a]; }
         else if (fn == PB200_AGG_MAX) { d.gmax[a] = (uint32_t*)d.u32max_block + (xi++) * groups; if (!need_count && !d.exists_max && !d.exists_min) d.exists_max = d.gmax[a]; }
@@ -1201,12 +1201,13 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   DevBuf dsegs;
   int rc = dsegs.alloc(ctx, sizeof(SegDesc) * nseg);
   if (rc) return rc;
-  struct Events {  // RAII: every early return below releases them
-    cudaEvent_t a = nullptr, b = nullptr;
-    ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
-  } ev;
-  PB200_CUDA(cudaEventCreate(&ev.a));
-  PB200_CUDA(cudaEventCreate(&ev.b));
+  struct Events {  // pooled per context (creating / destroying two events per query costs more than the launch itself)
+    pb200_ctx* c; cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() { give_event(c, a); give_event(c, b); }
+  } ev{ctx};
+  ev.a = take_event(ctx);
+  ev.b = take_event(ctx);
+  if (!ev.a || !ev.b) { set_error("cudaEventCreate failed"); return PB200_E_CUDA; }
   cudaEvent_t e0 = ev.a, e1 = ev.b;
   cudaError_t le = cudaSuccess;
   int grid = 0;
@@ -1249,9 +1250,9 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   }
   if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); return PB200_E_CUDA; }
   PB200_CUDA(cudaEventRecord(e1, st));
+  PB200_CUDA(cudaMemcpyAsync(host_acc, accum_buf.p, sizeof(AggAccum) * nres, cudaMemcpyDeviceToHost, st));
   cudaError_t se = cudaStreamSynchronize(st);
   if (se != cudaSuccess) { set_error("scan kernel failed: %s", cudaGetErrorString(se)); return PB200_E_CUDA; }
-  PB200_CUDA(cudaMemcpy(host_acc.data(), accum_buf.p, sizeof(AggAccum) * nres, cudaMemcpyDeviceToHost));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
 
@@ -1297,7 +1298,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         };
         if (fn == PB200_AGG_COUNT) { l = (int64_t)acc.count; d = (double)l; }
         else if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
-          d = (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) ? acc.dsum[a] : (double)acc.isum[a];
+          d = sum_in_double(vk) ? acc.dsum[a] : (double)acc.isum[a];
           l = (int64_t)acc.count;
         } else if (fn == PB200_AGG_MIN) {
           if (acc.min_id[a] == 0xFFFFFFFFu || acc.count == 0) d = INFINITY; else { id = (int32_t)acc.min_id[a]; d = c->dict_host.empty() && vk != VAL_RAW_I32 ? (double)id : value_of(acc.min_id[a]); }
@@ -1327,7 +1328,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   } else if (plan.group_by) {  // all results of the submission are extracted together (two device round trips in total)
     std::vector<pb200_result*> rs;
     for (int r = 0; r < nres; r++) rs.push_back(res[r].get());
-    int frc = finalize_many(ctx, rs.data(), nres, st);
+    int frc = extract_groups(ctx, rs.data(), nres, st);
     if (frc) return frc;
     if (!merge) {  // per-segment results do not need the dense state any more
       for (int r = 0; r < nres; r++) {
@@ -1346,181 +1347,6 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   return PB200_OK;
 }
 
-// Extracts the non-empty groups of the (possibly all-reduced) dense tables into the host-side result arrays, for ALL
-// results of a submission with two device round trips in total: (1) ordered stream compaction of every table
-// (cub::DeviceSelect, raw-key order == ArrayBasedHolder's iteration order: no host sort) + one read-back of the group
-// counts; (2) one gather launch per result writing all its columns into one block + one read-back into pinned memory.
-static int finalize_many(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cudaStream_t st) {
-  if (nres <= 0) return PB200_OK;
-  int rc;
-  struct Job { DevBuf idx, block; unsigned long long n = 0; GatherPlan gp; size_t block_bytes = 0, stage_off = 0; std::vector<int> col_of_agg; int count_col = -1, key_col = -1; };
-  std::vector<Job> jobs(nres);
-  DevBuf counters, tmp;
-  if ((rc = counters.alloc(ctx, 8ull * nres))) return rc;
-  PB200_CUDA(cudaMemsetAsync(counters.p, 0, 8ull * nres, st));
-  size_t tmp_cap = 0;
-  for (int r = 0; r < nres; r++) {
-    const pb200_result::Dense& d = Rs[r]->dense;
-    size_t tb = 0;
-    cub::CountingInputIterator<uint32_t> first(0u);
-    PB200_CUDA(cub::DeviceSelect::If(nullptr, tb, first, (uint32_t*)nullptr, (unsigned long long*)nullptr, (long long)d.groups, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min, d.hkeys}, st));
-    tmp_cap = std::max(tmp_cap, tb);
-  }
-  if ((rc = tmp.alloc(ctx, tmp_cap + 16))) return rc;  // reused by the selects: they are ordered on one stream
-  for (int r = 0; r < nres; r++) {
-    const pb200_result::Dense& d = Rs[r]->dense;
-    if ((rc = jobs[r].idx.alloc(ctx, (size_t)d.groups * 4))) return rc;
-    cub::CountingInputIterator<uint32_t> first(0u);
-    size_t tb = tmp_cap;
-    PB200_CUDA(cub::DeviceSelect::If(tmp.p, tb, first, (uint32_t*)jobs[r].idx.p, (unsigned long long*)counters.p + r, (long long)d.groups, NonEmptyGroup{d.count, d.seen, d.exists_max, d.exists_min, d.hkeys}, st));
-  }
-  void* pin = nullptr; size_t pin_bytes = 0;
-  if ((rc = pinned_alloc(ctx, 8ull * nres, &pin, &pin_bytes))) return rc;
-  struct PinReturn { pb200_ctx* c; void** p; size_t* b; ~PinReturn() { pinned_free(c, *p, *b); } } pin_return{ctx, &pin, &pin_bytes};
-  PB200_CUDA(cudaMemcpyAsync(pin, counters.p, 8ull * nres, cudaMemcpyDeviceToHost, st));
-  PB200_CUDA(cudaStreamSynchronize(st));
-  for (int r = 0; r < nres; r++) {  // hash tables: more groups than numGroupsLimit (or a full table) -> the result is unusable
-    const pb200_result::Dense& d = Rs[r]->dense;
-    if (!d.hctl) continue;
-    uint32_t ctl[2] = {0, 0};
-    PB200_CUDA(cudaMemcpy(ctl, d.hctl, 8, cudaMemcpyDeviceToHost));
-    if (ctl[1]) {
-      set_error("numGroupsLimit %d would bind (hash table saw more groups): fall back to the reference operator", d.num_groups_limit);
-      return PB200_E_LIMIT;
-    }
-  }
-  size_t stage_total = 0;
-  for (int r = 0; r < nres; r++) {
-    pb200_result* R = Rs[r];
-    const pb200_result::Dense& d = R->dense;
-    Job& J = jobs[r];
-    J.n = ((const unsigned long long*)pin)[r];
-    R->meta.num_groups = (int32_t)J.n;
-    R->meta.groups_limit_reached = (long long)J.n >= d.num_groups_limit;
-    if ((long long)J.n > d.num_groups_limit) {
-      // the reference admits groups in doc order until the limit binds (IntGroupIdMap.getGroupId :1022-1047); that order
-      // is not reproducible by a parallel scan -> the caller must run the Java operator for this segment
-      set_error("numGroupsLimit %d would bind (%llu groups): fall back to the reference operator", d.num_groups_limit, J.n);
-      return PB200_E_LIMIT;
-    }
-    // column plan: [idx u32][count u64]?[per aggregation one column]
-    const int nagg = (int)d.aggs.size();
-    const size_t n8 = (J.n + 1) / 2 * 8;  // bytes of a 4-byte column, 8-byte aligned
-    size_t off = n8;                       // column "idx" is copied device-to-device below
-    J.gp.ncols = 0;
-    J.col_of_agg.assign(nagg, -1);
-    auto add = [&](const void* src, uint32_t esz) { J.gp.col[J.gp.ncols] = GatherCol{src, off, esz, 0}; off += esz == 8 ? J.n * 8 : n8; return J.gp.ncols++; };
-    if (d.hkeys) J.key_col = add(d.hkeys, 8);
-    if (d.count) J.count_col = add(d.count, 8);
-    for (int a = 0; a < nagg; a++) {
-      const int fn = d.aggs[a].function, vk = d.val_kind[a];
-      if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) J.col_of_agg[a] = (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) ? add(d.dsum[a], 8) : add(d.isum[a], 8);
-      else if (fn == PB200_AGG_MIN) J.col_of_agg[a] = add(d.gmin[a], 4);
-      else if (fn == PB200_AGG_MAX) J.col_of_agg[a] = add(d.gmax[a], 4);
-    }
-    J.block_bytes = off;
-    J.stage_off = stage_total;
-    stage_total += (off + 63) / 64 * 64;
-  }
-  pinned_free(ctx, pin, pin_bytes);
-  pin = nullptr;
-  if ((rc = pinned_alloc(ctx, std::max<size_t>(stage_total, 64), &pin, &pin_bytes))) return rc;
-  for (int r = 0; r < nres; r++) {
-    Job& J = jobs[r];
-    if (!J.n) continue;
-    if ((rc = J.block.alloc(ctx, J.block_bytes))) return rc;
-    PB200_CUDA(cudaMemcpyAsync(J.block.p, J.idx.p, J.n * 4, cudaMemcpyDeviceToDevice, st));
-    if (J.gp.ncols) {
-      const int gb = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((J.n + 255) / 256, 148 * 8));
-      gather_columns_kernel<<<gb, 256, 0, st>>>(J.gp, (const uint32_t*)J.idx.p, (long long)J.n, (unsigned char*)J.block.p);
-    }
-    PB200_CUDA(cudaMemcpyAsync((unsigned char*)pin + J.stage_off, J.block.p, J.block_bytes, cudaMemcpyDeviceToHost, st));
-  }
-  PB200_CUDA(cudaGetLastError());
-  PB200_CUDA(cudaStreamSynchronize(st));
-  // ---- host side: raw columns -> the result's intermediate representation ----
-  for (int r = 0; r < nres; r++) {
-    pb200_result* R = Rs[r];
-    const pb200_result::Dense& d = R->dense;
-    const Job& J = jobs[r];
-    const size_t n = J.n;
-    const int nagg = (int)d.aggs.size(), ngb = (int)d.cards.size();
-    const unsigned char* blk = (const unsigned char*)pin + J.stage_off;
-    const uint32_t* hidx = (const uint32_t*)blk;
-    R->keys.resize(n * ngb);
-    if (J.key_col >= 0) {  // hash table: the slot's 64-bit raw key, column 0 least significant
-      const unsigned long long* hk = n ? (const unsigned long long*)(blk + J.gp.col[J.key_col].dst_off) : nullptr;
-      for (size_t i = 0; i < n; i++) {
-        unsigned long long raw = hk[i];
-        for (int g = 0; g < ngb; g++) { R->keys[i * ngb + g] = (int32_t)(raw % (unsigned long long)d.cards[g]); raw /= (unsigned long long)d.cards[g]; }
-      }
-    } else if (ngb == 1) { for (size_t i = 0; i < n; i++) R->keys[i] = (int32_t)hidx[i]; }
-    else for (size_t i = 0; i < n; i++) {
-      uint32_t raw = hidx[i];
-      for (int g = 0; g < ngb; g++) { R->keys[i * ngb + g] = (int32_t)(raw % (uint32_t)d.cards[g]); raw /= (uint32_t)d.cards[g]; }
-    }
-    R->dbl.assign(nagg, {}); R->lng.assign(nagg, {}); R->ids.assign(nagg, {}); R->distinct.assign(nagg, {});
-    const unsigned long long* counts = J.count_col >= 0 && n ? (const unsigned long long*)(blk + J.gp.col[J.count_col].dst_off) : nullptr;
-    for (int a = 0; a < nagg; a++) {
-      const int fn = d.aggs[a].function, vk = d.val_kind[a];
-      std::vector<double>& D = R->dbl[a];
-      std::vector<int64_t>& L = R->lng[a];
-      std::vector<int32_t>& I = R->ids[a];
-      D.resize(n); L.resize(n); I.assign(n, -1);
-      const DeviceColumn* c = d.agg_cols[a];
-      const unsigned char* col = J.col_of_agg[a] >= 0 && n ? blk + J.gp.col[J.col_of_agg[a]].dst_off : nullptr;
-      auto value_of = [&](uint32_t x) -> double {
-        if (vk == VAL_RAW_I32) return (double)(int32_t)(x ^ 0x80000000u);
-        if (c->dict_host.empty()) return (double)x;
-        const unsigned char* h = c->dict_host.data();
-        switch (vk) {
-          case VAL_DICT_I32: { int32_t v; memcpy(&v, h + 4ull * x, 4); return (double)v; }
-          case VAL_DICT_I64: { int64_t v; memcpy(&v, h + 8ull * x, 8); return (double)v; }
-          case VAL_DICT_F32: { float v; memcpy(&v, h + 4ull * x, 4); return (double)v; }
-          default: { double v; memcpy(&v, h + 8ull * x, 8); return v; }
-        }
-      };
-      if (fn == PB200_AGG_COUNT) {
-        for (size_t i = 0; i < n; i++) { L[i] = (int64_t)counts[i]; D[i] = (double)counts[i]; }
-      } else if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
-        if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) { if (n) memcpy(D.data(), col, n * 8); }
-        else { const long long* t = (const long long*)col; for (size_t i = 0; i < n; i++) D[i] = (double)t[i]; }
-        if (counts) for (size_t i = 0; i < n; i++) L[i] = (int64_t)counts[i]; else std::fill(L.begin(), L.end(), 0);
-      } else if (fn == PB200_AGG_MIN || fn == PB200_AGG_MAX) {
-        const uint32_t* t = (const uint32_t*)col;
-        std::fill(L.begin(), L.end(), 0);
-        for (size_t i = 0; i < n; i++) {
-          if (fn == PB200_AGG_MIN) {
-            if (t[i] == 0xFFFFFFFFu) D[i] = INFINITY; else { I[i] = (int32_t)t[i]; D[i] = value_of(t[i]); }
-          } else {
-            if (t[i] == 0) D[i] = -INFINITY; else { I[i] = (int32_t)(t[i] - 1); D[i] = value_of(t[i] - 1); }
-          }
-        }
-      } else if (fn == PB200_AGG_DISTINCTCOUNT && d.dbits[a]) {
-        // the groups' bitset rows: gathered on the device, decoded here into dictId lists (what extractGroupByResult's
-        // value-set conversion starts from, BaseDistinctAggregateAggregationFunction :306-321)
-        const size_t wpg = d.dwords[a];
-        std::vector<uint32_t> rows(n * wpg);
-        if (n) {
-          DevBuf g;
-          if ((rc = g.alloc(ctx, n * wpg * 4))) return rc;
-          const int gb2 = (int)std::max<size_t>(1, std::min<size_t>((n * wpg + 255) / 256, 148 * 8));
-          gather_rows_kernel<<<gb2, 256, 0, st>>>(d.dbits[a], (const uint32_t*)J.idx.p, (long long)n, (int)wpg, (uint32_t*)g.p);
-          PB200_CUDA(cudaMemcpyAsync(rows.data(), g.p, n * wpg * 4, cudaMemcpyDeviceToHost, st));
-          PB200_CUDA(cudaStreamSynchronize(st));
-        }
-        R->distinct[a].resize(n);
-        for (size_t i = 0; i < n; i++) {
-          std::vector<int32_t>& ids = R->distinct[a][i];
-          for (size_t w = 0; w < wpg; w++) { uint32_t x = rows[i * wpg + w]; while (x) { ids.push_back((int32_t)(w * 32 + __builtin_ctz(x))); x &= x - 1; } }
-          L[i] = (int64_t)ids.size(); D[i] = (double)ids.size();
-        }
-      } else { std::fill(D.begin(), D.end(), 0.0); std::fill(L.begin(), L.end(), 0); }
-    }
-  }
-  return PB200_OK;
-}
-
 extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
   if (!ctx || !R) { set_error("null argument"); return PB200_E_INVALID; }
   pb200_result::Dense& d = R->dense;
@@ -1529,13 +1355,18 @@ extern "C" int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* R) {
   cudaStream_t st = take_stream(ctx);
   struct StreamReturn { pb200_ctx* c; cudaStream_t s; ~StreamReturn() { give_stream(c, s); } } stream_return{ctx, st};
   pb200_result* one[1] = {R};
-  return finalize_many(ctx, one, 1, st);
+  return extract_groups(ctx, one, 1, st);
 }
 
 extern "C" int32_t pb200_result_device_buffers(pb200_result* R, int32_t kind, void** p, int64_t* n) {
   if (!R || !p || !n) { set_error("null argument"); return PB200_E_INVALID; }
   pb200_result::Dense& d = R->dense;
   if (d.hkeys) { set_error("hash group tables of different GPUs are not element-wise reducible"); return PB200_E_UNSUPPORTED; }
+  for (int a = 0; a < kMaxAggs; a++)
+    if (d.dbits[a]) {  // per-group DISTINCTCOUNT bitsets are not one of the four reducible blocks: never reduce "around" them
+      set_error("group-by DISTINCTCOUNT keeps per-group dictId bitsets on the device: a cross-GPU reduce of the tables would drop the other ranks' sets");
+      return PB200_E_UNSUPPORTED;
+    }
   switch (kind) {
     case 0: *p = d.i64_block; *n = d.i64_elems; break;
     case 1: *p = d.f64_block; *n = d.f64_elems; break;
@@ -1552,24 +1383,55 @@ extern "C" int32_t pb200_result_meta_get(const pb200_result* R, pb200_result_met
   return PB200_OK;
 }
 extern "C" int32_t pb200_result_group_keys(const pb200_result* R, int32_t* out) {
-  if (!R || (!out && !R->keys.empty())) { set_error("null argument"); return PB200_E_INVALID; }
+  if (!R) { set_error("null argument"); return PB200_E_INVALID; }
+  if (R->view.block) {
+    const size_t n = R->view.rows * (size_t)R->meta.num_group_by;
+    if (n && !out) { set_error("null argument"); return PB200_E_INVALID; }
+    if (n) memcpy(out, R->view.keys, n * 4);
+    return PB200_OK;
+  }
+  if (!out && !R->keys.empty()) { set_error("null argument"); return PB200_E_INVALID; }
   if (!R->keys.empty()) memcpy(out, R->keys.data(), R->keys.size() * 4);
   return PB200_OK;
 }
+namespace {
+// one column of a view-backed result -> caller memory (absent columns: the neutral value)
+void copy_dbl(const pb200_result::View& v, int a, double* out) { if (v.dbl[a]) memcpy(out, v.dbl[a], v.rows * 8); else std::fill(out, out + v.rows, 0.0); }
+void copy_lng(const pb200_result::View& v, int a, int64_t* out) { if (v.lng[a]) memcpy(out, v.lng[a], v.rows * 8); else std::fill(out, out + v.rows, (int64_t)0); }
+void copy_ids(const pb200_result::View& v, int a, int32_t* out) { if (v.ids[a]) memcpy(out, v.ids[a], v.rows * 4); else std::fill(out, out + v.rows, (int32_t)-1); }
+}  // namespace
 extern "C" int32_t pb200_result_agg(const pb200_result* R, int32_t a, double* od, int64_t* ol) {
-  if (!R || a < 0 || a >= (int)R->dbl.size()) { set_error("bad aggregation index"); return PB200_E_INVALID; }
+  if (!R || a < 0 || a >= R->meta.num_aggs) { set_error("bad aggregation index"); return PB200_E_INVALID; }
+  if (R->view.block) {
+    if (od && R->view.rows) copy_dbl(R->view, a, od);
+    if (ol && R->view.rows) copy_lng(R->view, a, ol);
+    return PB200_OK;
+  }
+  if (a >= (int)R->dbl.size()) { set_error("bad aggregation index"); return PB200_E_INVALID; }
   if (od && !R->dbl[a].empty()) memcpy(od, R->dbl[a].data(), R->dbl[a].size() * 8);
   if (ol && !R->lng[a].empty()) memcpy(ol, R->lng[a].data(), R->lng[a].size() * 8);
   return PB200_OK;
 }
 extern "C" int32_t pb200_result_agg_dict_ids(const pb200_result* R, int32_t a, int32_t* out) {
-  if (!R || a < 0 || a >= (int)R->ids.size() || !out) { set_error("bad aggregation index"); return PB200_E_INVALID; }
+  if (!R || a < 0 || a >= R->meta.num_aggs || !out) { set_error("bad aggregation index"); return PB200_E_INVALID; }
+  if (R->view.block) { if (R->view.rows) copy_ids(R->view, a, out); return PB200_OK; }
+  if (a >= (int)R->ids.size()) { set_error("bad aggregation index"); return PB200_E_INVALID; }
   if (!R->ids[a].empty()) memcpy(out, R->ids[a].data(), R->ids[a].size() * 4);
   return PB200_OK;
 }
 extern "C" int32_t pb200_result_fetch(const pb200_result* R, int32_t* keys, double* dbl, int64_t* lng, int32_t* ids) {
   if (!R) { set_error("null result"); return PB200_E_INVALID; }
   const size_t rows = R->meta.num_groups < 0 ? 1 : (size_t)R->meta.num_groups;
+  if (R->view.block) {
+    const pb200_result::View& v = R->view;
+    if (keys && v.rows && R->meta.num_group_by) memcpy(keys, v.keys, v.rows * (size_t)R->meta.num_group_by * 4);
+    for (int a = 0; a < R->meta.num_aggs && v.rows; a++) {
+      if (dbl) copy_dbl(v, a, dbl + (size_t)a * rows);
+      if (lng) copy_lng(v, a, lng + (size_t)a * rows);
+      if (ids) copy_ids(v, a, ids + (size_t)a * rows);
+    }
+    return PB200_OK;
+  }
   if (keys && !R->keys.empty()) memcpy(keys, R->keys.data(), R->keys.size() * 4);
   for (size_t a = 0; a < R->dbl.size(); a++) {
     if (dbl && R->dbl[a].size() == rows && rows) memcpy(dbl + a * rows, R->dbl[a].data(), rows * 8);

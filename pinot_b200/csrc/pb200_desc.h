@@ -27,6 +27,12 @@ enum : int32_t { CMP_BOTH = 0, CMP_GE = 1, CMP_LT = 2 };
 // aggregation value kinds (how a dictId / raw word becomes a number)
 enum : int32_t { VAL_NONE = 0, VAL_DICT_I32 = 1, VAL_DICT_I64 = 2, VAL_DICT_F32 = 3, VAL_DICT_F64 = 4, VAL_RAW_I32 = 5 };
 
+// SUM / AVG accumulate in double for FLOAT / DOUBLE and for LONG dictionaries -- what SumAggregationFunction does for every
+// type (core/query/aggregation/function/SumAggregationFunction.java:69-145: `sum += values[i]` on a double).  A 64-bit
+// integer accumulator over LONG values would wrap silently (epoch millis x 5 M rows > 2^63); INT values keep the exact
+// int64 accumulator (|v| x rows < 2^31 x 2^31, cannot wrap).
+__host__ __device__ constexpr bool sum_in_double(int vk) { return vk == VAL_DICT_F32 || vk == VAL_DICT_F64 || vk == VAL_DICT_I64; }
+
 struct SlotDesc {
   const uint32_t* data;  // device: packed words, padded to whole tiles
   int32_t bits;          // 1..32 (32 = raw big-endian 32-bit values)
@@ -167,6 +173,9 @@ struct QueryDesc {
   int32_t queue_max;
   int8_t smem_slot[kMaxAggs];  // aggregation -> index of its (lo, hi) pair, -1: none (COUNT)
   int8_t pad_tail[2];
+  // group-by fast path for few survivors per thread (pb200_scan.cuh): COUNT + <= 2 pipelined aggregations, dense tables
+  int32_t gb_simple;
+  int32_t sparse_max_gb;   // taken when no thread of the warp has more surviving rows than this
 };
 
 // ---- shared-memory header of the scan kernel (the host sizes the dynamic shared memory with it) ----

@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -65,6 +66,7 @@ struct Tuning {
   long long dense_max = 1ll << 24;   // PB200_DENSE_MAX: dense group table up to this many raw keys, hash table beyond
   int defer = 1;                 // !PB200_NO_DEFER: software-pipelined gathers, aggregation-only kernel
   int gb_defer = 1;              // !PB200_NO_GB_DEFER: software-pipelined last queue batch, group-by kernel
+  int sparse_max_gb = 12;        // PB200_SPARSE_MAX_GB: group-by rows walked per thread (no queue) up to this many survivors per thread
   int skip = 1;                  // !PB200_NO_SKIP: bitmap-driven slice skipping
   int always_count = 0;          // PB200_ALWAYS_COUNT
 };
@@ -77,6 +79,7 @@ struct pb200_ctx {
   int max_smem_optin = 0;
   std::mutex mu;
   std::vector<cudaStream_t> free_streams;
+  std::vector<cudaEvent_t> free_events;
   std::multimap<size_t, void*> free_blocks;  // caching allocator: size -> block
   std::map<void*, size_t> block_size;
   size_t pooled_bytes = 0;
@@ -106,8 +109,29 @@ struct pb200_segment {
   pb200_domain* domain = nullptr;  // holds one reference
 };
 
+namespace pb200 {
+// A pinned (mapped) host block shared by the results whose extracted groups live in it; goes back to the context's pinned
+// pool when the last result is freed.
+struct PinnedBlock {
+  pb200_ctx* ctx = nullptr;
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~PinnedBlock();
+};
+}  // namespace pb200
+
 struct pb200_result {
   pb200_result_meta meta{};
+  // Extracted groups in their final layout inside a pinned block written by the device (pb200_extract.cu); when
+  // view.block is set the accessors read these columns, else the vectors below (host-built results).
+  struct View {
+    std::shared_ptr<pb200::PinnedBlock> block;
+    size_t rows = 0;
+    const int32_t* keys = nullptr;                 // [rows x num_group_by]
+    const double* dbl[pb200::kMaxAggs] = {};       // NULL: all zero
+    const int64_t* lng[pb200::kMaxAggs] = {};      // NULL: all zero
+    const int32_t* ids[pb200::kMaxAggs] = {};      // NULL: all -1
+  } view;
   std::vector<int32_t> keys;                     // [G x k]
   std::vector<std::vector<double>> dbl;          // per agg [rows]
   std::vector<std::vector<int64_t>> lng;
@@ -153,6 +177,21 @@ int pinned_alloc(pb200_ctx* ctx, size_t bytes, void** out, size_t* got);  // cud
 void pinned_free(pb200_ctx* ctx, void* p, size_t bytes);
 cudaStream_t take_stream(pb200_ctx* ctx);
 void give_stream(pb200_ctx* ctx, cudaStream_t s);
+cudaEvent_t take_event(pb200_ctx* ctx);
+void give_event(pb200_ctx* ctx, cudaEvent_t e);
+
+struct DevBufRaw {  // RAII pooled device buffer
+  pb200_ctx* ctx;
+  void* p = nullptr;
+  explicit DevBufRaw(pb200_ctx* c) : ctx(c) {}
+  DevBufRaw(const DevBufRaw&) = delete;
+  DevBufRaw& operator=(const DevBufRaw&) = delete;
+  ~DevBufRaw() { dev_free(ctx, p); }
+  int alloc(size_t bytes) { return dev_alloc(ctx, bytes, &p); }
+};
+// pb200_extract.cu: non-empty groups of the results' device tables -> final layout in pinned memory (all results at once)
+int extract_groups(pb200_ctx* ctx, pb200_result* const* results, int nres, cudaStream_t st);
+void result_materialize(pb200_result* R);  // view -> the std::vector fields
 
 // pb200_roaring.cu
 // One serialized RoaringBitmap (posting list of one dictId) to be OR-ed into `mask` (1 bit per doc, bit j of 32-bit

@@ -482,7 +482,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
         const int fn = hdr->aggs[a].function;
         if (fn == 1 || fn == 4) {  // SUM / AVG
           const unsigned long long raw = acc64[a * kConsumers + group];
-          if (hdr->aggs[a].val_kind == VAL_DICT_F32 || hdr->aggs[a].val_kind == VAL_DICT_F64) {
+          if (sum_in_double(hdr->aggs[a].val_kind)) {
             double d = warp_sum(__longlong_as_double((long long)raw));
             if (lane == 0) atomicAdd(&sd.accum->dsum[a], d);
           } else {
@@ -674,15 +674,15 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
         const int abits = (int)((ac >> 12) & 63u);
         const uint32_t id = read_one_group(st + (ac >> 18) + group_in_stage * abits, j, abits);
         if (fn == 1 || fn == 4) {
-          if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
+          if (sum_in_double(vk)) {
             const double x = vk == VAL_DICT_F32 ? (double)__ldg(static_cast<const float*>(sd.dict[a]) + id)
+                           : vk == VAL_DICT_I64 ? (double)__ldg(static_cast<const long long*>(sd.dict[a]) + id)
                                                 : __ldg(static_cast<const double*>(sd.dict[a]) + id);
             double* slot = reinterpret_cast<double*>(acc64 + a * kConsumers + group);
             *slot += x;
           } else {
             const long long x = vk == VAL_DICT_I32 ? (long long)(int)(__ldg(static_cast<const uint32_t*>(sd.dict[a]) + id) ^ 0x80000000u)
-                                : vk == VAL_DICT_I64 ? __ldg(static_cast<const long long*>(sd.dict[a]) + id)
-                                                     : (long long)(int)id;
+                                                   : (long long)(int)id;
             acc64[a * kConsumers + group] += (unsigned long long)x;
           }
         } else if (fn == 2 || fn == 3) {
@@ -696,7 +696,91 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
       }
     };
     bool handled = false;
-    if (GROUPBY) {
+    if (GROUPBY && wmax2 == 0) handled = true;
+    if (GROUPBY && !handled && q.gb_simple && wmax2 <= q.sparse_max_gb && !sd.h_keys) {
+      // ---- few survivors per thread, simple shape (COUNT + at most kGD pipelined aggregations, dense table): every
+      //      thread walks ITS OWN surviving rows -- no compaction, no queue traffic, no warp scan.  The loop is warp-uniform
+      //      (wmax2 iterations, lanes without a row left are predicated off), a row costs two extractions straight from
+      //      the thread's own words (FixedBitIntReader.readUnchecked shape), one dictionary gather and the reductions.
+      //      The first kQB rows of each thread are software-pipelined exactly like the queue's last batch: loads issued
+      //      here, reductions after the next tile's filter (drain_gb); later rows (rare at <= 12 % selectivity) reduce
+      //      at once.  At 10 % selectivity this is ~520 warp instructions per slice instead of ~800 through the queue.
+      const int ncodes = sd.num_agg_codes;   // == num_defer_codes here (host rule for gb_simple)
+      uint32_t ac[kGD];
+      const uint32_t* abase[kGD];
+#pragma unroll
+      for (int k = 0; k < kGD; ++k) {
+        ac[k] = k < ncodes ? sd.agg_code[k] : 0u;
+        abase[k] = st + (ac[k] >> 18) + group_in_stage * (int)((ac[k] >> 12) & 63u);
+      }
+      uint32_t mm = m, okm = 0;
+      auto key_of = [&](int j) {
+        uint32_t g = 0;
+#pragma unroll 1
+        for (int gi = 0; gi < q.num_group_by; ++gi) {
+          const SlotDesc& sl = sd.slots[hdr->group_slot[gi]];
+          g += read_one_group(st + sl.stage_words + group_in_stage * sl.bits, j, sl.bits) * sd.group_mult[gi];
+        }
+        return g;
+      };
+      auto mark = [&](uint32_t g, bool has) {
+        if (sd.g_count) { if (has) red_add_u64(sd.g_count + g, 1ull); }
+        else if (sd.g_seen) { if (has) sd.g_seen[g] = 1u; }
+      };
+#pragma unroll
+      for (int u = 0; u < kQB; ++u) {
+        if (u < wmax2) {
+          const bool has = mm != 0u;
+          const int j = has ? 31 - __clz(mm) : 0;
+          mm &= ~(1u << j);
+          const uint32_t g = key_of(j);
+          pg[u] = g;
+          okm |= (has ? 1u : 0u) << u;
+          mark(g, has);
+#pragma unroll
+          for (int k = 0; k < kGD; ++k) {
+            if (k < ncodes) {
+              const int a = (int)(ac[k] & 7u), fn = (int)((ac[k] >> 4) & 7u), vk = (int)((ac[k] >> 8) & 7u);
+              const uint32_t id = read_one_group(abase[k], j, (int)((ac[k] >> 12) & 63u));
+              if (fn == 1 || fn == 4) {
+                px[k][u] = (uint32_t)ldg_pred_s32(reinterpret_cast<const int*>(static_cast<const uint32_t*>(sd.dict[a]) + id), has ? 1u : 0u);
+              } else {
+                const uint32_t* tab = fn == 2 ? sd.g_min[a] : sd.g_max[a];
+                pq[k][u] = id ^ (vk == VAL_RAW_I32 ? 0x80000000u : 0u);
+                px[k][u] = has ? __ldcg(tab + g) : (fn == 2 ? 0u : 0xFFFFFFFFu);
+              }
+            }
+          }
+        }
+      }
+      pend_ok = okm;
+      for (int it = kQB; it < wmax2; ++it) {   // rows beyond the pipelined ones: reduce immediately
+        const bool has = mm != 0u;
+        const int j = has ? 31 - __clz(mm) : 0;
+        mm &= ~(1u << j);
+        const uint32_t g = key_of(j);
+        mark(g, has);
+#pragma unroll
+        for (int k = 0; k < kGD; ++k) {
+          if (k < ncodes) {
+            const int a = (int)(ac[k] & 7u), fn = (int)((ac[k] >> 4) & 7u), vk = (int)((ac[k] >> 8) & 7u);
+            const uint32_t id = read_one_group(abase[k], j, (int)((ac[k] >> 12) & 63u));
+            if (fn == 1 || fn == 4) {
+              const uint32_t w = (uint32_t)ldg_pred_s32(reinterpret_cast<const int*>(static_cast<const uint32_t*>(sd.dict[a]) + id), has ? 1u : 0u);
+              if (has) {
+                if (vk == VAL_DICT_F32) red_add_f64(sd.g_dsum[a] + g, (double)__uint_as_float(w));
+                else red_add_u64(reinterpret_cast<unsigned long long*>(sd.g_isum[a]) + g, (unsigned long long)(long long)(int)(w ^ 0x80000000u));
+              }
+            } else if (has) {
+              const uint32_t x = id ^ (vk == VAL_RAW_I32 ? 0x80000000u : 0u);
+              if (fn == 2) atomicMin(sd.g_min[a] + g, x); else atomicMax(sd.g_max[a] + g, x + 1u);
+            }
+          }
+        }
+      }
+      handled = true;
+    }
+    if (GROUPBY && !handled) {
       // ---- survivor queue: the warp's surviving rows are compacted into a shared-memory queue (exclusive scan of the
       //      per-thread counts), then the lanes take queue entries round-robin: every table update and dictionary gather
       //      is a DENSE warp instruction over survivors (the DocIdSet -> Projection step of the reference) instead of a
@@ -808,11 +892,12 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 #pragma unroll
             for (int u = 0; u < kQB; ++u) id[u] = read_one_group(base + (e[u] >> 5) * abits, (int)(e[u] & 31u), abits);
             if (fn == 1 || fn == 4) {
-              if (vk == VAL_DICT_F32 || vk == VAL_DICT_F64) {
+              if (sum_in_double(vk)) {
                 double x[kQB];
 #pragma unroll
                 for (int u = 0; u < kQB; ++u)
                   x[u] = vk == VAL_DICT_F32 ? (double)__ldg(static_cast<const float*>(sd.dict[a]) + id[u])
+                       : vk == VAL_DICT_I64 ? (double)__ldg(static_cast<const long long*>(sd.dict[a]) + id[u])
                                             : __ldg(static_cast<const double*>(sd.dict[a]) + id[u]);
 #pragma unroll
                 for (int u = 0; u < kQB; ++u) if (ok[u]) red_add_f64(sd.g_dsum[a] + g[u], x[u]);
@@ -821,8 +906,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 #pragma unroll
                 for (int u = 0; u < kQB; ++u)
                   x[u] = vk == VAL_DICT_I32 ? (long long)(int)(__ldg(static_cast<const uint32_t*>(sd.dict[a]) + id[u]) ^ 0x80000000u)
-                         : vk == VAL_DICT_I64 ? __ldg(static_cast<const long long*>(sd.dict[a]) + id[u])
-                                              : (long long)(int)id[u];
+                                            : (long long)(int)id[u];
                 if (TG) {
                   uint32_t* lo = tcnt + tcopy + TA * (1u + 2u * q.smem_slot[a]);
 #pragma unroll
@@ -908,15 +992,13 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc += ((m >> j) & 1u) ? (long long)(int)v[j] : 0ll;
                 acc64[a * kConsumers + group] += (unsigned long long)acc;
-              } else if (vk == VAL_DICT_I64) {
-                const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
-                long long acc = 0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc += ldg_pred_s64(d + v[j], (m >> j) & 1u);
-                acc64[a * kConsumers + group] += (unsigned long long)acc;
               } else {
                 double acc = 0.0;
-                if (vk == VAL_DICT_F32) {
+                if (vk == VAL_DICT_I64) {
+                  const long long* __restrict__ d = static_cast<const long long*>(sd.dict[a]);
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) acc += (double)ldg_pred_s64(d + v[j], (m >> j) & 1u);
+                } else if (vk == VAL_DICT_F32) {
                   const float* __restrict__ d = static_cast<const float*>(sd.dict[a]);
 #pragma unroll
                   for (int j = 0; j < 32; ++j) acc += (double)__int_as_float(ldg_pred_s32(reinterpret_cast<const int*>(d + v[j]), (m >> j) & 1u));

@@ -115,7 +115,7 @@ def test_domain_merge_equals_oracle_merge_by_value(oracle, ctx, pm, sizes):
     dom = None
     try:
         unbound = [{c: d.column_info(c) for c in ("k", "l", "s", "f", "g", "t")} for d in devs]
-        dom = DictionaryDomain.build(ctx, devs, ["k", "l", "s", "f", "g", "t"])
+        dom = DictionaryDomain.build(ctx, devs, ["k", "l", "s", "f", "g", "t", "v"])
         for c in ("k", "l", "f", "g", "t"):   # union == np.unique over the segments' dictionaries
             want = np.unique(np.concatenate([s.column(c).dict_values for s in segs]))
             assert dom.info(c)["cardinality"] == len(want), c

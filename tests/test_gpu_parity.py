@@ -433,3 +433,26 @@ def test_c_abi_dictid_space_every_width(ctx, bits):
             L.pb200_result_free(res[0])
     finally:
         L.pb200_segment_release(ctx.handle, seg)
+
+
+def test_long_sum_does_not_wrap(oracle, ctx, pm):
+    """SUM / AVG over a LONG dictionary accumulate in double like SumAggregationFunction.java:69-145: values whose sum
+    passes 2^63 (epoch-millis-sized values x a few million rows, or a few ~1e18 values) must not wrap."""
+    rng = np.random.default_rng(63)
+    n = 70_000
+    big = (rng.integers(1, 9, size=n).astype(np.int64) * 1_000_000_000_000_000_000) + rng.integers(0, 1000, size=n)   # ~1e18 .. 8e18
+    seg = oracle.build_segment("long", {"e": big, "k": rng.integers(0, 5, size=n).astype(np.int32),
+                                        "h": rng.integers(0, 3000, size=n).astype(np.int32)})
+    assert float(big.astype(np.float64).sum()) > 2.0 ** 63
+    dev = to_device(ctx, seg)
+    try:
+        for text in ("SELECT SUM(e), AVG(e), COUNT(*) FROM t", "SELECT SUM(e), AVG(e) FROM t WHERE k < 4",
+                     "SELECT SUM(e), AVG(e), MAX(e) FROM t GROUP BY k",          # shared-memory-table sized key space
+                     "SELECT SUM(e), COUNT(*) FROM t WHERE k > 0 GROUP BY h"):   # global tables, survivor queue
+            r, block = check_query(oracle, pm, seg, dev, sql.parse(text), "LONG sum: " + text)
+            assert all(v > 0 for v in block.doubles[0]), text
+        merged = pm.execute_segments([dev, dev, dev], sql.parse("SELECT SUM(e) FROM t GROUP BY k"), merge=True)[0]
+        single = pm.execute_segments([dev], sql.parse("SELECT SUM(e) FROM t GROUP BY k"))[0]
+        assert np.allclose(merged.doubles[0], 3.0 * single.doubles[0], rtol=1e-12)
+    finally:
+        dev.destroy()

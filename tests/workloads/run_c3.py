@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mode", default="bitmap", choices=["bitmap", "range", "range2", "range3"])
     ap.add_argument("--check-rows", type=int, default=0, help="also verify against the oracle on a small segment")
+    ap.add_argument("--query", default="", help="time this query instead of the mode's (columns d1 d2 d3 g m f g2); --bits = touched bits per row")
+    ap.add_argument("--bits", type=int, default=0)
     ap.add_argument("--variants", default="", help="space separated name:knob=value,knob=value tuning variants "
                     "(pb200_tuning_set) timed on the same resident segments, one JSON line each")
     args = ap.parse_args()
@@ -57,6 +59,8 @@ def main():
     else:
         text = "SELECT SUM(m), MAX(f), COUNT(*) FROM t WHERE f BETWEEN 3002 AND 5999 GROUP BY g, g2"  # 1M-group key space
         bits = 14 + 14 + 7 + 17
+    if args.query:
+        text, bits = args.query, args.bits
     q = sql.parse(text, num_groups_limit=2_000_000)
 
     if args.check_rows:
@@ -83,7 +87,7 @@ def main():
     segs = [IndexSegment.synthetic(ctx, f"s{s}", args.rows, specs(s, inverted=args.mode == "bitmap")) for s in range(args.segments)]
     gen_s = time.perf_counter() - t0
     defaults = {"warps": 6, "ctas_per_sm": 2, "stages": 0, "grid": 0, "sparse_max": 4, "sparse_max_agg": -1, "smem_groups": 1,
-                "smem_groups_max": 2048, "smem_copies": 0, "gb_defer": 1, "skip": 1, "always_count": 0}
+                "smem_groups_max": 2048, "smem_copies": 0, "gb_defer": 1, "skip": 1, "always_count": 0, "sparse_max_gb": 0}
     rows = args.segments * args.rows
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     reference_result = None
@@ -103,7 +107,7 @@ def main():
             kms.append(blocks[0].device_ms)
         el = time.perf_counter() - t0
         # every variant must return the same tables
-        digest = [(b.num_groups, float(b.doubles[0].sum()), int(b.longs[-1].sum()), b.stats.num_docs_scanned) for b in blocks]
+        digest = [(b.num_groups, float(sum(d.sum() for d in b.doubles)), int(b.longs[-1].sum()), b.stats.num_docs_scanned) for b in blocks]
         if reference_result is None:
             reference_result = digest
         k = sum(kms) / len(kms)
