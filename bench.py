@@ -298,7 +298,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        from pinot_b200.distributed import combine_across_ranks
+        from pinot_b200.distributed import execute_and_combine
 
     ctx = B200Context(local_rank)
     pm = B200PlanMaker(ctx)
@@ -306,6 +306,12 @@ def main():
     segs = [IndexSegment.synthetic(ctx, f"r{rank}s{s}", args.rows, column_specs(rank, s)) for s in range(args.segments)]
     gen_s = time.perf_counter() - t_gen
     rows_per_step = args.segments * args.rows
+    domain = None
+    if dist is not None:
+        # the per-GPU group tables are merged BY VALUE: all ranks' segments share table-wide dictionaries for the group key
+        # and the summed column (synthetic dictionaries are identical, so binding re-encodes nothing)
+        from pinot_b200.distributed import global_domain
+        domain = global_domain(ctx, segs, ["c3", "c5"], dist)
 
     def barrier():
         if dist is not None:
@@ -315,8 +321,8 @@ def main():
     def gb_step():
         """The headline step: the whole table's results block on rank 0."""
         if dist is not None:
-            block = pm.execute_segments(segs, q_gb, merge=True, keep_handle=True)[0]
-            return combine_across_ranks(pm, block, q_gb, dist, dst=0), block.device_ms
+            block = execute_and_combine(pm, segs, q_gb, dist, dst=0, merged_docs_bound=rows_per_step * world)
+            return block, (block.device_ms if block is not None else pm.last_device_ms)
         block = pm.execute_segments(segs, q_gb, merge=True)[0]
         return block, block.device_ms
 
@@ -505,6 +511,8 @@ def main():
         print(json.dumps(line))
     for sgm in segs:
         sgm.destroy()
+    if domain is not None:
+        domain.release()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PB200_ABI_VERSION 1
+#define PB200_ABI_VERSION 2 /* 2: pb200_query.reduce_world / merged_docs_bound, domains, tuning, pb200_result_meta.reserved bits */
 
 enum {
   PB200_OK = 0,
@@ -200,6 +200,12 @@ typedef struct {
                                                  PB200_Q_PER_SEGMENT_FILTER is set, else shared by all segments */
   const int32_t* group_by_columns;
   const pb200_agg* aggs;
+  /* PB200_Q_DEFER_FINALIZE only: how many such tables (one per GPU) will be summed into the final one, and an upper bound
+   * of the docs of ALL of them (0: this call's docs x reduce_world).  They size the count field of a count-carrying sum
+   * identically on every rank; 0 / 1 = no cross-GPU reduce follows. */
+  int32_t reduce_world;
+  int32_t reserved;
+  int64_t merged_docs_bound;
 } pb200_query;
 
 #define PB200_Q_PER_SEGMENT_FILTER 1 /* filter[] holds one tree per segment (segment-local dictIds) */
@@ -207,6 +213,7 @@ typedef struct {
                                         AggregationCombineOperator analogue).  Every group-by, MIN / MAX and DISTINCTCOUNT
                                         column must have the SAME dictionary in all segments (bind them to a domain);
                                         otherwise PB200_E_UNSUPPORTED -- never a merge of unrelated dictIds */
+#define PB200_Q_NO_COUNT_CARRIER 8   /* keep a separate COUNT table (the retry of a cross-GPU combine whose carrier overflowed) */
 #define PB200_Q_DEFER_FINALIZE 4     /* group-by with PB200_Q_MERGE_SEGMENTS: leave the groups in the dense device tables
                                         (pb200_result_device_buffers) and extract them later with pb200_result_finalize --
                                         for a cross-GPU reduce of the tables in between; only the reduce root extracts */
@@ -228,7 +235,9 @@ typedef struct {
   int32_t num_aggs;
   int32_t regime;              /* which key-holder regime the reference would have used (informational) */
   int32_t groups_limit_reached;
-  int32_t reserved;
+  int32_t reserved;            /* bit 0: group-by row counts were carried inside an INT sum's reductions (informational);
+                                  bit 1 (PB200_Q_DEFER_FINALIZE results): that sum's field is NOT provably safe for the
+                                  cross-GPU reduce -- every rank must run the query again with PB200_Q_NO_COUNT_CARRIER */
   /* ExecutionStatistics (core/operator/ExecutionStatistics.java) */
   int64_t num_docs_scanned;
   int64_t num_entries_scanned_in_filter; /* see DESIGN.md: device semantics = docs x scan leaves evaluated */

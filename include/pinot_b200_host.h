@@ -131,6 +131,9 @@ typedef struct {
                              dictionaries in all segments -- bind them to a domain -- else PB200_E_UNSUPPORTED);
                              2: combine and defer the group extraction (PB200_Q_DEFER_FINALIZE) */
   int32_t skip_star_tree; /* query option useStarTree=false */
+  int32_t reduce_world;   /* merge_segments == 2: pb200_query.reduce_world */
+  int32_t no_count_carrier; /* PB200_Q_NO_COUNT_CARRIER */
+  int64_t merged_docs_bound;
 } pb200h_query;
 
 /* Which operator the plan maker chose per segment (AggregationPlanNode / GroupByPlanNode decisions). */

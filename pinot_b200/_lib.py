@@ -53,7 +53,8 @@ class Query(C.Structure):
     _fields_ = [("num_filter_nodes", C.c_int32), ("num_group_by", C.c_int32), ("num_aggs", C.c_int32),
                 ("num_groups_limit", C.c_int32), ("max_initial_result_holder_capacity", C.c_int32),
                 ("flags", C.c_int32), ("filter", C.POINTER(FilterNode)), ("group_by_columns", C.POINTER(C.c_int32)),
-                ("aggs", C.POINTER(Agg))]
+                ("aggs", C.POINTER(Agg)), ("reduce_world", C.c_int32), ("reserved", C.c_int32),
+                ("merged_docs_bound", C.c_int64)]
 
 
 class ResultMeta(C.Structure):
@@ -101,7 +102,8 @@ class HQuery(C.Structure):
                 ("num_group_by", C.c_int32), ("group_by", C.POINTER(C.c_char_p)), ("num_aggs", C.c_int32),
                 ("aggs", C.POINTER(HAgg)), ("num_groups_limit", C.c_int32),
                 ("max_initial_result_holder_capacity", C.c_int32), ("merge_segments", C.c_int32),
-                ("skip_star_tree", C.c_int32)]
+                ("skip_star_tree", C.c_int32), ("reduce_world", C.c_int32), ("no_count_carrier", C.c_int32),
+                ("merged_docs_bound", C.c_int64)]
 
 
 class HStarMetric(C.Structure):

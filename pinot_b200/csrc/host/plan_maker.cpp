@@ -59,6 +59,22 @@ Evaluated evaluate(const HostColumn& c, const pb200h_filter_node& n, const pb200
   return e;
 }
 
+
+// Predicate on a raw (no-dictionary) INT column -> PB200_F_RAW_RANGE (value space).  EQ is the one-value range; NEQ / IN /
+// NOT_IN and the other raw types stay with the reference's operator.
+bool raw_leaf(const HostColumn& c, const pb200h_filter_node& n, const pb200h_literal* lits, pb200_filter_node& d) {
+  if (c.data_type != PB200_INT) return false;
+  const pb200h_literal* v = lits + n.values_offset;
+  if (n.type == PB200H_RANGE) {
+    d.op = PB200_F_RAW_RANGE;
+    d.raw_lo = n.lower_unbounded ? 0.0 : (double)v[0].i; d.raw_hi = n.upper_unbounded ? 0.0 : (double)v[1].i;
+    d.raw_flags = (n.lower_unbounded ? 1 : 0) | (n.upper_unbounded ? 2 : 0) | (n.lower_inclusive ? 0 : 4) | (n.upper_inclusive ? 0 : 8);
+    return true;
+  }
+  if (n.type == PB200H_EQ) { d.op = PB200_F_RAW_RANGE; d.raw_lo = d.raw_hi = (double)v[0].i; d.raw_flags = 0; return true; }
+  return false;
+}
+
 // One segment's device filter tree + the arrays its nodes point to.
 struct SegmentFilter {
   std::vector<pb200_filter_node> nodes;
@@ -134,7 +150,13 @@ int build_segment_filter(const pb200h_segment& seg, const pb200h_query& q, Segme
     const int ci = seg.column_index(n.column);
     if (ci < 0) { set_error("unknown column '%s'", n.column ? n.column : "(null)"); return PB200_E_INVALID; }
     const HostColumn& c = seg.cols[ci];
-    if (!c.has_dictionary) { set_error("predicate on raw column '%s' is not accelerated", c.name.c_str()); return PB200_E_UNSUPPORTED; }
+    if (!c.has_dictionary) {
+      d.column = ci;
+      if (!raw_leaf(c, n, q.literals, d)) { set_error("this predicate on raw column '%s' is not accelerated", c.name.c_str()); return PB200_E_UNSUPPORTED; }
+      constant.push_back(0);
+      text.push_back(std::string("FILTER_FULL_SCAN(") + (n.type == PB200H_RANGE ? "RANGE," : "EQ,") + c.name + ")");
+      continue;
+    }
     Evaluated e = evaluate(c, n, q.literals);
     d.column = ci;
     if (e.always_false) { d.op = PB200_F_EMPTY; constant.push_back(2); text.push_back("FILTER_EMPTY"); continue; }
@@ -241,7 +263,11 @@ int leaf_to_device(const pb200h_segment& seg, int column, const pb200h_filter_no
                    SegmentFilterStore& store, pb200_filter_node& d) {
   memset(&d, 0, sizeof d);
   const HostColumn& c = seg.cols[column];
-  if (!c.has_dictionary) { set_error("predicate on raw column '%s' is not accelerated", c.name.c_str()); return PB200_E_UNSUPPORTED; }
+  if (!c.has_dictionary) {
+    d.column = column;
+    if (!raw_leaf(c, n, lits, d)) { set_error("this predicate on raw column '%s' is not accelerated", c.name.c_str()); return PB200_E_UNSUPPORTED; }
+    return PB200_OK;
+  }
   Evaluated e = evaluate(c, n, lits);
   d.column = column;
   if (e.always_false) { d.op = PB200_F_EMPTY; return PB200_OK; }
@@ -534,6 +560,14 @@ extern "C" int32_t pb200h_segment_load_dir(pb200_ctx* ctx, const char* path, pb2
     const std::string dt = get("dataType");
     int type = dt == "INT" ? PB200_INT : dt == "LONG" ? PB200_LONG : dt == "FLOAT" ? PB200_FLOAT : dt == "DOUBLE" ? PB200_DOUBLE : dt == "STRING" ? PB200_STRING : -1;
     if (type < 0) continue;
+    // Only zero padding of STRING dictionaries is supported, as in the reference (ColumnMetadataImpl.java:250-253
+    // "Only support zero padding"; segments written before segment.padding.character existed pad with '%').  The
+    // reference refuses such a segment as a whole; here the STRING columns are left out and the numeric ones load.
+    if (type == PB200_STRING) {
+      auto pad = meta.find("segment.padding.character");
+      const bool zero = pad != meta.end() && (pad->second == "\\u0000" || pad->second == std::string(1, '\0') || pad->second == "\\0");
+      if (!zero) continue;
+    }
     const bool has_dict = get("hasDictionary") != "false";
     const bool sorted = get("isSorted") == "true" && has_dict;
     Bufs b;
@@ -662,7 +696,10 @@ extern "C" int32_t pb200h_execute(pb200_ctx* ctx, const pb200h_query* q, pb200h_
     dq.num_aggs = q->num_aggs;
     dq.num_groups_limit = q->num_groups_limit > 0 ? q->num_groups_limit : 100000;
     dq.max_initial_result_holder_capacity = q->max_initial_result_holder_capacity > 0 ? q->max_initial_result_holder_capacity : 10000;
-    dq.flags = PB200_Q_PER_SEGMENT_FILTER | (merge ? PB200_Q_MERGE_SEGMENTS : 0) | (q->merge_segments == 2 ? PB200_Q_DEFER_FINALIZE : 0);
+    dq.flags = PB200_Q_PER_SEGMENT_FILTER | (merge ? PB200_Q_MERGE_SEGMENTS : 0) | (q->merge_segments == 2 ? PB200_Q_DEFER_FINALIZE : 0) |
+               (q->no_count_carrier ? PB200_Q_NO_COUNT_CARRIER : 0);
+    dq.reduce_world = q->reduce_world;
+    dq.merged_docs_bound = q->merged_docs_bound;
     dq.filter = flat.data();
     dq.group_by_columns = gb.data();
     dq.aggs = aggs.data();

@@ -230,7 +230,8 @@ extern "C" int32_t pb200_init(int32_t device, pb200_ctx** out) {
     t.dense_max = env_i("PB200_DENSE_MAX", t.dense_max);
     t.defer = getenv("PB200_NO_DEFER") ? 0 : 1;
     t.gb_defer = getenv("PB200_NO_GB_DEFER") ? 0 : 1;
-    t.sparse_max_gb = (int)env_i("PB200_SPARSE_MAX_GB", t.sparse_max_gb);
+    t.pack_count = getenv("PB200_NO_PACK_COUNT") ? 0 : 1;
+    t.pack_shift = (int)env_i("PB200_PACK_SHIFT", 0);
     t.skip = getenv("PB200_NO_SKIP") ? 0 : 1;
     t.always_count = getenv("PB200_ALWAYS_COUNT") ? 1 : 0;
   }
@@ -255,7 +256,8 @@ extern "C" int32_t pb200_tuning_set(pb200_ctx* ctx, const char* name, int64_t va
   else if (n == "dense_max") t.dense_max = value;
   else if (n == "defer") t.defer = value != 0;
   else if (n == "gb_defer") t.gb_defer = value != 0;
-  else if (n == "sparse_max_gb") t.sparse_max_gb = (int)value;
+  else if (n == "pack_count") t.pack_count = value != 0;
+  else if (n == "pack_shift") t.pack_shift = (int)value;
   else if (n == "skip") t.skip = value != 0;
   else if (n == "always_count") t.always_count = value != 0;
   else { set_error("unknown tuning knob '%s'", name); return PB200_E_INVALID; }
@@ -542,7 +544,7 @@ int slot_of(Plan& p, int col, uint32_t role) {
   return (int)p.slot_cols.size() - 1;
 }
 
-bool is_scan_leaf(int op) { return op == PB200_F_SCAN_RANGE || op == PB200_F_SCAN_IN || op == PB200_F_SCAN_NOT_IN; }
+bool is_scan_leaf(int op) { return op == PB200_F_SCAN_RANGE || op == PB200_F_SCAN_IN || op == PB200_F_SCAN_NOT_IN || op == PB200_F_RAW_RANGE; }
 bool is_leaf(int op) { return op >= PB200_F_MATCH_ALL; }
 
 int regime_of(const std::vector<int>& cards, int array_threshold) {
@@ -583,8 +585,35 @@ cudaError_t launch_scan_variant(const ScanVariant& v, size_t smem_bytes, int gri
 }  // namespace pb200
 
 
+// Internal return code of execute_impl: a count-carrying sum overflowed its field (detected exactly, see the verification
+// after the launch) -- the caller runs the submission again with separate COUNT reductions.
+constexpr int kRetryWithoutCountCarrier = 1;
+static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment* const* segments, int32_t nseg,
+                        pb200_result** results, bool allow_count_carrier);
+
 extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200_segment* const* segments,
                                  int32_t nseg, pb200_result** results) {
+  int rc = execute_impl(ctx, query, segments, nseg, results, true);
+  if (rc == kRetryWithoutCountCarrier) rc = execute_impl(ctx, query, segments, nseg, results, false);
+  return rc;
+}
+
+// Per result: sum over the table of the carried counts, and the largest low field (pb200_execute's verification).
+__global__ void carrier_verify_kernel(const unsigned long long* __restrict__ tab, long long n, int shift, unsigned long long* __restrict__ out) {
+  unsigned long long c = 0, mx = 0;
+  const unsigned long long mask = (1ull << shift) - 1ull;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long v = tab[i];
+    c += v >> shift;
+    mx = max(mx, v & mask);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xFFFFFFFFu, c, o); mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o)); }
+  if ((threadIdx.x & 31) == 0) { if (c) atomicAdd(out, c); if (mx) atomicMax(out + 1, mx); }
+}
+
+static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment* const* segments, int32_t nseg,
+                        pb200_result** results, bool allow_count_carrier) {
   if (!ctx || !query || !segments || !results || nseg <= 0) { set_error("invalid argument to pb200_execute"); return PB200_E_INVALID; }
   PB200_CUDA(cudaSetDevice(ctx->device));
   const bool per_seg_filter = query->flags & PB200_Q_PER_SEGMENT_FILTER;
@@ -642,7 +671,6 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   for (int s = 0; s < (per_seg_filter ? nseg : 1); s++) {
     for (int i = 0; i < nnodes; i++) {
       const pb200_filter_node& n = f0[(size_t)s * nnodes + i];
-      if (n.op == PB200_F_RAW_RANGE) { set_error("raw-value range predicates are not accelerated yet"); return PB200_E_UNSUPPORTED; }
       if (is_leaf(n.op) != is_leaf(f0[i].op) || (!is_leaf(n.op) && (n.op != f0[i].op || n.num_children != f0[i].num_children))) {
         set_error("per-segment filter trees must share their shape"); return PB200_E_INVALID;
       }
@@ -881,7 +909,22 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         for (int k = 0; k < q.num_slots; k++) if (plan.slot_cols[k] == n.column) slot = k;
         if (slot < 0) { set_error("scan leaf column %d has no slot (per-segment trees must scan the same columns)", n.column); return PB200_E_INVALID; }
         lf.slot = slot;
-        if (n.op == PB200_F_SCAN_RANGE) {
+        if (n.op == PB200_F_RAW_RANGE) {
+          // Raw (no-dictionary) INT column, value-space range: IntRawValueBasedRangePredicateEvaluator
+          // (core/operator/filter/predicate/RangePredicateEvaluatorFactory.java:227-262).  On two's complement words
+          // lo <= x <= hi  <=>  (uint32)(x - lo) < (uint32)(hi - lo + 1): the dictId range compare of the kernel, unchanged.
+          if (c.bits != 32 || c.dict_native || c.stored_type != PB200_INT) { set_error("RAW_RANGE is accelerated for raw INT columns only (column %d)", n.column); return PB200_E_UNSUPPORTED; }
+          double dlo = (n.raw_flags & 1) ? -2147483648.0 : std::ceil(n.raw_lo), dhi = (n.raw_flags & 2) ? 2147483647.0 : std::floor(n.raw_hi);
+          if (!(n.raw_flags & 1) && (n.raw_flags & 4) && dlo == n.raw_lo) dlo += 1.0;   // exclusive bounds on integral literals
+          if (!(n.raw_flags & 2) && (n.raw_flags & 8) && dhi == n.raw_hi) dhi -= 1.0;
+          dlo = std::max(dlo, -2147483648.0); dhi = std::min(dhi, 2147483647.0);
+          if (!(dlo <= dhi)) { lf.kind = LEAF_NONE; lf.slot = -1; continue; }   // also catches NaN bounds
+          const long long lo = (long long)dlo, hi = (long long)dhi;
+          if (hi - lo + 1 >= (1ll << 32)) { lf.kind = LEAF_ALL; lf.slot = -1; continue; }
+          lf.kind = LEAF_RANGE;
+          lf.lo = (uint32_t)(int32_t)lo; lf.span = (uint32_t)(hi - lo + 1);
+          lf.cmp = CMP_BOTH;   // one-sided shortcuts assume unsigned order
+        } else if (n.op == PB200_F_SCAN_RANGE) {
           lf.kind = LEAF_RANGE;
           int lo = std::max(n.lo, 0), hi = std::max(n.hi, lo);
           lf.lo = (uint32_t)lo; lf.span = (uint32_t)(hi - lo);
@@ -1018,11 +1061,6 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         sd.agg_code[n++] = agg_code(a, q.aggs[a].function, q.aggs[a].val_kind, sl.bits, sl.stage_words);
       }
     sd.num_defer_codes = plan.group_by ? npipe : 0;
-    if (plan.group_by && s == 0) {  // every aggregation that reads a column is pipelined: the per-thread sparse path applies
-      q.gb_simple = (npipe == n && tune.gb_defer && q.smem_groups == 0) ? 1 : 0;
-      q.sparse_max_gb = tune.sparse_max_gb;
-    }
-    sd.num_agg_codes = n;
   }
 
   // ---- outputs ----
@@ -1036,17 +1074,25 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     ~PinnedScratch() { pinned_free(c, p, bytes); }
   } pacc{ctx};
   {
-    int rc = pinned_alloc(ctx, 2 * sizeof(AggAccum) * nres, &pacc.p, &pacc.bytes);
+    int rc = pinned_alloc(ctx, 2 * (sizeof(AggAccum) + 16) * nres, &pacc.p, &pacc.bytes);
     if (rc) return rc;
   }
-  AggAccum* host_acc = static_cast<AggAccum*>(pacc.p) + nres;  // [0, nres): initial values, [nres, 2 nres): read-back
+  // block layout (device and both pinned halves): nres AggAccum records, then 2 words per result for the count-carrier
+  // verification {sum of carried counts, largest low field}
+  const size_t acc_bytes = (sizeof(AggAccum) + 16) * nres;
+  unsigned char* const pin_init = static_cast<unsigned char*>(pacc.p);
+  unsigned char* const pin_back = pin_init + acc_bytes;
+  AggAccum* host_acc = reinterpret_cast<AggAccum*>(pin_back);
+  const unsigned long long* host_verify = reinterpret_cast<const unsigned long long*>(pin_back + sizeof(AggAccum) * nres);
   {
-    AggAccum* init = static_cast<AggAccum*>(pacc.p);
+    memset(pin_init, 0, acc_bytes);
+    AggAccum* init = reinterpret_cast<AggAccum*>(pin_init);
     for (int r = 0; r < nres; r++) init[r] = init_acc;
-    int rc = accum_buf.alloc(ctx, sizeof(AggAccum) * nres);
+    int rc = accum_buf.alloc(ctx, acc_bytes);
     if (rc) return rc;
-    PB200_CUDA(cudaMemcpyAsync(accum_buf.p, init, sizeof(AggAccum) * nres, cudaMemcpyHostToDevice, st));
+    PB200_CUDA(cudaMemcpyAsync(accum_buf.p, pin_init, acc_bytes, cudaMemcpyHostToDevice, st));
   }
+  unsigned long long* const dev_verify = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(accum_buf.p) + sizeof(AggAccum) * nres);
   for (int s = 0; s < nseg; s++) {
     const pb200_segment* seg = segments[s];
     SegDesc& sd = plan.segs[s];
@@ -1137,7 +1183,50 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         need_count |= q.aggs[a].function == PB200_AGG_COUNT || q.aggs[a].function == PB200_AGG_AVG;
         has_minmax |= q.aggs[a].function == PB200_AGG_MIN || q.aggs[a].function == PB200_AGG_MAX;
       }
-      const bool need_seen = !need_count && !has_minmax && !hashed;  // a hash table's keys mark the groups that exist
+      bool need_seen = !need_count && !has_minmax && !hashed;  // a hash table's keys mark the groups that exist
+      // ---- count carrier.  Every RED into the tables is an L2 read-modify-write, and on this path the L2 sector rate is
+      // the bound (lts__t_sectors ~ 3.7x the streamed bytes at 10 % selectivity, profiles/r2_*).  When the query needs the
+      // per-group row count (COUNT / AVG, or only as the group-exists marker) and sums an INT dictionary column, the
+      // count rides in the upper bits of that sum: each row adds (value - min) + 2^shift with ONE reduction.  shift =
+      // 64 - bits(docs that can reach the table), so the count field cannot overflow; the sum field can (a group whose
+      // sum of (value - min) reaches 2^shift) -- which is detected EXACTLY after the launch: every overflow carries
+      // into the count field, counts only ever grow (value - min >= 0), so sum_g count_g == matched docs iff nothing
+      // overflowed (the table total cannot wrap 2^64 since docs x 2^32 / 2^shift < 2^bits(docs) for shift >= 32).  On a
+      // mismatch the submission runs again with a separate COUNT table (kRetryWithoutCountCarrier).
+      d.pack_agg = -1;
+      const bool deferred = merge && (query->flags & PB200_Q_DEFER_FINALIZE);
+      d.reduce_world = deferred ? std::max(query->reduce_world, 1) : 1;
+      if (allow_count_carrier && !(query->flags & PB200_Q_NO_COUNT_CARRIER) && tune.pack_count && q.smem_groups == 0 &&
+          (need_count || need_seen)) {
+        unsigned long long docs = 0;
+        for (int s = 0; s < nseg; s++) if (merge || s == r) docs += (unsigned long long)segments[s]->num_docs;
+        // a table that will be summed with the other GPUs' tables: size the fields for the docs of ALL of them (every rank
+        // must arrive at the same shift, hence the explicit bound)
+        if (deferred) docs = query->merged_docs_bound > 0 ? (unsigned long long)query->merged_docs_bound : docs * (unsigned long long)d.reduce_world;
+        int bits = 1;
+        while (bits < 64 && (docs >> bits)) bits++;
+        for (int a = 0; a < nagg && d.pack_agg < 0; a++) {
+          const int fn = q.aggs[a].function;
+          if ((fn != PB200_AGG_SUM && fn != PB200_AGG_AVG) || q.aggs[a].val_kind != VAL_DICT_I32) continue;
+          if (bits > 32) break;
+          long long vmin = std::numeric_limits<long long>::max();
+          bool ok = true;
+          for (int s = 0; s < nseg && ok; s++) {
+            if (!merge && s != r) continue;
+            const DeviceColumn& c = segments[s]->cols[query->aggs[a].column];
+            if (c.dict_host.size() < 4 || c.stored_type != PB200_INT) { ok = false; break; }
+            // the other GPUs must subtract the SAME minimum: only a table-wide (domain) dictionary guarantees that
+            if (d.reduce_world > 1 && !c.dict_shared) { ok = false; break; }
+            int32_t v0; memcpy(&v0, c.dict_host.data(), 4);   // sorted dictionary: entry 0 is the minimum
+            vmin = std::min<long long>(vmin, v0);
+          }
+          if (!ok) continue;
+          d.pack_agg = a;
+          d.pack_shift = tune.pack_shift > 0 ? tune.pack_shift : 64 - bits;
+          d.pack_vmin = vmin;
+        }
+        if (d.pack_agg >= 0) { need_count = false; need_seen = false; }
+      }
       long long n_i64 = need_count ? 1 : 0, n_f64 = 0, n_max = need_seen ? 1 : 0, n_min = 0;
       for (int a = 0; a < nagg; a++) {
         const int fn = q.aggs[a].function, vk = q.aggs[a].val_kind;
@@ -1166,6 +1255,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
         if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
           if (sum_in_double(vk)) d.dsum[a] = (double*)d.f64_block + (fi++) * groups;
           else d.isum[a] = (long long*)d.i64_block + (ii++) * groups;
+          if (a == d.pack_agg) d.exists_packed = (const unsigned long long*)d.isum[a];
         } else if (fn == PB200_AGG_MIN) { d.gmin[a] = (uint32_t*)d.u32min_block + (ni++) * groups; if (!need_count && !d.exists_max && !d.exists_min) d.exists_min = d.gmin[a]; }
         else if (fn == PB200_AGG_MAX) { d.gmax[a] = (uint32_t*)d.u32max_block + (xi++) * groups; if (!need_count && !d.exists_max && !d.exists_min) d.exists_max = d.gmax[a]; }
         else if (fn == PB200_AGG_DISTINCTCOUNT) {  // one dictId bitset per group / slot
@@ -1188,6 +1278,10 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
       pb200_result::Dense& d = res[merge ? 0 : s]->dense;
       sd.g_count = d.count;
       sd.g_seen = d.seen;
+      for (int a = 0; a < nagg; a++) {
+        sd.sum_addend[a] = 0ull - (1ull << 31);  // plain INT-dictionary sum: remove the device copy's bias
+        if (a == d.pack_agg) sd.sum_addend[a] = (1ull << d.pack_shift) - (unsigned long long)((uint32_t)(int32_t)d.pack_vmin ^ 0x80000000u);
+      }
       for (int a = 0; a < nagg; a++) { sd.g_isum[a] = d.isum[a]; sd.g_dsum[a] = d.dsum[a]; sd.g_min[a] = d.gmin[a]; sd.g_max[a] = d.gmax[a]; sd.distinct_bits[a] = d.dbits[a]; sd.distinct_words[a] = d.dwords[a]; }
       for (int g = 0; g < ngb; g++) { sd.group_mult[g] = d.mult[g]; sd.group_mult64[g] = d.mult64[g]; }
       sd.h_keys = d.hkeys;
@@ -1250,9 +1344,37 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   }
   if (le != cudaSuccess) { set_error("scan kernel launch failed: %s (smem %zu B, grid %d)", cudaGetErrorString(le), plan.smem_bytes, grid); return PB200_E_CUDA; }
   PB200_CUDA(cudaEventRecord(e1, st));
-  PB200_CUDA(cudaMemcpyAsync(host_acc, accum_buf.p, sizeof(AggAccum) * nres, cudaMemcpyDeviceToHost, st));
+  if (plan.group_by)
+    for (int r = 0; r < nres; r++) {
+      const pb200_result::Dense& d = res[r]->dense;
+      if (d.pack_agg < 0) continue;
+      const int vb = (int)std::max<long long>(1, std::min<long long>((d.groups + 1023) / 1024, 148 * 4));
+      carrier_verify_kernel<<<vb, 256, 0, st>>>((const unsigned long long*)d.isum[d.pack_agg], d.groups, d.pack_shift, dev_verify + 2 * r);
+    }
+  PB200_CUDA(cudaMemcpyAsync(pin_back, accum_buf.p, acc_bytes, cudaMemcpyDeviceToHost, st));
   cudaError_t se = cudaStreamSynchronize(st);
   if (se != cudaSuccess) { set_error("scan kernel failed: %s", cudaGetErrorString(se)); return PB200_E_CUDA; }
+  if (plan.group_by)
+    for (int r = 0; r < nres; r++) {
+      const pb200_result::Dense& d = res[r]->dense;
+      if (d.pack_agg < 0) continue;
+      // cross-GPU: the reduce adds `reduce_world` low fields; it cannot overflow if every rank's largest one stays below
+      // 2^shift / reduce_world.  A rank cannot rerun on its own (its peers' tables would have another layout): it marks
+      // the result and the combine layer reruns the query on all ranks (PB200_Q_NO_COUNT_CARRIER).
+      const bool exact = host_verify[2 * r] == host_acc[r].count;
+      if (d.reduce_world > 1) {
+        const unsigned long long lim = ((1ull << d.pack_shift) - 1ull) / (unsigned long long)d.reduce_world;
+        res[r]->dense.carrier_unsafe = !exact || host_verify[2 * r + 1] > lim;
+        continue;
+      }
+      if (exact) continue;
+      if (d.hctl) {  // a hash table that refused rows (numGroupsLimit) also loses counts: that is PB200_E_LIMIT, reported by the extraction
+        uint32_t ctl[2] = {0, 0};
+        PB200_CUDA(cudaMemcpy(ctl, d.hctl, 8, cudaMemcpyDeviceToHost));
+        if (ctl[1]) continue;
+      }
+      return kRetryWithoutCountCarrier;  // ResultCleanup frees the tables
+    }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
 
@@ -1320,6 +1442,7 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
     } else {
       std::vector<int> cards = R.dense.cards;
       R.meta.regime = regime_of(cards, query->max_initial_result_holder_capacity);
+      R.meta.reserved = (R.dense.pack_agg >= 0 ? 1 : 0) | (R.dense.carrier_unsafe ? 2 : 0);  // include/pinot_b200.h pb200_result_meta.reserved
     }
   }
   const bool defer_finalize = merge && (query->flags & PB200_Q_DEFER_FINALIZE);

@@ -104,6 +104,11 @@ struct SegDesc {
   uint32_t h_mask;
   int32_t h_limit;
   unsigned long long group_mult64[kMaxGroupBy];
+  // group-by SUM / AVG over an INT dictionary: the 64-bit value added to the table is (zero-extended biased dictionary
+  // word) + sum_addend[a].  Plain sums: -2^31 (removes the bias).  The sum that CARRIES the row count of its group
+  // (pb200_api.cu "count carrier"): 2^shift - biased(min value), i.e. one reduction adds (value - min) to the low `shift`
+  // bits and 1 to the bits above them -- the separate COUNT reduction (an L2 read-modify-write per surviving row) is gone.
+  unsigned long long sum_addend[kMaxAggs];
 };
 
 // Everything lane 0 needs to refill a warp's TMA ring, for every segment of the launch, passed BY VALUE as a kernel
@@ -173,9 +178,7 @@ struct QueryDesc {
   int32_t queue_max;
   int8_t smem_slot[kMaxAggs];  // aggregation -> index of its (lo, hi) pair, -1: none (COUNT)
   int8_t pad_tail[2];
-  // group-by fast path for few survivors per thread (pb200_scan.cuh): COUNT + <= 2 pipelined aggregations, dense tables
-  int32_t gb_simple;
-  int32_t sparse_max_gb;   // taken when no thread of the warp has more surviving rows than this
+  int32_t reserved_tail[2];
 };
 
 // ---- shared-memory header of the scan kernel (the host sizes the dynamic shared memory with it) ----

@@ -34,6 +34,9 @@ struct ExtractDesc {
   const uint32_t* maxk;
   const uint32_t* mink;
   const unsigned long long* hkeys;
+  const unsigned long long* packed;  // count-carrying sum table (pb200_api.cu): sum(value - vmin) + count << shift
+  long long pack_vmin;
+  int32_t pack_agg, pack_shift;
   long long groups;                  // table entries (dense: raw key space, hash: capacity)
   int32_t ngb, nagg;
   uint32_t cards[kMaxGroupBy];
@@ -49,6 +52,7 @@ struct ExtractDesc {
 
 __device__ __forceinline__ bool non_empty(const ExtractDesc& d, long long i) {
   if (d.hkeys) return d.hkeys[i] != ~0ull;
+  if (d.packed) return d.packed[i] != 0ull;
   return (d.count && d.count[i] != 0ull) || (d.seen && d.seen[i] != 0u) || (d.maxk && d.maxk[i] != 0u) || (d.mink && d.mink[i] != 0xFFFFFFFFu);
 }
 __device__ __forceinline__ int find_result(const ExtractDesc* descs, int nres, uint32_t chunk) {
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(kExtractThreads) extract_write_kernel(const Ex
       for (int k = 0; k < d.ngb; ++k) { kp[k] = (int32_t)(raw % d.cards[k]); raw /= d.cards[k]; }
     }
     if (d.off_idx != kNoCol) reinterpret_cast<uint32_t*>(out + d.off_idx)[row] = (uint32_t)g;
-    const unsigned long long cnt = d.count ? d.count[g] : 0ull;
+    const unsigned long long cnt = d.packed ? d.packed[g] >> d.pack_shift : (d.count ? d.count[g] : 0ull);
     for (int a = 0; a < d.nagg; ++a) {
       const int fn = d.fn[a], vk = d.vk[a];
       double dv = 0.0;
@@ -138,7 +142,12 @@ __global__ void __launch_bounds__(kExtractThreads) extract_write_kernel(const Ex
       int32_t id = -1;
       if (fn == PB200_AGG_COUNT) { lv = (long long)cnt; dv = (double)cnt; }
       else if (fn == PB200_AGG_SUM || fn == PB200_AGG_AVG) {
-        dv = sum_in_double(vk) ? static_cast<const double*>(d.src[a])[g] : (double)static_cast<const long long*>(d.src[a])[g];
+        if (a == d.pack_agg) {  // low field = sum(value - vmin): exact integer arithmetic, then to double like every sum
+          const unsigned long long f = d.packed[g] & ((1ull << d.pack_shift) - 1ull);
+          dv = (double)((long long)f + (long long)cnt * d.pack_vmin);
+        } else {
+          dv = sum_in_double(vk) ? static_cast<const double*>(d.src[a])[g] : (double)static_cast<const long long*>(d.src[a])[g];
+        }
         lv = (long long)cnt;
       } else if (fn == PB200_AGG_MIN || fn == PB200_AGG_MAX) {
         const uint32_t t = static_cast<const uint32_t*>(d.src[a])[g];
@@ -199,6 +208,7 @@ int extract_groups(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cudaStream
     ExtractDesc& e = descs[r];
     memset(&e, 0, sizeof e);
     e.count = d.count; e.seen = d.seen; e.maxk = d.exists_max; e.mink = d.exists_min; e.hkeys = d.hkeys;
+    e.packed = d.exists_packed; e.pack_agg = d.pack_agg; e.pack_shift = d.pack_shift; e.pack_vmin = d.pack_vmin;
     e.groups = d.groups;
     e.ngb = (int)d.cards.size();
     e.nagg = (int)d.aggs.size();

@@ -66,7 +66,8 @@ struct Tuning {
   long long dense_max = 1ll << 24;   // PB200_DENSE_MAX: dense group table up to this many raw keys, hash table beyond
   int defer = 1;                 // !PB200_NO_DEFER: software-pipelined gathers, aggregation-only kernel
   int gb_defer = 1;              // !PB200_NO_GB_DEFER: software-pipelined last queue batch, group-by kernel
-  int sparse_max_gb = 12;        // PB200_SPARSE_MAX_GB: group-by rows walked per thread (no queue) up to this many survivors per thread
+  int pack_count = 1;            // !PB200_NO_PACK_COUNT: group-by COUNT carried inside an INT SUM's reductions (pb200_api.cu)
+  int pack_shift = 0;            // PB200_PACK_SHIFT: force the carrier's count shift (tests of the overflow fallback); 0 = from the doc count
   int skip = 1;                  // !PB200_NO_SKIP: bitmap-driven slice skipping
   int always_count = 0;          // PB200_ALWAYS_COUNT
 };
@@ -146,6 +147,12 @@ struct pb200_result {
     uint32_t* seen = nullptr;                    // group-exists flags (inside the u32max block) or NULL
     uint32_t* exists_max = nullptr;              // a MAX table doubling as the group-exists marker, or NULL
     uint32_t* exists_min = nullptr;              // a MIN table doubling as the group-exists marker, or NULL
+    // count carrier (pb200_api.cu): aggregation pack_agg's int64 table holds  sum(value - pack_vmin) + count << pack_shift
+    int pack_agg = -1, pack_shift = 0;
+    long long pack_vmin = 0;
+    const unsigned long long* exists_packed = nullptr;  // that table: non-zero <=> the group exists
+    int reduce_world = 1;                               // tables of this many GPUs will be summed into it
+    bool carrier_unsafe = false;                        // its sum field may overflow in that reduce: rerun without carrier
     long long* isum[pb200::kMaxAggs] = {};
     double* dsum[pb200::kMaxAggs] = {};
     uint32_t* gmin[pb200::kMaxAggs] = {};

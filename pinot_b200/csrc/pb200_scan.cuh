@@ -440,10 +440,13 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
 #pragma unroll
                 for (int u = 0; u < kQB; ++u) if ((pend_ok >> u) & 1u) red_add_f64(t + pg[u], (double)__uint_as_float(px[k][u]));
               } else {
+                // device INT dictionaries are biased (value + 2^31): the addend removes the bias -- or, when this sum
+                // CARRIES the group's row count (SegDesc.sum_addend), re-bases the value to (value - min) + 2^shift
                 unsigned long long* t = reinterpret_cast<unsigned long long*>(sd.g_isum[a]);
+                const unsigned long long addend = sd.sum_addend[a];
 #pragma unroll
                 for (int u = 0; u < kQB; ++u)
-                  if ((pend_ok >> u) & 1u) red_add_u64(t + pg[u], (unsigned long long)(long long)(int)(px[k][u] ^ 0x80000000u));
+                  if ((pend_ok >> u) & 1u) red_add_u64(t + pg[u], (unsigned long long)px[k][u] + addend);
               }
             } else if (fn == 2) {
               uint32_t* t = sd.g_min[a];
@@ -697,89 +700,6 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
     };
     bool handled = false;
     if (GROUPBY && wmax2 == 0) handled = true;
-    if (GROUPBY && !handled && q.gb_simple && wmax2 <= q.sparse_max_gb && !sd.h_keys) {
-      // ---- few survivors per thread, simple shape (COUNT + at most kGD pipelined aggregations, dense table): every
-      //      thread walks ITS OWN surviving rows -- no compaction, no queue traffic, no warp scan.  The loop is warp-uniform
-      //      (wmax2 iterations, lanes without a row left are predicated off), a row costs two extractions straight from
-      //      the thread's own words (FixedBitIntReader.readUnchecked shape), one dictionary gather and the reductions.
-      //      The first kQB rows of each thread are software-pipelined exactly like the queue's last batch: loads issued
-      //      here, reductions after the next tile's filter (drain_gb); later rows (rare at <= 12 % selectivity) reduce
-      //      at once.  At 10 % selectivity this is ~520 warp instructions per slice instead of ~800 through the queue.
-      const int ncodes = sd.num_agg_codes;   // == num_defer_codes here (host rule for gb_simple)
-      uint32_t ac[kGD];
-      const uint32_t* abase[kGD];
-#pragma unroll
-      for (int k = 0; k < kGD; ++k) {
-        ac[k] = k < ncodes ? sd.agg_code[k] : 0u;
-        abase[k] = st + (ac[k] >> 18) + group_in_stage * (int)((ac[k] >> 12) & 63u);
-      }
-      uint32_t mm = m, okm = 0;
-      auto key_of = [&](int j) {
-        uint32_t g = 0;
-#pragma unroll 1
-        for (int gi = 0; gi < q.num_group_by; ++gi) {
-          const SlotDesc& sl = sd.slots[hdr->group_slot[gi]];
-          g += read_one_group(st + sl.stage_words + group_in_stage * sl.bits, j, sl.bits) * sd.group_mult[gi];
-        }
-        return g;
-      };
-      auto mark = [&](uint32_t g, bool has) {
-        if (sd.g_count) { if (has) red_add_u64(sd.g_count + g, 1ull); }
-        else if (sd.g_seen) { if (has) sd.g_seen[g] = 1u; }
-      };
-#pragma unroll
-      for (int u = 0; u < kQB; ++u) {
-        if (u < wmax2) {
-          const bool has = mm != 0u;
-          const int j = has ? 31 - __clz(mm) : 0;
-          mm &= ~(1u << j);
-          const uint32_t g = key_of(j);
-          pg[u] = g;
-          okm |= (has ? 1u : 0u) << u;
-          mark(g, has);
-#pragma unroll
-          for (int k = 0; k < kGD; ++k) {
-            if (k < ncodes) {
-              const int a = (int)(ac[k] & 7u), fn = (int)((ac[k] >> 4) & 7u), vk = (int)((ac[k] >> 8) & 7u);
-              const uint32_t id = read_one_group(abase[k], j, (int)((ac[k] >> 12) & 63u));
-              if (fn == 1 || fn == 4) {
-                px[k][u] = (uint32_t)ldg_pred_s32(reinterpret_cast<const int*>(static_cast<const uint32_t*>(sd.dict[a]) + id), has ? 1u : 0u);
-              } else {
-                const uint32_t* tab = fn == 2 ? sd.g_min[a] : sd.g_max[a];
-                pq[k][u] = id ^ (vk == VAL_RAW_I32 ? 0x80000000u : 0u);
-                px[k][u] = has ? __ldcg(tab + g) : (fn == 2 ? 0u : 0xFFFFFFFFu);
-              }
-            }
-          }
-        }
-      }
-      pend_ok = okm;
-      for (int it = kQB; it < wmax2; ++it) {   // rows beyond the pipelined ones: reduce immediately
-        const bool has = mm != 0u;
-        const int j = has ? 31 - __clz(mm) : 0;
-        mm &= ~(1u << j);
-        const uint32_t g = key_of(j);
-        mark(g, has);
-#pragma unroll
-        for (int k = 0; k < kGD; ++k) {
-          if (k < ncodes) {
-            const int a = (int)(ac[k] & 7u), fn = (int)((ac[k] >> 4) & 7u), vk = (int)((ac[k] >> 8) & 7u);
-            const uint32_t id = read_one_group(abase[k], j, (int)((ac[k] >> 12) & 63u));
-            if (fn == 1 || fn == 4) {
-              const uint32_t w = (uint32_t)ldg_pred_s32(reinterpret_cast<const int*>(static_cast<const uint32_t*>(sd.dict[a]) + id), has ? 1u : 0u);
-              if (has) {
-                if (vk == VAL_DICT_F32) red_add_f64(sd.g_dsum[a] + g, (double)__uint_as_float(w));
-                else red_add_u64(reinterpret_cast<unsigned long long*>(sd.g_isum[a]) + g, (unsigned long long)(long long)(int)(w ^ 0x80000000u));
-              }
-            } else if (has) {
-              const uint32_t x = id ^ (vk == VAL_RAW_I32 ? 0x80000000u : 0u);
-              if (fn == 2) atomicMin(sd.g_min[a] + g, x); else atomicMax(sd.g_max[a] + g, x + 1u);
-            }
-          }
-        }
-      }
-      handled = true;
-    }
     if (GROUPBY && !handled) {
       // ---- survivor queue: the warp's surviving rows are compacted into a shared-memory queue (exclusive scan of the
       //      per-thread counts), then the lanes take queue entries round-robin: every table update and dictionary gather
@@ -905,7 +825,7 @@ scan_kernel(const __grid_constant__ QueryDesc q, const __grid_constant__ TmaTabl
                 long long x[kQB];
 #pragma unroll
                 for (int u = 0; u < kQB; ++u)
-                  x[u] = vk == VAL_DICT_I32 ? (long long)(int)(__ldg(static_cast<const uint32_t*>(sd.dict[a]) + id[u]) ^ 0x80000000u)
+                  x[u] = vk == VAL_DICT_I32 ? (long long)((unsigned long long)__ldg(static_cast<const uint32_t*>(sd.dict[a]) + id[u]) + sd.sum_addend[a])
                                             : (long long)(int)id[u];
                 if (TG) {
                   uint32_t* lo = tcnt + tcopy + TA * (1u + 2u * q.smem_slot[a]);

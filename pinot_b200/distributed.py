@@ -6,22 +6,27 @@ What this replaces in the reference: the JVM-side merge of per-segment results b
 
 Segments are independent units (the reference already runs one task per segment), so the data path needs no
 collective: every rank scans its own segments with ``PB200_Q_MERGE_SEGMENTS`` (device-side combine into one dense table
-keyed by raw dictId key -- valid because the shards share dictionaries) and the tables meet exactly once:
+keyed by raw dictId key -- a merge by VALUE because the shards share dictionaries: synthetic tables by construction, real
+ones after ``DictionaryDomain`` binding, see ``global_domain``) and the tables meet exactly once:
 
     kind      contents                               reduce op        merge() it equals
     i64       COUNT(*) per group + integer SUMs       SUM              Count/Sum/Avg merge (a + b)
-    f64       FLOAT/DOUBLE SUMs                       SUM              Sum/Avg merge
+    f64       FLOAT/DOUBLE/LONG SUMs                  SUM              Sum/Avg merge
     u32max    MAX as (dictId + 1), 0 = empty          MAX              MaxAggregationFunction.merge
     u32min    MIN as dictId, 0xFFFFFFFF = empty       MIN              MinAggregationFunction.merge
 
 ``torch.distributed`` (NCCL over NVLink / NVSwitch) is plumbing only: the tensors handed to it alias the library's own
 device buffers (``pb200_result_device_buffers``), nothing is copied.  The tables are O(groups), not O(rows): the
 exchange is latency-bound (C4: 100 000 groups x (8+8+4) B = 2 MB per rank).
+
+The control flow (``execute_and_combine``) talks to the tables through a small backend interface so that the SAME code is
+exercised by the world_size-2 gloo test on CPU (tests/test_distributed_cpu.py, tables built from the oracle) and by the
+NCCL test on GPUs (tests/test_gpu_multi.py, ``DeviceBackend``).
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List
+from typing import Dict, List, Optional, Sequence
 
 
 KINDS = {"i64": 0, "f64": 1, "u32max": 2, "u32min": 3}
@@ -83,20 +88,144 @@ def device_buffers(ctx, block) -> Dict[str, "torch.Tensor"]:
     return out
 
 
-def combine_across_ranks(plan_maker, block, query, dist, dst: int = 0):
-    """All ranks call this with their merged block; rank `dst` gets the block of the whole table, others get None."""
-    import torch
-    from .plan_maker import _read_result
-    ctx = plan_maker.ctx
-    bufs = device_buffers(ctx, block)  # pb200_execute returned after its stream finished: the tables are complete
-    reduce_buffers(bufs, dist, dst)
-    torch.cuda.synchronize(ctx.device)  # the extraction below runs on the library's own stream
-    out = None
-    if dist.get_rank() == dst:
+class DeviceBackend:
+    """The tables of libpinot_b200.so results (the product path)."""
+
+    def __init__(self, plan_maker):
+        self.pm = plan_maker
+        self.ctx = plan_maker.ctx
+
+    def execute(self, segments, query, reduce_world: int, merged_docs_bound: int, no_count_carrier: bool):
+        """-> a merged, NOT yet extracted results block (dense tables on the device) with .count_carrier / .carrier_unsafe"""
+        return self.pm.execute_segments(segments, query, merge=True, keep_handle=True, reduce_world=reduce_world,
+                                        merged_docs_bound=merged_docs_bound, no_count_carrier=no_count_carrier)[0]
+
+    def buffers(self, block):
+        return device_buffers(self.ctx, block)
+
+    def flag_tensor(self, value: int):
+        import torch
+        return torch.tensor([value], dtype=torch.int32, device=f"cuda:{self.ctx.device}")
+
+    def synchronize(self):
+        import torch
+        torch.cuda.synchronize(self.ctx.device)  # the extraction runs on the library's own stream
+
+    def finish(self, block, query, is_root: bool):
         from . import _lib
-        _lib.check(ctx.lib.pb200_result_finalize(ctx.handle, block.handle))
-        out = _read_result(ctx, block.handle, query, 1, keep_handle=False)
-    else:
-        ctx.lib.pb200_result_free(block.handle)
-    block.handle = None
+        from .plan_maker import _read_result
+        out = None
+        if is_root:
+            _lib.check(self.ctx.lib.pb200_result_finalize(self.ctx.handle, block.handle))
+            out = _read_result(self.ctx, block.handle, query, 1, keep_handle=False)
+        else:
+            self.ctx.lib.pb200_result_free(block.handle)
+        block.handle = None
+        return out
+
+    def free(self, block):
+        if block.handle is not None:
+            self.ctx.lib.pb200_result_free(block.handle)
+            block.handle = None
+
+
+def combine_tables(backend, block, query, dist, dst: int = 0):
+    """All ranks call this with their merged, unextracted block: reduce of the tables to `dst`, which extracts the groups.
+
+    Count-carrying sums ("count carrier", pb200_api.cu: the per-group row count rides in the upper bits of an INT sum)
+    add field by field in the same int64 reduce; whether that is safe is decided per rank BEFORE the reduce (the rank's
+    largest sum field must leave room for the other ranks': block.carrier_unsafe) and agreed on with one 4-byte MAX
+    all-reduce that travels with the tables.  Returns (result or None, retry): retry == True on EVERY rank iff some rank
+    said unsafe -- then all ranks must run the query again without the carrier (the tables of all ranks must share one
+    layout, so the fallback is collective)."""
+    flag = None
+    if block.count_carrier:
+        flag = backend.flag_tensor(1 if block.carrier_unsafe else 0)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    reduce_buffers(backend.buffers(block), dist, dst)
+    backend.synchronize()
+    if flag is not None and int(flag.item()) != 0:
+        backend.free(block)
+        return None, True
+    return backend.finish(block, query, dist.get_rank() == dst), False
+
+
+def execute_and_combine(plan_maker_or_backend, segments: Sequence, query, dist, dst: int = 0, merged_docs_bound: int = 0):
+    """One query over the whole table: every rank scans its segments with the device-side combine, the per-GPU group tables
+    are reduced ONCE to rank `dst`, which gets the results block of the whole table (others get None)."""
+    backend = plan_maker_or_backend if hasattr(plan_maker_or_backend, "finish") else DeviceBackend(plan_maker_or_backend)
+    world = dist.get_world_size()
+    if not query.is_group_by:
+        return _combine_scalars(backend, segments, query, dist, dst)
+    for no_carrier in (False, True):
+        block = backend.execute(segments, query, world, merged_docs_bound, no_carrier)
+        out, retry = combine_tables(backend, block, query, dist, dst)
+        if not retry:
+            return out
+    raise AssertionError("unreachable: the second pass carries no counts")
+
+
+def _combine_scalars(backend, segments, query, dist, dst):
+    """Aggregation-only queries: a handful of scalars per rank (AggregationResultsBlockMerger.java:34-44)."""
+    import torch
+    block = backend.pm.execute_segments(segments, query, merge=True)[0]
+    fns = [a.function for a in query.aggregations]
+    if "DISTINCTCOUNT" in fns:
+        raise NotImplementedError("cross-GPU DISTINCTCOUNT (bitset OR) is not wired up")
+    dev = f"cuda:{backend.ctx.device}"
+    sums = torch.tensor([float(block.doubles[a][0]) if f in ("SUM", "AVG") else 0.0 for a, f in enumerate(fns)] +
+                        [float(block.longs[a][0]) for a in range(len(fns))] + [float(block.stats.num_docs_scanned)],
+                        dtype=torch.float64, device=dev)          # counts < 2^53: exact in float64
+    mins = torch.tensor([float(block.doubles[a][0]) if f == "MIN" else float("inf") for a, f in enumerate(fns)], dtype=torch.float64, device=dev)
+    maxs = torch.tensor([float(block.doubles[a][0]) if f == "MAX" else float("-inf") for a, f in enumerate(fns)], dtype=torch.float64, device=dev)
+    dist.reduce(sums, dst=dst, op=dist.ReduceOp.SUM)
+    if "MIN" in fns:
+        dist.reduce(mins, dst=dst, op=dist.ReduceOp.MIN)
+    if "MAX" in fns:
+        dist.reduce(maxs, dst=dst, op=dist.ReduceOp.MAX)
+    if dist.get_rank() != dst:
+        return None
+    n = len(fns)
+    sums, mins, maxs = sums.cpu().numpy(), mins.cpu().numpy(), maxs.cpu().numpy()
+    for a, f in enumerate(fns):
+        block.longs[a][0] = int(sums[n + a])
+        block.doubles[a][0] = mins[a] if f == "MIN" else maxs[a] if f == "MAX" else sums[a] if f in ("SUM", "AVG") else float(sums[n + a])
+        if f in ("MIN", "MAX"):
+            block.dict_ids[a][0] = -1   # ids are rank local unless the segments are bound to one domain
+    block.stats.num_docs_scanned = int(sums[2 * n])
+    return block
+
+
+def combine_across_ranks(plan_maker, block, query, dist, dst: int = 0):
+    """Reduce + extraction of an already executed block (merge=True, keep_handle=True; executed WITHOUT reduce_world, i.e.
+    with separate COUNT tables).  Rank `dst` gets the block of the whole table, others get None."""
+    if getattr(block, "count_carrier", False) and dist.get_world_size() > 1:
+        raise ValueError("a block whose counts ride in a sum must go through execute_and_combine (it sizes the packed fields "
+                         "for all ranks and agrees on the fallback collectively)")
+    out, _ = combine_tables(DeviceBackend(plan_maker), block, query, dist, dst)
     return out
+
+
+def global_domain(ctx, segments: Sequence, columns: Sequence[str], dist):
+    """Table-wide dictionaries across ALL ranks: every rank contributes the union of its own segments' dictionaries (built
+    by the library), the unions are all-gathered as bytes, and every rank builds the same global domain from them and binds
+    its segments.  After this the per-GPU tables share one id space: the reduce is a merge by value
+    (GroupByCombineOperator.java:130-146).  Returns the DictionaryDomain (release it when the table is dropped)."""
+    from . import _lib
+    from .plan_maker import DictionaryDomain
+    local = DictionaryDomain.build(ctx, segments, columns)
+    mine = {c: (local.dictionary_bytes(c).tobytes(), local.info(c)) for c in columns}
+    ids = list(local.column_ids)
+    local.release()
+    everyone: List[Optional[dict]] = [None] * dist.get_world_size()
+    dist.all_gather_object(everyone, mine)
+    import numpy as np
+    parts, widths, types = [], [], []
+    for c in columns:
+        parts.append([np.frombuffer(e[c][0], dtype=np.uint8) for e in everyone])
+        widths.append([e[c][1]["entry_bytes"] for e in everyone])
+        types.append(mine[c][1]["stored_type"])
+    dom = DictionaryDomain.from_dictionaries(ctx, columns, ids, types, parts, widths)
+    for s in segments:
+        s.bind_domain(dom)
+    return dom

@@ -267,6 +267,8 @@ class ResultsBlock:
     device_ms: float = 0.0
     operator_kind: str = "AGGREGATION"
     handle: Optional[C.c_void_p] = None  # kept only for merged results (multi-GPU combine)
+    count_carrier: bool = False  # the per-group row counts rode in an INT sum's reductions (pb200_api.cu)
+    carrier_unsafe: bool = False  # deferred result: that sum may overflow in the cross-GPU reduce, rerun without carrier
 
     def get_results(self, query: QueryContext) -> List[object]:
         """AggregationResultsBlock.getResults(): Long for COUNT, Double for SUM/MIN/MAX, (sum, count) for AVG,
@@ -284,7 +286,8 @@ class ResultsBlock:
         return out
 
 
-def _marshal_query(q: QueryContext, merge: bool):
+def _marshal_query(q: QueryContext, merge: bool, reduce_world: int = 0, no_count_carrier: bool = False,
+                   merged_docs_bound: int = 0):
     nodes = postfix(q.filter)
     keep: List[bytes] = []
     lits: List[_lib.HLiteral] = []
@@ -326,7 +329,8 @@ def _marshal_query(q: QueryContext, merge: bool):
         keep.append(nm)
         aggs[i] = _lib.HAgg(_lib.AGG_CODES[a.function], nm)
     hq = _lib.HQuery(len(nodes), c_nodes, c_lits, len(q.group_by), gb, len(q.aggregations), aggs, q.num_groups_limit,
-                     q.max_initial_result_holder_capacity, int(merge), int(not getattr(q, "use_star_tree", True)))
+                     q.max_initial_result_holder_capacity, int(merge), int(not getattr(q, "use_star_tree", True)),
+                     int(reduce_world), int(no_count_carrier), int(merged_docs_bound))
     return hq, (c_nodes, c_lits, gb, gb_names, aggs, keep)
 
 
@@ -357,6 +361,8 @@ def _read_result(ctx: B200Context, handle, q: QueryContext, kind: int, keep_hand
                                 meta.num_entries_scanned_post_filter, meta.num_total_docs)
     block = ResultsBlock(g, _lib.REGIMES[meta.regime], bool(meta.groups_limit_reached), stats, keys, doubles, longs,
                          ids, distinct, meta.device_ms, _lib.OPERATOR_KINDS.get(kind, "AGGREGATION"))
+    block.count_carrier = bool(meta.reserved & 1)
+    block.carrier_unsafe = bool(meta.reserved & 2)
     if keep_handle:
         block.handle = handle
     else:
@@ -399,6 +405,7 @@ class B200PlanMaker:
 
     def __init__(self, ctx: B200Context):
         self.ctx = ctx
+        self.last_device_ms = 0.0  # CUDA-event time of the scan kernel(s) of the latest execute_segments call
 
     def make_segment_plan_node(self, segment: IndexSegment, query: QueryContext) -> PlanNode:
         return PlanNode(self, segment, query)
@@ -412,18 +419,22 @@ class B200PlanMaker:
         return buf.value.decode()
 
     def execute_segments(self, segments: Sequence[IndexSegment], query: QueryContext, merge: bool = False,
-                         keep_handle: bool = False) -> List[ResultsBlock]:
+                         keep_handle: bool = False, reduce_world: int = 0, merged_docs_bound: int = 0,
+                         no_count_carrier: bool = False) -> List[ResultsBlock]:
         """All segments of one query in ONE device submission (makeInstancePlan-level batching).  With merge=True the
         segments (sharing dictionaries) are combined on the device and one block is returned; with keep_handle=True as
         well, a group-by block comes back WITHOUT its groups extracted (PB200_Q_DEFER_FINALIZE): its dense device tables
         are meant to be reduced across GPUs (pinot_b200.distributed.combine_across_ranks), which extracts on the root."""
         # merge + keep_handle: the caller reduces the dense tables across GPUs first; groups are extracted afterwards
-        hq, _keep = _marshal_query(query, 2 if (merge and keep_handle and query.is_group_by) else merge)
+        hq, _keep = _marshal_query(query, 2 if (merge and keep_handle and query.is_group_by) else merge, reduce_world,
+                                   no_count_carrier, merged_docs_bound)
         n = len(segments)
         segs = (C.c_void_p * n)(*[s.handle for s in segments])
         nres = 1 if merge else n
         res = (C.c_void_p * nres)()
         kinds = (C.c_int32 * n)()
         _lib.check(self.ctx.lib.pb200h_execute(self.ctx.handle, C.byref(hq), segs, n, res, kinds))
-        return [_read_result(self.ctx, C.c_void_p(res[i]), query, kinds[i if not merge else 0], keep_handle and merge)
-                for i in range(nres)]
+        blocks = [_read_result(self.ctx, C.c_void_p(res[i]), query, kinds[i if not merge else 0], keep_handle and merge)
+                  for i in range(nres)]
+        self.last_device_ms = blocks[0].device_ms
+        return blocks

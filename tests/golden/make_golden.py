@@ -126,6 +126,14 @@ def main():
                 data = tf.extractfile(m).read()
                 open(os.path.join(HERE, "padding_old_" + base.replace(".", "_") + ".bin"), "wb").write(data)
 
+    # ... and the whole directory as the reference wrote it (v1 layout: metadata.properties + one file per index), for the
+    # native segment-directory loader (tests/test_gpu_segment_dir.py)
+    with tarfile.open(f"{REF}/pinot-core/src/test/resources/data/paddingOld.tar.gz") as tf:
+        os.makedirs(os.path.join(HERE, "paddingOld"), exist_ok=True)
+        for m in tf.getmembers():
+            if m.isfile():
+                open(os.path.join(HERE, "paddingOld", os.path.basename(m.name)), "wb").write(tf.extractfile(m).read())
+
     st = f"{REF}/pinot-segment-local/src/test/resources/data/startree/segment"
     shutil.copyfile(f"{st}/star_tree_index", os.path.join(HERE, "star_tree_index.bin"))
     with open(f"{st}/star_tree_index_map") as f, open(os.path.join(HERE, "star_tree_index_map.txt"), "w") as g:
@@ -139,7 +147,8 @@ def main():
                     line.startswith(f"column.{c}.") for c in ("AirlineID", "Origin", "Dest", "ArrDelay")):
                 g.write(line)
     for fn in sorted(os.listdir(HERE)):
-        print(fn, os.path.getsize(os.path.join(HERE, fn)))
+        if os.path.isfile(os.path.join(HERE, fn)):
+            print(fn, os.path.getsize(os.path.join(HERE, fn)))
 
 
 if __name__ == "__main__":

@@ -17,7 +17,9 @@ MAGIC = struct.pack(">Q", 0xDEADBEEFDEAFBEAD)
 
 
 def _metadata_lines(seg, star_tree=None):
-    lines = [f"segment.name = {seg.name}", f"segment.total.docs = {seg.num_docs}"]
+    # segment.padding.character: SegmentColumnarIndexCreator.java:484 writes the zero pad character, which the properties
+    # writer escapes as \\u0000; the loaders (the reference's and ours) accept STRING dictionaries only with it
+    lines = [f"segment.name = {seg.name}", f"segment.total.docs = {seg.num_docs}", "segment.padding.character = \\u0000"]
     for c in seg.columns:
         p = f"column.{c.name}."
         lines += [p + f"cardinality = {c.cardinality}", p + f"totalDocs = {seg.num_docs}", p + f"dataType = {TYPE_NAMES[c.data_type]}",

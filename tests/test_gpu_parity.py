@@ -349,8 +349,17 @@ def test_raw_forward_index_column(oracle, ctx, pm):
     dev = to_device(ctx, seg)
     try:
         for text in ("SELECT SUM(m), MIN(m), MAX(m), AVG(m), COUNT(*) FROM t WHERE k > 3",
-                     "SELECT SUM(m), MAX(m), MIN(m) FROM t GROUP BY k"):
+                     "SELECT SUM(m), MAX(m), MIN(m) FROM t GROUP BY k",
+                     # value-space predicates on the raw column itself (PB200_F_RAW_RANGE; IntRawValueBasedRangePredicateEvaluator)
+                     "SELECT COUNT(*), SUM(m) FROM t WHERE m > 0",
+                     "SELECT COUNT(*), SUM(m), MIN(m), MAX(m) FROM t WHERE m BETWEEN -500000000 AND 250000000 AND k < 7",
+                     "SELECT COUNT(*) FROM t WHERE m >= -1000000000 AND m < -999000000",
+                     f"SELECT COUNT(*), MAX(k) FROM t WHERE m = {int(seg.column('m').raw_values[17])} OR k = 2",
+                     "SELECT COUNT(*), SUM(m) FROM t WHERE NOT (m > 5 AND m <= 700000000) GROUP BY k",
+                     "SELECT COUNT(*) FROM t WHERE m > 2000000000"):                       # empty
             check_query(oracle, pm, seg, dev, sql.parse(text), text)
+        with pytest.raises(UnsupportedQueryError):                                       # IN on a raw column: stock operator
+            pm.execute_segments([dev], sql.parse("SELECT COUNT(*) FROM t WHERE m IN (1, 2, 3)"))
     finally:
         dev.destroy()
 
@@ -455,4 +464,40 @@ def test_long_sum_does_not_wrap(oracle, ctx, pm):
         single = pm.execute_segments([dev], sql.parse("SELECT SUM(e) FROM t GROUP BY k"))[0]
         assert np.allclose(merged.doubles[0], 3.0 * single.doubles[0], rtol=1e-12)
     finally:
+        dev.destroy()
+
+
+def test_count_carrier_and_its_overflow_fallback(oracle, ctx, pm):
+    """Group-by COUNT / AVG counts ride in the upper bits of an INT sum's reductions (one L2 read-modify-write per row
+    instead of two).  A sum field that overflows is detected exactly (sum of carried counts != matched docs) and the
+    submission reruns with a separate COUNT table: results are exact either way."""
+    rng = np.random.default_rng(64)
+    n = 90_000
+    seg = oracle.build_segment("carrier", {
+        "k": rng.integers(0, 5000, size=n).astype(np.int32),                      # global tables (> shared-memory limit)
+        "big": rng.integers(-2_000_000_000, 2_000_000_000, size=n).astype(np.int32),
+        "small": rng.integers(-50, 50, size=n).astype(np.int32),
+        "w": rng.integers(0, 40, size=n).astype(np.int32)})
+    dev = to_device(ctx, seg)
+    queries = ["SELECT SUM(big), COUNT(*) FROM t WHERE w > 3 GROUP BY k",
+               "SELECT AVG(small), SUM(big), MAX(w) FROM t GROUP BY k",
+               "SELECT SUM(small) FROM t WHERE w < 30 GROUP BY k",                 # count only as the group-exists marker
+               "SELECT COUNT(*), SUM(small), SUM(big), AVG(big) FROM t WHERE w != 7 GROUP BY k, w"]
+    try:
+        for text in queries:
+            q = sql.parse(text, num_groups_limit=1_000_000)
+            _, block = check_query(oracle, pm, seg, dev, q, "carrier: " + text)
+            assert block.count_carrier, text                                        # 90 000 docs: 47-bit sum field, no overflow
+        ctx.set_tuning("pack_shift", 33)   # 33-bit sum field: groups of `big` overflow it (18 rows x ~2e9 each), `small` does not
+        for text in queries:
+            q = sql.parse(text, num_groups_limit=1_000_000)
+            _, block = check_query(oracle, pm, seg, dev, q, "carrier, shift 33: " + text)
+            carried_first = [a.column for a in q.aggregations if a.function in ("SUM", "AVG")][0]
+            assert block.count_carrier == (carried_first == "small"), (text, block.count_carrier)
+        ctx.set_tuning("pack_count", 0)
+        _, block = check_query(oracle, pm, seg, dev, sql.parse(queries[0], num_groups_limit=1_000_000), "carrier off")
+        assert not block.count_carrier
+    finally:
+        ctx.set_tuning("pack_shift", 0)
+        ctx.set_tuning("pack_count", 1)
         dev.destroy()

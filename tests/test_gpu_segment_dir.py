@@ -63,3 +63,39 @@ def test_load_directory_with_star_tree(oracle, ctx, tmp_path):
             assert star.stats.num_docs_scanned <= scan.stats.num_docs_scanned
     finally:
         dev.destroy()
+
+
+def test_load_reference_written_v1_directory(oracle, ctx):
+    """tests/golden/paddingOld/: a segment directory WRITTEN BY THE REFERENCE (pinot-core/src/test/resources/data/
+    paddingOld.tar.gz, v1 layout with its own metadata.properties; extracted by tests/golden/make_golden.py).  It predates
+    segment.padding.character, so its STRING column is padded with '%': like the reference (ColumnMetadataImpl.java:250-253)
+    only zero padding is accepted -- the loader leaves `name` out and loads the INT / FLOAT / LONG columns, whose decoded
+    contents and query results are checked against the golden bytes."""
+    import os
+    from oracle import segment_builder as sb
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "paddingOld")
+    dev = IndexSegment.load(ctx, root)
+    pm = B200PlanMaker(ctx)
+    try:
+        assert dev.num_docs == 5
+        assert sorted(dev.column_names) == ["age", "outgoingName1", "percent"]     # `name`: legacy '%' padding, not loaded
+        cols = []
+        for name, dt, be in (("age", sb.INT, ">i4"), ("percent", sb.FLOAT, ">f4"), ("outgoingName1", sb.LONG, ">i8")):
+            dct = np.frombuffer(open(os.path.join(root, name + ".dict"), "rb").read(), dtype=np.uint8)
+            fwd = np.frombuffer(open(os.path.join(root, name + ".sv.unsorted.fwd"), "rb").read(), dtype=np.uint8)
+            vals = np.frombuffer(dct.tobytes(), dtype=be)
+            info = dev.column_info(name)
+            assert (info["bits"], info["cardinality"]) == (3, 5), name
+            assert [dev.dictionary_value(name, i) for i in range(5)] == [v.item() for v in vals.astype(be[1:])], name
+            assert np.array_equal(dev.read_index(name, "fwd"), fwd), name                     # the file's bytes, back from HBM
+            cols.append(sb.ColumnData(name, dt, True, 3, 5, False, vals.dtype.itemsize, fwd, dct, None,
+                                      dict_values=vals.astype(be[1:]), dict_ids=sb.unpack_fixed_bits(fwd, 5, 3)))
+        seg = sb.SegmentData("mySegment_0", 5, cols)
+        assert [seg.value_of("age", int(i)) for i in cols[0].dict_ids] == [1228, 837, 1209, 617, 824]
+        for text in ("SELECT COUNT(*), SUM(age), MIN(percent), MAX(outgoingName1), AVG(age) FROM t",
+                     "SELECT COUNT(*), SUM(outgoingName1) FROM t WHERE age > 800 AND percent < 900.0",
+                     "SELECT SUM(percent), MAX(age) FROM t WHERE outgoingName1 >= 310 GROUP BY age",
+                     "SELECT DISTINCTCOUNT(age), COUNT(*) FROM t WHERE age IN (617, 1228, 5)"):
+            check_query(oracle, pm, seg, dev, sql.parse(text), what="paddingOld: " + text)
+    finally:
+        dev.destroy()
