@@ -151,6 +151,15 @@ enum {
  * super.makeSegmentPlanNode(). */
 int32_t pb200h_execute(pb200_ctx* ctx, const pb200h_query* query, pb200h_segment* const* segments,
                        int32_t num_segments, pb200_result** results, int32_t* operator_kinds);
+/* The result as the server -> broker wire format: DataTableImplV4 bytes (pinot-common/.../datatable/DataTableImplV4.java:49-81)
+ * exactly as GroupByResultsBlock.getDataTable() / AggregationResultsBlock.getDataTable() build them for the same rows
+ * (GroupByResultsBlock.java:186-236): typed group-key values (STRING keys through the DataTable's own string dictionary),
+ * COUNT as LONG, SUM / MIN / MAX as DOUBLE, AVG as OBJECT AvgPair, DISTINCTCOUNT as OBJECT value set, + the execution
+ * statistics as metadata.  `segment` supplies the dictionaries the result's ids refer to (any segment of a merged
+ * result: they share dictionaries).  Returns the size (or the size needed when out == NULL), < 0 on error. */
+int64_t pb200h_result_to_datatable(const pb200h_query* query, const pb200h_segment* segment, const pb200_result* result,
+                                   void* out, uint64_t capacity);
+
 /* toExplainString()-style description of the plan of one segment (for tests / EXPLAIN); returns chars written. */
 int32_t pb200h_explain(pb200_ctx* ctx, const pb200h_query* query, pb200h_segment* segment, char* out,
                        int32_t capacity);

@@ -2,7 +2,9 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <deque>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -101,6 +103,12 @@ struct StarTreeIndex {
   std::vector<int> metric_base_col;  // its column in the base segment (-1 for count__*)
   int num_docs = 0;
   pb200h_segment* star_segment = nullptr;  // columns: dimensions..., metrics...
+  // Traversal results by (predicate dictId sets per dimension, group-by mask): the BFS over a tree with 10^5..10^6 nodes
+  // costs more host time than the device scan of the docs it selects, and dashboards repeat their predicates.  The
+  // tree is immutable, so an entry never goes stale; a handful of entries, oldest evicted first.
+  struct Traversal { std::string key; std::vector<uint32_t> mask; uint32_t remaining = 0; };
+  mutable std::mutex cache_mu;
+  mutable std::deque<std::shared_ptr<const Traversal>> cache;
   ~StarTreeIndex();
 };
 }  // namespace pb200h

@@ -319,22 +319,43 @@ int try_star_tree(pb200_ctx* ctx, const pb200h_segment& seg, const StarTreeIndex
   }
   if ((int)star_aggs.size() > 6) return 0;
 
-  // ---- traversal -> doc mask ----
-  std::vector<std::pair<int32_t, int32_t>> docs;
-  uint32_t remaining = 0;
-  const bool non_empty = st.tree.traverse(preds, gb_mask, docs, remaining);
+  // ---- traversal -> doc mask (cached per predicate set) ----
   const int sdocs = st.num_docs;
-  std::vector<uint32_t> mask(((size_t)sdocs + 31) / 32 + 1, 0u);
-  if (non_empty) {
-    for (auto [s, e] : docs) {  // word-wise fill of [s, e)
-      s = std::max(s, 0); e = std::min(e, sdocs);
-      if (s >= e) continue;
-      const int ws = s >> 5, we = (e - 1) >> 5;
-      const uint32_t first = 0xFFFFFFFFu << (s & 31), last = 0xFFFFFFFFu >> (31 - ((e - 1) & 31));
-      if (ws == we) mask[ws] |= first & last;
-      else { mask[ws] |= first; for (int w = ws + 1; w < we; w++) mask[w] = 0xFFFFFFFFu; mask[we] |= last; }
-    }
+  std::string key(reinterpret_cast<const char*>(&gb_mask), sizeof gb_mask);
+  for (int d = 0; d < ndims; d++) {
+    const int32_t n = preds[d] ? (int32_t)preds[d]->size() : -1;
+    key.append(reinterpret_cast<const char*>(&n), sizeof n);
+    if (n > 0) key.append(reinterpret_cast<const char*>(preds[d]->data()), (size_t)n * 4);
   }
+  std::shared_ptr<const StarTreeIndex::Traversal> tr;
+  {
+    std::lock_guard<std::mutex> g(st.cache_mu);
+    for (auto& e : st.cache) if (e->key == key) { tr = e; break; }
+  }
+  if (!tr) {
+    auto fresh = std::make_shared<StarTreeIndex::Traversal>();
+    fresh->key = std::move(key);
+    std::vector<std::pair<int32_t, int32_t>> docs;
+    const bool non_empty = st.tree.traverse(preds, gb_mask, docs, fresh->remaining);
+    fresh->mask.assign(((size_t)sdocs + 31) / 32 + 1, 0u);
+    std::vector<uint32_t>& mask = fresh->mask;
+    if (non_empty) {
+      for (auto [s, e] : docs) {  // word-wise fill of [s, e)
+        s = std::max(s, 0); e = std::min(e, sdocs);
+        if (s >= e) continue;
+        const int ws = s >> 5, we = (e - 1) >> 5;
+        const uint32_t first = 0xFFFFFFFFu << (s & 31), last = 0xFFFFFFFFu >> (31 - ((e - 1) & 31));
+        if (ws == we) mask[ws] |= first & last;
+        else { mask[ws] |= first; for (int w = ws + 1; w < we; w++) mask[w] = 0xFFFFFFFFu; mask[we] |= last; }
+      }
+    }
+    tr = fresh;
+    std::lock_guard<std::mutex> g(st.cache_mu);
+    st.cache.push_back(tr);
+    if (st.cache.size() > 8) st.cache.pop_front();
+  }
+  const std::vector<uint32_t>& mask = tr->mask;
+  const uint32_t remaining = tr->remaining;
 
   // ---- device query on the star-tree segment: DOC_MASK AND remaining predicates ----
   std::vector<pb200_filter_node> nodes;

@@ -270,6 +270,12 @@ class ResultsBlock:
     count_carrier: bool = False  # the per-group row counts rode in an INT sum's reductions (pb200_api.cu)
     carrier_unsafe: bool = False  # deferred result: that sum may overflow in the cross-GPU reduce, rerun without carrier
 
+    def release(self, ctx: "B200Context") -> None:
+        """Frees the native result of a block executed with keep_handle=True."""
+        if self.handle is not None:
+            ctx.lib.pb200_result_free(self.handle)
+            self.handle = None
+
     def get_results(self, query: QueryContext) -> List[object]:
         """AggregationResultsBlock.getResults(): Long for COUNT, Double for SUM/MIN/MAX, (sum, count) for AVG,
         set size for DISTINCTCOUNT -- row 0 (aggregation only)."""
@@ -418,23 +424,41 @@ class B200PlanMaker:
             _lib.check(n)
         return buf.value.decode()
 
+    def to_datatable(self, segment: IndexSegment, query: QueryContext, block: "ResultsBlock") -> bytes:
+        """DataTableImplV4 bytes of a results block that still owns its handle (execute_segments(..., keep_handle=True) /
+        finalized merged block): what the server would send to the broker for these rows."""
+        if block.handle is None:
+            raise ValueError("the block's native handle was released (execute with keep_handle=True)")
+        hq, _keep = _marshal_query(query, False)
+        L = self.ctx.lib
+        n = L.pb200h_result_to_datatable(C.byref(hq), segment.handle, block.handle, None, 0)
+        if n < 0:
+            _lib.check(int(n))
+        buf = C.create_string_buffer(int(n))
+        r = L.pb200h_result_to_datatable(C.byref(hq), segment.handle, block.handle, buf, int(n))
+        if r < 0:
+            _lib.check(int(r))
+        return buf.raw[: int(r)]
+
     def execute_segments(self, segments: Sequence[IndexSegment], query: QueryContext, merge: bool = False,
                          keep_handle: bool = False, reduce_world: int = 0, merged_docs_bound: int = 0,
-                         no_count_carrier: bool = False) -> List[ResultsBlock]:
+                         no_count_carrier: bool = False, defer: Optional[bool] = None) -> List[ResultsBlock]:
         """All segments of one query in ONE device submission (makeInstancePlan-level batching).  With merge=True the
         segments (sharing dictionaries) are combined on the device and one block is returned; with keep_handle=True as
         well, a group-by block comes back WITHOUT its groups extracted (PB200_Q_DEFER_FINALIZE): its dense device tables
         are meant to be reduced across GPUs (pinot_b200.distributed.combine_across_ranks), which extracts on the root."""
         # merge + keep_handle: the caller reduces the dense tables across GPUs first; groups are extracted afterwards
-        hq, _keep = _marshal_query(query, 2 if (merge and keep_handle and query.is_group_by) else merge, reduce_world,
-                                   no_count_carrier, merged_docs_bound)
+        # defer=False with keep_handle=True: extracted blocks that keep their native handle (to_datatable); release() them
+        if defer is None:
+            defer = merge and keep_handle and query.is_group_by
+        hq, _keep = _marshal_query(query, 2 if defer else merge, reduce_world, no_count_carrier, merged_docs_bound)
         n = len(segments)
         segs = (C.c_void_p * n)(*[s.handle for s in segments])
         nres = 1 if merge else n
         res = (C.c_void_p * nres)()
         kinds = (C.c_int32 * n)()
         _lib.check(self.ctx.lib.pb200h_execute(self.ctx.handle, C.byref(hq), segs, n, res, kinds))
-        blocks = [_read_result(self.ctx, C.c_void_p(res[i]), query, kinds[i if not merge else 0], keep_handle and merge)
+        blocks = [_read_result(self.ctx, C.c_void_p(res[i]), query, kinds[i if not merge else 0], keep_handle)
                   for i in range(nres)]
         self.last_device_ms = blocks[0].device_ms
         return blocks
