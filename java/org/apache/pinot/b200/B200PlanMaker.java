@@ -9,6 +9,7 @@
 package org.apache.pinot.b200;
 
 import java.util.List;
+import org.apache.pinot.segment.spi.AggregationFunctionType;
 import org.apache.pinot.common.request.context.ExpressionContext;
 import org.apache.pinot.core.plan.PlanNode;
 import org.apache.pinot.core.plan.maker.InstancePlanMakerImplV2;
@@ -67,6 +68,19 @@ public class B200PlanMaker extends InstancePlanMakerImplV2 {
             || !segment.getDataSource(expression.getIdentifier()).getDataSourceMetadata().isSingleValue()) {
           return false;
         }
+        // MIN / MAX of a STRING column come back as dictIds, which DoubleAggregationResultHolder cannot carry: stock operator
+        if ((function.getType() == AggregationFunctionType.MIN || function.getType() == AggregationFunctionType.MAX)
+            && segment.getDataSource(expression.getIdentifier()).getDataSourceMetadata().getDataType().getStoredType()
+            == org.apache.pinot.spi.data.FieldSpec.DataType.STRING) {
+          return false;
+        }
+      }
+      // DISTINCTCOUNT with GROUP BY: the combine step merges value SETS per group (BaseDistinctAggregateAggregationFunction
+      // :109-121, :306-321); B200Operator.toResultsBlock only builds the per-group sets for the aggregation-only case, so
+      // the grouped form stays with the stock operator until that holder (ObjectGroupByResultHolder of Sets) is written
+      if (function.getType() == AggregationFunctionType.DISTINCTCOUNT && queryContext.getGroupByExpressions() != null
+          && !queryContext.getGroupByExpressions().isEmpty()) {
+        return false;
       }
     }
     List<ExpressionContext> groupBy = queryContext.getGroupByExpressions();

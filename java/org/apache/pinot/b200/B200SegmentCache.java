@@ -67,8 +67,10 @@ public final class B200SegmentCache {
   private Resident upload(IndexSegment segment) {
     SegmentMetadata metadata = segment.getSegmentMetadata();
     Set<String> names = segment.getPhysicalColumnNames();
-    String[] columns = names.stream().filter(c -> metadata.getColumnMetadataFor(c).isSingleValue())
-        .toArray(String[]::new);
+    // Only columns the library can hold are registered; every other column is simply ABSENT from the resident copy
+    // (columnId == -1), which makes B200PlanMaker fall back to the stock operator for queries that touch it -- a
+    // segment with a raw STRING / LONG / DOUBLE metric or an LZ4 chunk column must still serve its other queries here.
+    String[] columns = names.stream().filter(c -> isUploadable(metadata.getColumnMetadataFor(c))).toArray(String[]::new);
     int n = columns.length;
     int[] fwdKind = new int[n];
     int[] storedType = new int[n];
@@ -106,6 +108,24 @@ public final class B200SegmentCache {
     } catch (Exception e) {
       throw new RuntimeException("Caught exception while uploading segment " + metadata.getName(), e);
     }
+  }
+
+  /**
+   * What pb200_segment_register accepts (include/pinot_b200.h): single-value columns that are dictionary encoded
+   * (fixed-bit or sorted forward index), or raw PASS_THROUGH fixed-byte INT / FLOAT columns.  Compressed raw chunks
+   * (the default for raw metrics), raw LONG / DOUBLE / STRING / BYTES and multi-value columns stay with the JVM.
+   */
+  static boolean isUploadable(ColumnMetadata cm) {
+    if (!cm.isSingleValue()) {
+      return false;
+    }
+    if (cm.hasDictionary()) {
+      return true;
+    }
+    DataType stored = cm.getDataType().getStoredType();
+    // the chunk compression type is only known from the forward index header; pb200_segment_register refuses anything
+    // but PASS_THROUGH, and upload() then retries without the column
+    return stored == DataType.INT || stored == DataType.FLOAT;
   }
 
   private static ByteBuffer whole(PinotDataBuffer buffer) {

@@ -232,6 +232,7 @@ extern "C" int32_t pb200_init(int32_t device, pb200_ctx** out) {
     t.gb_defer = getenv("PB200_NO_GB_DEFER") ? 0 : 1;
     t.pack_count = getenv("PB200_NO_PACK_COUNT") ? 0 : 1;
     t.pack_shift = (int)env_i("PB200_PACK_SHIFT", 0);
+    t.table_stride = (int)env_i("PB200_TABLE_STRIDE", 0);
     t.skip = getenv("PB200_NO_SKIP") ? 0 : 1;
     t.always_count = getenv("PB200_ALWAYS_COUNT") ? 1 : 0;
   }
@@ -258,6 +259,7 @@ extern "C" int32_t pb200_tuning_set(pb200_ctx* ctx, const char* name, int64_t va
   else if (n == "gb_defer") t.gb_defer = value != 0;
   else if (n == "pack_count") t.pack_count = value != 0;
   else if (n == "pack_shift") t.pack_shift = (int)value;
+  else if (n == "table_stride") t.table_stride = (int)value;
   else if (n == "skip") t.skip = value != 0;
   else if (n == "always_count") t.always_count = value != 0;
   else { set_error("unknown tuning knob '%s'", name); return PB200_E_INVALID; }
@@ -598,18 +600,23 @@ extern "C" int32_t pb200_execute(pb200_ctx* ctx, const pb200_query* query, pb200
   return rc;
 }
 
-// Per result: sum over the table of the carried counts, and the largest low field (pb200_execute's verification).
+// Per result: {sum over the table of the carried counts, largest low (sum) field, largest carried count} -- pb200_execute's verification.
 __global__ void carrier_verify_kernel(const unsigned long long* __restrict__ tab, long long n, int shift, unsigned long long* __restrict__ out) {
-  unsigned long long c = 0, mx = 0;
+  unsigned long long c = 0, mx = 0, mc = 0;
   const unsigned long long mask = (1ull << shift) - 1ull;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const unsigned long long v = tab[i];
     c += v >> shift;
+    mc = max(mc, v >> shift);
     mx = max(mx, v & mask);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xFFFFFFFFu, c, o); mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o)); }
-  if ((threadIdx.x & 31) == 0) { if (c) atomicAdd(out, c); if (mx) atomicMax(out + 1, mx); }
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    mc = max(mc, __shfl_xor_sync(0xFFFFFFFFu, mc, o));
+  }
+  if ((threadIdx.x & 31) == 0) { if (c) atomicAdd(out, c); if (mx) atomicMax(out + 1, mx); if (mc) atomicMax(out + 2, mc); }
 }
 
 static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment* const* segments, int32_t nseg,
@@ -1060,6 +1067,7 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
         const SlotDesc& sl = sd.slots[q.aggs[a].slot];
         sd.agg_code[n++] = agg_code(a, q.aggs[a].function, q.aggs[a].val_kind, sl.bits, sl.stage_words);
       }
+    sd.num_agg_codes = n;
     sd.num_defer_codes = plan.group_by ? npipe : 0;
   }
 
@@ -1074,12 +1082,12 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
     ~PinnedScratch() { pinned_free(c, p, bytes); }
   } pacc{ctx};
   {
-    int rc = pinned_alloc(ctx, 2 * (sizeof(AggAccum) + 16) * nres, &pacc.p, &pacc.bytes);
+    int rc = pinned_alloc(ctx, 2 * (sizeof(AggAccum) + 32) * nres, &pacc.p, &pacc.bytes);
     if (rc) return rc;
   }
-  // block layout (device and both pinned halves): nres AggAccum records, then 2 words per result for the count-carrier
-  // verification {sum of carried counts, largest low field}
-  const size_t acc_bytes = (sizeof(AggAccum) + 16) * nres;
+  // block layout (device and both pinned halves): nres AggAccum records, then 4 words per result for the count-carrier
+  // verification {sum of carried counts, largest sum field, largest carried count, unused}
+  const size_t acc_bytes = (sizeof(AggAccum) + 32) * nres;
   unsigned char* const pin_init = static_cast<unsigned char*>(pacc.p);
   unsigned char* const pin_back = pin_init + acc_bytes;
   AggAccum* host_acc = reinterpret_cast<AggAccum*>(pin_back);
@@ -1169,6 +1177,21 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
         PB200_CUDA(cudaMemsetAsync(hc, 0, 8, st));
       } else {
         groups = (long long)space;
+        // Small dense tables are SPREAD: entry of raw key k sits at k * stride.  A 10 000-group table is 80 KB = 312 of the
+        // 256-byte chunks the L2 address hash distributes over ~184 slices -- some slices own three chunks, some none, and
+        // every surviving row sends a reduction to them (ncu: hottest slice 75 % tag-request utilisation vs 56 % average).
+        // With one entry per 128 bytes the same reductions spread over >= 4096 chunks.  Costs table bytes (<= 2 MB each,
+        // memset + extraction scan), no instruction in the kernel: the stride is folded into the key multipliers.
+        bool any_bitset = false;
+        for (int a = 0; a < nagg; a++) any_bitset |= q.aggs[a].function == PB200_AGG_DISTINCTCOUNT;
+        if (q.smem_groups == 0 && !any_bitset && tune.table_stride != 1) {
+          long long s = 1;
+          if (tune.table_stride > 1) s = tune.table_stride;
+          else while (s < 16 && groups * 8 * s * 2 <= (2ll << 20)) s *= 2;   // keep each table within 2 MB
+          while (s > 1 && groups * s > (1ll << 26)) s /= 2;
+          d.stride = (int)s;
+          groups *= s;
+        }
       }
       d.groups = groups;
       d.live = true;
@@ -1187,12 +1210,15 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
       // ---- count carrier.  Every RED into the tables is an L2 read-modify-write, and on this path the L2 sector rate is
       // the bound (lts__t_sectors ~ 3.7x the streamed bytes at 10 % selectivity, profiles/r2_*).  When the query needs the
       // per-group row count (COUNT / AVG, or only as the group-exists marker) and sums an INT dictionary column, the
-      // count rides in the upper bits of that sum: each row adds (value - min) + 2^shift with ONE reduction.  shift =
-      // 64 - bits(docs that can reach the table), so the count field cannot overflow; the sum field can (a group whose
-      // sum of (value - min) reaches 2^shift) -- which is detected EXACTLY after the launch: every overflow carries
-      // into the count field, counts only ever grow (value - min >= 0), so sum_g count_g == matched docs iff nothing
-      // overflowed (the table total cannot wrap 2^64 since docs x 2^32 / 2^shift < 2^bits(docs) for shift >= 32).  On a
-      // mismatch the submission runs again with a separate COUNT table (kRetryWithoutCountCarrier).
+      // count rides in the upper bits of that sum: each row adds (value - vmin) + 2^shift with ONE reduction.
+      //   Fields: sum field = `shift` bits, count field = 64 - shift bits, balanced so that both overflow at about the
+      //   same rows per group: shift = ceil((64 + bits(R)) / 2), R = vmax - vmin + 1 from the dictionary (a 20-bit value
+      //   range leaves 22 bits = 4 M rows per group; a full 32-bit range 65 535).
+      //   Either field CAN overflow; both are detected EXACTLY after the launch from one number: a sum field overflow
+      //   carries into the count field (counts only grow: value - vmin >= 0), a count overflow drops 2^(64-shift) from
+      //   it, so  sum_g count_g == matched docs  iff neither happened -- the two cannot cancel because the carries total
+      //   at most docs x R / 2^shift < 2^(64-shift) when docs x R < 2^64 (the admission test below).  On a mismatch the
+      //   submission runs again with a separate COUNT table (kRetryWithoutCountCarrier); results are exact either way.
       d.pack_agg = -1;
       const bool deferred = merge && (query->flags & PB200_Q_DEFER_FINALIZE);
       d.reduce_world = deferred ? std::max(query->reduce_world, 1) : 1;
@@ -1200,29 +1226,31 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
           (need_count || need_seen)) {
         unsigned long long docs = 0;
         for (int s = 0; s < nseg; s++) if (merge || s == r) docs += (unsigned long long)segments[s]->num_docs;
-        // a table that will be summed with the other GPUs' tables: size the fields for the docs of ALL of them (every rank
-        // must arrive at the same shift, hence the explicit bound)
+        // a table that will be summed with the other GPUs' tables: the admission test covers the docs of ALL of them
         if (deferred) docs = query->merged_docs_bound > 0 ? (unsigned long long)query->merged_docs_bound : docs * (unsigned long long)d.reduce_world;
-        int bits = 1;
-        while (bits < 64 && (docs >> bits)) bits++;
+        auto bits_of = [](unsigned long long x) { int b = 0; while (b < 64 && (x >> b)) b++; return b; };
         for (int a = 0; a < nagg && d.pack_agg < 0; a++) {
           const int fn = q.aggs[a].function;
           if ((fn != PB200_AGG_SUM && fn != PB200_AGG_AVG) || q.aggs[a].val_kind != VAL_DICT_I32) continue;
-          if (bits > 32) break;
-          long long vmin = std::numeric_limits<long long>::max();
+          long long vmin = std::numeric_limits<long long>::max(), vmax = std::numeric_limits<long long>::min();
           bool ok = true;
           for (int s = 0; s < nseg && ok; s++) {
             if (!merge && s != r) continue;
             const DeviceColumn& c = segments[s]->cols[query->aggs[a].column];
-            if (c.dict_host.size() < 4 || c.stored_type != PB200_INT) { ok = false; break; }
+            if (c.dict_host.size() < 4ull * std::max(c.cardinality, 1) || c.stored_type != PB200_INT) { ok = false; break; }
             // the other GPUs must subtract the SAME minimum: only a table-wide (domain) dictionary guarantees that
             if (d.reduce_world > 1 && !c.dict_shared) { ok = false; break; }
-            int32_t v0; memcpy(&v0, c.dict_host.data(), 4);   // sorted dictionary: entry 0 is the minimum
+            int32_t v0, v1;   // sorted dictionary: first / last entry
+            memcpy(&v0, c.dict_host.data(), 4);
+            memcpy(&v1, c.dict_host.data() + 4ull * (c.cardinality - 1), 4);
             vmin = std::min<long long>(vmin, v0);
+            vmax = std::max<long long>(vmax, v1);
           }
           if (!ok) continue;
+          const int rbits = bits_of((unsigned long long)(vmax - vmin));   // value - vmin fits rbits bits
+          if (bits_of(docs) + rbits > 63) continue;                        // docs x R < 2^63: the detection is airtight
           d.pack_agg = a;
-          d.pack_shift = tune.pack_shift > 0 ? tune.pack_shift : 64 - bits;
+          d.pack_shift = tune.pack_shift > 0 ? tune.pack_shift : (64 + rbits + 1) / 2;
           d.pack_vmin = vmin;
         }
         if (d.pack_agg >= 0) { need_count = false; need_seen = false; }
@@ -1283,7 +1311,7 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
         if (a == d.pack_agg) sd.sum_addend[a] = (1ull << d.pack_shift) - (unsigned long long)((uint32_t)(int32_t)d.pack_vmin ^ 0x80000000u);
       }
       for (int a = 0; a < nagg; a++) { sd.g_isum[a] = d.isum[a]; sd.g_dsum[a] = d.dsum[a]; sd.g_min[a] = d.gmin[a]; sd.g_max[a] = d.gmax[a]; sd.distinct_bits[a] = d.dbits[a]; sd.distinct_words[a] = d.dwords[a]; }
-      for (int g = 0; g < ngb; g++) { sd.group_mult[g] = d.mult[g]; sd.group_mult64[g] = d.mult64[g]; }
+      for (int g = 0; g < ngb; g++) { sd.group_mult[g] = d.mult[g] * (uint32_t)d.stride; sd.group_mult64[g] = d.mult64[g]; }  // hash tables: stride 1
       sd.h_keys = d.hkeys;
       sd.h_ctl = d.hctl;
       sd.h_mask = d.hkeys ? (uint32_t)(d.groups - 1) : 0u;
@@ -1349,7 +1377,7 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
       const pb200_result::Dense& d = res[r]->dense;
       if (d.pack_agg < 0) continue;
       const int vb = (int)std::max<long long>(1, std::min<long long>((d.groups + 1023) / 1024, 148 * 4));
-      carrier_verify_kernel<<<vb, 256, 0, st>>>((const unsigned long long*)d.isum[d.pack_agg], d.groups, d.pack_shift, dev_verify + 2 * r);
+      carrier_verify_kernel<<<vb, 256, 0, st>>>((const unsigned long long*)d.isum[d.pack_agg], d.groups, d.pack_shift, dev_verify + 4 * r);
     }
   PB200_CUDA(cudaMemcpyAsync(pin_back, accum_buf.p, acc_bytes, cudaMemcpyDeviceToHost, st));
   cudaError_t se = cudaStreamSynchronize(st);
@@ -1358,13 +1386,15 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
     for (int r = 0; r < nres; r++) {
       const pb200_result::Dense& d = res[r]->dense;
       if (d.pack_agg < 0) continue;
-      // cross-GPU: the reduce adds `reduce_world` low fields; it cannot overflow if every rank's largest one stays below
-      // 2^shift / reduce_world.  A rank cannot rerun on its own (its peers' tables would have another layout): it marks
-      // the result and the combine layer reruns the query on all ranks (PB200_Q_NO_COUNT_CARRIER).
-      const bool exact = host_verify[2 * r] == host_acc[r].count;
+      const unsigned long long* vw = host_verify + 4 * r;   // {sum of counts, largest sum field, largest count}
+      const bool exact = vw[0] == host_acc[r].count;
       if (d.reduce_world > 1) {
-        const unsigned long long lim = ((1ull << d.pack_shift) - 1ull) / (unsigned long long)d.reduce_world;
-        res[r]->dense.carrier_unsafe = !exact || host_verify[2 * r + 1] > lim;
+        // cross-GPU: the reduce adds `reduce_world` fields of each kind; neither can overflow if every rank's largest one
+        // stays below its capacity / reduce_world.  A rank cannot rerun on its own (its peers' tables would have another
+        // layout): it marks the result and the combine layer reruns the query on all ranks (PB200_Q_NO_COUNT_CARRIER).
+        const unsigned long long w = (unsigned long long)d.reduce_world;
+        const unsigned long long sum_lim = ((1ull << d.pack_shift) - 1ull) / w, cnt_lim = ((1ull << (64 - d.pack_shift)) - 1ull) / w;
+        res[r]->dense.carrier_unsafe = !exact || vw[1] > sum_lim || vw[2] > cnt_lim;
         continue;
       }
       if (exact) continue;

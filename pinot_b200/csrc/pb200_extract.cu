@@ -37,7 +37,8 @@ struct ExtractDesc {
   const unsigned long long* packed;  // count-carrying sum table (pb200_api.cu): sum(value - vmin) + count << shift
   long long pack_vmin;
   int32_t pack_agg, pack_shift;
-  long long groups;                  // table entries (dense: raw key space, hash: capacity)
+  long long groups;                  // table entries (dense: raw key space x stride, hash: capacity)
+  int32_t stride, pad_stride;        // dense tables: only entries at multiples of `stride` are ever written
   int32_t ngb, nagg;
   uint32_t cards[kMaxGroupBy];
   uint32_t first_chunk, num_chunks;  // position in the launch-wide chunk sequence
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kExtractThreads) extract_write_kernel(const Ex
     // ---- key dictIds: raw key = sum dictId_k * prod_{m<k} card_m (column 0 least significant) ----
     if (d.ngb > 0) {
       int32_t* kp = reinterpret_cast<int32_t*>(out + d.off_keys) + row * d.ngb;
-      unsigned long long raw = d.hkeys ? d.hkeys[g] : (unsigned long long)g;
+      unsigned long long raw = d.hkeys ? d.hkeys[g] : (unsigned long long)g / (unsigned)d.stride;
       for (int k = 0; k < d.ngb; ++k) { kp[k] = (int32_t)(raw % d.cards[k]); raw /= d.cards[k]; }
     }
     if (d.off_idx != kNoCol) reinterpret_cast<uint32_t*>(out + d.off_idx)[row] = (uint32_t)g;
@@ -210,6 +211,7 @@ int extract_groups(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cudaStream
     e.count = d.count; e.seen = d.seen; e.maxk = d.exists_max; e.mink = d.exists_min; e.hkeys = d.hkeys;
     e.packed = d.exists_packed; e.pack_agg = d.pack_agg; e.pack_shift = d.pack_shift; e.pack_vmin = d.pack_vmin;
     e.groups = d.groups;
+    e.stride = std::max(d.stride, 1);
     e.ngb = (int)d.cards.size();
     e.nagg = (int)d.aggs.size();
     for (int k = 0; k < e.ngb; k++) e.cards[k] = (uint32_t)d.cards[k];

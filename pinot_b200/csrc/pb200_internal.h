@@ -67,6 +67,7 @@ struct Tuning {
   int defer = 1;                 // !PB200_NO_DEFER: software-pipelined gathers, aggregation-only kernel
   int gb_defer = 1;              // !PB200_NO_GB_DEFER: software-pipelined last queue batch, group-by kernel
   int pack_count = 1;            // !PB200_NO_PACK_COUNT: group-by COUNT carried inside an INT SUM's reductions (pb200_api.cu)
+  int table_stride = 0;          // PB200_TABLE_STRIDE: dense group tables hold raw key k at k * stride (0 = auto, 1 = off)
   int pack_shift = 0;            // PB200_PACK_SHIFT: force the carrier's count shift (tests of the overflow fallback); 0 = from the doc count
   int skip = 1;                  // !PB200_NO_SKIP: bitmap-driven slice skipping
   int always_count = 0;          // PB200_ALWAYS_COUNT
@@ -141,7 +142,8 @@ struct pb200_result {
   // merged dense-table state kept on the device for multi-GPU combine
   struct Dense {
     pb200_ctx* ctx = nullptr;
-    long long groups = 0;                        // size of the dense key space
+    long long groups = 0;                        // table entries: dense key space x stride, or hash capacity
+    int stride = 1;                              // dense tables: raw key k lives at entry k * stride (pb200_api.cu)
     bool live = false;                           // device tables still allocated
     unsigned long long* count = nullptr;         // NULL when no COUNT / AVG
     uint32_t* seen = nullptr;                    // group-exists flags (inside the u32max block) or NULL

@@ -80,9 +80,10 @@ class OracleBackend:
         carrier = -1
         if not no_count_carrier and (need_count or not has_minmax):
             carrier = next((a for a, ag in enumerate(query.aggregations) if ag.function in ("SUM", "AVG")), -1)
-        docs = merged_docs_bound or sum(s.num_docs for s in segments) * reduce_world
-        shift = self.force_shift or 64 - int(docs).bit_length()
-        vmin = int(segments[0].column(query.aggregations[carrier].column).dict_values.min()) if carrier >= 0 else 0
+        # the library's field sizing (pb200_api.cu "count carrier"): balanced fields from the dictionary's value range
+        dv = segments[0].column(query.aggregations[carrier].column).dict_values if carrier >= 0 else np.zeros(1, dtype=np.int64)
+        vmin, rbits = int(dv.min()), int(int(dv.max()) - int(dv.min())).bit_length()
+        shift = self.force_shift or (64 + rbits + 1) // 2
         count = np.zeros(groups, dtype=np.int64)
         isum = {a: np.zeros(groups, dtype=np.int64) for a, f in enumerate(fns) if f in ("SUM", "AVG")}
         gmax = {a: np.zeros(groups, dtype=np.uint32) for a, f in enumerate(fns) if f == "MAX"}
@@ -120,8 +121,7 @@ class OracleBackend:
         if carrier >= 0:
             f_field = isum[carrier] - count * vmin
             assert (f_field >= 0).all()
-            lim = ((1 << shift) - 1) // reduce_world
-            unsafe = bool((f_field > lim).any())
+            unsafe = bool((f_field > ((1 << shift) - 1) // reduce_world).any() or (count > ((1 << (64 - shift)) - 1) // reduce_world).any())
             isum[carrier] = (f_field + (count << shift)) if not unsafe else np.zeros(groups, dtype=np.int64)  # unsafe: garbage anyway
         elif need_count or not has_minmax:
             i64.append(count)

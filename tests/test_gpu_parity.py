@@ -487,8 +487,8 @@ def test_count_carrier_and_its_overflow_fallback(oracle, ctx, pm):
         for text in queries:
             q = sql.parse(text, num_groups_limit=1_000_000)
             _, block = check_query(oracle, pm, seg, dev, q, "carrier: " + text)
-            assert block.count_carrier, text                                        # 90 000 docs: 47-bit sum field, no overflow
-        ctx.set_tuning("pack_shift", 33)   # 33-bit sum field: groups of `big` overflow it (18 rows x ~2e9 each), `small` does not
+            assert block.count_carrier, text                                        # ~18 rows per group: neither field overflows
+        ctx.set_tuning("pack_shift", 33)   # 33-bit sum field: groups of `big` overflow it (~18 rows x up to 4e9 each), `small` does not
         for text in queries:
             q = sql.parse(text, num_groups_limit=1_000_000)
             _, block = check_query(oracle, pm, seg, dev, q, "carrier, shift 33: " + text)
