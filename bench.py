@@ -492,8 +492,10 @@ def main():
                         "steps": args.e2e_steps,
                         "note": "every step re-uploads the touched columns from pinned host memory (PCIe bound) and reads the "
                                 "results block back; `value` is the same plugin call with the segments resident in HBM"},
-                "gpu_launches": args.steps * 4,
-                "gpu_launches_note": "per step: 1 scan_kernel + 3 extraction kernels (count, scan, write); memsets and NCCL not counted",
+                "gpu_launches": args.steps * (5 if getattr(gb_out, "count_carrier", False) else 4),
+                "gpu_launches_note": "per step: 1 scan_kernel (+ 1 carrier_verify_kernel when the counts ride in the sum) + 3 extraction "
+                                     "kernels (count, scan, write); memsets and NCCL not counted",
+                "count_carrier": bool(getattr(gb_out, "count_carrier", False)),
                 "per_segment_blocks": {"ms_per_step": sb_elapsed / sb_steps * 1e3, "kernel_ms": sb_kms, "steps": sb_steps,
                                        "value": rows_per_step * world / (sb_elapsed / sb_steps),
                                        "note": "same query, one results block per segment (8 x 10 000 groups extracted) "

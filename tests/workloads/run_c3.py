@@ -87,7 +87,7 @@ def main():
     segs = [IndexSegment.synthetic(ctx, f"s{s}", args.rows, specs(s, inverted=args.mode == "bitmap")) for s in range(args.segments)]
     gen_s = time.perf_counter() - t0
     defaults = {"warps": 6, "ctas_per_sm": 2, "stages": 0, "grid": 0, "sparse_max": 4, "sparse_max_agg": -1, "smem_groups": 1,
-                "smem_groups_max": 2048, "smem_copies": 0, "gb_defer": 1, "skip": 1, "always_count": 0, "pack_count": 1, "pack_shift": 0}
+                "smem_groups_max": 2048, "smem_copies": 0, "gb_defer": 1, "skip": 1, "always_count": 0, "pack_count": 1, "pack_shift": 0, "table_stride": 0}
     rows = args.segments * args.rows
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     reference_result = None
