@@ -65,6 +65,24 @@ int32_t pb200h_segment_column_info(const pb200h_segment* segment, int32_t column
 int32_t pb200h_dictionary_get(const pb200h_segment* segment, int32_t column, int32_t dict_id, double* num, int64_t* lng,
                               char* str, int32_t str_capacity);
 
+/* ---- HBM residency (what BaseTableDataManager + SegmentDataManager reference counting are to the JVM heap / page cache) ---- */
+/* Segments resident on the device, keyed by (segment name, CRC) -- SegmentMetadata.getName() / getCrc(); a new CRC under a
+ * known name is a refresh (BaseTableDataManager.replaceSegment).  A byte budget (0 = 80 % of the device) with least-recently-
+ * used eviction of segments no query holds; acquire / release bracket a query exactly like
+ * SegmentDataManager.increaseReferenceCount / decreaseReferenceCount (ServerQueryExecutorV1Impl.java:217). */
+typedef struct pb200h_cache pb200h_cache;
+int32_t pb200h_cache_create(pb200_ctx* ctx, int64_t max_device_bytes, pb200h_cache** cache);
+/* Hit: pins and returns the resident segment.  Miss: frees LRU unpinned segments until `size_hint` bytes (0 = unknown)
+ * fit, loads `index_dir` (pb200h_segment_load_dir), pins.  PB200_E_NOMEM when everything resident is in use. */
+int32_t pb200h_cache_acquire(pb200h_cache* cache, const char* segment_name, uint64_t crc, const char* index_dir,
+                             int64_t size_hint, pb200h_segment** segment);
+int32_t pb200h_cache_release(pb200h_cache* cache, pb200h_segment* segment);
+/* The table dropped the segment (IndexSegment.destroy()): freed now, or by the last release. */
+int32_t pb200h_cache_evict(pb200h_cache* cache, const char* segment_name, uint64_t crc);
+/* {resident segments, resident bytes, budget, hits, misses, evictions} */
+int32_t pb200h_cache_stats(pb200h_cache* cache, int64_t out[6]);
+int32_t pb200h_cache_destroy(pb200h_cache* cache);
+
 /* ---- table-wide dictionaries (include/pinot_b200.h "domains") by column NAME ------------------------------------- */
 /* Union of the given segments' dictionaries for the named columns (every segment must hold them at the same position). */
 int32_t pb200h_domain_build(pb200_ctx* ctx, pb200h_segment* const* segments, int32_t num_segments, int32_t num_columns,

@@ -122,7 +122,8 @@ EXPORTED_SYMBOLS = [
     "pb200h_segment_device", "pb200h_segment_num_docs", "pb200h_segment_num_columns", "pb200h_segment_column_index",
     "pb200h_segment_column_name", "pb200h_segment_column_info", "pb200h_dictionary_get", "pb200h_execute",
     "pb200h_explain", "pb200h_startree_attach", "pb200h_domain_build", "pb200h_segment_bind_domain",
-    "pb200h_result_to_datatable",
+    "pb200h_result_to_datatable", "pb200h_cache_create", "pb200h_cache_acquire", "pb200h_cache_release", "pb200h_cache_evict",
+    "pb200h_cache_stats", "pb200h_cache_destroy",
     "pb200_domain_create", "pb200_domain_from_segments", "pb200_domain_column_info", "pb200_domain_dictionary",
     "pb200_domain_release", "pb200_segment_bind_domain", "pb200_segment_local_ids",
 ]
@@ -180,6 +181,12 @@ def load() -> C.CDLL:
     L.pb200h_explain.argtypes = [vp, C.POINTER(HQuery), vp, C.c_char_p, i32]
     L.pb200h_startree_attach.argtypes = [vp, vp, vp, C.c_uint64, i32, i32, C.POINTER(C.c_char_p), C.POINTER(vp),
                                          C.POINTER(C.c_uint64), i32, C.POINTER(HStarMetric)]
+    L.pb200h_cache_create.argtypes = [vp, i64, C.POINTER(vp)]
+    L.pb200h_cache_acquire.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_char_p, i64, C.POINTER(vp)]
+    L.pb200h_cache_release.argtypes = [vp, vp]
+    L.pb200h_cache_evict.argtypes = [vp, C.c_char_p, C.c_uint64]
+    L.pb200h_cache_stats.argtypes = [vp, C.POINTER(i64)]
+    L.pb200h_cache_destroy.argtypes = [vp]
     L.pb200h_result_to_datatable.restype = i64
     L.pb200h_result_to_datatable.argtypes = [C.POINTER(HQuery), vp, vp, vp, C.c_uint64]
     L.pb200h_domain_build.argtypes = [vp, C.POINTER(vp), i32, i32, C.POINTER(C.c_char_p), C.POINTER(vp)]

@@ -183,6 +183,40 @@ class IndexSegment:
             self.handle = None
 
 
+class SegmentCache:
+    """HBM residency manager (pb200h_cache_*): segments on the device keyed by (name, CRC), byte budget, LRU eviction of
+    segments no query holds -- TableDataManager + SegmentDataManager reference counting for device memory."""
+
+    def __init__(self, ctx: B200Context, max_device_bytes: int = 0):
+        self.ctx = ctx
+        h = C.c_void_p()
+        _lib.check(ctx.lib.pb200h_cache_create(ctx.handle, int(max_device_bytes), C.byref(h)))
+        self.handle = h
+
+    def acquire(self, name: str, crc: int, index_dir: Optional[str] = None, size_hint: int = 0) -> IndexSegment:
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.pb200h_cache_acquire(self.handle, name.encode(), int(crc),
+                                                     None if index_dir is None else index_dir.encode(), int(size_hint), C.byref(h)))
+        return IndexSegment(self.ctx, h, name)   # owned by the cache: release() it, never destroy()
+
+    def release(self, segment: IndexSegment) -> None:
+        _lib.check(self.ctx.lib.pb200h_cache_release(self.handle, segment.handle))
+        segment.handle = None
+
+    def evict(self, name: str, crc: int) -> None:
+        _lib.check(self.ctx.lib.pb200h_cache_evict(self.handle, name.encode(), int(crc)))
+
+    def stats(self) -> Dict[str, int]:
+        out = (C.c_int64 * 6)()
+        _lib.check(self.ctx.lib.pb200h_cache_stats(self.handle, out))
+        return dict(zip(("segments", "bytes", "budget", "hits", "misses", "evictions"), [int(x) for x in out]))
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.lib.pb200h_cache_destroy(self.handle)
+            self.handle = None
+
+
 class DictionaryDomain:
     """Table-wide dictionaries (include/pinot_b200.h "domains"): the sorted union of per-segment dictionaries, the common
     id space that makes device-side and cross-GPU merges merges BY VALUE (GroupByCombineOperator.java:130-146)."""
@@ -451,7 +485,13 @@ class B200PlanMaker:
         # defer=False with keep_handle=True: extracted blocks that keep their native handle (to_datatable); release() them
         if defer is None:
             defer = merge and keep_handle and query.is_group_by
-        hq, _keep = _marshal_query(query, 2 if defer else merge, reduce_world, no_count_carrier, merged_docs_bound)
+        # the marshalled (ctypes) form of a query is cached on the query object: a server compiles a query once and runs it
+        # over many segments / steps
+        mkey = (2 if defer else int(merge), int(reduce_world), bool(no_count_carrier), int(merged_docs_bound))
+        cache = query.__dict__.setdefault("_pb200_marshalled", {})
+        if mkey not in cache:
+            cache[mkey] = _marshal_query(query, 2 if defer else merge, reduce_world, no_count_carrier, merged_docs_bound)
+        hq, _keep = cache[mkey]
         n = len(segments)
         segs = (C.c_void_p * n)(*[s.handle for s in segments])
         nres = 1 if merge else n

@@ -99,3 +99,54 @@ def test_load_reference_written_v1_directory(oracle, ctx):
             check_query(oracle, pm, seg, dev, sql.parse(text), what="paddingOld: " + text)
     finally:
         dev.destroy()
+
+
+def test_segment_cache_residency(oracle, ctx, tmp_path):
+    """pb200h_cache_*: keyed by (name, CRC), pinned while a query holds the segment, LRU eviction under a byte budget,
+    refresh (same name, new CRC) and drop while pinned are deferred to the last release."""
+    from pinot_b200._lib import Pb200Error
+    from pinot_b200.plan_maker import SegmentCache
+    rng = np.random.default_rng(31)
+    segs, roots = [], []
+    for i in range(4):
+        s = oracle.build_segment(f"cs{i}", {"a": rng.integers(0, 50, size=60_000).astype(np.int32),
+                                            "b": rng.integers(0, 5000, size=60_000).astype(np.int32) + i})
+        segs.append(s)
+        roots.append(write_segment_dir(str(tmp_path / f"cs{i}"), s, "v1"))
+    probe = IndexSegment.load(ctx, roots[0])
+    one = probe.device_bytes()
+    probe.destroy()
+    cache = SegmentCache(ctx, max_device_bytes=int(2.5 * one))       # room for two segments
+    pm = B200PlanMaker(ctx)
+    q = sql.parse("SELECT COUNT(*), SUM(b) FROM t WHERE a < 25 GROUP BY a")
+    try:
+        s0 = cache.acquire("cs0", 100, roots[0], one)
+        check_query(oracle, pm, segs[0], s0, q, "cached cs0")
+        s1 = cache.acquire("cs1", 101, roots[1], one)
+        with pytest.raises(Pb200Error):                                # both residents are pinned: no room for a third
+            cache.acquire("cs2", 102, roots[2], one)
+        cache.release(s1)
+        s2 = cache.acquire("cs2", 102, roots[2], one)                 # evicts the unpinned cs1, never the pinned cs0
+        st = cache.stats()
+        assert (st["segments"], st["evictions"], st["misses"]) == (2, 1, 4) and st["bytes"] <= st["budget"]
+        again = cache.acquire("cs0", 100)                             # hit: no directory needed
+        assert cache.stats()["hits"] == 1
+        cache.release(again)
+        cache.release(s0)
+        cache.release(s2)
+        # LRU: cs0 was touched last, so loading cs3 evicts cs2
+        s3 = cache.acquire("cs3", 103, roots[3], one)
+        cache.acquire("cs0", 100)
+        with pytest.raises(Pb200Error):
+            cache.acquire("cs2", 102)                                  # gone, and no directory given
+        # refresh: same name, new CRC -> the old version stays usable for its holder and is freed by its release
+        cache.release(s3)
+        new0 = cache.acquire("cs0", 999, roots[1], one)               # content of cs1 under the name cs0
+        check_query(oracle, pm, segs[1], new0, q, "refreshed cs0")
+        st = cache.stats()
+        assert st["segments"] >= 2
+        cache.evict("cs0", 999)                                        # dropped while pinned: freed by the release
+        check_query(oracle, pm, segs[1], new0, q, "dropped but still held")
+        cache.release(new0)
+    finally:
+        cache.close()
