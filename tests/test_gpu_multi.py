@@ -18,7 +18,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 QUERIES = [
-    "SELECT SUM(v), COUNT(*) FROM t WHERE v > -400 GROUP BY k",           # count carried in SUM(v)
+    "SELECT SUM(v), COUNT(*) FROM t WHERE v > -400 GROUP BY k, j",        # > 2048 keys: global tables, count carried in SUM(v)
+    "SELECT SUM(v), COUNT(*) FROM t WHERE v > -400 GROUP BY k",           # small key space: CTA-private shared-memory tables
     "SELECT AVG(v), MAX(l), MIN(k) FROM t WHERE j != 2 GROUP BY k, j",      # carrier + MIN / MAX ids in domain space
     "SELECT SUM(f), MAX(v) FROM t GROUP BY j",                              # float sums, shared-memory sized key space
     "SELECT SUM(v) FROM t WHERE l > 5000000000 GROUP BY k",                 # count only as the group-exists marker
@@ -97,7 +98,7 @@ def test_two_gpus_domain_and_table_reduce_equal_oracle_merge(tmp_path, pack_shif
     for text, (got, parts, carrier) in report.items():
         q = sql.parse(text)
         assert_tables_equal(q, got, combine([a.function for a in q.aggregations], parts), f"2 GPUs: {text}")
-        if "COUNT(*) FROM t WHERE v > -400" in text:
+        if text.endswith("WHERE v > -400 GROUP BY k, j"):
             # default: 46-bit sum field, safe -> counts carried.  A 12-bit field (values span 2000) cannot be proven safe
             # for the reduce: BOTH ranks agree through the flag all-reduce and rerun without the carrier.
             assert carrier is (pack_shift == 0), (pack_shift, carrier)
