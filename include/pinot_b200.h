@@ -237,7 +237,9 @@ typedef struct {
   int32_t groups_limit_reached;
   int32_t reserved;            /* bit 0: group-by row counts were carried inside an INT sum's reductions (informational);
                                   bit 1 (PB200_Q_DEFER_FINALIZE results): that sum's field is NOT provably safe for the
-                                  cross-GPU reduce -- every rank must run the query again with PB200_Q_NO_COUNT_CARRIER */
+                                  cross-GPU reduce -- every rank must run the query again with PB200_Q_NO_COUNT_CARRIER;
+                                  bit 2: the int64 block of pb200_result_device_buffers ends with one extra element holding
+                                  that verdict (0 / 1): SUM-all-reduce the block and every rank reads the agreed verdict there */
   /* ExecutionStatistics (core/operator/ExecutionStatistics.java) */
   int64_t num_docs_scanned;
   int64_t num_entries_scanned_in_filter; /* see DESIGN.md: device semantics = docs x scan leaves evaluated */

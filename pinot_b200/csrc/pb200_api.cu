@@ -1270,6 +1270,10 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
         return PB200_OK;
       };
       d.i64_elems = n_i64 * groups; d.f64_elems = n_f64 * groups; d.u32max_elems = n_max * groups; d.u32min_elems = n_min * groups;
+      // cross-GPU combine of a count-carrying table: ONE extra int64 behind the tables carries this rank's "not provably
+      // safe" verdict (0 / 1), so that the verdicts of all ranks are summed by the same collective that sums the tables
+      d.flag_slot = d.pack_agg >= 0 && d.reduce_world > 1;
+      if (d.flag_slot) d.i64_elems += 1;
       int rc;
       if ((rc = alloc_block(&d.i64_block, d.i64_elems, 8, 0))) return rc;
       if ((rc = alloc_block(&d.f64_block, d.f64_elems, 8, 0))) return rc;
@@ -1395,6 +1399,10 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
         const unsigned long long w = (unsigned long long)d.reduce_world;
         const unsigned long long sum_lim = ((1ull << d.pack_shift) - 1ull) / w, cnt_lim = ((1ull << (64 - d.pack_shift)) - 1ull) / w;
         res[r]->dense.carrier_unsafe = !exact || vw[1] > sum_lim || vw[2] > cnt_lim;
+        if (d.flag_slot) {   // the stream is idle (synchronised above): a blocking 8-byte copy, done before the call returns
+          const long long verdict = res[r]->dense.carrier_unsafe ? 1 : 0;
+          PB200_CUDA(cudaMemcpy((long long*)d.i64_block + (d.i64_elems - 1), &verdict, 8, cudaMemcpyHostToDevice));
+        }
         continue;
       }
       if (exact) continue;
@@ -1472,7 +1480,7 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
     } else {
       std::vector<int> cards = R.dense.cards;
       R.meta.regime = regime_of(cards, query->max_initial_result_holder_capacity);
-      R.meta.reserved = (R.dense.pack_agg >= 0 ? 1 : 0) | (R.dense.carrier_unsafe ? 2 : 0);  // include/pinot_b200.h pb200_result_meta.reserved
+      R.meta.reserved = (R.dense.pack_agg >= 0 ? 1 : 0) | (R.dense.carrier_unsafe ? 2 : 0) | (R.dense.flag_slot ? 4 : 0);  // include/pinot_b200.h
     }
   }
   const bool defer_finalize = merge && (query->flags & PB200_Q_DEFER_FINALIZE);

@@ -138,15 +138,26 @@ def combine_tables(backend, block, query, dist, dst: int = 0):
     all-reduce that travels with the tables.  Returns (result or None, retry): retry == True on EVERY rank iff some rank
     said unsafe -- then all ranks must run the query again without the carrier (the tables of all ranks must share one
     layout, so the fallback is collective)."""
+    bufs = backend.buffers(block)
     flag = None
-    if block.count_carrier:
-        flag = backend.flag_tensor(1 if block.carrier_unsafe else 0)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-    reduce_buffers(backend.buffers(block), dist, dst)
-    backend.synchronize()
-    if flag is not None and int(flag.item()) != 0:
-        backend.free(block)
-        return None, True
+    if block.count_carrier and getattr(block, "flag_slot", False):
+        # the verdict rides as the last element of the int64 block: one SUM all-reduce moves tables and verdicts together
+        # (a separate 4-byte collective costs as much as the 1 MB one: both are latency bound)
+        dist.all_reduce(bufs["i64"], op=dist.ReduceOp.SUM)
+        flag = bufs["i64"][-1:]
+        reduce_buffers({k: v for k, v in bufs.items() if k != "i64"}, dist, dst)
+    else:
+        if block.count_carrier:
+            flag = backend.flag_tensor(1 if block.carrier_unsafe else 0)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        reduce_buffers(bufs, dist, dst)
+    if flag is not None:
+        unsafe = int(flag.item()) != 0   # host waits for the collectives queued before it
+        if unsafe:
+            backend.free(block)
+            return None, True
+    else:
+        backend.synchronize()
     return backend.finish(block, query, dist.get_rank() == dst), False
 
 

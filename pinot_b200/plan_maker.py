@@ -303,6 +303,7 @@ class ResultsBlock:
     handle: Optional[C.c_void_p] = None  # kept only for merged results (multi-GPU combine)
     count_carrier: bool = False  # the per-group row counts rode in an INT sum's reductions (pb200_api.cu)
     carrier_unsafe: bool = False  # deferred result: that sum may overflow in the cross-GPU reduce, rerun without carrier
+    flag_slot: bool = False  # the int64 table block ends with this rank's unsafe verdict: all-reduce it with the tables
 
     def release(self, ctx: "B200Context") -> None:
         """Frees the native result of a block executed with keep_handle=True."""
@@ -403,6 +404,7 @@ def _read_result(ctx: B200Context, handle, q: QueryContext, kind: int, keep_hand
                          ids, distinct, meta.device_ms, _lib.OPERATOR_KINDS.get(kind, "AGGREGATION"))
     block.count_carrier = bool(meta.reserved & 1)
     block.carrier_unsafe = bool(meta.reserved & 2)
+    block.flag_slot = bool(meta.reserved & 4)
     if keep_handle:
         block.handle = handle
     else:
