@@ -166,6 +166,8 @@ def execute_and_combine(plan_maker_or_backend, segments: Sequence, query, dist, 
     are reduced ONCE to rank `dst`, which gets the results block of the whole table (others get None)."""
     backend = plan_maker_or_backend if hasattr(plan_maker_or_backend, "finish") else DeviceBackend(plan_maker_or_backend)
     world = dist.get_world_size()
+    if any(a.function == "DISTINCTCOUNT" for a in query.aggregations):
+        return _combine_with_sets(backend, segments, query, dist, dst)
     if not query.is_group_by:
         return _combine_scalars(backend, segments, query, dist, dst)
     for no_carrier in (False, True):
@@ -176,13 +178,72 @@ def execute_and_combine(plan_maker_or_backend, segments: Sequence, query, dist, 
     raise AssertionError("unreachable: the second pass carries no counts")
 
 
+def _combine_with_sets(backend, segments, query, dist, dst):
+    """Queries with DISTINCTCOUNT: the per-group dictId SETS are not one of the element-wise reducible table blocks (NCCL has
+    no bitwise OR), so this path merges on the host like the reference's combine does (BaseDistinctAggregateAggregationFunction
+    .merge :109-121 = set union): every rank extracts its combined block, the (key ids, intermediates, id sets) travel with
+    all_gather_object and rank `dst` merges them by key.  Ids are only comparable across ranks when the key and DISTINCTCOUNT
+    columns are bound to one dictionary domain (global_domain) -- the caller's precondition, as for every cross-GPU merge."""
+    import numpy as np
+    from .plan_maker import ResultsBlock
+    block = backend.pm.execute_segments(segments, query, merge=True)[0]
+    fns = [a.function for a in query.aggregations]
+    rows = 1 if block.num_groups < 0 else block.num_groups
+    mine = {}
+    for g in range(rows):
+        key = () if block.num_groups < 0 else tuple(int(x) for x in block.keys[g])
+        mine[key] = [frozenset(int(d) for d in block.distinct[(a, g)]) if f == "DISTINCTCOUNT"
+                     else (float(block.doubles[a][g]), int(block.longs[a][g]), int(block.dict_ids[a][g])) for a, f in enumerate(fns)]
+    stats = (block.stats.num_docs_scanned, block.stats.num_entries_scanned_in_filter, block.stats.num_entries_scanned_post_filter,
+             block.stats.num_total_docs)
+    everyone = [None] * dist.get_world_size()
+    dist.all_gather_object(everyone, (mine, stats))
+    if dist.get_rank() != dst:
+        return None
+    merged = {}
+    for part, _ in everyone:
+        for key, vals in part.items():
+            cur = merged.get(key)
+            if cur is None:
+                merged[key] = list(vals)
+                continue
+            for a, f in enumerate(fns):
+                if f == "DISTINCTCOUNT":
+                    cur[a] = cur[a] | vals[a]
+                elif f in ("COUNT", "SUM", "AVG"):
+                    cur[a] = (cur[a][0] + vals[a][0], cur[a][1] + vals[a][1], -1)
+                elif f == "MIN":
+                    cur[a] = min(cur[a], vals[a], key=lambda t: t[0])
+                else:
+                    cur[a] = max(cur[a], vals[a], key=lambda t: t[0])
+    keys_sorted = sorted(merged)   # raw-key order is not defined across tables: ascending ids, column 0 most significant
+    n, k = len(keys_sorted), len(query.group_by)
+    out_keys = np.asarray(keys_sorted, dtype=np.int32).reshape(n, k) if query.is_group_by else np.zeros((0, 0), dtype=np.int32)
+    doubles, longs, ids, distinct = [], [], [], {}
+    for a, f in enumerate(fns):
+        d, l, i = np.zeros(max(n, 1)), np.zeros(max(n, 1), dtype=np.int64), np.full(max(n, 1), -1, dtype=np.int32)
+        for g, key in enumerate(keys_sorted):
+            v = merged[key][a]
+            if f == "DISTINCTCOUNT":
+                distinct[(a, g)] = np.asarray(sorted(v), dtype=np.int32)
+                d[g], l[g] = float(len(v)), len(v)
+            else:
+                d[g], l[g], i[g] = v
+        doubles.append(d[:n] if query.is_group_by else d); longs.append(l[:n] if query.is_group_by else l); ids.append(i[:n] if query.is_group_by else i)
+    block.num_groups = n if query.is_group_by else -1
+    block.keys, block.doubles, block.longs, block.dict_ids, block.distinct = out_keys, doubles, longs, ids, distinct
+    block.stats.num_docs_scanned = sum(s[0] for _, s in everyone)
+    block.stats.num_entries_scanned_in_filter = sum(s[1] for _, s in everyone)
+    block.stats.num_entries_scanned_post_filter = sum(s[2] for _, s in everyone)
+    block.stats.num_total_docs = sum(s[3] for _, s in everyone)
+    return block
+
+
 def _combine_scalars(backend, segments, query, dist, dst):
     """Aggregation-only queries: a handful of scalars per rank (AggregationResultsBlockMerger.java:34-44)."""
     import torch
     block = backend.pm.execute_segments(segments, query, merge=True)[0]
     fns = [a.function for a in query.aggregations]
-    if "DISTINCTCOUNT" in fns:
-        raise NotImplementedError("cross-GPU DISTINCTCOUNT (bitset OR) is not wired up")
     dev = f"cuda:{backend.ctx.device}"
     sums = torch.tensor([float(block.doubles[a][0]) if f in ("SUM", "AVG") else 0.0 for a, f in enumerate(fns)] +
                         [float(block.longs[a][0]) for a in range(len(fns))] + [float(block.stats.num_docs_scanned)],

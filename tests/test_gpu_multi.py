@@ -24,6 +24,8 @@ QUERIES = [
     "SELECT SUM(f), MAX(v) FROM t GROUP BY j",                              # float sums, shared-memory sized key space
     "SELECT SUM(v) FROM t WHERE l > 5000000000 GROUP BY k",                 # count only as the group-exists marker
     "SELECT COUNT(*), SUM(v), MIN(l), MAX(f) FROM t WHERE v < 400",         # aggregation only
+    "SELECT DISTINCTCOUNT(k), DISTINCTCOUNT(l), COUNT(*) FROM t WHERE v > 0",                 # id sets: merged on the host by set union
+    "SELECT DISTINCTCOUNT(v), SUM(v), MAX(l) FROM t WHERE j < 6 GROUP BY j",
 ]
 
 
@@ -72,7 +74,9 @@ def _worker(rank, world, port, out_dir, pack_shift):
                 vals = []
                 for a, agg in enumerate(q.aggregations):
                     vals.append(int(got.longs[a][g]) if agg.function == "COUNT" else
-                                (float(got.doubles[a][g]), int(got.longs[a][g])) if agg.function == "AVG" else float(got.doubles[a][g]))
+                                (float(got.doubles[a][g]), int(got.longs[a][g])) if agg.function == "AVG" else
+                                frozenset(devs[0].dictionary_value(agg.column, int(d)) for d in got.distinct[(a, g)])
+                                if agg.function == "DISTINCTCOUNT" else float(got.doubles[a][g]))
                 table[key] = vals
             report[text] = (table, [t for part in everyone for t in part], got.count_carrier if q.is_group_by else None)
     if rank == 0:
