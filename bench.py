@@ -310,8 +310,10 @@ def main():
     if dist is not None:
         # the per-GPU group tables are merged BY VALUE: all ranks' segments share table-wide dictionaries for the group key
         # and the summed column (synthetic dictionaries are identical, so binding re-encodes nothing)
-        from pinot_b200.distributed import global_domain
+        from pinot_b200.distributed import global_domain, init_comm
         domain = global_domain(ctx, segs, ["c3", "c5"], dist)
+        if os.environ.get("PB200_TORCH_REDUCE", "0") != "1":
+            init_comm(ctx, dist)   # the reduce of the group tables runs inside libpinot_b200.so (pb200_result_combine)
 
     def barrier():
         if dist is not None:

@@ -273,6 +273,27 @@ int32_t pb200_result_free(pb200_result* result);
 int32_t pb200_result_device_buffers(pb200_result* result, int32_t kind, void** device_ptr, int64_t* num_elements);
 int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* result);
 
+/* ---- where a query's host time goes (diagnostics; thread-local, the calling thread's last pb200_execute) ------------- */
+enum { PB200_PHASE_PLAN = 0, PB200_PHASE_LAUNCH = 1, PB200_PHASE_DEVICE_WAIT = 2, PB200_PHASE_RESULTS = 3,
+       PB200_PHASE_EXTRACT = 4, PB200_PHASE_TOTAL = 5, PB200_NUM_PHASES = 6 };
+int32_t pb200_last_phases(double* out_ms /* PB200_NUM_PHASES */);
+
+/* ---- cross-GPU combine inside the library (NCCL over NVLink / NVSwitch; one process per GPU) ---------------------- */
+/* NCCL is bound at run time (dlopen libnccl.so.2): everything else works without it.  Rank 0 creates the id, ships the
+ * bytes to the other ranks over any transport (the JVM's own RPC, torch.distributed, a file), every rank calls
+ * pb200_comm_init with its rank.  The reference merges per-server partial results by value on the JVM
+ * (GroupByCombineOperator.java:130-146); with table-wide dictionaries the per-GPU group tables are element-wise mergeable. */
+#define PB200_COMM_ID_BYTES 128
+int32_t pb200_comm_unique_id(void* id_out /* PB200_COMM_ID_BYTES */);
+int32_t pb200_comm_init(pb200_ctx* ctx, const void* id, int32_t rank, int32_t world_size);
+int32_t pb200_comm_shutdown(pb200_ctx* ctx);
+/* Every rank calls this with ITS deferred result (PB200_Q_MERGE_SEGMENTS | PB200_Q_DEFER_FINALIZE, reduce_world = world size)
+ * of the same query: all table blocks are reduced into rank `root` in ONE NCCL group on the context's stream and the root
+ * extracts the groups (the result is then read with the accessors; on the other ranks it stays empty -- free it).
+ * *retry = 1 on EVERY rank when a count-carrying sum was not provably safe for the reduce: all ranks free the result and
+ * execute again with PB200_Q_NO_COUNT_CARRIER. */
+int32_t pb200_result_combine(pb200_ctx* ctx, pb200_result* result, int32_t root, int32_t* retry);
+
 /* ---- synthetic segments (SegmentIndexCreationDriverImpl stand-in for benchmarks; bytes are Pinot's formats) ---- */
 typedef struct {
   int32_t cardinality;   /* dictionary = { value_base + value_step * i } (sorted INT) */

@@ -5,6 +5,7 @@
 // space (DictionaryBasedGroupKeyGenerator.java:105-186) and extracting results (GroupByOperator.java:116-140,
 // AggregationFunction.extractAggregationResult).
 #include <cuda_runtime.h>
+#include <chrono>
 
 #include <algorithm>
 #include <cmath>
@@ -21,6 +22,9 @@
 namespace pb200 {
 
 static thread_local char g_error[1024] = "";
+// Host wall-clock of the calling thread's last pb200_execute, by phase (pb200_last_phases): a few steady_clock reads per query.
+static thread_local double g_phase_ms[PB200_NUM_PHASES] = {};
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -191,6 +195,11 @@ using namespace pb200;
 // ------------------------------------------------------------------------------------------------------------------
 extern "C" const char* pb200_last_error(void) { return g_error; }
 extern "C" int32_t pb200_abi_version(void) { return PB200_ABI_VERSION; }
+extern "C" int32_t pb200_last_phases(double* out_ms) {
+  if (!out_ms) { set_error("null argument"); return PB200_E_INVALID; }
+  memcpy(out_ms, g_phase_ms, sizeof g_phase_ms);
+  return PB200_OK;
+}
 
 extern "C" int32_t pb200_init(int32_t device, pb200_ctx** out) {
   if (!out) { set_error("ctx out pointer is NULL"); return PB200_E_INVALID; }
@@ -270,6 +279,7 @@ extern "C" int32_t pb200_shutdown(pb200_ctx* ctx) {
   if (!ctx) return PB200_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  pb200_comm_shutdown(ctx);
   for (auto s : ctx->free_streams) cudaStreamDestroy(s);
   for (auto e : ctx->free_events) cudaEventDestroy(e);
   for (auto& kv : ctx->block_size) cudaFree(kv.first);
@@ -622,6 +632,7 @@ __global__ void carrier_verify_kernel(const unsigned long long* __restrict__ tab
 static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment* const* segments, int32_t nseg,
                         pb200_result** results, bool allow_count_carrier) {
   if (!ctx || !query || !segments || !results || nseg <= 0) { set_error("invalid argument to pb200_execute"); return PB200_E_INVALID; }
+  const double t_enter = now_ms();
   PB200_CUDA(cudaSetDevice(ctx->device));
   const bool per_seg_filter = query->flags & PB200_Q_PER_SEGMENT_FILTER;
   const bool merge = query->flags & PB200_Q_MERGE_SEGMENTS;
@@ -1343,6 +1354,7 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
     for (int s = c0; s < std::min(nseg, c0 + kMaxLaunchSegs); s++) { launch_segs[s].first_tile = cursor; cursor += launch_segs[s].num_tiles; }
   }
   PB200_CUDA(cudaMemcpyAsync(dsegs.p, launch_segs.data(), sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, st));
+  const double t_launch = now_ms();
   PB200_CUDA(cudaEventRecord(e0, st));
   for (int c0 = 0; c0 < nseg && le == cudaSuccess; c0 += kMaxLaunchSegs) {
     const int cn = std::min(nseg - c0, (int)kMaxLaunchSegs);
@@ -1384,8 +1396,10 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
       carrier_verify_kernel<<<vb, 256, 0, st>>>((const unsigned long long*)d.isum[d.pack_agg], d.groups, d.pack_shift, dev_verify + 4 * r);
     }
   PB200_CUDA(cudaMemcpyAsync(pin_back, accum_buf.p, acc_bytes, cudaMemcpyDeviceToHost, st));
+  const double t_queued = now_ms();
   cudaError_t se = cudaStreamSynchronize(st);
   if (se != cudaSuccess) { set_error("scan kernel failed: %s", cudaGetErrorString(se)); return PB200_E_CUDA; }
+  const double t_synced = now_ms();
   if (plan.group_by)
     for (int r = 0; r < nres; r++) {
       const pb200_result::Dense& d = res[r]->dense;
@@ -1484,6 +1498,7 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
     }
   }
   const bool defer_finalize = merge && (query->flags & PB200_Q_DEFER_FINALIZE);
+  const double t_results = now_ms();
   if (plan.group_by && defer_finalize) {
     for (int r = 0; r < nres; r++) { res[r]->meta.num_groups = 0; res[r]->dbl.assign(nagg, {}); res[r]->lng.assign(nagg, {}); res[r]->ids.assign(nagg, {}); res[r]->distinct.assign(nagg, {}); }
   } else if (plan.group_by) {  // all results of the submission are extracted together (two device round trips in total)
@@ -1505,6 +1520,13 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
   }
   cleanup.armed = false;
   for (int r = 0; r < nres; r++) results[r] = res[r].release();
+  const double t_exit = now_ms();
+  g_phase_ms[PB200_PHASE_PLAN] = t_launch - t_enter;       // validation, plan, table allocation + memsets queued, descriptors
+  g_phase_ms[PB200_PHASE_LAUNCH] = t_queued - t_launch;    // kernel launches queued
+  g_phase_ms[PB200_PHASE_DEVICE_WAIT] = t_synced - t_queued;
+  g_phase_ms[PB200_PHASE_RESULTS] = t_results - t_synced;  // carrier verdict, metadata, scalar results
+  g_phase_ms[PB200_PHASE_EXTRACT] = t_exit - t_results;    // group extraction (device kernels + their sync) and table release
+  g_phase_ms[PB200_PHASE_TOTAL] = t_exit - t_enter;
   return PB200_OK;
 }
 

@@ -82,6 +82,11 @@ struct pb200_ctx {
   std::mutex mu;
   std::vector<cudaStream_t> free_streams;
   std::vector<cudaEvent_t> free_events;
+  void* nccl_comm = nullptr;      // ncclComm_t of the cross-GPU combine (pb200_comm.cu), NULL until pb200_comm_init
+  int comm_rank = 0, comm_world = 1;
+  long long* comm_scratch = nullptr;  // device: 4 statistics in, 4 reduced out
+  long long* comm_pinned = nullptr;   // pinned host staging for the statistics and the carrier verdict
+  std::mutex comm_mu;
   std::multimap<size_t, void*> free_blocks;  // caching allocator: size -> block
   std::map<void*, size_t> block_size;
   size_t pooled_bytes = 0;

@@ -95,6 +95,29 @@ class DeviceBackend:
         self.pm = plan_maker
         self.ctx = plan_maker.ctx
 
+    @property
+    def native(self) -> bool:
+        """True once init_comm gave the context its own NCCL communicator: the reduce then runs INSIDE the library
+        (pb200_result_combine: one NCCL group + verdict + extraction on the library's stream, no torch tensors)."""
+        return getattr(self.ctx, "comm_world", 0) > 1
+
+    def combine_native(self, block, query, dst: int):
+        """-> (result or None, retry).  pb200_comm.cu."""
+        from . import _lib
+        from .plan_maker import _read_result
+        retry = C.c_int32(0)
+        _lib.check(self.ctx.lib.pb200_result_combine(self.ctx.handle, block.handle, dst, C.byref(retry)))
+        if retry.value:
+            self.free(block)
+            return None, True
+        out = None
+        if self.ctx.comm_rank == dst:
+            out = _read_result(self.ctx, block.handle, query, 1, keep_handle=False)
+        else:
+            self.ctx.lib.pb200_result_free(block.handle)
+        block.handle = None
+        return out, False
+
     def execute(self, segments, query, reduce_world: int, merged_docs_bound: int, no_count_carrier: bool):
         """-> a merged, NOT yet extracted results block (dense tables on the device) with .count_carrier / .carrier_unsafe"""
         return self.pm.execute_segments(segments, query, merge=True, keep_handle=True, reduce_world=reduce_world,
@@ -172,7 +195,10 @@ def execute_and_combine(plan_maker_or_backend, segments: Sequence, query, dist, 
         return _combine_scalars(backend, segments, query, dist, dst)
     for no_carrier in (False, True):
         block = backend.execute(segments, query, world, merged_docs_bound, no_carrier)
-        out, retry = combine_tables(backend, block, query, dist, dst)
+        if getattr(backend, "native", False):
+            out, retry = backend.combine_native(block, query, dst)
+        else:
+            out, retry = combine_tables(backend, block, query, dist, dst)
         if not retry:
             return out
     raise AssertionError("unreachable: the second pass carries no counts")
@@ -276,6 +302,23 @@ def combine_across_ranks(plan_maker, block, query, dist, dst: int = 0):
                          "for all ranks and agrees on the fallback collectively)")
     out, _ = combine_tables(DeviceBackend(plan_maker), block, query, dist, dst)
     return out
+
+
+def init_comm(ctx, dist) -> None:
+    """Give the context its own NCCL communicator (pb200_comm_init): rank 0 creates the id, torch.distributed (any backend)
+    only ships its 128 bytes.  After this execute_and_combine reduces inside the library."""
+    from . import _lib
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world < 2 or getattr(ctx, "comm_world", 0) > 1:
+        return
+    box = [None]
+    if rank == 0:
+        buf = (C.c_ubyte * 128)()
+        _lib.check(ctx.lib.pb200_comm_unique_id(buf))
+        box[0] = bytes(buf)
+    dist.broadcast_object_list(box, src=0)
+    _lib.check(ctx.lib.pb200_comm_init(ctx.handle, box[0], rank, world))
+    ctx.comm_rank, ctx.comm_world = rank, world
 
 
 def global_domain(ctx, segments: Sequence, columns: Sequence[str], dist):

@@ -45,6 +45,12 @@ class B200Context:
         """pb200_tuning_set: launch knobs of the scan kernel (defaults come from PB200_* environment variables at init)."""
         _lib.check(self.lib.pb200_tuning_set(self.handle, name.encode(), int(value)))
 
+    def last_phases(self) -> dict:
+        """pb200_last_phases: host wall-clock (ms) of this thread's last pb200_execute by phase."""
+        out = (C.c_double * 6)()
+        _lib.check(self.lib.pb200_last_phases(out))
+        return dict(zip(("plan", "launch", "device_wait", "results", "extract", "total"), (round(x, 4) for x in out)))
+
     def close(self):
         if self.handle:
             self.lib.pb200_shutdown(self.handle)

@@ -29,7 +29,7 @@ QUERIES = [
 ]
 
 
-def _worker(rank, world, port, out_dir, pack_shift):
+def _worker(rank, world, port, out_dir, pack_shift, native):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -39,7 +39,7 @@ def _worker(rank, world, port, out_dir, pack_shift):
     from gpu_util import oracle_table, to_device
     from oracle.pinot_oracle import oracle as get_oracle
     from pinot_b200 import sql
-    from pinot_b200.distributed import execute_and_combine, global_domain
+    from pinot_b200.distributed import execute_and_combine, global_domain, init_comm
     from pinot_b200.plan_maker import B200Context, B200PlanMaker
     o = get_oracle()
     rng = np.random.default_rng(77 + 13 * rank)
@@ -55,6 +55,8 @@ def _worker(rank, world, port, out_dir, pack_shift):
             "v": pv[rng.integers(0, len(pv), size=n)]}))
     ctx = B200Context(rank)
     pm = B200PlanMaker(ctx)
+    if native:
+        init_comm(ctx, dist)   # the reduce runs inside libpinot_b200.so (pb200_result_combine), torch only ships the NCCL id
     if pack_shift:
         ctx.set_tuning("pack_shift", pack_shift)
     devs = [to_device(ctx, s) for s in segs]
@@ -78,7 +80,8 @@ def _worker(rank, world, port, out_dir, pack_shift):
                                 frozenset(devs[0].dictionary_value(agg.column, int(d)) for d in got.distinct[(a, g)])
                                 if agg.function == "DISTINCTCOUNT" else float(got.doubles[a][g]))
                 table[key] = vals
-            report[text] = (table, [t for part in everyone for t in part], got.count_carrier if q.is_group_by else None)
+            report[text] = (table, [t for part in everyone for t in part], got.count_carrier if q.is_group_by else None,
+                            (got.stats.num_docs_scanned, got.stats.num_total_docs))
     if rank == 0:
         pickle.dump(report, open(os.path.join(out_dir, "report.pkl"), "wb"))
     for d in devs:
@@ -88,20 +91,23 @@ def _worker(rank, world, port, out_dir, pack_shift):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("pack_shift", [0, 12])
-def test_two_gpus_domain_and_table_reduce_equal_oracle_merge(tmp_path, pack_shift):
+@pytest.mark.parametrize("pack_shift,native", [(0, False), (12, False), (0, True), (12, True)])
+def test_two_gpus_domain_and_table_reduce_equal_oracle_merge(tmp_path, pack_shift, native):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from pinot_b200 import sql
     from gpu_util import assert_tables_equal
     from reduce_util import combine
-    port = 33000 + (os.getpid() % 1500) + pack_shift
-    mp.spawn(_worker, args=(2, port, str(tmp_path), pack_shift), nprocs=2, join=True)
+    port = 33000 + (os.getpid() % 1500) + pack_shift + int(native)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), pack_shift, native), nprocs=2, join=True)
     report = pickle.load(open(tmp_path / "report.pkl", "rb"))
-    for text, (got, parts, carrier) in report.items():
+    for text, (got, parts, carrier, stats) in report.items():
         q = sql.parse(text)
         assert_tables_equal(q, got, combine([a.function for a in q.aggregations], parts), f"2 GPUs: {text}")
+        if native and q.is_group_by and "DISTINCTCOUNT" not in text:
+            # the in-library combine also sums the execution statistics over the ranks (the broker's reduce of the metadata)
+            assert stats[1] == 2 * (30_000 + 50_001) + 8193 + 8194, stats
         if text.endswith("WHERE v > -400 GROUP BY k, j"):
             # default: 46-bit sum field, safe -> counts carried.  A 12-bit field (values span 2000) cannot be proven safe
             # for the reduce: BOTH ranks agree through the flag all-reduce and rerun without the carrier.

@@ -36,7 +36,7 @@ def main():
     import torch
     import torch.distributed as dist
     from pinot_b200 import sql
-    from pinot_b200.distributed import execute_and_combine
+    from pinot_b200.distributed import execute_and_combine, init_comm
     from pinot_b200.plan_maker import B200Context, B200PlanMaker, IndexSegment
 
     rank = int(os.environ.get("RANK", "0"))
@@ -47,6 +47,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = B200Context(local)
     pm = B200PlanMaker(ctx)
+    if world > 1 and os.environ.get("PB200_TORCH_REDUCE", "0") != "1":
+        init_comm(ctx, dist)
     segs = [IndexSegment.synthetic(ctx, f"r{rank}s{s}", args.rows,
                                    [{"name": n, "cardinality": c, "value_base": 1, "value_step": 3,
                                      "seed": 7919 * (rank * 1000 + s) + i} for i, (n, c) in enumerate(COLS)])
