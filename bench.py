@@ -310,7 +310,8 @@ def main():
     if dist is not None:
         # the per-GPU group tables are merged BY VALUE: all ranks' segments share table-wide dictionaries for the group key
         # and the summed column (synthetic dictionaries are identical, so binding re-encodes nothing)
-        from pinot_b200.distributed import global_domain, init_comm
+        from pinot_b200.distributed import DeviceBackend, global_domain, init_comm
+        combine_backend = DeviceBackend(pm, views=True)
         domain = global_domain(ctx, segs, ["c3", "c5"], dist)
         if os.environ.get("PB200_TORCH_REDUCE", "0") != "1":
             init_comm(ctx, dist)   # the reduce of the group tables runs inside libpinot_b200.so (pb200_result_combine)
@@ -322,10 +323,12 @@ def main():
 
     def gb_step():
         """The headline step: the whole table's results block on rank 0."""
+        # views=True: the block's columns alias the pinned host block the device extracted the groups into (what a JVM
+        # wraps with NewDirectByteBuffer) instead of being copied once more into numpy arrays
         if dist is not None:
-            block = execute_and_combine(pm, segs, q_gb, dist, dst=0, merged_docs_bound=rows_per_step * world)
+            block = execute_and_combine(combine_backend, segs, q_gb, dist, dst=0, merged_docs_bound=rows_per_step * world)
             return block, (block.device_ms if block is not None else pm.last_device_ms)
-        block = pm.execute_segments(segs, q_gb, merge=True)[0]
+        block = pm.execute_segments(segs, q_gb, merge=True, views=True)[0]
         return block, block.device_ms
 
     def c2_step():
@@ -365,6 +368,8 @@ def main():
         gb_table = block_table(gb_out)
         assert gb_table == block_table(gb_first), "non-deterministic result across steps"
         matched = sum(c for _, c in gb_table.values())
+    gb_out = gb_first = None   # blocks alias native results: dropped before the context closes
+    if rank == 0:
         expect = rows_per_step * world * args.selectivity
         assert abs(matched - expect) < 0.02 * expect + 10, (matched, expect)
 

@@ -175,8 +175,11 @@ typedef struct {
   const int32_t* ids;   /* host pointer; sorted ascending */
   double raw_lo, raw_hi;
   int32_t raw_flags;    /* bit0 lower unbounded, bit1 upper unbounded, bit2 lower exclusive, bit3 upper exclusive */
-  int32_t reserved;
+  int32_t reserved;     /* PB200_NODE_* bits */
 } pb200_filter_node;
+/* DOC_MASK whose `ids` is a DEVICE mask made by pb200_doc_mask_upload (a doc-id set reused by many queries, e.g. a cached
+ * star-tree traversal): nothing is copied at query time; the caller keeps it alive until the queries using it returned. */
+#define PB200_NODE_IDS_ON_DEVICE 1
 
 /* Aggregation functions accelerated on this path (core/query/aggregation/function/{Count,Sum,Min,Max,Avg,
  * DistinctCount}AggregationFunction.java). */
@@ -263,6 +266,12 @@ int64_t pb200_result_distinct(const pb200_result* result, int32_t agg, int32_t r
  * are read): keys [rows x num_group_by] (may be NULL), doubles / longs / dict_ids [num_aggs x rows] each (row-major by
  * aggregation; any may be NULL).  rows = num_groups, or 1 for an aggregation-only result. */
 int32_t pb200_result_fetch(const pb200_result* result, int32_t* keys, double* doubles, int64_t* longs, int32_t* dict_ids);
+/* Zero-copy face of the same data: pointers to the result's columns (group extraction leaves them in their final layout in
+ * a pinned host block -- a JVM wraps them with NewDirectByteBuffer, numpy with frombuffer).  keys -> [rows x num_group_by];
+ * doubles / longs / dict_ids -> arrays of num_aggs column pointers [rows] each; a NULL column means the neutral value
+ * (0.0 / 0 / -1) for every row.  Valid until pb200_result_free(result). */
+int32_t pb200_result_columns(const pb200_result* result, const int32_t** keys, const double** doubles, const int64_t** longs,
+                             const int32_t** dict_ids);
 int32_t pb200_result_free(pb200_result* result);
 
 /* ---- multi-GPU combine support (dense group tables with shared dictionaries) ----------------------------------- */
@@ -272,6 +281,11 @@ int32_t pb200_result_free(pb200_result* result);
  * After the collective, pb200_result_finalize() re-extracts the groups on the root rank. */
 int32_t pb200_result_device_buffers(pb200_result* result, int32_t kind, void** device_ptr, int64_t* num_elements);
 int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* result);
+
+/* ---- resident doc-id sets for PB200_F_DOC_MASK | PB200_NODE_IDS_ON_DEVICE ------------------------------------------- */
+int32_t pb200_doc_mask_upload(pb200_ctx* ctx, int32_t num_docs, const uint32_t* words, int64_t num_words /* >= ceil(num_docs/32) */,
+                              uint32_t** device_mask);
+int32_t pb200_doc_mask_free(pb200_ctx* ctx, uint32_t* device_mask);
 
 /* ---- where a query's host time goes (diagnostics; thread-local, the calling thread's last pb200_execute) ------------- */
 enum { PB200_PHASE_PLAN = 0, PB200_PHASE_LAUNCH = 1, PB200_PHASE_DEVICE_WAIT = 2, PB200_PHASE_RESULTS = 3,

@@ -395,6 +395,13 @@ struct Column {
       default: return std::nan("");
     }
   }
+  // identity of a raw value as a group key: the long for INT / LONG, doubleToLongBits of the (widened) value for FLOAT / DOUBLE
+  uint64_t raw_value_bits(int doc) const {
+    if (c->data_type == PO_INT || c->data_type == PO_LONG) return (uint64_t)raw_as_long(doc);
+    const double d = raw_as_double(doc);
+    uint64_t u; memcpy(&u, &d, 8);
+    return u;
+  }
   int64_t raw_as_long(int doc) const {
     const uint8_t* p = c->fwd + raw.raw_data_start;
     return c->data_type == PO_INT ? (int64_t)(int32_t)be32(p + 4ll * doc) : (int64_t)be64(p + 8ll * doc);
@@ -1102,14 +1109,55 @@ struct GroupKeyGenerator {
       }
     }
   }
+  // ---- NoDictionarySingleColumnGroupKeyGenerator.java:60-147,  NoDictionaryMultiColumnGroupKeyGenerator.java ----
+  // Chosen by DefaultGroupByExecutor.java:87-117 as soon as ONE group-by expression has no dictionary.  Raw columns get an
+  // on-the-fly dictionary (value -> id in first-seen order, ValueToIdMap), dictionary columns keep their dictIds; the id
+  // tuple maps to a group id in first-seen order, INVALID_ID once numGroupsLimit groups exist.  (With a single column the
+  // value itself is the map key -- the same first-seen numbering.)  Group keys of raw columns are VALUES in the result.
+  std::vector<uint8_t> col_raw;
+  std::vector<std::unordered_map<uint64_t, int>> otf;   // per raw column: value bits -> on-the-fly id
+  std::vector<std::vector<uint64_t>> otf_values;        // per raw column: value bits in id order
+  void init_no_dictionary(const std::vector<uint8_t>& raw_flags, int groups_limit) {
+    col_raw = raw_flags;
+    k = (int)raw_flags.size();
+    cards.assign(k, 0);
+    regime = PO_REGIME_NO_DICT;
+    num_groups_limit = groups_limit;
+    upper_bound = groups_limit;
+    otf.assign(k, {});
+    otf_values.assign(k, {});
+  }
+  // ids[j][i]: dictId (dictionary column) ; bits[j][i]: value bits (raw column)
+  void generate_no_dictionary(int n, const std::vector<std::vector<int>>& ids, const std::vector<std::vector<uint64_t>>& bits, int* out) {
+    std::vector<int> key(k);
+    for (int i = 0; i < n; i++) {
+      for (int j = 0; j < k; j++) {
+        if (!col_raw[j]) { key[j] = ids[j][i]; continue; }
+        auto f = otf[j].find(bits[j][i]);
+        if (f != otf[j].end()) key[j] = f->second;
+        else { key[j] = (int)otf_values[j].size(); otf[j].emplace(bits[j][i], key[j]); otf_values[j].push_back(bits[j][i]); }
+      }
+      auto it = array_map.find(key);
+      if (it != array_map.end()) { out[i] = it->second; continue; }
+      if ((int)array_map.size() < upper_bound) {
+        int id = (int)array_map.size();
+        array_map.emplace(key, id);
+        array_keys_in_order.push_back(key);
+        out[i] = id;
+      } else {
+        out[i] = -1;
+      }
+    }
+  }
   int current_upper_bound() const {  // getCurrentGroupKeyUpperBound
+    if (regime == PO_REGIME_NO_DICT) return (int)array_map.size();
     if (regime == PO_REGIME_ARRAY) return upper_bound;
     if (regime == PO_REGIME_ARRAY_MAP) return (int)array_map.size();
     return (int)map.size();
   }
   int num_keys_total() const {
     if (regime == PO_REGIME_ARRAY) return num_keys;
-    if (regime == PO_REGIME_ARRAY_MAP) return (int)array_map.size();
+    if (regime == PO_REGIME_ARRAY_MAP || regime == PO_REGIME_NO_DICT) return (int)array_map.size();
     return (int)map.size();
   }
 };
@@ -1126,7 +1174,9 @@ struct po_result {
   bool limit_reached = false;
   int64_t stats[4] = {0, 0, 0, 0};
   int num_group_by = 0;
-  std::vector<int32_t> keys;                       // [G x k]
+  std::vector<int32_t> keys;                       // [G x k]: dictIds; for raw group-by columns ids of raw_key_bits[j]
+  std::vector<std::vector<uint64_t>> raw_key_bits; // per group-by column: on-the-fly dictionary (empty for dictionary columns)
+  std::vector<int> raw_key_type;                   // per group-by column: PO_* stored type of a raw column, else -1
   std::vector<std::vector<double>> dbl;            // per agg: [G]
   std::vector<std::vector<int64_t>> lng;           // per agg: [G]
   std::vector<std::vector<std::vector<int32_t>>> distinct;  // per agg: per group: sorted dictIds
@@ -1172,14 +1222,20 @@ void run_query(const Segment& seg, const po_query_t& q, po_result& res, std::vec
   GroupKeyGenerator gkg;
   if (k > 0) {
     std::vector<int> cards;
+    std::vector<uint8_t> raw_flags;
+    bool any_raw = false;
     for (int j = 0; j < k; j++) {
       const Column& c = seg.cols[q.group_by_columns[j]];
-      if (!c.c->has_dictionary) { res.error = "group-by on raw column not supported by the oracle"; return; }
+      raw_flags.push_back(c.c->has_dictionary ? 0 : 1);
+      any_raw |= !c.c->has_dictionary;
+      if (!c.c->has_dictionary && (!c.raw.ok || c.c->data_type == PO_STRING)) { res.error = "group-by on this raw column is not supported by the oracle"; return; }
       cards.push_back(c.card());
     }
-    gkg.init(cards, q.num_groups_limit, q.max_initial_result_holder_capacity);
+    if (any_raw) gkg.init_no_dictionary(raw_flags, q.num_groups_limit);
+    else gkg.init(cards, q.num_groups_limit, q.max_initial_result_holder_capacity);
     res.regime = gkg.regime;
   }
+  std::vector<std::vector<uint64_t>> gb_raw_bits(k);
 
   std::vector<int> doc_ids(kMaxDocPerCall), group_keys(kMaxDocPerCall);
   std::vector<std::vector<int>> gb_dict_ids(k, std::vector<int>(kMaxDocPerCall));
@@ -1214,10 +1270,17 @@ void run_query(const Segment& seg, const po_query_t& q, po_result& res, std::vec
     };
     if (k > 0) {
       for (int j = 0; j < k; j++) {
+        const Column& gc = seg.cols[q.group_by_columns[j]];
+        if (!gc.c->has_dictionary) {  // values of the block (ProjectionBlockValSet.get{Int,Long,Float,Double}ValuesSV)
+          gb_raw_bits[j].resize(n);
+          for (int i = 0; i < n; i++) gb_raw_bits[j][i] = gc.raw_value_bits(doc_ids[i]);
+          continue;
+        }
         const std::vector<int>& v = dict_ids_of(q.group_by_columns[j]);
         std::copy(v.begin(), v.begin() + n, gb_dict_ids[j].begin());
       }
-      gkg.generate(n, gb_dict_ids, group_keys.data());
+      if (gkg.regime == PO_REGIME_NO_DICT) gkg.generate_no_dictionary(n, gb_dict_ids, gb_raw_bits, group_keys.data());
+      else gkg.generate(n, gb_dict_ids, group_keys.data());
       int cap = gkg.current_upper_bound();
       for (auto& a : aggs) a.ensure(cap);
     }
@@ -1311,15 +1374,19 @@ void run_query(const Segment& seg, const po_query_t& q, po_result& res, std::vec
   std::vector<std::pair<int64_t, int>> groups;  // (raw key or index, group id)
   if (gkg.regime == PO_REGIME_ARRAY) {
     for (int r = 0; r < gkg.upper_bound; r++) if (gkg.flags[r]) groups.push_back({r, r});
-  } else if (gkg.regime == PO_REGIME_ARRAY_MAP) {
+  } else if (gkg.regime == PO_REGIME_ARRAY_MAP || gkg.regime == PO_REGIME_NO_DICT) {
     for (int g = 0; g < (int)gkg.array_keys_in_order.size(); g++) groups.push_back({g, g});
   } else {
     for (int g = 0; g < (int)gkg.keys_in_order.size(); g++) groups.push_back({gkg.keys_in_order[g], g});
   }
   res.num_groups = (int)groups.size();
   for (auto& a : aggs) a.ensure(gkg.regime == PO_REGIME_ARRAY ? gkg.upper_bound : res.num_groups);
+  if (gkg.regime == PO_REGIME_NO_DICT) {
+    res.raw_key_bits = gkg.otf_values;
+    for (int j = 0; j < k; j++) res.raw_key_type.push_back(gkg.col_raw[j] ? seg.cols[q.group_by_columns[j]].c->data_type : -1);
+  }
   for (auto& gr : groups) {
-    if (gkg.regime == PO_REGIME_ARRAY_MAP) {
+    if (gkg.regime == PO_REGIME_ARRAY_MAP || gkg.regime == PO_REGIME_NO_DICT) {
       for (int j = 0; j < k; j++) res.keys.push_back(gkg.array_keys_in_order[gr.second][j]);
     } else {
       int64_t raw = gr.first;
@@ -1411,6 +1478,19 @@ int64_t po_result_distinct(const po_result_t* r, int32_t a, int32_t g, int32_t* 
   if (a >= (int)r->distinct.size() || g >= (int)r->distinct[a].size()) return 0;
   const auto& v = r->distinct[a][g];
   for (int64_t i = 0; i < (int64_t)v.size() && i < cap; i++) out[i] = v[i];
+  return (int64_t)v.size();
+}
+// Raw group-by column j: the on-the-fly dictionary (id -> value); returns its size, 0 for dictionary columns.
+int64_t po_result_raw_key_values(const po_result_t* r, int32_t j, double* out_d, int64_t* out_l, int64_t cap) {
+  if (j < 0 || j >= (int)r->raw_key_bits.size()) return 0;
+  const auto& v = r->raw_key_bits[j];
+  const bool integral = r->raw_key_type[j] == PO_INT || r->raw_key_type[j] == PO_LONG;
+  for (int64_t i = 0; i < (int64_t)v.size() && i < cap; i++) {
+    double d; int64_t l;
+    if (integral) { l = (int64_t)v[i]; d = (double)l; } else { memcpy(&d, &v[i], 8); l = (int64_t)d; }
+    if (out_d) out_d[i] = d;
+    if (out_l) out_l[i] = l;
+  }
   return (int64_t)v.size();
 }
 void po_result_free(po_result_t* r) { delete r; }

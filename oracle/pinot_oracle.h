@@ -93,7 +93,7 @@ typedef struct {
   const int32_t* doc_ids;
 } po_query_t;
 
-enum { PO_REGIME_NONE = 0, PO_REGIME_ARRAY = 1, PO_REGIME_INT_MAP = 2, PO_REGIME_LONG_MAP = 3, PO_REGIME_ARRAY_MAP = 4 };
+enum { PO_REGIME_NONE = 0, PO_REGIME_ARRAY = 1, PO_REGIME_INT_MAP = 2, PO_REGIME_LONG_MAP = 3, PO_REGIME_ARRAY_MAP = 4, PO_REGIME_NO_DICT = 5 };
 
 typedef struct po_result po_result_t;
 
@@ -131,6 +131,7 @@ void po_result_agg_double(const po_result_t* r, int32_t agg, double* out);
 void po_result_agg_long(const po_result_t* r, int32_t agg, int64_t* out);
 /* DISTINCTCOUNT: sorted dictIds of one group (group = 0 for aggregation only); returns count */
 int64_t po_result_distinct(const po_result_t* r, int32_t agg, int32_t group, int32_t* out, int64_t cap);
+int64_t po_result_raw_key_values(const po_result_t* r, int32_t group_by_column, double* out_d, int64_t* out_l, int64_t cap);
 void po_result_free(po_result_t* r);
 
 /* ---- star-tree (OffHeapStarTree / StarTreeFilterOperator.traverseStarTree) ---- */

@@ -21,7 +21,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libpinot_oracle.so")
 
 _TYPE_CODES = {"AND": 0, "OR": 1, "NOT": 2, "EQ": 3, "NEQ": 4, "IN": 5, "NOT_IN": 6, "RANGE": 7}
 _FN_CODES = {"COUNT": 0, "SUM": 1, "MIN": 2, "MAX": 3, "AVG": 4, "DISTINCTCOUNT": 5}
-REGIMES = {0: "NONE", 1: "ARRAY", 2: "INT_MAP", 3: "LONG_MAP", 4: "ARRAY_MAP"}
+REGIMES = {0: "NONE", 1: "ARRAY", 2: "INT_MAP", 3: "LONG_MAP", 4: "ARRAY_MAP", 5: "NO_DICTIONARY"}
 
 
 class _Column(C.Structure):
@@ -85,6 +85,8 @@ class OracleResult:
     doubles: List[np.ndarray]  # per aggregation [G or 1]
     longs: List[np.ndarray]
     distinct: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)  # (agg, group) -> sorted dictIds
+    # group-by position j of a RAW column -> its on-the-fly dictionary (id -> value): keys[:, j] are ids into it
+    raw_key_values: Dict[int, np.ndarray] = field(default_factory=dict)
 
 
 class Oracle:
@@ -104,6 +106,8 @@ class Oracle:
         L.po_result_agg_long.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.po_result_distinct.restype = C.c_int64
         L.po_result_distinct.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+        L.po_result_raw_key_values.restype = C.c_int64
+        L.po_result_raw_key_values.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
         L.po_result_free.argtypes = [C.c_void_p]
         L.po_filter_doc_ids.restype = C.c_int64
         L.po_filter_doc_ids.argtypes = [C.POINTER(_Segment), C.POINTER(_Query), C.c_void_p, C.c_int64,
@@ -216,15 +220,16 @@ class Oracle:
         return out
 
     # ---------------------------------------------------------------- segments / queries
-    def build_segment(self, name, columns, inverted=(), raw=()) -> sb.SegmentData:
-        return sb.build_segment(name, columns, inverted=inverted, raw=raw, lib=self)
+    def build_segment(self, name, columns, inverted=(), raw=(), raw_compression=None) -> sb.SegmentData:
+        return sb.build_segment(name, columns, inverted=inverted, raw=raw, lib=self, raw_compression=raw_compression)
 
     @staticmethod
     def _c_segment(seg: sb.SegmentData):
         cols = (_Column * len(seg.columns))()
         for i, c in enumerate(seg.columns):
+            fwd = c.fwd if getattr(c, "oracle_fwd", None) is None else c.oracle_fwd   # compressed raw chunks: decoded by chunk_codecs
             cols[i] = _Column(c.data_type, int(c.has_dictionary), c.bits, c.cardinality, int(c.is_sorted),
-                              c.dict_entry_bytes, _ptr(c.fwd), len(c.fwd), _ptr(c.dict),
+                              c.dict_entry_bytes, _ptr(fwd), len(fwd), _ptr(c.dict),
                               0 if c.dict is None else len(c.dict), _ptr(c.inv), 0 if c.inv is None else len(c.inv))
         return _Segment(seg.num_docs, len(seg.columns), cols), cols
 
@@ -338,9 +343,16 @@ class Oracle:
                         ids = np.zeros(int(l[grp]), dtype=np.int32)
                         self.lib.po_result_distinct(r, a, grp, _ptr(ids), len(ids))
                         distinct[(a, grp)] = ids
+            raw_keys = {}
+            for j, name in enumerate(q.group_by):
+                n = self.lib.po_result_raw_key_values(r, j, None, None, 0)
+                if n > 0:
+                    d, l = np.zeros(n, dtype=np.float64), np.zeros(n, dtype=np.int64)
+                    self.lib.po_result_raw_key_values(r, j, _ptr(d), _ptr(l), n)
+                    raw_keys[j] = l if seg.column(name).data_type in (sb.INT, sb.LONG) else d
             return OracleResult(g, REGIMES[self.lib.po_result_regime(r)],
                                 bool(self.lib.po_result_groups_limit_reached(r)), tuple(stats), keys, doubles, longs,
-                                distinct)
+                                distinct, raw_keys)
         finally:
             self.lib.po_result_free(r)
 

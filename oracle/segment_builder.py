@@ -69,6 +69,9 @@ class ColumnData:
     dict_values: Optional[np.ndarray] = None  # decoded dictionary (numeric array or array of bytes)
     dict_ids: Optional[np.ndarray] = None  # int32 per doc (kept for tests)
     raw_values: Optional[np.ndarray] = None
+    # raw column written with compressed chunks: `fwd` is that file (what a loader gets), `oracle_fwd` the same values as
+    # PASS_THROUGH chunks -- the C oracle reads those; the chunk codecs are the oracle's Python half (oracle/chunk_codecs.py)
+    oracle_fwd: Optional[np.ndarray] = None
 
 
 @dataclass
@@ -106,23 +109,21 @@ def _np_type_of(values: np.ndarray) -> int:
     raise TypeError(values.dtype)
 
 
-def build_raw_column(name: str, values: np.ndarray, version: int = 2) -> ColumnData:
-    """No-dictionary fixed-byte SV column, PASS_THROUGH chunks (FixedByteChunkForwardIndexWriter layout)."""
+def build_raw_column(name: str, values: np.ndarray, version: int = 2, compression: int = 0, docs_per_chunk: int = 1000) -> ColumnData:
+    """No-dictionary fixed-byte SV column (FixedByteChunkForwardIndexWriter layout); `compression` is a ChunkCompressionType
+    ordinal (0 PASS_THROUGH, 1 SNAPPY, 3 LZ4, 4 LZ4_LENGTH_PREFIXED)."""
+    from . import chunk_codecs as cc
     values = np.asarray(values)
     dt = _np_type_of(values)
     width = np.dtype(_NP_BE[dt]).itemsize
     n = values.shape[0]
-    docs_per_chunk = 1000
-    num_chunks = (n + docs_per_chunk - 1) // docs_per_chunk
-    off_size = 4 if version <= 2 else 8
-    header = [version, num_chunks, docs_per_chunk, width, n, 0, 7 * 4]  # ..., totalDocs, PASS_THROUGH(0), dataHeaderStart
-    hdr = np.asarray(header, dtype=">i4").tobytes()
-    data_start = len(hdr) + num_chunks * off_size
-    offs = np.asarray([data_start + c * docs_per_chunk * width for c in range(num_chunks)],
-                      dtype=">i4" if off_size == 4 else ">i8").tobytes()
     body = values.astype(_NP_BE[dt]).tobytes()
-    fwd = np.frombuffer(hdr + offs + body, dtype=np.uint8).copy()
-    return ColumnData(name, dt, False, 0, 0, False, width, fwd, None, None, raw_values=values)
+    plain = cc.encode_fixed_byte_forward(body, width, n, cc.PASS_THROUGH, 2 if version == 1 else version, docs_per_chunk)
+    if compression == cc.PASS_THROUGH and version != 1:
+        return ColumnData(name, dt, False, 0, 0, False, width, plain, None, None, raw_values=values)
+    fwd = cc.encode_fixed_byte_forward(body, width, n, compression, version, docs_per_chunk)
+    assert cc.decode_fixed_byte_forward(fwd, width, n) == body
+    return ColumnData(name, dt, False, 0, 0, False, width, fwd, None, None, raw_values=values, oracle_fwd=plain)
 
 
 def build_column(name: str, values: np.ndarray, inverted: bool = False, lib=None) -> ColumnData:
@@ -155,7 +156,7 @@ def build_column(name: str, values: np.ndarray, inverted: bool = False, lib=None
 
 
 def build_segment(name: str, columns: Dict[str, np.ndarray], inverted: Sequence[str] = (), raw: Sequence[str] = (),
-                  lib=None) -> SegmentData:
+                  lib=None, raw_compression: Optional[Dict[str, int]] = None) -> SegmentData:
     n = None
     cols = []
     for cname, vals in columns.items():
@@ -163,7 +164,7 @@ def build_segment(name: str, columns: Dict[str, np.ndarray], inverted: Sequence[
         n = vals.shape[0] if n is None else n
         assert vals.shape[0] == n
         if cname in raw:
-            cols.append(build_raw_column(cname, vals))
+            cols.append(build_raw_column(cname, vals, compression=(raw_compression or {}).get(cname, 0)))
         else:
             cols.append(build_column(cname, vals, inverted=cname in inverted, lib=lib))
     return SegmentData(name, int(n), cols)

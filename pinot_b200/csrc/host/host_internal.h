@@ -12,6 +12,7 @@
 #include "../pb200_internal.h"
 
 namespace pb200h {
+using pb200::set_error;
 
 inline uint32_t hbe32(const unsigned char* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
 inline uint64_t hbe64(const unsigned char* p) { return (uint64_t)hbe32(p) << 32 | hbe32(p + 4); }
@@ -20,6 +21,7 @@ struct HostColumn {
   std::string name;
   int data_type = 0, has_dictionary = 0, bits = 0, cardinality = 0, is_sorted = 0, entry_bytes = 0;
   bool has_inverted = false;
+  bool synthesized_dictionary = false;    // the segment stores this column raw: `dict` was built from its values at load (raw_forward.cpp)
   std::vector<unsigned char> dict;        // big-endian values or padded strings (host copy): the SEGMENT's own dictionary
   std::vector<unsigned char> sorted_idx;  // (start,end) BE pairs when is_sorted
   // Bound to a table-wide dictionary domain (pb200h_segment_bind_domain): predicates are still resolved against the
@@ -106,7 +108,11 @@ struct StarTreeIndex {
   // Traversal results by (predicate dictId sets per dimension, group-by mask): the BFS over a tree with 10^5..10^6 nodes
   // costs more host time than the device scan of the docs it selects, and dashboards repeat their predicates.  The
   // tree is immutable, so an entry never goes stale; a handful of entries, oldest evicted first.
-  struct Traversal { std::string key; std::vector<uint32_t> mask; uint32_t remaining = 0; };
+  struct Traversal {
+    std::string key; std::vector<uint32_t> mask; uint32_t remaining = 0;
+    pb200_ctx* ctx = nullptr; uint32_t* dev_mask = nullptr;   // the mask resident in HBM (pb200_doc_mask_upload): no per-query copy
+    ~Traversal() { if (dev_mask) pb200_doc_mask_free(ctx, dev_mask); }
+  };
   mutable std::mutex cache_mu;
   mutable std::deque<std::shared_ptr<const Traversal>> cache;
   ~StarTreeIndex();
@@ -128,6 +134,12 @@ struct pb200h_segment {
 };
 
 namespace pb200h {
+// raw_forward.cpp: no-dictionary fixed-width SV forward indexes at load time
+int raw_value_width(int data_type);
+int decode_fixed_byte_forward(const unsigned char* file, uint64_t len, int width, int64_t num_docs, std::vector<unsigned char>& values_be);
+void wrap_pass_through(const std::vector<unsigned char>& values_be, int width, int64_t num_docs, std::vector<unsigned char>& file);
+bool synthesize_dictionary(const std::vector<unsigned char>& values_be, int data_type, int64_t num_docs, int max_cardinality,
+                           std::vector<unsigned char>& dict_be, std::vector<unsigned char>& fwd_packed, int* cardinality, int* bits);
 // ids[] storage that must outlive the pb200_execute call
 struct SegmentFilterStore { std::vector<std::unique_ptr<std::vector<int32_t>>> ids; };
 // PredicateEvaluator.getMatchingDictIds (sorted) of one predicate on a dictionary column

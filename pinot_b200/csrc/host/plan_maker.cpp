@@ -296,6 +296,10 @@ extern "C" int32_t pb200h_segment_create(pb200_ctx* ctx, const char* name, int32
   std::unique_ptr<pb200h_segment> seg(new pb200h_segment());
   seg->ctx = ctx; seg->name = name ? name : ""; seg->num_docs = num_docs;
   std::vector<pb200_col_desc> descs(ncols);
+  // Raw (no-dictionary) columns: all chunks are decoded once here; a column with at most PB200_RAW_DICT_MAX (default 2^20)
+  // distinct values is dictionary-encoded on the fly and is an ordinary dictionary column from here on (raw_forward.cpp)
+  std::vector<std::vector<unsigned char>> owned_fwd(ncols), owned_dict(ncols);
+  const int raw_dict_max = [&]() { std::lock_guard<std::mutex> g(ctx->mu); return ctx->tune.raw_dict_max; }();
   for (int i = 0; i < ncols; i++) {
     const pb200h_column& c = cols[i];
     HostColumn h;
@@ -303,11 +307,35 @@ extern "C" int32_t pb200h_segment_create(pb200_ctx* ctx, const char* name, int32
     h.data_type = c.data_type; h.has_dictionary = c.has_dictionary; h.bits = c.bits_per_value;
     h.cardinality = c.cardinality; h.is_sorted = c.is_sorted; h.entry_bytes = c.dict_entry_bytes;
     h.has_inverted = c.inv != nullptr && c.inv_bytes > 0 && !c.is_sorted;
-    if (c.dict && c.dict_bytes) h.dict.assign((const unsigned char*)c.dict, (const unsigned char*)c.dict + c.dict_bytes);
-    if (c.is_sorted && c.fwd) h.sorted_idx.assign((const unsigned char*)c.fwd, (const unsigned char*)c.fwd + c.fwd_bytes);
     pb200_col_desc& d = descs[i];
     memset(&d, 0, sizeof d);
-    d.fwd_kind = !c.has_dictionary ? PB200_FWD_RAW_FIXEDBYTE : c.is_sorted ? PB200_FWD_DICT_SORTED : PB200_FWD_DICT_FIXEDBIT;
+    if (!c.has_dictionary) {
+      const int width = raw_value_width(c.data_type);
+      if (width == 0) { set_error("raw column '%s' of type %d is not loadable (fixed-width numeric types only)", h.name.c_str(), c.data_type); return PB200_E_UNSUPPORTED; }
+      std::vector<unsigned char> values;
+      int rc = decode_fixed_byte_forward((const unsigned char*)c.fwd, c.fwd_bytes, width, num_docs, values);
+      if (rc) return rc;
+      int card = 0, nb = 0;
+      if (raw_dict_max > 0 && synthesize_dictionary(values, c.data_type, num_docs, raw_dict_max, owned_dict[i], owned_fwd[i], &card, &nb)) {
+        h.has_dictionary = 1; h.synthesized_dictionary = true; h.bits = nb; h.cardinality = card; h.entry_bytes = width;
+        h.is_sorted = 0; h.has_inverted = false;
+        h.dict = owned_dict[i];
+        d.fwd_kind = PB200_FWD_DICT_FIXEDBIT;
+        d.stored_type = c.data_type; d.bits_per_value = nb; d.cardinality = card;
+        d.fwd = owned_fwd[i].data(); d.fwd_bytes = owned_fwd[i].size();
+        d.dict = owned_dict[i].data(); d.dict_bytes = owned_dict[i].size();
+      } else {
+        wrap_pass_through(values, width, num_docs, owned_fwd[i]);
+        d.fwd_kind = PB200_FWD_RAW_FIXEDBYTE;
+        d.stored_type = c.data_type;
+        d.fwd = owned_fwd[i].data(); d.fwd_bytes = owned_fwd[i].size();
+      }
+      seg->cols.push_back(std::move(h));
+      continue;
+    }
+    if (c.dict && c.dict_bytes) h.dict.assign((const unsigned char*)c.dict, (const unsigned char*)c.dict + c.dict_bytes);
+    if (c.is_sorted && c.fwd) h.sorted_idx.assign((const unsigned char*)c.fwd, (const unsigned char*)c.fwd + c.fwd_bytes);
+    d.fwd_kind = c.is_sorted ? PB200_FWD_DICT_SORTED : PB200_FWD_DICT_FIXEDBIT;
     d.stored_type = c.data_type; d.bits_per_value = c.bits_per_value; d.cardinality = c.cardinality;
     d.fwd = c.fwd; d.fwd_bytes = c.fwd_bytes;
     d.dict = c.dict; d.dict_bytes = c.dict_bytes;  // STRING: kept on the host by the device layer too (hashing / domains)

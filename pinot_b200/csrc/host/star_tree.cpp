@@ -349,6 +349,8 @@ int try_star_tree(pb200_ctx* ctx, const pb200h_segment& seg, const StarTreeIndex
         else { mask[ws] |= first; for (int w = ws + 1; w < we; w++) mask[w] = 0xFFFFFFFFu; mask[we] |= last; }
       }
     }
+    if (pb200_doc_mask_upload(ctx, sdocs, fresh->mask.data(), (int64_t)fresh->mask.size(), &fresh->dev_mask) == PB200_OK) fresh->ctx = ctx;
+    else fresh->dev_mask = nullptr;  // the per-query upload still works
     tr = fresh;
     std::lock_guard<std::mutex> g(st.cache_mu);
     st.cache.push_back(tr);
@@ -363,6 +365,7 @@ int try_star_tree(pb200_ctx* ctx, const pb200h_segment& seg, const StarTreeIndex
   pb200_filter_node mn;
   memset(&mn, 0, sizeof mn);
   mn.op = PB200_F_DOC_MASK; mn.column = -1; mn.ids = (const int32_t*)mask.data(); mn.num_ids = (int32_t)mask.size();
+  if (tr->dev_mask) { mn.ids = (const int32_t*)tr->dev_mask; mn.reserved = PB200_NODE_IDS_ON_DEVICE; }
   nodes.push_back(mn);
   int extra = 0;
   for (int li : leaves) {
@@ -408,11 +411,13 @@ int try_star_tree(pb200_ctx* ctx, const pb200h_segment& seg, const StarTreeIndex
       v.ids[a] = nullptr;   // all -1: star-tree metrics are raw values
       const int src = m.fn == PB200_AGG_COUNT ? m.a0 : m.fn == PB200_AGG_AVG ? m.a1 : -1;
       if (src >= 0 && sv.dbl[src]) {
-        std::vector<int64_t>& l = R->lng[a];
-        l.resize(rows);
+        // row counts = sums of the star-tree COUNT metric: non-negative integers, exact in double.  The SUM's own (unused)
+        // long column inside the pinned block takes them -- no allocation, no libm call per row
         const double* d = sv.dbl[src];
-        for (size_t r = 0; r < rows; r++) l[r] = (int64_t)std::llround(d[r]);
-        v.lng[a] = l.data();
+        int64_t* l = const_cast<int64_t*>(sv.lng[src]);
+        if (!l) { R->lng[a].resize(rows); l = R->lng[a].data(); }
+        for (size_t r = 0; r < rows; r++) l[r] = (int64_t)(d[r] + 0.5);
+        v.lng[a] = l;
       }
     }
   } else {

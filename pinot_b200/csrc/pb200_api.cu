@@ -195,6 +195,31 @@ using namespace pb200;
 // ------------------------------------------------------------------------------------------------------------------
 extern "C" const char* pb200_last_error(void) { return g_error; }
 extern "C" int32_t pb200_abi_version(void) { return PB200_ABI_VERSION; }
+// words a device doc mask needs: whole tiles + one spare tile (the kernel reads masks tile-wise) + a tail
+static size_t doc_mask_words(long long num_docs) { return (((size_t)num_docs + kMaxTileRows - 1) / kMaxTileRows + 1) * (kMaxTileRows / 32) + 8; }
+
+extern "C" int32_t pb200_doc_mask_upload(pb200_ctx* ctx, int32_t num_docs, const uint32_t* words_in, int64_t num_words, uint32_t** out) {
+  if (!ctx || !words_in || !out || num_docs < 0) { set_error("invalid argument to pb200_doc_mask_upload"); return PB200_E_INVALID; }
+  const size_t need = ((size_t)num_docs + 31) / 32, words = doc_mask_words(num_docs);
+  if ((size_t)num_words < need) { set_error("doc mask needs %zu words, got %lld", need, (long long)num_words); return PB200_E_INVALID; }
+  PB200_CUDA(cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  int rc = dev_alloc(ctx, words * 4, &p);
+  if (rc) return rc;
+  cudaStream_t st = take_stream(ctx);
+  cudaError_t e = cudaMemsetAsync((uint32_t*)p + need, 0, (words - need) * 4, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p, words_in, need * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  give_stream(ctx, st);
+  if (e != cudaSuccess) { dev_free(ctx, p); set_error("doc mask upload failed: %s", cudaGetErrorString(e)); return PB200_E_CUDA; }
+  *out = (uint32_t*)p;
+  return PB200_OK;
+}
+extern "C" int32_t pb200_doc_mask_free(pb200_ctx* ctx, uint32_t* mask) {
+  if (ctx && mask) dev_free(ctx, mask);
+  return PB200_OK;
+}
+
 extern "C" int32_t pb200_last_phases(double* out_ms) {
   if (!out_ms) { set_error("null argument"); return PB200_E_INVALID; }
   memcpy(out_ms, g_phase_ms, sizeof g_phase_ms);
@@ -244,6 +269,7 @@ extern "C" int32_t pb200_init(int32_t device, pb200_ctx** out) {
     t.table_stride = (int)env_i("PB200_TABLE_STRIDE", 0);
     t.skip = getenv("PB200_NO_SKIP") ? 0 : 1;
     t.always_count = getenv("PB200_ALWAYS_COUNT") ? 1 : 0;
+    if (const char* e = getenv("PB200_RAW_DICT_MAX")) t.raw_dict_max = std::max(0, atoi(e));
   }
   *out = ctx;
   return PB200_OK;
@@ -271,6 +297,7 @@ extern "C" int32_t pb200_tuning_set(pb200_ctx* ctx, const char* name, int64_t va
   else if (n == "table_stride") t.table_stride = (int)value;
   else if (n == "skip") t.skip = value != 0;
   else if (n == "always_count") t.always_count = value != 0;
+  else if (n == "raw_dict_max") t.raw_dict_max = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 28));
   else { set_error("unknown tuning knob '%s'", name); return PB200_E_INVALID; }
   return PB200_OK;
 }
@@ -994,14 +1021,19 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
       } else if (n.op == PB200_F_DOC_MASK) {
         const size_t need = ((size_t)seg->num_docs + 31) / 32;
         if ((size_t)n.num_ids < need || !n.ids) { set_error("DOC_MASK needs %zu words, got %d", need, n.num_ids); return PB200_E_INVALID; }
-        size_t words = (((size_t)seg->num_docs + kMaxTileRows - 1) / kMaxTileRows + 1) * (kMaxTileRows / 32) + 8;
-        plan.temps.emplace_back(new DevBuf());
-        int rc = plan.temps.back()->alloc(ctx, words * 4);
-        if (rc) return rc;
-        uint32_t* mask = (uint32_t*)plan.temps.back()->p;
-        PB200_CUDA(cudaMemsetAsync(mask + need, 0, (words - need) * 4, st));
-        PB200_CUDA(cudaMemcpyAsync(mask, n.ids, need * 4, cudaMemcpyHostToDevice, st));
-        PB200_CUDA(cudaStreamSynchronize(st));  // caller's buffer may be a temporary
+        uint32_t* mask;
+        if (n.reserved & PB200_NODE_IDS_ON_DEVICE) {
+          mask = reinterpret_cast<uint32_t*>(const_cast<int32_t*>(n.ids));  // made by pb200_doc_mask_upload: padded, resident
+        } else {
+          const size_t words = doc_mask_words(seg->num_docs);
+          plan.temps.emplace_back(new DevBuf());
+          int rc = plan.temps.back()->alloc(ctx, words * 4);
+          if (rc) return rc;
+          mask = (uint32_t*)plan.temps.back()->p;
+          PB200_CUDA(cudaMemsetAsync(mask + need, 0, (words - need) * 4, st));
+          PB200_CUDA(cudaMemcpyAsync(mask, n.ids, need * 4, cudaMemcpyHostToDevice, st));
+          PB200_CUDA(cudaStreamSynchronize(st));  // caller's buffer may be a temporary
+        }
         lf.kind = LEAF_DOCMASK;
         lf.bits = mask;
       } else if (n.op == PB200_F_DOC_RANGES) {
@@ -1620,6 +1652,28 @@ extern "C" int32_t pb200_result_fetch(const pb200_result* R, int32_t* keys, doub
     if (dbl && R->dbl[a].size() == rows && rows) memcpy(dbl + a * rows, R->dbl[a].data(), rows * 8);
     if (lng && R->lng[a].size() == rows && rows) memcpy(lng + a * rows, R->lng[a].data(), rows * 8);
     if (ids && R->ids[a].size() == rows && rows) memcpy(ids + a * rows, R->ids[a].data(), rows * 4);
+  }
+  return PB200_OK;
+}
+extern "C" int32_t pb200_result_columns(const pb200_result* R, const int32_t** keys, const double** dbl, const int64_t** lng, const int32_t** ids) {
+  if (!R) { set_error("null result"); return PB200_E_INVALID; }
+  const size_t rows = R->meta.num_groups < 0 ? 1 : (size_t)R->meta.num_groups;
+  const int nagg = R->meta.num_aggs;
+  if (R->view.block) {
+    const pb200_result::View& v = R->view;
+    if (keys) *keys = v.rows && R->meta.num_group_by ? v.keys : nullptr;
+    for (int a = 0; a < nagg; a++) {
+      if (dbl) dbl[a] = v.rows ? v.dbl[a] : nullptr;
+      if (lng) lng[a] = v.rows ? v.lng[a] : nullptr;
+      if (ids) ids[a] = v.rows ? v.ids[a] : nullptr;
+    }
+    return PB200_OK;
+  }
+  if (keys) *keys = R->keys.empty() ? nullptr : R->keys.data();
+  for (int a = 0; a < nagg; a++) {
+    if (dbl) dbl[a] = (a < (int)R->dbl.size() && R->dbl[a].size() == rows && rows) ? R->dbl[a].data() : nullptr;
+    if (lng) lng[a] = (a < (int)R->lng.size() && R->lng[a].size() == rows && rows) ? R->lng[a].data() : nullptr;
+    if (ids) ids[a] = (a < (int)R->ids.size() && R->ids[a].size() == rows && rows) ? R->ids[a].data() : nullptr;
   }
   return PB200_OK;
 }

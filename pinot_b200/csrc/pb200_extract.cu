@@ -9,10 +9,12 @@
 //   scan    one CTA per result turns the chunk counts into exclusive offsets and the result's group count;
 //   write   every chunk compacts its groups IN RAW-KEY ORDER (the iteration order of the reference's array based holder)
 //           and writes, per group, the decoded key dictIds and per aggregation the intermediate the caller reads
-//           (double value incl. dictionary lookups for MIN / MAX, long count, MIN / MAX dictId) straight into a mapped
-//           pinned block -- no device staging copy, no host conversion loop; accessors memcpy columns out of that block.
-// Small results (worst case <= kSpeculativeBytes) do all three launches back to back and synchronise ONCE; large ones
-// read the group counts first and then size the block exactly.
+//           (double value incl. dictionary lookups for MIN / MAX, long count, MIN / MAX dictId) in the final column layout
+//           -- no host conversion loop; accessors read (or hand out) columns of that pinned block.
+// Small results (worst case <= kSpeculativeBytes) do all three launches back to back, write STRAIGHT into the mapped
+// pinned block and synchronise ONCE.  Larger ones read the group counts first, size the block exactly, compact into a
+// device staging buffer and move it with ONE DMA copy: device stores into mapped host memory reach ~5 GB/s (measured:
+// 1 M groups x 48 B in 9.2 ms, 100 000 groups in 0.77 ms), the copy engine ~50 GB/s.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -25,7 +27,7 @@ namespace pb200 {
 
 constexpr int kChunk = 2048;             // table entries per CTA
 constexpr int kExtractThreads = 256;     // 8 consecutive entries per thread
-constexpr size_t kSpeculativeBytes = 64ull << 20;
+constexpr size_t kSpeculativeBytes = 512ull << 10;
 constexpr unsigned long long kNoCol = ~0ull;
 
 struct ExtractDesc {
@@ -276,9 +278,13 @@ int extract_groups(pb200_ctx* ctx, pb200_result* const* Rs, int nres, cudaStream
     if ((rc = pinned_alloc(ctx, off, &pin2->p, &pin2->bytes))) return rc;
     pin = pin2;
     out = static_cast<unsigned char*>(pin->p);
+    DevBufRaw staging(ctx);
+    if ((rc = staging.alloc(off))) return rc;
     PB200_CUDA(cudaMemcpyAsync(ddesc.p, descs.data(), sizeof(ExtractDesc) * nres, cudaMemcpyHostToDevice, st));
-    if (chunks) extract_write_kernel<<<chunks, kExtractThreads, 0, st>>>((const ExtractDesc*)ddesc.p, nres, (const uint32_t*)dcount.p, out);
+    if (chunks) extract_write_kernel<<<chunks, kExtractThreads, 0, st>>>((const ExtractDesc*)ddesc.p, nres, (const uint32_t*)dcount.p, (unsigned char*)staging.p);
     PB200_CUDA(cudaGetLastError());
+    const size_t head = 64 + 8ull * nres;  // the block's header is not written by the kernel
+    if (off > head) PB200_CUDA(cudaMemcpyAsync(out + head, (unsigned char*)staging.p + head, off - head, cudaMemcpyDeviceToHost, st));
     PB200_CUDA(cudaStreamSynchronize(st));
   }
   // ---- results point into the block ----

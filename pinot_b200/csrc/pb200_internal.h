@@ -71,6 +71,7 @@ struct Tuning {
   int pack_shift = 0;            // PB200_PACK_SHIFT: force the carrier's count shift (tests of the overflow fallback); 0 = from the doc count
   int skip = 1;                  // !PB200_NO_SKIP: bitmap-driven slice skipping
   int always_count = 0;          // PB200_ALWAYS_COUNT
+  int raw_dict_max = 1 << 20;    // PB200_RAW_DICT_MAX: raw columns with at most this many distinct values are dictionary-encoded at load (0 = never)
 };
 }  // namespace pb200
 

@@ -91,9 +91,10 @@ def device_buffers(ctx, block) -> Dict[str, "torch.Tensor"]:
 class DeviceBackend:
     """The tables of libpinot_b200.so results (the product path)."""
 
-    def __init__(self, plan_maker):
+    def __init__(self, plan_maker, views: bool = False):
         self.pm = plan_maker
         self.ctx = plan_maker.ctx
+        self.views = views   # results on the root alias the pinned block (plan_maker._read_views) instead of being copied
 
     @property
     def native(self) -> bool:
@@ -112,7 +113,7 @@ class DeviceBackend:
             return None, True
         out = None
         if self.ctx.comm_rank == dst:
-            out = _read_result(self.ctx, block.handle, query, 1, keep_handle=False)
+            out = _read_result(self.ctx, block.handle, query, 1, keep_handle=False, views=getattr(self, "views", False))
         else:
             self.ctx.lib.pb200_result_free(block.handle)
         block.handle = None
@@ -140,7 +141,7 @@ class DeviceBackend:
         out = None
         if is_root:
             _lib.check(self.ctx.lib.pb200_result_finalize(self.ctx.handle, block.handle))
-            out = _read_result(self.ctx, block.handle, query, 1, keep_handle=False)
+            out = _read_result(self.ctx, block.handle, query, 1, keep_handle=False, views=getattr(self, "views", False))
         else:
             self.ctx.lib.pb200_result_free(block.handle)
         block.handle = None

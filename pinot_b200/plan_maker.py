@@ -312,7 +312,12 @@ class ResultsBlock:
     flag_slot: bool = False  # the int64 table block ends with this rank's unsafe verdict: all-reduce it with the tables
 
     def release(self, ctx: "B200Context") -> None:
-        """Frees the native result of a block executed with keep_handle=True."""
+        """Frees the native result of a block executed with keep_handle=True (or views=True: the arrays die with it)."""
+        native = getattr(self, "_native", None)
+        if native is not None:
+            native.free()
+            self.handle = None
+            return
         if self.handle is not None:
             ctx.lib.pb200_result_free(self.handle)
             self.handle = None
@@ -381,13 +386,66 @@ def _marshal_query(q: QueryContext, merge: bool, reduce_world: int = 0, no_count
     return hq, (c_nodes, c_lits, gb, gb_names, aggs, keep)
 
 
-def _read_result(ctx: B200Context, handle, q: QueryContext, kind: int, keep_handle: bool) -> ResultsBlock:
+class _NativeResult:
+    """Owner of a native pb200_result whose columns numpy arrays alias (views=True): freed with the block (or release())."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+
+    def free(self):
+        if self.handle is not None:
+            self.lib.pb200_result_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _read_views(ctx: B200Context, handle, q: QueryContext, meta):
+    """Zero-copy face (pb200_result_columns): numpy arrays over the pinned block the device extracted the groups into --
+    what a JVM does with NewDirectByteBuffer.  Absent columns are read-only broadcast constants."""
+    g = meta.num_groups
+    rows = 1 if g < 0 else g
+    k, na = len(q.group_by), len(q.aggregations)
+    kp = C.c_void_p()
+    dp, lp, ip = (C.c_void_p * na)(), (C.c_void_p * na)(), (C.c_void_p * na)()
+    _lib.check(ctx.lib.pb200_result_columns(handle, C.byref(kp), dp, lp, ip))
+
+    def wrap(ptr, n, ctype, dtype, neutral):
+        if not ptr or n == 0:
+            return np.broadcast_to(np.asarray(neutral, dtype=dtype), (n,))
+        return np.frombuffer((ctype * n).from_address(ptr), dtype=dtype)
+    keys = (wrap(kp.value, max(g, 0) * k, C.c_int32, np.int32, 0).reshape(max(g, 0), k) if (g > 0 and k > 0 and kp.value)
+            else np.zeros((max(g, 0), k), dtype=np.int32))
+    doubles = [wrap(dp[a], rows, C.c_double, np.float64, 0.0) for a in range(na)]
+    longs = [wrap(lp[a], rows, C.c_int64, np.int64, 0) for a in range(na)]
+    ids = [wrap(ip[a], rows, C.c_int32, np.int32, -1) for a in range(na)]
+    return keys, doubles, longs, ids
+
+
+def _read_result(ctx: B200Context, handle, q: QueryContext, kind: int, keep_handle: bool, views: bool = False) -> ResultsBlock:
     L = ctx.lib
     meta = _lib.ResultMeta()
     _lib.check(L.pb200_result_meta_get(handle, C.byref(meta)))
     g = meta.num_groups
     rows = 1 if g < 0 else g
     k = len(q.group_by)
+    if views and not any(a.function == "DISTINCTCOUNT" for a in q.aggregations):
+        keys, doubles, longs, ids = _read_views(ctx, handle, q, meta)
+        stats = ExecutionStatistics(meta.num_docs_scanned, meta.num_entries_scanned_in_filter,
+                                    meta.num_entries_scanned_post_filter, meta.num_total_docs)
+        block = ResultsBlock(g, _lib.REGIMES[meta.regime], bool(meta.groups_limit_reached), stats, keys, doubles, longs,
+                             ids, {}, meta.device_ms, _lib.OPERATOR_KINDS.get(kind, "AGGREGATION"))
+        block.count_carrier = bool(meta.reserved & 1)
+        block.carrier_unsafe = bool(meta.reserved & 2)
+        block.flag_slot = bool(meta.reserved & 4)
+        block._native = _NativeResult(L, handle)   # the arrays alias the result's pinned block: it lives as long as the block
+        if keep_handle:
+            block.handle = handle
+        return block
     keys = np.zeros((max(g, 0), k), dtype=np.int32)
     na = len(q.aggregations)
     d_all = np.zeros((na, rows), dtype=np.float64)
@@ -484,7 +542,7 @@ class B200PlanMaker:
 
     def execute_segments(self, segments: Sequence[IndexSegment], query: QueryContext, merge: bool = False,
                          keep_handle: bool = False, reduce_world: int = 0, merged_docs_bound: int = 0,
-                         no_count_carrier: bool = False, defer: Optional[bool] = None) -> List[ResultsBlock]:
+                         no_count_carrier: bool = False, defer: Optional[bool] = None, views: bool = False) -> List[ResultsBlock]:
         """All segments of one query in ONE device submission (makeInstancePlan-level batching).  With merge=True the
         segments (sharing dictionaries) are combined on the device and one block is returned; with keep_handle=True as
         well, a group-by block comes back WITHOUT its groups extracted (PB200_Q_DEFER_FINALIZE): its dense device tables
@@ -506,7 +564,9 @@ class B200PlanMaker:
         res = (C.c_void_p * nres)()
         kinds = (C.c_int32 * n)()
         _lib.check(self.ctx.lib.pb200h_execute(self.ctx.handle, C.byref(hq), segs, n, res, kinds))
-        blocks = [_read_result(self.ctx, C.c_void_p(res[i]), query, kinds[i if not merge else 0], keep_handle)
+        # views=True: the blocks' arrays alias the native results' pinned memory (no copy); keep the block alive while you
+        # use them and drop it before the context closes
+        blocks = [_read_result(self.ctx, C.c_void_p(res[i]), query, kinds[i if not merge else 0], keep_handle, views)
                   for i in range(nres)]
         self.last_device_ms = blocks[0].device_ms
         return blocks

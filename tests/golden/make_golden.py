@@ -18,6 +18,11 @@ Outputs (all small, committed):
                          star_tree_index_map.txt): a real star-tree built by the reference, golden bytes for
                          OffHeapStarTree / fixed-bit dims / raw fixed-byte metric chunks.
 
+  raw_forward/           pinot-segment-local/src/test/resources/data/{fixedByteRaw.v2, fixedByteCompressed.v2,
+                         fixedByteSVRDoubles.v1}: raw (no-dictionary) DOUBLE forward indexes written by old versions of the
+                         reference (PASS_THROUGH v2, SNAPPY v2, SNAPPY v1); expected values per
+                         FixedByteChunkSVForwardIndexTest.java:340-377: value i == i + 100.2356 (2000 docs) / i + 0 (10009 docs).
+
 Only DATA is copied, never reference source code.  The Avro container reader below is written from the Avro 1.x
 specification (null codec, zig-zag varints, union branch index per field, 16-byte sync marker per block).
 """
@@ -133,6 +138,11 @@ def main():
         for m in tf.getmembers():
             if m.isfile():
                 open(os.path.join(HERE, "paddingOld", os.path.basename(m.name)), "wb").write(tf.extractfile(m).read())
+
+    os.makedirs(os.path.join(HERE, "raw_forward"), exist_ok=True)
+    for name in ("fixedByteRaw.v2", "fixedByteCompressed.v2", "fixedByteSVRDoubles.v1"):
+        shutil.copyfile(f"{REF}/pinot-segment-local/src/test/resources/data/{name}", os.path.join(HERE, "raw_forward", name))
+        os.chmod(os.path.join(HERE, "raw_forward", name), 0o644)
 
     st = f"{REF}/pinot-segment-local/src/test/resources/data/startree/segment"
     shutil.copyfile(f"{st}/star_tree_index", os.path.join(HERE, "star_tree_index.bin"))

@@ -12,12 +12,44 @@ def to_device(ctx, seg_data) -> IndexSegment:
     return IndexSegment.from_columns(ctx, seg_data.name, seg_data.num_docs, seg_data.columns)
 
 
-def gpu_table(seg_data, q, block):
-    return normalise(seg_data, q, block.num_groups, block.keys, block.doubles, block.longs, block.distinct)
+class _ProductValues:
+    """id -> value for PRODUCT results: columns the segment stores raw got a dictionary at load (raw_forward.cpp), their ids
+    are resolved through the product's own accessor (pb200h_dictionary_get), everything else through the oracle-built data."""
+
+    def __init__(self, seg_data, dev_seg):
+        self.seg_data, self.dev = seg_data, dev_seg
+        self.cache = {}
+
+    def value_of(self, column, dict_id):
+        if self.seg_data.column(column).has_dictionary:
+            return self.seg_data.value_of(column, dict_id)
+        key = (column, dict_id)
+        if key not in self.cache:
+            self.cache[key] = self.dev.dictionary_value(column, dict_id)
+        return self.cache[key]
+
+
+class _OracleValues:
+    """id -> value for ORACLE results: raw group-by keys are ids of the result's on-the-fly dictionary
+    (NoDictionary*GroupKeyGenerator), see OracleResult.raw_key_values."""
+
+    def __init__(self, seg_data, q, r):
+        self.seg_data = seg_data
+        self.raw = {q.group_by[j]: v for j, v in getattr(r, "raw_key_values", {}).items()}
+
+    def value_of(self, column, dict_id):
+        if column in self.raw:
+            return self.raw[column][dict_id].item()
+        return self.seg_data.value_of(column, dict_id)
+
+
+def gpu_table(seg_data, q, block, dev_seg=None):
+    values = seg_data if dev_seg is None else _ProductValues(seg_data, dev_seg)
+    return normalise(values, q, block.num_groups, block.keys, block.doubles, block.longs, block.distinct)
 
 
 def oracle_table(seg_data, q, r):
-    return normalise(seg_data, q, r.num_groups, r.keys, r.doubles, r.longs, r.distinct)
+    return normalise(_OracleValues(seg_data, q, r), q, r.num_groups, r.keys, r.doubles, r.longs, r.distinct)
 
 
 def assert_tables_equal(q, got, want, what=""):
@@ -38,7 +70,7 @@ def assert_tables_equal(q, got, want, what=""):
 def check_query(oracle, pm, seg_data, dev_seg, q, what=""):
     r = oracle.execute(seg_data, q)
     block = pm.make_segment_plan_node(dev_seg, q).run().next_block()
-    assert_tables_equal(q, gpu_table(seg_data, q, block), oracle_table(seg_data, q, r), what)
+    assert_tables_equal(q, gpu_table(seg_data, q, block, dev_seg), oracle_table(seg_data, q, r), what)
     assert block.stats.num_docs_scanned == r.stats[0], what
     assert block.stats.num_total_docs == r.stats[3], what
     return r, block

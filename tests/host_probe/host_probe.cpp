@@ -94,4 +94,28 @@ int32_t probe_explain(const pb200h_column* cols, int32_t ncols, int32_t num_docs
   return pb200h_explain(nullptr, q, &seg, out, cap);
 }
 
+// raw_forward.cpp: every chunk of a fixed-width raw SV forward index decoded into big-endian values (out: num_docs * width B)
+int32_t probe_decode_fixed_byte_forward(const unsigned char* file, uint64_t len, int32_t width, int64_t num_docs, unsigned char* out) {
+  std::vector<unsigned char> v;
+  int rc = pb200h::decode_fixed_byte_forward(file, len, width, num_docs, v);
+  if (rc) return rc;
+  memcpy(out, v.data(), v.size());
+  return 0;
+}
+
+// raw_forward.cpp: dictionary synthesised from raw values.  Returns 1 (built), 0 (more than max_cardinality distinct values).
+int32_t probe_synthesize_dictionary(const unsigned char* values_be, int32_t data_type, int64_t num_docs, int32_t max_cardinality,
+                                    unsigned char* dict_out, int64_t dict_cap, unsigned char* fwd_out, int64_t fwd_cap,
+                                    int32_t* cardinality, int32_t* bits) {
+  const int w = pb200h::raw_value_width(data_type);
+  std::vector<unsigned char> values(values_be, values_be + (size_t)num_docs * w), dict, fwd;
+  int card = 0, nb = 0;
+  if (!pb200h::synthesize_dictionary(values, data_type, num_docs, max_cardinality, dict, fwd, &card, &nb)) return 0;
+  if ((int64_t)dict.size() > dict_cap || (int64_t)fwd.size() > fwd_cap) return -1;
+  memcpy(dict_out, dict.data(), dict.size());
+  memcpy(fwd_out, fwd.data(), fwd.size());
+  *cardinality = card; *bits = nb;
+  return 1;
+}
+
 }  // extern "C"

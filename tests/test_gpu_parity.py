@@ -346,7 +346,11 @@ def test_raw_forward_index_column(oracle, ctx, pm):
     n = 25_000
     seg = oracle.build_segment("raw", {"m": rng.integers(-10**9, 10**9, size=n).astype(np.int32),
                                        "k": rng.integers(0, 9, size=n).astype(np.int32)}, raw=["m"])
-    dev = to_device(ctx, seg)
+    ctx.set_tuning("raw_dict_max", 0)   # keep the column RAW on the device (default: dictionary synthesised at load, test_gpu_raw.py)
+    try:
+        dev = to_device(ctx, seg)
+    finally:
+        ctx.set_tuning("raw_dict_max", 1 << 20)
     try:
         for text in ("SELECT SUM(m), MIN(m), MAX(m), AVG(m), COUNT(*) FROM t WHERE k > 3",
                      "SELECT SUM(m), MAX(m), MIN(m) FROM t GROUP BY k",

@@ -39,6 +39,11 @@ def probe():
     lib.probe_matching_dict_ids.restype = C.c_int64
     lib.probe_matching_dict_ids.argtypes = [C.POINTER(_lib.HColumn), C.POINTER(_lib.HFilterNode), C.POINTER(_lib.HLiteral),
                                             C.c_void_p, C.c_int64]
+    lib.probe_decode_fixed_byte_forward.restype = C.c_int32
+    lib.probe_decode_fixed_byte_forward.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p]
+    lib.probe_synthesize_dictionary.restype = C.c_int32
+    lib.probe_synthesize_dictionary.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                                C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     return lib
 
 
@@ -284,3 +289,82 @@ def test_product_plan_constant_folding_and_operator_choice(oracle, probe):
     assert explain("SELECT SUM(a) FROM t WHERE NOT (a > 1000)") == "AGGREGATE(FILTER_MATCH_ENTIRE_SEGMENT)"
     g = explain("SELECT SUM(a) FROM t WHERE b != 3 AND s = 2 AND a < 10 GROUP BY b")
     assert g.startswith("GROUP_BY(FILTER_AND(") and "FILTER_SORTED_INDEX" in g and "FILTER_INVERTED_INDEX" in g and "FILTER_FULL_SCAN(RANGE,a,[0,10))" in g
+
+
+# ---- raw (no-dictionary) forward indexes at load: pinot_b200/csrc/host/raw_forward.cpp ------------------------------------
+RAW_FIXTURES = [("fixedByteRaw.v2", 2000, 100.2356), ("fixedByteCompressed.v2", 2000, 100.2356), ("fixedByteSVRDoubles.v1", 10009, 0.0)]
+
+
+def _product_decode(probe, file_bytes, width, n):
+    buf = np.ascontiguousarray(np.frombuffer(bytes(file_bytes), dtype=np.uint8))
+    out = np.zeros(n * width, dtype=np.uint8)
+    rc = probe.probe_decode_fixed_byte_forward(buf.ctypes.data, len(buf), width, n, out.ctypes.data)
+    return rc, out
+
+
+@pytest.mark.parametrize("name,num_docs,start", RAW_FIXTURES)
+def test_product_decodes_the_reference_written_raw_forward_indexes(probe, name, num_docs, start):
+    """FixedByteChunkSVForwardIndexTest.java:340-377 (testBackwardCompatibilityV1 / V2): value i == i + startValue, read from
+    files old versions of the reference wrote (PASS_THROUGH v2, SNAPPY v2, SNAPPY v1)."""
+    from oracle import chunk_codecs as cc
+    blob = np.fromfile(os.path.join(HERE, "golden", "raw_forward", name), dtype=np.uint8)
+    rc, out = _product_decode(probe, blob, 8, num_docs)
+    assert rc == 0
+    want = np.arange(num_docs) + start
+    assert np.array_equal(out.view(">f8"), want)
+    assert np.array_equal(np.frombuffer(cc.decode_fixed_byte_forward(blob, 8, num_docs), dtype=">f8"), want)  # the oracle's codec too
+
+
+@pytest.mark.parametrize("compression", [0, 1, 3, 4])
+@pytest.mark.parametrize("version", [2, 3, 4])
+def test_product_chunk_decoders_equal_the_oracle_codecs(probe, compression, version):
+    """PASS_THROUGH / SNAPPY / LZ4 / LZ4_LENGTH_PREFIXED chunks, int and long chunk offsets, ragged last chunk."""
+    from oracle import chunk_codecs as cc
+    rng = np.random.default_rng(100 * version + compression)
+    for dt, n in ((">i4", 2501), (">i8", 1000), (">f4", 999), (">f8", 4097), (">i4", 1)):
+        kind = rng.integers(0, 3)
+        vals = (rng.integers(0, 40, size=n) if kind == 0 else rng.integers(-2**31, 2**31 - 1, size=n) if kind == 1
+                else np.repeat(rng.integers(0, 1000, size=n // 7 + 1), 7)[:n])
+        body = vals.astype(dt).tobytes()
+        width = np.dtype(dt).itemsize
+        f = cc.encode_fixed_byte_forward(body, width, n, compression, version, docs_per_chunk=int(rng.choice([100, 1000, 4096])))
+        rc, out = _product_decode(probe, f, width, n)
+        assert rc == 0 and out.tobytes() == body == cc.decode_fixed_byte_forward(f, width, n), (dt, n, compression, version)
+    # truncated file: an error, not a crash or silent garbage
+    body = np.arange(3000).astype(">f8").tobytes()
+    f = cc.encode_fixed_byte_forward(body, 8, 3000, compression, version, docs_per_chunk=1000)
+    assert _product_decode(probe, f[: len(f) - 9], 8, 3000)[0] != 0
+    width, n = 8, 3000
+    # ZSTANDARD / GZIP: refused
+    z = f.copy(); z[20:24] = [0, 0, 0, 2]
+    assert _product_decode(probe, z, width, n)[0] != 0
+
+
+@pytest.mark.parametrize("np_type,data_type", [(np.int32, sb.INT), (np.int64, sb.LONG), (np.float32, sb.FLOAT), (np.float64, sb.DOUBLE)])
+def test_product_dictionary_synthesis_equals_a_sorted_unique_dictionary(oracle, probe, np_type, data_type):
+    """A raw column with few distinct values becomes dictionary + fixed-bit forward index at load: the dictionary must be the
+    sorted distinct values (SegmentDictionaryCreator order) and the forward index the FixedBitSVForwardIndexWriter layout."""
+    rng = np.random.default_rng(int(data_type) + 5)
+    for card, n in ((1, 10), (2, 33), (3, 1000), (257, 5000), (4000, 4000)):
+        pool = (rng.integers(-10**9, 10**9, size=card) * (1 if np_type in (np.int32,) else 3)).astype(np_type)
+        if np_type in (np.float32, np.float64):
+            pool = (pool / 7.0).astype(np_type)
+            pool[0] = -0.0 if card > 1 else pool[0]
+        vals = pool[rng.integers(0, card, size=n)]
+        be = {np.int32: ">i4", np.int64: ">i8", np.float32: ">f4", np.float64: ">f8"}[np_type]
+        body = np.ascontiguousarray(np.frombuffer(vals.astype(be).tobytes(), dtype=np.uint8))
+        width = np.dtype(be).itemsize
+        dict_out = np.zeros(n * width, dtype=np.uint8)
+        fwd_out = np.zeros(n * 4 + 8, dtype=np.uint8)
+        c, b = C.c_int32(), C.c_int32()
+        assert probe.probe_synthesize_dictionary(body.ctypes.data, data_type, n, 1 << 20, dict_out.ctypes.data, len(dict_out),
+                                                 fwd_out.ctypes.data, len(fwd_out), C.byref(c), C.byref(b)) == 1
+        uniq, inv = np.unique(vals, return_inverse=True)
+        assert c.value == len(uniq) and b.value == sb.num_bits_per_value(len(uniq) - 1)
+        assert np.array_equal(dict_out[: c.value * width].view(be).astype(np_type), uniq)
+        ids = oracle.read_dict_ids(fwd_out, n, b.value, np.arange(n, dtype=np.int32))
+        assert np.array_equal(ids, inv.astype(np.int32))
+        # too many distinct values: stays raw
+        if len(uniq) > 2:
+            assert probe.probe_synthesize_dictionary(body.ctypes.data, data_type, n, len(uniq) - 1, dict_out.ctypes.data, len(dict_out),
+                                                     fwd_out.ctypes.data, len(fwd_out), C.byref(c), C.byref(b)) == 0

@@ -57,10 +57,13 @@ def main():
     q = sql.parse("SELECT SUM(m1), MAX(m2) FROM t WHERE f BETWEEN 3001 AND 5998 GROUP BY g1, g2",
                   num_groups_limit=1_000_000)
 
+    from pinot_b200.distributed import DeviceBackend
+    backend = DeviceBackend(pm, views=True)   # the root's results block aliases the pinned block the device extracted into
+
     def step():
         if world > 1:  # dense tables stay on the device, are reduced once over NCCL, rank 0 extracts the groups
-            return execute_and_combine(pm, segs, q, dist, dst=0)
-        return pm.execute_segments(segs, q, merge=True)[0]
+            return execute_and_combine(backend, segs, q, dist, dst=0)
+        return pm.execute_segments(segs, q, merge=True, views=True)[0]
 
     for _ in range(args.warmup):
         out = step()
@@ -105,6 +108,7 @@ def main():
         print(json.dumps({"workload": "C4", "n_gpus": world, "segments_per_gpu": args.segments_per_gpu, "rows_per_segment": args.rows,
                           "groups": out.num_groups, "ms_per_step": el / args.steps * 1e3, "rows_per_s": rows / (el / args.steps),
                           "kernel_ms_rank0": pm.last_device_ms, "check": ok}))
+    out = None
     for s in segs:
         s.destroy()
     ctx.close()

@@ -81,10 +81,10 @@ def main():
         for plan, use in (("raw_scan", False), ("star_tree", True)):
             q = sql.parse(text, use_star_tree=use, num_groups_limit=2_000_000)
             for _ in range(args.warmup):
-                b = pm.execute_segments([seg], q)[0]
+                b = pm.execute_segments([seg], q, views=True)[0]
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                b = pm.execute_segments([seg], q)[0]
+                b = pm.execute_segments([seg], q, views=True)[0]
             ms = (time.perf_counter() - t0) / args.steps * 1e3
             assert b.operator_kind == ("STAR_TREE" if use else ("GROUP_BY" if q.is_group_by else "AGGREGATION")), b.operator_kind
             tables[plan] = gpu_table(host, q, b)
@@ -96,6 +96,7 @@ def main():
         res["identical"] = True
         out["queries"].append(res)
     print(json.dumps(out))
+    b = None
     seg.destroy()
     ctx.close()
 
