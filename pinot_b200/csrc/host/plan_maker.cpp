@@ -610,6 +610,14 @@ extern "C" int32_t pb200h_segment_load_dir(pb200_ctx* ctx, const char* path, pb2
       read_file(dir + "/" + n + ".bitmap.inv", b.inv);
     }
     if (!ok) continue;  // index kinds outside this path: column not registered
+    if (!has_dict) {
+      // raw columns this loader cannot decode (var-byte types, ZSTANDARD / GZIP chunks) are left out like any other index
+      // kind outside the path: queries touching them fall back to the stock operator, the rest of the segment loads
+      if (raw_value_width(type) == 0 || b.fwd.size() < 16) continue;
+      const int version = (int)hbe32(b.fwd.data());
+      const int compression = version > 1 && b.fwd.size() >= 28 ? (int)hbe32(b.fwd.data() + 20) : 1;
+      if (compression != 0 && compression != 1 && compression != 3 && compression != 4) continue;
+    }
     bufs.push_back(std::move(b));
     kept.push_back(n);
     pb200h_column c;

@@ -39,6 +39,32 @@ def test_load_segment_directory(oracle, ctx, tmp_path, version):
         dev.destroy()
 
 
+@pytest.mark.parametrize("version", ["v1", "v3"])
+def test_load_directory_with_compressed_raw_columns(oracle, ctx, tmp_path, version):
+    """Raw metric / dimension columns as a table config with noDictionaryColumns writes them (`<col>.sv.raw.fwd` /
+    `forward_index` in columns.psf; Snappy, LZ4 and PASS_THROUGH chunks): loaded from disk, decoded and dictionary-encoded
+    at load, queried as aggregation arguments, filter columns and GROUP BY keys."""
+    rng = np.random.default_rng(13)
+    n = 12_345
+    seg = oracle.build_segment("raw_disk", {
+        "ts": (1_700_000_000_000 + rng.integers(0, 500, size=n).astype(np.int64) * 60_000),     # raw LONG, LZ4 (dimension default)
+        "price": (rng.integers(0, 2000, size=n) / 100.0).astype(np.float64),                     # raw DOUBLE, PASS_THROUGH (metric default)
+        "qty": rng.integers(1, 50, size=n).astype(np.int32),                                     # raw INT, SNAPPY
+        "k": rng.integers(0, 12, size=n).astype(np.int32)},
+        raw=["ts", "price", "qty"], raw_compression={"ts": 3, "price": 0, "qty": 1})
+    root = write_segment_dir(str(tmp_path / version), seg, version)
+    dev = IndexSegment.load(ctx, root)
+    pm = B200PlanMaker(ctx)
+    try:
+        for text in ("SELECT SUM(price), MAX(ts), MIN(qty), COUNT(*) FROM t WHERE ts >= 1700000600000 AND qty < 40",
+                     "SELECT SUM(qty), AVG(price) FROM t WHERE price BETWEEN 2.5 AND 17.25 GROUP BY k",
+                     "SELECT COUNT(*), SUM(price) FROM t WHERE k != 3 GROUP BY ts",
+                     "SELECT MAX(price) FROM t GROUP BY qty, k"):
+            check_query(oracle, pm, seg, dev, sql.parse(text, num_groups_limit=1_000_000), what=f"{version}: {text}")
+    finally:
+        dev.destroy()
+
+
 def test_load_directory_with_star_tree(oracle, ctx, tmp_path):
     rng = np.random.default_rng(12)
     n = 40_000
