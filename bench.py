@@ -307,14 +307,29 @@ def main():
     gen_s = time.perf_counter() - t_gen
     rows_per_step = args.segments * args.rows
     domain = None
+    combine_kind = "none (one GPU)"
     if dist is not None:
         # the per-GPU group tables are merged BY VALUE: all ranks' segments share table-wide dictionaries for the group key
         # and the summed column (synthetic dictionaries are identical, so binding re-encodes nothing)
         from pinot_b200.distributed import DeviceBackend, global_domain, init_comm
         combine_backend = DeviceBackend(pm, views=True)
         domain = global_domain(ctx, segs, ["c3", "c5"], dist)
+        combine_kind = "torch.distributed reduce of the aliased device tables"
         if os.environ.get("PB200_TORCH_REDUCE", "0") != "1":
-            init_comm(ctx, dist)   # the reduce of the group tables runs inside libpinot_b200.so (pb200_result_combine)
+            # the reduce of the group tables runs inside libpinot_b200.so (pb200_result_combine); every rank must take the
+            # same route, so the outcome of the attempt is agreed on first
+            try:
+                init_comm(ctx, dist)
+                ok = 1
+            except Exception as e:  # NCCL not loadable by the library: the torch-driven reduce is the same protocol
+                sys.stderr.write(f"in-library combine unavailable ({e}); using torch.distributed\n")
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{local_rank}")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                combine_kind = "in-library NCCL group (pb200_result_combine)"
+            else:
+                ctx.comm_world = 0
 
     def barrier():
         if dist is not None:
@@ -514,7 +529,7 @@ def main():
                                     "kernel": "pb200::scan_kernel<6,false> (aggregation only)", "kernel_ms": c2_kms,
                                     "algorithmic_bytes_per_launch": alg},
                        "result": {"sum_c5": c2_out[0], "count": c2_out[1], "scope": "rank 0's segments"}},
-                "clocks": clocks, "segment_generation_s": gen_s,
+                "clocks": clocks, "segment_generation_s": gen_s, "cross_gpu_combine": combine_kind,
                 "result": {"groups": len(gb_table), "matched": sum(c for _, c in gb_table.values()),
                            "sum_c5": sum(s for s, _ in gb_table.values()), "scope": "all ranks (reduced to rank 0)"}}
         print(json.dumps(line))

@@ -172,3 +172,89 @@ JNIEXPORT jintArray JNICALL CLS(resultDistinct)(JNIEnv* env, jclass cls, jlong r
 JNIEXPORT jint JNICALL CLS(resultFree)(JNIEnv* env, jclass cls, jlong result) {
   return pb200_result_free((pb200_result*)(intptr_t)result);
 }
+
+/* pb200_result_columns: one direct ByteBuffer per column of the pinned block (no copy); the Java side sets ByteOrder.nativeOrder() */
+JNIEXPORT jobjectArray JNICALL CLS(resultColumns)(JNIEnv* env, jclass cls, jlong result) {
+  const pb200_result* R = (const pb200_result*)(intptr_t)result;
+  pb200_result_meta m;
+  if (pb200_result_meta_get(R, &m) != PB200_OK) return NULL;
+  const int32_t* keys = NULL;
+  const double* d[8] = {0};
+  const int64_t* l[8] = {0};
+  const int32_t* ids[8] = {0};
+  if (pb200_result_columns(R, &keys, d, l, ids) != PB200_OK) return NULL;
+  const jlong rows = m.num_groups < 0 ? 1 : m.num_groups;
+  jclass bb = (*env)->FindClass(env, "java/nio/ByteBuffer");
+  jobjectArray out = (*env)->NewObjectArray(env, 1 + 3 * m.num_aggs, bb, NULL);
+  if (keys) (*env)->SetObjectArrayElement(env, out, 0, (*env)->NewDirectByteBuffer(env, (void*)keys, rows * m.num_group_by * 4));
+  for (int a = 0; a < m.num_aggs; a++) {
+    if (d[a]) (*env)->SetObjectArrayElement(env, out, 1 + a, (*env)->NewDirectByteBuffer(env, (void*)d[a], rows * 8));
+    if (l[a]) (*env)->SetObjectArrayElement(env, out, 1 + m.num_aggs + a, (*env)->NewDirectByteBuffer(env, (void*)l[a], rows * 8));
+    if (ids[a]) (*env)->SetObjectArrayElement(env, out, 1 + 2 * m.num_aggs + a, (*env)->NewDirectByteBuffer(env, (void*)ids[a], rows * 4));
+  }
+  return out;
+}
+
+JNIEXPORT jbyteArray JNICALL CLS(commUniqueId)(JNIEnv* env, jclass cls) {
+  unsigned char id[PB200_COMM_ID_BYTES];
+  if (pb200_comm_unique_id(id) != PB200_OK) return NULL;
+  jbyteArray out = (*env)->NewByteArray(env, PB200_COMM_ID_BYTES);
+  (*env)->SetByteArrayRegion(env, out, 0, PB200_COMM_ID_BYTES, (const jbyte*)id);
+  return out;
+}
+
+JNIEXPORT jint JNICALL CLS(commInit)(JNIEnv* env, jclass cls, jlong ctx, jbyteArray id, jint rank, jint world) {
+  jbyte* p = (*env)->GetByteArrayElements(env, id, NULL);
+  int rc = pb200_comm_init((pb200_ctx*)(intptr_t)ctx, p, rank, world);
+  (*env)->ReleaseByteArrayElements(env, id, p, JNI_ABORT);
+  return rc;
+}
+
+JNIEXPORT jint JNICALL CLS(resultCombine)(JNIEnv* env, jclass cls, jlong ctx, jlong result, jint root) {
+  int32_t retry = 0;
+  int rc = pb200_result_combine((pb200_ctx*)(intptr_t)ctx, (pb200_result*)(intptr_t)result, root, &retry);
+  return rc != PB200_OK ? rc : retry;
+}
+
+JNIEXPORT jlong JNICALL CLS(docMaskUpload)(JNIEnv* env, jclass cls, jlong ctx, jint numDocs, jintArray words) {
+  jint* p = (*env)->GetIntArrayElements(env, words, NULL);
+  uint32_t* dev = NULL;
+  int rc = pb200_doc_mask_upload((pb200_ctx*)(intptr_t)ctx, numDocs, (const uint32_t*)p, (*env)->GetArrayLength(env, words), &dev);
+  (*env)->ReleaseIntArrayElements(env, words, p, JNI_ABORT);
+  return rc == PB200_OK ? (jlong)(intptr_t)dev : 0;
+}
+
+JNIEXPORT jint JNICALL CLS(docMaskFree)(JNIEnv* env, jclass cls, jlong ctx, jlong mask) {
+  return pb200_doc_mask_free((pb200_ctx*)(intptr_t)ctx, (uint32_t*)(intptr_t)mask);
+}
+
+JNIEXPORT jint JNICALL CLS(tuningSet)(JNIEnv* env, jclass cls, jlong ctx, jstring name, jlong value) {
+  const char* n = (*env)->GetStringUTFChars(env, name, NULL);
+  int rc = pb200_tuning_set((pb200_ctx*)(intptr_t)ctx, n, value);
+  (*env)->ReleaseStringUTFChars(env, name, n);
+  return rc;
+}
+
+JNIEXPORT jlong JNICALL CLS(domainFromSegments)(JNIEnv* env, jclass cls, jlong ctx, jlongArray segments, jintArray columns) {
+  const jsize n = (*env)->GetArrayLength(env, segments), k = (*env)->GetArrayLength(env, columns);
+  jlong* s = (*env)->GetLongArrayElements(env, segments, NULL);
+  jint* c = (*env)->GetIntArrayElements(env, columns, NULL);
+  pb200_segment* segs[1024];
+  pb200_domain* dom = NULL;
+  int rc = PB200_E_INVALID;
+  if (n <= 1024) {
+    for (jsize i = 0; i < n; i++) segs[i] = (pb200_segment*)(intptr_t)s[i];
+    rc = pb200_domain_from_segments((pb200_ctx*)(intptr_t)ctx, segs, n, k, (const int32_t*)c, &dom);
+  }
+  (*env)->ReleaseLongArrayElements(env, segments, s, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, columns, c, JNI_ABORT);
+  return rc == PB200_OK ? (jlong)(intptr_t)dom : 0;
+}
+
+JNIEXPORT jint JNICALL CLS(segmentBindDomain)(JNIEnv* env, jclass cls, jlong ctx, jlong segment, jlong domain) {
+  return pb200_segment_bind_domain((pb200_ctx*)(intptr_t)ctx, (pb200_segment*)(intptr_t)segment, (pb200_domain*)(intptr_t)domain);
+}
+
+JNIEXPORT jint JNICALL CLS(domainRelease)(JNIEnv* env, jclass cls, jlong ctx, jlong domain) {
+  return pb200_domain_release((pb200_ctx*)(intptr_t)ctx, (pb200_domain*)(intptr_t)domain);
+}

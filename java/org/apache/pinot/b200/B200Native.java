@@ -57,4 +57,35 @@ public final class B200Native {
   /** pb200_result_fetch: keys [rows x groupBy], doubles / longs / dictIds [aggs x rows] in ONE JNI call (any may be null). */
   public static native int resultFetch(long result, int[] keysOut, double[] doublesOut, long[] longsOut, int[] dictIdsOut);
   public static native int resultFree(long result);
+
+  /**
+   * pb200_result_columns: the result's columns IN PLACE.  Group extraction leaves them in their final layout inside a pinned
+   * host block; each returned buffer is a NewDirectByteBuffer over one column (native byte order; null = neutral column:
+   * 0.0 / 0 / -1 for every row).  Layout of the returned array: [keys, doubles[0..aggs), longs[0..aggs), dictIds[0..aggs)].
+   * Valid until resultFree(result).
+   */
+  public static native java.nio.ByteBuffer[] resultColumns(long result);
+
+  // ---- table-wide dictionaries (pb200_domain_*), see INTEGRATION.md section 6
+  public static native long domainFromSegments(long ctx, long[] segments, int[] columns);
+  public static native int segmentBindDomain(long ctx, long segment, long domain);
+  public static native int domainRelease(long ctx, long domain);
+
+  // ---- cross-GPU combine inside the library (pb200_comm_*): one process (or one context + thread) per GPU
+  /** pb200_comm_unique_id: 128 bytes made by rank 0; ship them to the other ranks over the server's own RPC. */
+  public static native byte[] commUniqueId();
+  public static native int commInit(long ctx, byte[] uniqueId, int rank, int worldSize);
+  /**
+   * pb200_result_combine: every rank passes ITS deferred result (execute with mergeSegments, deferFinalize, reduceWorld =
+   * worldSize).  Returns 0 = combined (read the result on `root`, free it elsewhere), 1 = every rank must run the query again
+   * with noCountCarrier, negative = error.
+   */
+  public static native int resultCombine(long ctx, long result, int root);
+
+  // ---- doc-id sets kept in HBM (pb200_doc_mask_upload): a cached StarTreeFilterOperator / BitmapBasedFilterOperator result
+  public static native long docMaskUpload(long ctx, int numDocs, int[] words);
+  public static native int docMaskFree(long ctx, long mask);
+
+  /** pb200_tuning_set: launch knobs (pinot.server.query.executor.b200.* properties). */
+  public static native int tuningSet(long ctx, String name, long value);
 }

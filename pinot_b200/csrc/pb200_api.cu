@@ -1472,6 +1472,8 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
     if (merge) for (int s = 0; s < nseg; s++) total_docs += segments[s]->num_docs; else total_docs = segments[r]->num_docs;
     R.meta.num_group_by = ngb;
     R.meta.num_aggs = nagg;
+    R.agg_functions.resize(nagg);
+    for (int a = 0; a < nagg; a++) R.agg_functions[a] = q.aggs[a].function;
     R.meta.num_docs_scanned = (int64_t)acc.count;
     long long in_filter = 0;  // device semantics: every scan leaf looks at every doc of its segment
     for (int s = 0; s < nseg; s++) {

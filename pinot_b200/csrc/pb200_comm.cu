@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
@@ -99,8 +100,8 @@ extern "C" int32_t pb200_comm_init(pb200_ctx* ctx, const void* id_bytes, int32_t
   memcpy(&id, id_bytes, sizeof id);
   ncclComm_t comm = nullptr;
   PB200_NCCL(api, api->CommInitRank(&comm, world_size, id, rank));
-  PB200_CUDA(cudaMalloc(&ctx->comm_scratch, 8 * sizeof(long long)));
-  PB200_CUDA(cudaHostAlloc(&ctx->comm_pinned, 16 * sizeof(long long), cudaHostAllocDefault));
+  PB200_CUDA(cudaMalloc(&ctx->comm_scratch, 128 * sizeof(long long)));
+  PB200_CUDA(cudaHostAlloc(&ctx->comm_pinned, 128 * sizeof(long long), cudaHostAllocDefault));
   ctx->nccl_comm = comm;
   ctx->comm_rank = rank;
   ctx->comm_world = world_size;
@@ -122,12 +123,64 @@ extern "C" int32_t pb200_comm_shutdown(pb200_ctx* ctx) {
   return PB200_OK;
 }
 
+// Aggregation-only results (AggregationResultsBlockMerger.java:34-44): a handful of scalars per rank -- sums and counts add,
+// MIN / MAX compare by VALUE (ids of different ranks are only comparable under a domain: dropped).  One NCCL group.
+static int combine_scalars(NcclApi* api, pb200_ctx* ctx, pb200_result* R, int root) {
+  const int nagg = R->meta.num_aggs;
+  if (nagg > kMaxAggs || (int)R->dbl.size() < nagg || (int)R->lng.size() < nagg) { set_error("result is not an aggregation-only result"); return PB200_E_INVALID; }
+  for (int a = 0; a < nagg; a++)
+    if ((int)R->distinct.size() > a && !R->distinct[a].empty()) { set_error("DISTINCTCOUNT sets are merged on the host"); return PB200_E_UNSUPPORTED; }
+  PB200_CUDA(cudaSetDevice(ctx->device));
+  ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+  cudaStream_t st = take_stream(ctx);
+  struct StreamReturn { pb200_ctx* c; cudaStream_t s; ~StreamReturn() { give_stream(c, s); } } stream_return{ctx, st};
+  std::lock_guard<std::mutex> g(ctx->comm_mu);
+  // pinned / device scratch (8-byte slots): [0,4) statistics | [8,16) double sums | [16,24) long counts | [24,32) double mins | [32,40) double maxs; outputs at +64
+  long long* pin = ctx->comm_pinned;
+  double* pd = reinterpret_cast<double*>(pin);
+  pin[0] = R->meta.num_docs_scanned; pin[1] = R->meta.num_entries_scanned_in_filter;
+  pin[2] = R->meta.num_entries_scanned_post_filter; pin[3] = R->meta.num_total_docs;
+  for (int a = 0; a < kMaxAggs; a++) { pd[8 + a] = 0.0; pin[16 + a] = 0; pd[24 + a] = INFINITY; pd[32 + a] = -INFINITY; }
+  for (int a = 0; a < nagg; a++) {
+    const double dv = R->dbl[a].empty() ? 0.0 : R->dbl[a][0];
+    const long long lv = R->lng[a].empty() ? 0 : R->lng[a][0];
+    pd[8 + a] = dv; pin[16 + a] = lv; pd[24 + a] = dv; pd[32 + a] = dv;
+  }
+  long long* dev = ctx->comm_scratch;
+  PB200_CUDA(cudaMemcpyAsync(dev, pin, 40 * sizeof(long long), cudaMemcpyHostToDevice, st));
+  PB200_NCCL(api, api->GroupStart());
+  ncclResult_t r = api->Reduce(dev, dev + 64, 4, ncclInt64, ncclSum, root, comm, st);
+  if (r == ncclSuccess) r = api->Reduce(dev + 8, dev + 64 + 8, 8, ncclFloat64, ncclSum, root, comm, st);
+  if (r == ncclSuccess) r = api->Reduce(dev + 16, dev + 64 + 16, 8, ncclInt64, ncclSum, root, comm, st);
+  if (r == ncclSuccess) r = api->Reduce(dev + 24, dev + 64 + 24, 8, ncclFloat64, ncclMin, root, comm, st);
+  if (r == ncclSuccess) r = api->Reduce(dev + 32, dev + 64 + 32, 8, ncclFloat64, ncclMax, root, comm, st);
+  ncclResult_t e = api->GroupEnd();
+  if (r != ncclSuccess || e != ncclSuccess) { set_error("NCCL reduce of the aggregation scalars failed"); return PB200_E_CUDA; }
+  PB200_CUDA(cudaMemcpyAsync(pin + 64, dev + 64, 40 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  PB200_CUDA(cudaStreamSynchronize(st));
+  if (ctx->comm_rank != root) return PB200_OK;
+  R->meta.num_docs_scanned = pin[64]; R->meta.num_entries_scanned_in_filter = pin[65];
+  R->meta.num_entries_scanned_post_filter = pin[66]; R->meta.num_total_docs = pin[67];
+  // which function each aggregation is: MIN leaves +inf / MAX -inf on empty input, sums 0 -- the caller told us through the
+  // values' roles at execute time (R->agg_functions)
+  for (int a = 0; a < nagg; a++) {
+    const int fn = a < (int)R->agg_functions.size() ? R->agg_functions[a] : PB200_AGG_SUM;
+    if (fn == PB200_AGG_MIN) R->dbl[a][0] = pd[64 + 24 + a];
+    else if (fn == PB200_AGG_MAX) R->dbl[a][0] = pd[64 + 32 + a];
+    else if (fn == PB200_AGG_COUNT) { R->lng[a][0] = pin[64 + 16 + a]; R->dbl[a][0] = (double)pin[64 + 16 + a]; }
+    else { R->dbl[a][0] = pd[64 + 8 + a]; R->lng[a][0] = pin[64 + 16 + a]; }
+    if ((fn == PB200_AGG_MIN || fn == PB200_AGG_MAX) && a < (int)R->ids.size() && !R->ids[a].empty()) R->ids[a][0] = -1;
+  }
+  return PB200_OK;
+}
+
 extern "C" int32_t pb200_result_combine(pb200_ctx* ctx, pb200_result* R, int32_t root, int32_t* retry) {
   if (!ctx || !R || !retry) { set_error("null argument"); return PB200_E_INVALID; }
   *retry = 0;
   NcclApi* api = nccl_api();
   if (!api || !ctx->nccl_comm) { set_error("no communicator: call pb200_comm_init first"); return PB200_E_INVALID; }
   if (root < 0 || root >= ctx->comm_world) { set_error("root %d out of range", root); return PB200_E_INVALID; }
+  if (R->meta.num_groups < 0) return combine_scalars(api, ctx, R, root);
   pb200_result::Dense& d = R->dense;
   if (!d.ctx || !d.live || d.groups <= 0) { set_error("result has no device tables (execute with PB200_Q_MERGE_SEGMENTS | PB200_Q_DEFER_FINALIZE)"); return PB200_E_INVALID; }
   if (d.hkeys) { set_error("hash group tables of different GPUs are not element-wise reducible"); return PB200_E_UNSUPPORTED; }

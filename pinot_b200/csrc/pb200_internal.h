@@ -140,6 +140,7 @@ struct pb200_result {
     const int64_t* lng[pb200::kMaxAggs] = {};      // NULL: all zero
     const int32_t* ids[pb200::kMaxAggs] = {};      // NULL: all -1
   } view;
+  std::vector<int32_t> agg_functions;            // PB200_AGG_* per aggregation (set by pb200_execute)
   std::vector<int32_t> keys;                     // [G x k]
   std::vector<std::vector<double>> dbl;          // per agg [rows]
   std::vector<std::vector<int64_t>> lng;

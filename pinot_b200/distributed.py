@@ -268,6 +268,9 @@ def _combine_with_sets(backend, segments, query, dist, dst):
 
 def _combine_scalars(backend, segments, query, dist, dst):
     """Aggregation-only queries: a handful of scalars per rank (AggregationResultsBlockMerger.java:34-44)."""
+    if getattr(backend, "native", False):   # the scalars meet inside the library too (pb200_comm.cu: combine_scalars)
+        block = backend.pm.execute_segments(segments, query, merge=True, keep_handle=True, defer=False)[0]
+        return backend.combine_native(block, query, dst)[0]
     import torch
     block = backend.pm.execute_segments(segments, query, merge=True)[0]
     fns = [a.function for a in query.aggregations]
@@ -315,9 +318,13 @@ def init_comm(ctx, dist) -> None:
     box = [None]
     if rank == 0:
         buf = (C.c_ubyte * 128)()
-        _lib.check(ctx.lib.pb200_comm_unique_id(buf))
-        box[0] = bytes(buf)
+        if ctx.lib.pb200_comm_unique_id(buf) == 0:
+            box[0] = bytes(buf)
+        else:   # e.g. no libnccl.so.2 for dlopen: tell the other ranks instead of leaving them in the broadcast
+            box[0] = ("error", ctx.lib.pb200_last_error().decode())
     dist.broadcast_object_list(box, src=0)
+    if isinstance(box[0], tuple):
+        raise RuntimeError(f"pb200_comm_unique_id failed on rank 0: {box[0][1]}")
     _lib.check(ctx.lib.pb200_comm_init(ctx.handle, box[0], rank, world))
     ctx.comm_rank, ctx.comm_world = rank, world
 
