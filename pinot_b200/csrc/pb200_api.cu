@@ -1315,8 +1315,12 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
       d.i64_elems = n_i64 * groups; d.f64_elems = n_f64 * groups; d.u32max_elems = n_max * groups; d.u32min_elems = n_min * groups;
       // cross-GPU combine of a count-carrying table: ONE extra int64 behind the tables carries this rank's "not provably
       // safe" verdict (0 / 1), so that the verdicts of all ranks are summed by the same collective that sums the tables
+      // ... and, in front of it, the four execution statistics of this rank: tables, verdict and statistics of a query then
+      // cross the GPUs in ONE collective (pb200_comm.cu).  Tail = {docs scanned, entries in filter, entries post filter,
+      // total docs, verdict}; the verdict stays the LAST element.
       d.flag_slot = d.pack_agg >= 0 && d.reduce_world > 1;
-      if (d.flag_slot) d.i64_elems += 1;
+      d.tail_slots = (d.reduce_world > 1 && d.i64_elems > 0) ? 5 : 0;
+      d.i64_elems += d.tail_slots;
       int rc;
       if ((rc = alloc_block(&d.i64_block, d.i64_elems, 8, 0))) return rc;
       if ((rc = alloc_block(&d.f64_block, d.f64_elems, 8, 0))) return rc;
@@ -1446,6 +1450,7 @@ static int execute_impl(pb200_ctx* ctx, const pb200_query* query, pb200_segment*
         const unsigned long long sum_lim = ((1ull << d.pack_shift) - 1ull) / w, cnt_lim = ((1ull << (64 - d.pack_shift)) - 1ull) / w;
         res[r]->dense.carrier_unsafe = !exact || vw[1] > sum_lim || vw[2] > cnt_lim;
         if (d.flag_slot) {   // the stream is idle (synchronised above): a blocking 8-byte copy, done before the call returns
+          // (callers that bring their own collective read it from the block; pb200_result_combine rewrites the whole tail)
           const long long verdict = res[r]->dense.carrier_unsafe ? 1 : 0;
           PB200_CUDA(cudaMemcpy((long long*)d.i64_block + (d.i64_elems - 1), &verdict, 8, cudaMemcpyHostToDevice));
         }

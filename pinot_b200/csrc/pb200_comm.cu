@@ -186,6 +186,7 @@ extern "C" int32_t pb200_result_combine(pb200_ctx* ctx, pb200_result* R, int32_t
   if (d.hkeys) { set_error("hash group tables of different GPUs are not element-wise reducible"); return PB200_E_UNSUPPORTED; }
   for (int a = 0; a < kMaxAggs; a++)
     if (d.dbits[a]) { set_error("group-by DISTINCTCOUNT bitsets are not reducible by NCCL (no bitwise OR): merge on the host"); return PB200_E_UNSUPPORTED; }
+  (void)root;
   if (d.pack_agg >= 0 && ctx->comm_world > 1 && !d.flag_slot) {
     set_error("count-carrying table was not sized for a reduce: execute with pb200_query.reduce_world = world size");
     return PB200_E_INVALID;
@@ -197,43 +198,44 @@ extern "C" int32_t pb200_result_combine(pb200_ctx* ctx, pb200_result* R, int32_t
   long long verdict = 0;
   {
     std::lock_guard<std::mutex> g(ctx->comm_mu);  // one communicator: collectives of concurrent queries must not interleave
-    // execution statistics of the whole table (the broker sums them over servers): 4 int64 ride in the same NCCL group
+    // Execution statistics of the whole table (the broker sums them over servers) and the carrier verdict travel in the
+    // TAIL of the int64 table block when there is one -- the headline query then needs exactly ONE collective.  Every block
+    // is all-reduced (NVSwitch: an all-reduce of 1-2 MB is latency bound and at least as fast as a rooted reduce; the other
+    // ranks free their tables anyway).
     long long* pin = ctx->comm_pinned;
     pin[0] = R->meta.num_docs_scanned; pin[1] = R->meta.num_entries_scanned_in_filter;
     pin[2] = R->meta.num_entries_scanned_post_filter; pin[3] = R->meta.num_total_docs;
-    PB200_CUDA(cudaMemcpyAsync(ctx->comm_scratch, pin, 4 * sizeof(long long), cudaMemcpyHostToDevice, st));
-    PB200_NCCL(api, api->GroupStart());
-    ncclResult_t r = api->Reduce(ctx->comm_scratch, ctx->comm_scratch + 4, 4, ncclInt64, ncclSum, root, comm, st);
-    if (r == ncclSuccess && d.i64_elems) {
-      // with a verdict slot every rank needs the summed verdict: all-reduce (same cost at these sizes: latency bound)
-      r = d.flag_slot ? api->AllReduce(d.i64_block, d.i64_block, (size_t)d.i64_elems, ncclInt64, ncclSum, comm, st)
-                      : api->Reduce(d.i64_block, d.i64_block, (size_t)d.i64_elems, ncclInt64, ncclSum, root, comm, st);
-    }
-    if (r == ncclSuccess && d.f64_elems) r = api->Reduce(d.f64_block, d.f64_block, (size_t)d.f64_elems, ncclFloat64, ncclSum, root, comm, st);
-    if (r == ncclSuccess && d.u32max_elems) r = api->Reduce(d.u32max_block, d.u32max_block, (size_t)d.u32max_elems, ncclUint32, ncclMax, root, comm, st);
-    if (r == ncclSuccess && d.u32min_elems) r = api->Reduce(d.u32min_block, d.u32min_block, (size_t)d.u32min_elems, ncclUint32, ncclMin, root, comm, st);
-    ncclResult_t e = api->GroupEnd();
+    pin[4] = d.carrier_unsafe ? 1 : 0;
+    long long* tail = d.tail_slots == 5 ? (long long*)d.i64_block + (d.i64_elems - 5) : ctx->comm_scratch;
+    PB200_CUDA(cudaMemcpyAsync(tail, pin, 5 * sizeof(long long), cudaMemcpyHostToDevice, st));
+    int nops = (d.tail_slots == 5 ? 0 : 1) + (d.i64_elems ? 1 : 0) + (d.f64_elems ? 1 : 0) + (d.u32max_elems ? 1 : 0) + (d.u32min_elems ? 1 : 0);
+    if (nops > 1) PB200_NCCL(api, api->GroupStart());
+    ncclResult_t r = ncclSuccess;
+    if (d.tail_slots != 5) r = api->AllReduce(tail, tail, 5, ncclInt64, ncclSum, comm, st);
+    if (r == ncclSuccess && d.i64_elems) r = api->AllReduce(d.i64_block, d.i64_block, (size_t)d.i64_elems, ncclInt64, ncclSum, comm, st);
+    if (r == ncclSuccess && d.f64_elems) r = api->AllReduce(d.f64_block, d.f64_block, (size_t)d.f64_elems, ncclFloat64, ncclSum, comm, st);
+    if (r == ncclSuccess && d.u32max_elems) r = api->AllReduce(d.u32max_block, d.u32max_block, (size_t)d.u32max_elems, ncclUint32, ncclMax, comm, st);
+    if (r == ncclSuccess && d.u32min_elems) r = api->AllReduce(d.u32min_block, d.u32min_block, (size_t)d.u32min_elems, ncclUint32, ncclMin, comm, st);
+    ncclResult_t e = nops > 1 ? api->GroupEnd() : ncclSuccess;
     if (r != ncclSuccess || e != ncclSuccess) {
       set_error("NCCL reduce of the group tables failed: %s", api->GetErrorString ? api->GetErrorString(r != ncclSuccess ? r : e) : "error");
       return PB200_E_CUDA;
     }
-    pin[8] = 0;
-    if (d.flag_slot) PB200_CUDA(cudaMemcpyAsync(pin + 8, (const long long*)d.i64_block + (d.i64_elems - 1), 8, cudaMemcpyDeviceToHost, st));
-    PB200_CUDA(cudaMemcpyAsync(pin + 4, ctx->comm_scratch + 4, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    PB200_CUDA(cudaMemcpyAsync(pin + 8, tail, 5 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     if (ctx->comm_rank == root) {
       // the root extracts SPECULATIVELY behind the reduce on the same stream (the verdict is almost always "safe"): one
       // host sync for reduce + verdict + extraction instead of two; an unsafe verdict just discards the extraction
       pb200_result* one[1] = {R};
-      const int rc = extract_groups(ctx, one, 1, st);
-      if (rc && !(d.flag_slot && pin[8] != 0)) return rc;
+      const int rc = extract_groups(ctx, one, 1, st);   // synchronises the stream: pin[8..13) has landed
+      if (rc && !(d.pack_agg >= 0 && pin[12] != 0)) return rc;
     }
     PB200_CUDA(cudaStreamSynchronize(st));
-    verdict = pin[8];
+    verdict = d.pack_agg >= 0 ? pin[12] : 0;
     if (ctx->comm_rank == root && verdict == 0) {
-      R->meta.num_docs_scanned = pin[4]; R->meta.num_entries_scanned_in_filter = pin[5];
-      R->meta.num_entries_scanned_post_filter = pin[6]; R->meta.num_total_docs = pin[7];
+      R->meta.num_docs_scanned = pin[8]; R->meta.num_entries_scanned_in_filter = pin[9];
+      R->meta.num_entries_scanned_post_filter = pin[10]; R->meta.num_total_docs = pin[11];
     }
   }
-  if (d.flag_slot && verdict != 0) *retry = 1;  // identical on every rank: all free the result and rerun without the carrier
+  if (verdict != 0) *retry = 1;  // identical on every rank: all free the result and rerun without the carrier
   return PB200_OK;
 }

@@ -162,7 +162,8 @@ struct pb200_result {
     const unsigned long long* exists_packed = nullptr;  // that table: non-zero <=> the group exists
     int reduce_world = 1;                               // tables of this many GPUs will be summed into it
     bool carrier_unsafe = false;                        // its sum field may overflow in that reduce: rerun without carrier
-    bool flag_slot = false;                             // i64 block has one extra element: this rank's unsafe verdict (0 / 1)
+    bool flag_slot = false;                             // the i64 block's LAST element is this rank's unsafe verdict (0 / 1)
+    int tail_slots = 0;                                 // i64 block ends with {4 execution statistics, verdict} (reduce_world > 1)
     long long* isum[pb200::kMaxAggs] = {};
     double* dsum[pb200::kMaxAggs] = {};
     uint32_t* gmin[pb200::kMaxAggs] = {};
