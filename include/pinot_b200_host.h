@@ -152,6 +152,14 @@ typedef struct {
   int32_t reduce_world;   /* merge_segments == 2: pb200_query.reduce_world */
   int32_t no_count_carrier; /* PB200_Q_NO_COUNT_CARRIER */
   int64_t merged_docs_bound;
+  /* FILTER (WHERE ...) clauses (QueryContext.getFilteredAggregationFunctions, AggregationFunctionUtils.java:312-403):
+   * aggregation a is filtered iff agg_filter_count[a] > 0; its postfix tree is agg_filter_nodes[agg_filter_start[a] ..
+   * + agg_filter_count[a]) (literals shared with `filter`); equal (start, count) = the same clause.  NULL arrays: none.
+   * Every distinct clause runs as one device submission over (filter AND clause), the functions without a clause over
+   * `filter`; results are aligned by group key like FilteredGroupByOperator's shared key generator does. */
+  const pb200h_filter_node* agg_filter_nodes;
+  const int32_t* agg_filter_start;
+  const int32_t* agg_filter_count;
 } pb200h_query;
 
 /* Which operator the plan maker chose per segment (AggregationPlanNode / GroupByPlanNode decisions). */

@@ -837,12 +837,12 @@ OpPtr make_empty(int n) { auto o = std::make_unique<FilterOp>(); o->kind = Filte
 OpPtr make_match_all(int n) { auto o = std::make_unique<FilterOp>(); o->kind = FilterOp::MATCH_ALL; o->num_docs = n; return o; }
 
 // FilterPlanNode.constructPhysicalOperator (core/plan/FilterPlanNode.java:195-320) + FilterOperatorUtils and/or/not
-OpPtr build_filter(const Segment& seg, const po_query_t& q) {
+OpPtr build_filter_nodes(const Segment& seg, const po_query_t& q, const po_filter_node_t* nodes, int num_nodes) {
   int nd = seg.num_docs();
-  if (q.num_filter_nodes == 0) return make_match_all(nd);
+  if (num_nodes == 0) return make_match_all(nd);
   std::vector<OpPtr> stack;
-  for (int i = 0; i < q.num_filter_nodes; i++) {
-    const po_filter_node_t& n = q.filter[i];
+  for (int i = 0; i < num_nodes; i++) {
+    const po_filter_node_t& n = nodes[i];
     if (n.type == PO_DOCIDS) {
       auto o = std::make_unique<FilterOp>();
       o->kind = FilterOp::DOCIDS; o->num_docs = nd; o->doc_ids = q.doc_ids; o->num_doc_ids = q.num_doc_ids;
@@ -878,6 +878,8 @@ OpPtr build_filter(const Segment& seg, const po_query_t& q) {
   }
   return std::move(stack.back());
 }
+
+OpPtr build_filter(const Segment& seg, const po_query_t& q) { return build_filter_nodes(seg, q, q.filter, q.num_filter_nodes); }
 
 struct ExecCtx {
   bool and_scan_reordering = false;
@@ -1201,23 +1203,65 @@ struct AggState {
 void run_query(const Segment& seg, const po_query_t& q, po_result& res, std::vector<int32_t>* doc_ids_out,
                int64_t doc_ids_cap) {
   const int num_docs = seg.num_docs();
-  ExecCtx ctx;
-  ctx.and_scan_reordering = q.and_scan_reordering != 0;
-  OpPtr filter = build_filter(seg, q);
-  ItPtr it = make_iterator(*filter, ctx);
-
   const int nagg = q.num_aggs, k = q.num_group_by;
-  std::vector<AggState> aggs(nagg);
-  std::vector<int> projected;  // distinct columns projected (aggregation args + group-by)
-  auto add_projected = [&](int c) { if (c >= 0 && std::find(projected.begin(), projected.end(), c) == projected.end()) projected.push_back(c); };
-  for (int a = 0; a < nagg; a++) {
-    aggs[a].spec = q.aggs[a];
-    if (q.aggs[a].function != PO_COUNT) {
-      aggs[a].col = &seg.cols[q.aggs[a].column];
-      add_projected(q.aggs[a].column);
+
+  // ---- aggregation infos: AggregationFunctionUtils.buildFilteredAggregationInfos (:312-403).  Without FILTER clauses: one
+  // info = (main filter, all functions).  With them: one info per distinct FILTER, its filter = main AND sub
+  // (CombinedFilterOperator; sub alone when the main filter matches everything or the sub filter matches nothing; a sub
+  // filter that matches everything makes its functions non-filtered), then the main info with the non-filtered functions --
+  // for GROUP BY queries even when that list is empty, so that every group of the main filter exists (:388-400).
+  struct Info { OpPtr filter; std::vector<int> aggs; };
+  std::vector<Info> infos;
+  bool any_filtered = false;
+  for (int a = 0; a < nagg && q.agg_filter_count; a++) any_filtered |= q.agg_filter_count[a] > 0;
+  {
+    OpPtr main_op = build_filter(seg, q);
+    if (!any_filtered || main_op->kind == FilterOp::EMPTY) {
+      Info one; one.filter = std::move(main_op);
+      for (int a = 0; a < nagg; a++) one.aggs.push_back(a);
+      infos.push_back(std::move(one));
+    } else {
+      std::vector<int> non_filtered;
+      std::vector<std::pair<int, int>> seen;  // (start, count) of distinct FILTER trees, first-appearance order
+      for (int a = 0; a < nagg; a++) {
+        if (q.agg_filter_count[a] <= 0) { non_filtered.push_back(a); continue; }
+        const std::pair<int, int> key(q.agg_filter_start[a], q.agg_filter_count[a]);
+        size_t at = std::find(seen.begin(), seen.end(), key) - seen.begin();
+        if (at == seen.size()) {
+          seen.push_back(key);
+          OpPtr sub = build_filter_nodes(seg, q, q.agg_filter_nodes + key.first, key.second);
+          Info inf;
+          if (sub->kind == FilterOp::MATCH_ALL && main_op->kind != FilterOp::MATCH_ALL) inf.filter = nullptr;  // == main: non-filtered
+          else if (main_op->kind == FilterOp::MATCH_ALL || sub->kind == FilterOp::EMPTY) inf.filter = std::move(sub);
+          else {
+            auto o = std::make_unique<FilterOp>();
+            o->kind = FilterOp::AND; o->num_docs = num_docs;
+            o->children.push_back(build_filter(seg, q));
+            o->children.push_back(std::move(sub));
+            inf.filter = std::move(o);
+          }
+          infos.push_back(std::move(inf));
+        }
+        infos[at].aggs.push_back(a);
+      }
+      std::vector<Info> kept;
+      for (auto& inf : infos) {
+        if (!inf.filter) non_filtered.insert(non_filtered.end(), inf.aggs.begin(), inf.aggs.end());
+        else kept.push_back(std::move(inf));
+      }
+      infos = std::move(kept);
+      if (!non_filtered.empty() || k > 0) {
+        Info m; m.filter = std::move(main_op); m.aggs = non_filtered;
+        infos.push_back(std::move(m));
+      }
     }
   }
-  for (int j = 0; j < k; j++) add_projected(q.group_by_columns[j]);
+
+  std::vector<AggState> aggs(nagg);
+  for (int a = 0; a < nagg; a++) {
+    aggs[a].spec = q.aggs[a];
+    if (q.aggs[a].function != PO_COUNT) aggs[a].col = &seg.cols[q.aggs[a].column];
+  }
 
   GroupKeyGenerator gkg;
   if (k > 0) {
@@ -1240,11 +1284,21 @@ void run_query(const Segment& seg, const po_query_t& q, po_result& res, std::vec
   std::vector<int> doc_ids(kMaxDocPerCall), group_keys(kMaxDocPerCall);
   std::vector<std::vector<int>> gb_dict_ids(k, std::vector<int>(kMaxDocPerCall));
   std::map<int, std::vector<int>> col_dict_ids;   // DataBlockCache: dictIds per projected dict column per block
-  int64_t docs_scanned = 0;
+  int64_t total_docs_scanned = 0, total_in_filter = 0, total_post_filter = 0;
 
   for (int a = 0; a < nagg; a++) aggs[a].ensure(1);
 
-  // GroupByOperator.getNextBlock :101-140 / AggregationOperator.getNextBlock :64-80
+  // FilteredGroupByOperator.getNextBlock :113-160 / FilteredAggregationOperator: the infos run one after the other and
+  // SHARE the group key generator; statistics add up.  (One info = GroupByOperator :101-140 / AggregationOperator :64-80.)
+  for (Info& info : infos) {
+  ExecCtx ctx;
+  ctx.and_scan_reordering = q.and_scan_reordering != 0;
+  ItPtr it = make_iterator(*info.filter, ctx);
+  std::vector<int> projected;  // distinct columns this info projects (its aggregation arguments + group-by)
+  auto add_projected = [&](int c) { if (c >= 0 && std::find(projected.begin(), projected.end(), c) == projected.end()) projected.push_back(c); };
+  for (int a : info.aggs) if (q.aggs[a].function != PO_COUNT) add_projected(q.aggs[a].column);
+  for (int j = 0; j < k; j++) add_projected(q.group_by_columns[j]);
+  int64_t docs_scanned = 0;
   while (true) {
     // DocIdSetOperator.getNextBlock :59-86
     int n = 0;
@@ -1284,7 +1338,8 @@ void run_query(const Segment& seg, const po_query_t& q, po_result& res, std::vec
       int cap = gkg.current_upper_bound();
       for (auto& a : aggs) a.ensure(cap);
     }
-    for (auto& a : aggs) {
+    for (int ai : info.aggs) {
+      AggState& a = aggs[ai];
       const int fn = a.spec.function;
       if (fn == PO_COUNT) {  // CountAggregationFunction.java:84-143
         if (k == 0) a.dbl[0] += n;
@@ -1335,12 +1390,16 @@ void run_query(const Segment& seg, const po_query_t& q, po_result& res, std::vec
     }
   }
 
-  // ExecutionStatistics (GroupByOperator.java:148-153 / AggregationOperator)
+  // ExecutionStatistics (GroupByOperator.java:148-153 / AggregationOperator; FilteredGroupByOperator.java:148-150 sums them)
   int64_t in_filter = 0;
   for (ScanIterator* s : ctx.scans) in_filter += s->entries_scanned();
-  res.stats[0] = docs_scanned;
-  res.stats[1] = in_filter;
-  res.stats[2] = docs_scanned * (int64_t)projected.size();
+  total_docs_scanned += docs_scanned;
+  total_in_filter += in_filter;
+  total_post_filter += docs_scanned * (int64_t)projected.size();
+  }  // infos
+  res.stats[0] = total_docs_scanned;
+  res.stats[1] = total_in_filter;
+  res.stats[2] = total_post_filter;
   res.stats[3] = num_docs;
 
   res.num_group_by = k;

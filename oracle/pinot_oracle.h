@@ -91,6 +91,12 @@ typedef struct {
   int32_t and_scan_reordering;                /* query option AndScanReordering, default 0 */
   int64_t num_doc_ids;                        /* PO_DOCIDS leaf: sorted doc ids */
   const int32_t* doc_ids;
+  /* FILTER (WHERE ...) per aggregation (QueryContext.getFilteredAggregationFunctions): aggregation a is filtered iff
+   * agg_filter_count[a] > 0, its postfix tree is agg_filter_nodes[agg_filter_start[a] .. + agg_filter_count[a]) (literals
+   * shared with the main filter); equal (start, count) = the same FILTER.  NULL arrays: no filtered aggregation. */
+  const po_filter_node_t* agg_filter_nodes;
+  const int32_t* agg_filter_start;
+  const int32_t* agg_filter_count;
 } po_query_t;
 
 enum { PO_REGIME_NONE = 0, PO_REGIME_ARRAY = 1, PO_REGIME_INT_MAP = 2, PO_REGIME_LONG_MAP = 3, PO_REGIME_ARRAY_MAP = 4, PO_REGIME_NO_DICT = 5 };

@@ -54,7 +54,9 @@ class _Query(C.Structure):
                 ("num_group_by", C.c_int32), ("group_by_columns", C.POINTER(C.c_int32)), ("num_aggs", C.c_int32),
                 ("aggs", C.POINTER(_Agg)), ("num_groups_limit", C.c_int32),
                 ("max_initial_result_holder_capacity", C.c_int32), ("and_scan_reordering", C.c_int32),
-                ("num_doc_ids", C.c_int64), ("doc_ids", C.c_void_p)]
+                ("num_doc_ids", C.c_int64), ("doc_ids", C.c_void_p),
+                ("agg_filter_nodes", C.POINTER(_FilterNode)), ("agg_filter_start", C.POINTER(C.c_int32)),
+                ("agg_filter_count", C.POINTER(C.c_int32))]
 
 
 class _StarPredicate(C.Structure):
@@ -280,26 +282,46 @@ class Oracle:
                 return _Literal(int(v), float(v), None)
             return _Literal(0, float(v), None)
 
-        c_nodes = (_FilterNode * max(1, len(nodes)))()
-        for i, n in enumerate(nodes):
-            if isinstance(n, str):
-                c_nodes[i] = _FilterNode(8, -1, 0, 0, 0, 0, 0, 0, 0)  # PO_DOCIDS
+        def encode(node_list):
+            out = []
+            for n in node_list:
+                if isinstance(n, str):
+                    out.append(_FilterNode(8, -1, 0, 0, 0, 0, 0, 0, 0))  # PO_DOCIDS
+                    continue
+                if isinstance(n, Filter):
+                    out.append(_FilterNode(_TYPE_CODES[n.type], -1, len(n.children), 0, 0, 0, 0, 0, 0))
+                    continue
+                ci = seg.column_index(n.column)
+                col = seg.columns[ci]
+                off = len(lits)
+                if n.type == "RANGE":
+                    lits.append(lit(col, n.lower if n.lower is not None else 0))
+                    lits.append(lit(col, n.upper if n.upper is not None else 0))
+                    out.append(_FilterNode(_TYPE_CODES["RANGE"], ci, 0, int(n.lower_inclusive), int(n.upper_inclusive),
+                                           int(n.lower is None), int(n.upper is None), 2, off))
+                else:
+                    for v in n.values:
+                        lits.append(lit(col, v))
+                    out.append(_FilterNode(_TYPE_CODES[n.type], ci, 0, 0, 0, 0, 0, len(n.values), off))
+            return out
+        enc = encode(nodes)
+        c_nodes = (_FilterNode * max(1, len(enc)))(*enc)
+        # FILTER (WHERE ...) clauses: one postfix tree per DISTINCT clause, concatenated
+        agg_nodes, starts, counts, seen = [], [], [], {}
+        for a in q.aggregations:
+            f = getattr(a, "filter", None)
+            if f is None:
+                starts.append(0); counts.append(0)
                 continue
-            if isinstance(n, Filter):
-                c_nodes[i] = _FilterNode(_TYPE_CODES[n.type], -1, len(n.children), 0, 0, 0, 0, 0, 0)
-                continue
-            ci = seg.column_index(n.column)
-            col = seg.columns[ci]
-            off = len(lits)
-            if n.type == "RANGE":
-                lits.append(lit(col, n.lower if n.lower is not None else 0))
-                lits.append(lit(col, n.upper if n.upper is not None else 0))
-                c_nodes[i] = _FilterNode(_TYPE_CODES["RANGE"], ci, 0, int(n.lower_inclusive), int(n.upper_inclusive),
-                                         int(n.lower is None), int(n.upper is None), 2, off)
-            else:
-                for v in n.values:
-                    lits.append(lit(col, v))
-                c_nodes[i] = _FilterNode(_TYPE_CODES[n.type], ci, 0, 0, 0, 0, 0, len(n.values), off)
+            key = repr(f)
+            if key not in seen:
+                e = encode(list(postfix(f)))
+                seen[key] = (len(agg_nodes), len(e))
+                agg_nodes += e
+            starts.append(seen[key][0]); counts.append(seen[key][1])
+        c_agg_nodes = (_FilterNode * max(1, len(agg_nodes)))(*agg_nodes)
+        c_starts = (C.c_int32 * max(1, len(starts)))(*starts)
+        c_counts = (C.c_int32 * max(1, len(counts)))(*counts)
         c_lits = (_Literal * max(1, len(lits)))(*lits)
         gb = (C.c_int32 * max(1, len(q.group_by)))(*[seg.column_index(c) for c in q.group_by])
         aggs = (_Agg * max(1, len(q.aggregations)))()
@@ -308,8 +330,9 @@ class Oracle:
         ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.int32)
         cq = _Query(len(nodes), c_nodes, c_lits, len(q.group_by), gb, len(q.aggregations), aggs, q.num_groups_limit,
                     q.max_initial_result_holder_capacity, int(q.and_scan_reordering),
-                    0 if ids is None else len(ids), _ptr(ids) if ids is not None and len(ids) else None)
-        return cq, (c_nodes, c_lits, gb, aggs, keep, ids)
+                    0 if ids is None else len(ids), _ptr(ids) if ids is not None and len(ids) else None,
+                    c_agg_nodes, c_starts, c_counts)
+        return cq, (c_nodes, c_lits, gb, aggs, keep, ids, c_agg_nodes, c_starts, c_counts)
 
     def execute(self, seg: sb.SegmentData, q: QueryContext, doc_ids: Optional[np.ndarray] = None) -> OracleResult:
         """== getOperator(query).nextBlock() on one segment (BaseQueriesTest.java:97-102).  `doc_ids` (star-tree

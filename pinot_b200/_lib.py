@@ -103,7 +103,8 @@ class HQuery(C.Structure):
                 ("aggs", C.POINTER(HAgg)), ("num_groups_limit", C.c_int32),
                 ("max_initial_result_holder_capacity", C.c_int32), ("merge_segments", C.c_int32),
                 ("skip_star_tree", C.c_int32), ("reduce_world", C.c_int32), ("no_count_carrier", C.c_int32),
-                ("merged_docs_bound", C.c_int64)]
+                ("merged_docs_bound", C.c_int64), ("agg_filter_nodes", C.POINTER(HFilterNode)),
+                ("agg_filter_start", C.POINTER(C.c_int32)), ("agg_filter_count", C.POINTER(C.c_int32))]
 
 
 class HStarMetric(C.Structure):

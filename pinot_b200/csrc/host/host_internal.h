@@ -140,6 +140,8 @@ int decode_fixed_byte_forward(const unsigned char* file, uint64_t len, int width
 void wrap_pass_through(const std::vector<unsigned char>& values_be, int width, int64_t num_docs, std::vector<unsigned char>& file);
 bool synthesize_dictionary(const std::vector<unsigned char>& values_be, int data_type, int64_t num_docs, int max_cardinality,
                            std::vector<unsigned char>& dict_be, std::vector<unsigned char>& fwd_packed, int* cardinality, int* bits);
+// filtered_agg.cpp: FILTER (WHERE ...) clauses = one device submission per distinct clause, aligned by group key
+int execute_filtered(pb200_ctx* ctx, const pb200h_query& q, pb200h_segment* const* segs, int nseg, pb200_result** results, int32_t* kinds);
 // ids[] storage that must outlive the pb200_execute call
 struct SegmentFilterStore { std::vector<std::unique_ptr<std::vector<int32_t>>> ids; };
 // PredicateEvaluator.getMatchingDictIds (sorted) of one predicate on a dictionary column

@@ -664,6 +664,9 @@ extern "C" int32_t pb200h_execute(pb200_ctx* ctx, const pb200h_query* q, pb200h_
                                   pb200_result** results, int32_t* kinds) {
   if (!ctx || !q || !segs || !results || nseg <= 0) { set_error("invalid argument to pb200h_execute"); return PB200_E_INVALID; }
   if (q->num_aggs <= 0) { set_error("selection queries are outside this path"); return PB200_E_UNSUPPORTED; }
+  if (q->agg_filter_count && q->agg_filter_start && q->agg_filter_nodes)
+    for (int a = 0; a < q->num_aggs; a++)
+      if (q->agg_filter_count[a] > 0) return execute_filtered(ctx, *q, segs, nseg, results, kinds);  // host/filtered_agg.cpp
   const bool merge = q->merge_segments != 0;
   // resolve columns by name against segment 0 (all segments of a table share the schema)
   const pb200h_segment& s0 = *segs[0];

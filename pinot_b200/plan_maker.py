@@ -355,23 +355,45 @@ def _marshal_query(q: QueryContext, merge: bool, reduce_world: int = 0, no_count
         iv = int(v) if float(v).is_integer() else int(np.floor(v))
         return _lib.HLiteral(iv, float(v), None)
 
-    c_nodes = (_lib.HFilterNode * max(1, len(nodes)))()
-    for i, n in enumerate(nodes):
-        if isinstance(n, Filter):
-            c_nodes[i] = _lib.HFilterNode(_lib.FILTER_CODES[n.type], None, len(n.children), 0, 0, 0, 0, 0, 0)
+    def encode(node_list):
+        out = []
+        for n in node_list:
+            if isinstance(n, Filter):
+                out.append(_lib.HFilterNode(_lib.FILTER_CODES[n.type], None, len(n.children), 0, 0, 0, 0, 0, 0))
+                continue
+            cname = n.column.encode()
+            keep.append(cname)
+            off = len(lits)
+            if n.type == "RANGE":
+                lits.append(lit(n.lower if n.lower is not None else 0))
+                lits.append(lit(n.upper if n.upper is not None else 0))
+                out.append(_lib.HFilterNode(_lib.FILTER_CODES["RANGE"], cname, 0, int(n.lower_inclusive),
+                                            int(n.upper_inclusive), int(n.lower is None), int(n.upper is None), 2, off))
+            else:
+                for v in n.values:
+                    lits.append(lit(v))
+                out.append(_lib.HFilterNode(_lib.FILTER_CODES[n.type], cname, 0, 0, 0, 0, 0, len(n.values), off))
+        return out
+    enc = encode(nodes)
+    c_nodes = (_lib.HFilterNode * max(1, len(enc)))(*enc)
+    # FILTER (WHERE ...) clauses: one postfix tree per DISTINCT clause, concatenated (pb200h_query.agg_filter_*)
+    agg_nodes, starts, counts, seen = [], [], [], {}
+    for a in q.aggregations:
+        f = getattr(a, "filter", None)
+        if f is None:
+            starts.append(0)
+            counts.append(0)
             continue
-        cname = n.column.encode()
-        keep.append(cname)
-        off = len(lits)
-        if n.type == "RANGE":
-            lits.append(lit(n.lower if n.lower is not None else 0))
-            lits.append(lit(n.upper if n.upper is not None else 0))
-            c_nodes[i] = _lib.HFilterNode(_lib.FILTER_CODES["RANGE"], cname, 0, int(n.lower_inclusive),
-                                          int(n.upper_inclusive), int(n.lower is None), int(n.upper is None), 2, off)
-        else:
-            for v in n.values:
-                lits.append(lit(v))
-            c_nodes[i] = _lib.HFilterNode(_lib.FILTER_CODES[n.type], cname, 0, 0, 0, 0, 0, len(n.values), off)
+        key = repr(f)
+        if key not in seen:
+            e = encode(postfix(f))
+            seen[key] = (len(agg_nodes), len(e))
+            agg_nodes += e
+        starts.append(seen[key][0])
+        counts.append(seen[key][1])
+    c_agg_nodes = (_lib.HFilterNode * max(1, len(agg_nodes)))(*agg_nodes)
+    c_starts = (C.c_int32 * max(1, len(starts)))(*starts)
+    c_counts = (C.c_int32 * max(1, len(counts)))(*counts)
     c_lits = (_lib.HLiteral * max(1, len(lits)))(*lits)
     gb_names = [c.encode() for c in q.group_by]
     gb = (C.c_char_p * max(1, len(gb_names)))(*gb_names)
@@ -382,8 +404,9 @@ def _marshal_query(q: QueryContext, merge: bool, reduce_world: int = 0, no_count
         aggs[i] = _lib.HAgg(_lib.AGG_CODES[a.function], nm)
     hq = _lib.HQuery(len(nodes), c_nodes, c_lits, len(q.group_by), gb, len(q.aggregations), aggs, q.num_groups_limit,
                      q.max_initial_result_holder_capacity, int(merge), int(not getattr(q, "use_star_tree", True)),
-                     int(reduce_world), int(no_count_carrier), int(merged_docs_bound))
-    return hq, (c_nodes, c_lits, gb, gb_names, aggs, keep)
+                     int(reduce_world), int(no_count_carrier), int(merged_docs_bound),
+                     c_agg_nodes if agg_nodes else None, c_starts if agg_nodes else None, c_counts if agg_nodes else None)
+    return hq, (c_nodes, c_lits, gb, gb_names, aggs, keep, c_agg_nodes, c_starts, c_counts)
 
 
 class _NativeResult:

@@ -47,6 +47,9 @@ FilterNode = Union[Filter, Predicate]
 class Aggregation:
     function: str  # COUNT | SUM | MIN | MAX | AVG | DISTINCTCOUNT
     column: Optional[str] = None  # None for COUNT(*)
+    # FILTER (WHERE ...) clause of this function (QueryContext.getFilteredAggregationFunctions: Pair<function, FilterContext>);
+    # evaluated together with the query's own filter (AggregationFunctionUtils.buildFilteredAggregationInfos)
+    filter: Optional["FilterNode"] = None
 
     def __str__(self):
         return f"{self.function.lower()}({self.column or '*'})"

@@ -171,6 +171,11 @@ def parse(sql: str, **options) -> QueryContext:
                 col = p.ident()
                 aggs.append(Aggregation("COUNT", None) if fn == "COUNT" else Aggregation(fn, col))
             p.expect_op(")")
+            if p.take_kw("FILTER"):   # SUM(x) FILTER (WHERE cond)
+                p.expect_op("(")
+                p.expect_kw("WHERE")
+                aggs[-1].filter = optimize_filter(p.cond())
+                p.expect_op(")")
         else:
             plain.append(name)
         if not p.take_op(","):
