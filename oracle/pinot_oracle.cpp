@@ -1179,6 +1179,8 @@ struct po_result {
   std::vector<int32_t> keys;                       // [G x k]: dictIds; for raw group-by columns ids of raw_key_bits[j]
   std::vector<std::vector<uint64_t>> raw_key_bits; // per group-by column: on-the-fly dictionary (empty for dictionary columns)
   std::vector<int> raw_key_type;                   // per group-by column: PO_* stored type of a raw column, else -1
+  std::vector<std::vector<uint64_t>> raw_distinct_bits;  // per aggregation: on-the-fly value numbering of a raw DISTINCTCOUNT
+  std::vector<int> raw_distinct_type;
   std::vector<std::vector<double>> dbl;            // per agg: [G]
   std::vector<std::vector<int64_t>> lng;           // per agg: [G]
   std::vector<std::vector<std::vector<int32_t>>> distinct;  // per agg: per group: sorted dictIds
@@ -1193,10 +1195,16 @@ struct AggState {
   std::vector<double> dbl;    // SUM / MIN / MAX / AVG.sum / COUNT (double holder, CountAggregationFunction.java:112-116)
   std::vector<int64_t> cnt;   // AVG.count
   std::vector<std::vector<uint8_t>> bits;  // DISTINCTCOUNT: dictId bitset per group (RoaringBitmap of dictIds)
+  // DISTINCTCOUNT over a raw column: value sets (DistinctCountAggregationFunction keeps an IntOpenHashSet / LongOpenHashSet /
+  // FloatOpenHashSet / DoubleOpenHashSet of VALUES when there is no dictionary, BaseDistinctAggregateAggregationFunction
+  // .java:157-200).  Values are numbered in first-seen order (raw_values) and the per-group sets hold those numbers.
+  std::unordered_map<uint64_t, int> raw_ids;
+  std::vector<uint64_t> raw_values;
+  std::vector<std::vector<uint8_t>> raw_bits;  // per group: bitset over raw value numbers
   double def() const { return spec.function == PO_MIN ? INFINITY : spec.function == PO_MAX ? -INFINITY : 0.0; }
   void ensure(int n) {
     if ((int)dbl.size() < n) { dbl.resize(n, def()); cnt.resize(n, 0); }
-    if (spec.function == PO_DISTINCTCOUNT && (int)bits.size() < n) bits.resize(n);
+    if (spec.function == PO_DISTINCTCOUNT && (int)bits.size() < n) { bits.resize(n); raw_bits.resize(n); }
   }
 };
 
@@ -1350,8 +1358,23 @@ void run_query(const Segment& seg, const po_query_t& q, po_result& res, std::vec
       const bool dict = col.c->has_dictionary;
       const std::vector<int>* ids = dict ? &dict_ids_of(a.spec.column) : nullptr;
       auto value_at = [&](int i) -> double { return dict ? col.dict_as_double((*ids)[i]) : col.raw_as_double(doc_ids[i]); };
+      if (fn == PO_DISTINCTCOUNT && !dict) {  // value set of a raw column
+        if (!col.raw.ok || col.c->data_type == PO_STRING) { res.error = "DISTINCTCOUNT on this raw column is not supported by the oracle"; return; }
+        for (int i = 0; i < n; i++) {
+          int g = k == 0 ? 0 : group_keys[i];
+          if (g < 0) continue;
+          const uint64_t vb = col.raw_value_bits(doc_ids[i]);
+          auto f = a.raw_ids.find(vb);
+          int id;
+          if (f != a.raw_ids.end()) id = f->second;
+          else { id = (int)a.raw_values.size(); a.raw_ids.emplace(vb, id); a.raw_values.push_back(vb); }
+          auto& b = a.raw_bits[g];
+          if ((int)b.size() <= id) b.resize(id + 1, 0);
+          b[id] = 1;
+        }
+        continue;
+      }
       if (fn == PO_DISTINCTCOUNT) {  // BaseDistinctAggregateAggregationFunction.java:144-155,306-321
-        if (!dict) { res.error = "DISTINCTCOUNT on raw column not supported by the oracle"; return; }
         for (int i = 0; i < n; i++) {
           int g = k == 0 ? 0 : group_keys[i];
           if (g < 0) continue;
@@ -1416,6 +1439,7 @@ void run_query(const Segment& seg, const po_query_t& q, po_result& res, std::vec
     if (fn == PO_DISTINCTCOUNT) {
       std::vector<int32_t> ids;
       if (g < (int)s.bits.size()) for (int i = 0; i < (int)s.bits[g].size(); i++) if (s.bits[g][i]) ids.push_back(i);
+      if (g < (int)s.raw_bits.size()) for (int i = 0; i < (int)s.raw_bits[g].size(); i++) if (s.raw_bits[g][i]) ids.push_back(i);
       l = (int64_t)ids.size();
       d = (double)l;
       res.distinct[a].push_back(std::move(ids));
@@ -1423,6 +1447,10 @@ void run_query(const Segment& seg, const po_query_t& q, po_result& res, std::vec
     res.dbl[a].push_back(d);
     res.lng[a].push_back(l);
   };
+  res.raw_distinct_bits.resize(nagg);
+  res.raw_distinct_type.assign(nagg, -1);
+  for (int a = 0; a < nagg; a++)
+    if (!aggs[a].raw_values.empty()) { res.raw_distinct_bits[a] = aggs[a].raw_values; res.raw_distinct_type[a] = aggs[a].col->c->data_type; }
   if (k == 0) {
     res.num_groups = -1;
     for (int a = 0; a < nagg; a++) emit_group(a, 0);
@@ -1544,6 +1572,19 @@ int64_t po_result_raw_key_values(const po_result_t* r, int32_t j, double* out_d,
   if (j < 0 || j >= (int)r->raw_key_bits.size()) return 0;
   const auto& v = r->raw_key_bits[j];
   const bool integral = r->raw_key_type[j] == PO_INT || r->raw_key_type[j] == PO_LONG;
+  for (int64_t i = 0; i < (int64_t)v.size() && i < cap; i++) {
+    double d; int64_t l;
+    if (integral) { l = (int64_t)v[i]; d = (double)l; } else { memcpy(&d, &v[i], 8); l = (int64_t)d; }
+    if (out_d) out_d[i] = d;
+    if (out_l) out_l[i] = l;
+  }
+  return (int64_t)v.size();
+}
+// Raw DISTINCTCOUNT of aggregation a: the value numbering its id sets (po_result_distinct) refer to; 0 for dictionary columns.
+int64_t po_result_raw_distinct_values(const po_result_t* r, int32_t a, double* out_d, int64_t* out_l, int64_t cap) {
+  if (a < 0 || a >= (int)r->raw_distinct_bits.size()) return 0;
+  const auto& v = r->raw_distinct_bits[a];
+  const bool integral = r->raw_distinct_type[a] == PO_INT || r->raw_distinct_type[a] == PO_LONG;
   for (int64_t i = 0; i < (int64_t)v.size() && i < cap; i++) {
     double d; int64_t l;
     if (integral) { l = (int64_t)v[i]; d = (double)l; } else { memcpy(&d, &v[i], 8); l = (int64_t)d; }

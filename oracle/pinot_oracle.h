@@ -138,6 +138,7 @@ void po_result_agg_long(const po_result_t* r, int32_t agg, int64_t* out);
 /* DISTINCTCOUNT: sorted dictIds of one group (group = 0 for aggregation only); returns count */
 int64_t po_result_distinct(const po_result_t* r, int32_t agg, int32_t group, int32_t* out, int64_t cap);
 int64_t po_result_raw_key_values(const po_result_t* r, int32_t group_by_column, double* out_d, int64_t* out_l, int64_t cap);
+int64_t po_result_raw_distinct_values(const po_result_t* r, int32_t agg, double* out_d, int64_t* out_l, int64_t cap);
 void po_result_free(po_result_t* r);
 
 /* ---- star-tree (OffHeapStarTree / StarTreeFilterOperator.traverseStarTree) ---- */

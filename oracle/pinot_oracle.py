@@ -89,6 +89,8 @@ class OracleResult:
     distinct: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)  # (agg, group) -> sorted dictIds
     # group-by position j of a RAW column -> its on-the-fly dictionary (id -> value): keys[:, j] are ids into it
     raw_key_values: Dict[int, np.ndarray] = field(default_factory=dict)
+    # aggregation index of a DISTINCTCOUNT over a RAW column -> value numbering (number -> value): distinct[(a, g)] holds numbers
+    raw_distinct_values: Dict[int, np.ndarray] = field(default_factory=dict)
 
 
 class Oracle:
@@ -110,6 +112,8 @@ class Oracle:
         L.po_result_distinct.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
         L.po_result_raw_key_values.restype = C.c_int64
         L.po_result_raw_key_values.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+        L.po_result_raw_distinct_values.restype = C.c_int64
+        L.po_result_raw_distinct_values.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
         L.po_result_free.argtypes = [C.c_void_p]
         L.po_filter_doc_ids.restype = C.c_int64
         L.po_filter_doc_ids.argtypes = [C.POINTER(_Segment), C.POINTER(_Query), C.c_void_p, C.c_int64,
@@ -373,9 +377,16 @@ class Oracle:
                     d, l = np.zeros(n, dtype=np.float64), np.zeros(n, dtype=np.int64)
                     self.lib.po_result_raw_key_values(r, j, _ptr(d), _ptr(l), n)
                     raw_keys[j] = l if seg.column(name).data_type in (sb.INT, sb.LONG) else d
+            raw_distinct = {}
+            for a, agg in enumerate(q.aggregations):
+                n = self.lib.po_result_raw_distinct_values(r, a, None, None, 0) if agg.function == "DISTINCTCOUNT" else 0
+                if n > 0:
+                    d, l = np.zeros(n, dtype=np.float64), np.zeros(n, dtype=np.int64)
+                    self.lib.po_result_raw_distinct_values(r, a, _ptr(d), _ptr(l), n)
+                    raw_distinct[a] = l if seg.column(agg.column).data_type in (sb.INT, sb.LONG) else d
             return OracleResult(g, REGIMES[self.lib.po_result_regime(r)],
                                 bool(self.lib.po_result_groups_limit_reached(r)), tuple(stats), keys, doubles, longs,
-                                distinct, raw_keys)
+                                distinct, raw_keys, raw_distinct)
         finally:
             self.lib.po_result_free(r)
 

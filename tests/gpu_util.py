@@ -49,7 +49,18 @@ def gpu_table(seg_data, q, block, dev_seg=None):
 
 
 def oracle_table(seg_data, q, r):
-    return normalise(_OracleValues(seg_data, q, r), q, r.num_groups, r.keys, r.doubles, r.longs, r.distinct)
+    table = normalise(_OracleValues(seg_data, q, r), q, r.num_groups, r.keys, r.doubles, r.longs,
+                      {k: (v if k[0] not in getattr(r, "raw_distinct_values", {}) else ()) for k, v in r.distinct.items()})
+    # DISTINCTCOUNT over a raw column: the oracle's sets hold numbers of its own value numbering (OracleResult.raw_distinct_values)
+    raw = getattr(r, "raw_distinct_values", {})
+    if raw:
+        rows = 1 if r.num_groups < 0 else r.num_groups
+        values = _OracleValues(seg_data, q, r)
+        for g in range(rows):
+            key = () if r.num_groups < 0 else tuple(values.value_of(c, int(r.keys[g, j])) for j, c in enumerate(q.group_by))
+            for a, numbering in raw.items():
+                table[key][a] = frozenset(numbering[int(i)].item() for i in r.distinct[(a, g)])
+    return table
 
 
 def assert_tables_equal(q, got, want, what=""):

@@ -63,6 +63,10 @@ QUERIES = [
     "SELECT SUM(v), COUNT(*) FROM t GROUP BY rf, k",
     "SELECT SUM(ri), AVG(rd) FROM t WHERE v > 0 GROUP BY rd, rl",
     "SELECT COUNT(*) FROM t GROUP BY k, ri, rf",
+    # DISTINCTCOUNT over raw columns: value sets (DistinctCountAggregationFunction without a dictionary)
+    "SELECT DISTINCTCOUNT(ri), DISTINCTCOUNT(rd), COUNT(*) FROM t WHERE k > 1",
+    "SELECT DISTINCTCOUNT(rl), DISTINCTCOUNT(rf) FROM t WHERE v > 0 GROUP BY k",
+    "SELECT DISTINCTCOUNT(rd) FROM t GROUP BY rf",
 ]
 
 
