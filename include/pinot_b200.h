@@ -34,7 +34,8 @@
 extern "C" {
 #endif
 
-#define PB200_ABI_VERSION 2 /* 2: pb200_query.reduce_world / merged_docs_bound, domains, tuning, pb200_result_meta.reserved bits */
+#define PB200_ABI_VERSION 3 /* 2: pb200_query.reduce_world / merged_docs_bound, domains, tuning, pb200_result_meta.reserved bits;
+                              3: pb200_comm_*, pb200_result_columns, doc masks, pb200h_query.agg_filter_* (the host query struct grew) */
 
 enum {
   PB200_OK = 0,

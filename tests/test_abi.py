@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     assert sorted(set(_lib.EXPORTED_SYMBOLS)) == sorted(set(declared))
-    assert lib.pb200_abi_version() == 2
+    assert lib.pb200_abi_version() == 3
 
 
 def test_init_fails_loudly_without_gpu():
