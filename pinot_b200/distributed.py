@@ -196,17 +196,27 @@ def execute_and_combine(plan_maker_or_backend, segments: Sequence, query, dist, 
         return _combine_scalars(backend, segments, query, dist, dst)
     for no_carrier in (False, True):
         block = backend.execute(segments, query, world, merged_docs_bound, no_carrier)
-        if getattr(backend, "native", False):
-            out, retry = backend.combine_native(block, query, dst)
-        else:
-            out, retry = combine_tables(backend, block, query, dist, dst)
+        try:
+            if getattr(backend, "native", False):
+                out, retry = backend.combine_native(block, query, dst)
+            else:
+                out, retry = combine_tables(backend, block, query, dist, dst)
+        except Exception as e:
+            # Key spaces beyond the dense tables live in per-GPU HASH tables whose slots mean different keys on every rank:
+            # not element-wise reducible.  Every rank gets this refusal before any collective was issued (the key space is the
+            # domain's, identical everywhere), so all of them take the host route together: merge by key like the reference's
+            # combine (IndexedTable.upsert).
+            if "hash group tables" not in str(e):
+                raise
+            backend.free(block)
+            return _combine_with_sets(backend, segments, query, dist, dst)
         if not retry:
             return out
     raise AssertionError("unreachable: the second pass carries no counts")
 
 
 def _combine_with_sets(backend, segments, query, dist, dst):
-    """Queries with DISTINCTCOUNT: the per-group dictId SETS are not one of the element-wise reducible table blocks (NCCL has
+    """Host-side merge BY KEY (also used for per-GPU hash group tables, see execute_and_combine).  Queries with DISTINCTCOUNT: the per-group dictId SETS are not one of the element-wise reducible table blocks (NCCL has
     no bitwise OR), so this path merges on the host like the reference's combine does (BaseDistinctAggregateAggregationFunction
     .merge :109-121 = set union): every rank extracts its combined block, the (key ids, intermediates, id sets) travel with
     all_gather_object and rank `dst` merges them by key.  Ids are only comparable across ranks when the key and DISTINCTCOUNT

@@ -26,6 +26,8 @@ QUERIES = [
     "SELECT COUNT(*), SUM(v), MIN(l), MAX(f) FROM t WHERE v < 400",         # aggregation only
     "SELECT DISTINCTCOUNT(k), DISTINCTCOUNT(l), COUNT(*) FROM t WHERE v > 0",                 # id sets: merged on the host by set union
     "SELECT DISTINCTCOUNT(v), SUM(v), MAX(l) FROM t WHERE j < 6 GROUP BY j",
+    # key space 600+ x 7 x 30 x 2000 > 2^24: per-GPU HASH tables, not element-wise reducible -> merged by key on the host
+    "SELECT SUM(v), COUNT(*), MAX(f) FROM t WHERE v > 900 GROUP BY k, j, l, v",
 ]
 
 
