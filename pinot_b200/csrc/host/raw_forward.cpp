@@ -163,6 +163,7 @@ int decode_fixed_byte_forward(const unsigned char* b, uint64_t len, int width, i
     set_error("raw forward index: version %d, %d chunks of %d docs, entry width %d (expected %d) not understood", version, nchunks, per_chunk, entry, width);
     return PB200_E_UNSUPPORTED;
   }
+  if ((uint64_t)per_chunk * (uint64_t)width > (1ull << 30)) { set_error("raw forward index: %d docs per chunk is not plausible", per_chunk); return PB200_E_INVALID; }
   const int osz = version <= 2 ? 4 : 8;
   const uint64_t data_start = header + (uint64_t)nchunks * osz;
   if (data_start > len || (int64_t)nchunks * per_chunk < num_docs) { set_error("raw forward index: chunk table does not cover %lld docs", (long long)num_docs); return PB200_E_INVALID; }
