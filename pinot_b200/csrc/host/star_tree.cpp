@@ -34,21 +34,32 @@ bool StarTree::parse(const unsigned char* b, uint64_t len) {
   if (len < 24 || le64(b) != 0xBADDA55B00DAD00Dull || le32(b + 8) != 1) return false;
   const uint64_t root = le32(b + 12);
   const int nd = (int)le32(b + 16);
+  if (nd < 0 || nd > 32) return false;  // dimensions are addressed by bits of a 32-bit mask
   uint64_t off = 20;
   dim_names.assign(nd, "");
   for (int i = 0; i < nd; i++) {
     if (off + 8 > len) return false;
     int id = (int)le32(b + off), n = (int)le32(b + off + 4);
     off += 8;
-    if (id < 0 || id >= nd || off + n > len) return false;
+    if (id < 0 || id >= nd || n < 0 || off + (uint64_t)n > len) return false;
     dim_names[id] = std::string((const char*)b + off, n);
     off += n;
   }
+  if (off + 4 > len) return false;
   num_nodes = (int)le32(b + off);
   off += 4;
-  if (off != root || off + 28ull * num_nodes != len) return false;
+  if (num_nodes <= 0 || off != root || off + 28ull * (uint64_t)num_nodes != len) return false;
   bytes.assign(b, b + len);
   nodes = bytes.data() + off;
+  // a malformed buffer must not send the traversal out of bounds or in circles: children lie behind their parent
+  // (OffHeapStarTreeBuilder writes nodes breadth first), inside the node array, first <= last; doc ranges are ordered
+  for (int n = 0; n < num_nodes; n++) {
+    const int fc = first_child(n), lc = last_child(n);
+    if (fc == -1) continue;
+    if (fc <= n || lc < fc || lc >= num_nodes) { nodes = nullptr; num_nodes = 0; return false; }
+  }
+  for (int n = 0; n < num_nodes; n++)
+    if ((!(start(n) == -1 && end(n) == -1) && (start(n) < 0 || end(n) < start(n))) || dim_id(n) >= nd) { nodes = nullptr; num_nodes = 0; return false; }  // (-1, -1): the root
   return true;
 }
 

@@ -397,3 +397,29 @@ def test_product_chunk_decoders_survive_malformed_input(probe):
         ok += rc == 0
         bad += rc != 0
     assert bad > 100 and ok > 0   # both outcomes occur (bit flips inside literals still decode)
+
+
+def test_star_tree_reader_survives_malformed_input(oracle, probe):
+    """Truncated / bit-flipped OffHeapStarTree buffers: rejected (-2) or traversed, never a crash or an endless walk."""
+    blob = np.fromfile(os.path.join(HERE, "golden", "star_tree_index.bin"), dtype=np.uint8)
+    tree = np.ascontiguousarray(blob[:18715])
+    rng = np.random.default_rng(5)
+    cases = [tree[: int(c)].copy() for c in rng.integers(0, len(tree), size=40)]
+    for _ in range(300):
+        g = tree.copy()
+        for pos in rng.integers(0, len(g), size=int(rng.integers(1, 4))):
+            g[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        cases.append(g)
+    dims = np.asarray([0], dtype=np.int32)
+    offsets = np.asarray([0, 2], dtype=np.int32)
+    ids = np.asarray([1, 3, 0], dtype=np.int32)
+    out = np.zeros(2 * 200_001, dtype=np.int32)
+    rejected = walked = 0
+    for g in cases:
+        buf = np.ascontiguousarray(np.concatenate([g, np.zeros(1, dtype=np.uint8)]))
+        rem = C.c_uint32(0)
+        n = probe.probe_startree_traverse(buf.ctypes.data, len(g), 3, 1, dims.ctypes.data, offsets.ctypes.data, ids.ctypes.data, 0b110,
+                                          out.ctypes.data, 200_000, C.byref(rem))
+        rejected += n == -2
+        walked += n >= -1
+    assert rejected > 40 and walked > 0
