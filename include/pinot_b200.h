@@ -283,6 +283,10 @@ int32_t pb200_result_free(pb200_result* result);
 int32_t pb200_result_device_buffers(pb200_result* result, int32_t kind, void** device_ptr, int64_t* num_elements);
 int32_t pb200_result_finalize(pb200_ctx* ctx, pb200_result* result);
 
+/* Structural validation of one serialized RoaringBitmap (portable format) as pb200_segment_register applies it to every
+ * posting list of an inverted index: containers inside the buffer, keys ascending, largest doc id < num_docs.  Pure host. */
+int32_t pb200_roaring_validate(const void* bytes, uint64_t length, int64_t num_docs);
+
 /* ---- resident doc-id sets for PB200_F_DOC_MASK | PB200_NODE_IDS_ON_DEVICE ------------------------------------------- */
 int32_t pb200_doc_mask_upload(pb200_ctx* ctx, int32_t num_docs, const uint32_t* words, int64_t num_words /* >= ceil(num_docs/32) */,
                               uint32_t** device_mask);

@@ -127,7 +127,7 @@ EXPORTED_SYMBOLS = [
     "pb200h_cache_stats", "pb200h_cache_destroy",
     "pb200_domain_create", "pb200_domain_from_segments", "pb200_domain_column_info", "pb200_domain_dictionary",
     "pb200_domain_release", "pb200_segment_bind_domain", "pb200_segment_local_ids",
-    "pb200_last_phases", "pb200_result_columns", "pb200_doc_mask_upload", "pb200_doc_mask_free", "pb200_comm_unique_id", "pb200_comm_init", "pb200_comm_shutdown", "pb200_result_combine",
+    "pb200_last_phases", "pb200_result_columns", "pb200_doc_mask_upload", "pb200_doc_mask_free", "pb200_roaring_validate", "pb200_comm_unique_id", "pb200_comm_init", "pb200_comm_shutdown", "pb200_result_combine",
 ]
 
 _LIB = None
@@ -184,6 +184,7 @@ def load() -> C.CDLL:
     L.pb200h_startree_attach.argtypes = [vp, vp, vp, C.c_uint64, i32, i32, C.POINTER(C.c_char_p), C.POINTER(vp),
                                          C.POINTER(C.c_uint64), i32, C.POINTER(HStarMetric)]
     L.pb200_result_columns.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.pb200_roaring_validate.argtypes = [vp, C.c_uint64, C.c_int64]
     L.pb200_doc_mask_upload.argtypes = [vp, i32, vp, C.c_int64, C.POINTER(vp)]
     L.pb200_doc_mask_free.argtypes = [vp, vp]
     L.pb200_last_phases.argtypes = [C.POINTER(C.c_double)]

@@ -195,6 +195,61 @@ using namespace pb200;
 // ------------------------------------------------------------------------------------------------------------------
 extern "C" const char* pb200_last_error(void) { return g_error; }
 extern "C" int32_t pb200_abi_version(void) { return PB200_ABI_VERSION; }
+// Structural check of ONE serialized RoaringBitmap (portable RoaringFormatSpec, little-endian) before the device reads it in
+// place: header and container table inside the buffer, keys ascending, every container's payload inside the buffer, and the
+// largest doc id below num_docs (so that the decode kernel's mask writes stay inside the mask).  O(containers), no decode.
+extern "C" int32_t pb200_roaring_validate(const void* bytes, uint64_t len, int64_t num_docs) {
+  const unsigned char* b = static_cast<const unsigned char*>(bytes);
+  auto l16 = [&](uint64_t at) { return (uint32_t)b[at] | (uint32_t)b[at + 1] << 8; };
+  auto l32 = [&](uint64_t at) { return (uint32_t)b[at] | (uint32_t)b[at + 1] << 8 | (uint32_t)b[at + 2] << 16 | (uint32_t)b[at + 3] << 24; };
+  if (!b || len < 8) { if (b && len == 0) return PB200_OK; set_error("roaring bitmap shorter than its header"); return PB200_E_INVALID; }
+  const uint32_t cookie = l32(0);
+  const bool has_run = (cookie & 0xFFFFu) == 12347u;
+  uint64_t n, pos;
+  uint64_t run_flags = 0;
+  if (has_run) { n = (uint64_t)(cookie >> 16) + 1; pos = 4; run_flags = pos; pos += (n + 7) / 8; }
+  else if (cookie == 12346u) { n = l32(4); pos = 8; }
+  else { set_error("roaring bitmap: unknown cookie %u", cookie); return PB200_E_INVALID; }
+  if (n > 65536) { set_error("roaring bitmap: %llu containers", (unsigned long long)n); return PB200_E_INVALID; }
+  if (n == 0) return PB200_OK;
+  const uint64_t desc = pos;
+  pos += 4 * n;
+  const bool has_offsets = !has_run || n >= 4;
+  const uint64_t offs = pos;
+  if (has_offsets) pos += 4 * n;
+  if (pos > len) { set_error("roaring bitmap: container table exceeds the buffer"); return PB200_E_INVALID; }
+  uint64_t walk = pos;
+  int64_t prev_key = -1;
+  for (uint64_t c = 0; c < n; c++) {
+    const int64_t key = l16(desc + 4 * c);
+    const uint32_t card = l16(desc + 4 * c + 2) + 1;
+    if (key <= prev_key) { set_error("roaring bitmap: container keys not ascending"); return PB200_E_INVALID; }
+    prev_key = key;
+    const bool is_run = has_run && ((b[run_flags + (c >> 3)] >> (c & 7)) & 1);
+    const uint64_t start = has_offsets ? l32(offs + 4 * c) : walk;
+    uint64_t bytes_c;
+    if (is_run) {
+      if (start + 2 > len) { set_error("roaring bitmap: run container outside the buffer"); return PB200_E_INVALID; }
+      bytes_c = 2 + 4ull * l16(start);
+    } else bytes_c = card > 4096 ? 8192 : 2ull * card;
+    if (start < pos || start + bytes_c > len) { set_error("roaring bitmap: container %llu outside the buffer", (unsigned long long)c); return PB200_E_INVALID; }
+    walk = start + bytes_c;
+    if (c + 1 == n) {  // largest value of the bitmap
+      int64_t top = -1;
+      if (is_run) {
+        const uint32_t nr = l16(start);
+        for (uint32_t r = 0; r < nr; r++) top = std::max<int64_t>(top, (int64_t)l16(start + 2 + 4 * r) + l16(start + 4 + 4 * r));
+      } else if (card > 4096) {
+        for (int w = 2047; w >= 0 && top < 0; w--) { const uint32_t x = l32(start + 4ull * w); if (x) top = 32ll * w + (31 - __builtin_clz(x)); }
+      } else {
+        top = l16(start + 2ull * (card - 1));
+      }
+      if (top > 65535 || (key << 16) + top >= num_docs) { set_error("roaring bitmap: doc id %lld beyond %lld docs", (long long)((key << 16) + top), (long long)num_docs); return PB200_E_INVALID; }
+    }
+  }
+  return PB200_OK;
+}
+
 // words a device doc mask needs: whole tiles + one spare tile (the kernel reads masks tile-wise) + a tail
 static size_t doc_mask_words(long long num_docs) { return (((size_t)num_docs + kMaxTileRows - 1) / kMaxTileRows + 1) * (kMaxTileRows / 32) + 8; }
 
@@ -497,6 +552,13 @@ extern "C" int32_t pb200_segment_register(pb200_ctx* ctx, const char* name, int3
       if (c.inv_offsets[0] != 4u * (c.cardinality + 1) || c.inv_offsets[c.cardinality] > d.inv_bytes) {
         set_error("column %d: inverted index offsets are not in BitmapInvertedIndexWriter layout", i);
         return fail(PB200_E_INVALID);
+      }
+      if (!on_device) {  // the device decodes these bitmaps in place: a corrupt file must fail here, not in a kernel
+        const unsigned char* ib = (const unsigned char*)d.inv;
+        for (int k = 0; k < c.cardinality; k++) {
+          if (c.inv_offsets[k + 1] < c.inv_offsets[k]) { set_error("column %d: inverted index offsets not ascending", i); return fail(PB200_E_INVALID); }
+          if (pb200_roaring_validate(ib + c.inv_offsets[k], c.inv_offsets[k + 1] - c.inv_offsets[k], num_docs) != PB200_OK) return fail(PB200_E_INVALID);
+        }
       }
       seg->device_bytes += (int64_t)d.inv_bytes;
     }

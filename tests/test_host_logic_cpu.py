@@ -423,3 +423,41 @@ def test_star_tree_reader_survives_malformed_input(oracle, probe):
         rejected += n == -2
         walked += n >= -1
     assert rejected > 40 and walked > 0
+
+
+def test_roaring_validation_before_the_device_reads_posting_lists(oracle):
+    """pb200_roaring_validate (applied to every posting list at pb200_segment_register): bitmaps written by the oracle's
+    serializer (array, bitmap and run containers, with and without the offset header) pass; a doc id beyond numDocs, truncated
+    and bit-flipped buffers are rejected or accepted, never crash the process."""
+    lib = _lib.load()
+    rng = np.random.default_rng(31)
+    num_docs = 300_000
+    shapes = [np.sort(rng.choice(num_docs, size=k, replace=False)).astype(np.uint32) for k in (1, 7, 4096, 5000, 70_000, 200_000)]
+    shapes.append(np.arange(1000, 250_000, dtype=np.uint32))                                  # runs
+    shapes.append(np.concatenate([np.arange(10, 60_000), np.arange(70_000, 70_010), np.arange(140_000, 200_000)]).astype(np.uint32))
+    shapes.append(np.zeros(0, dtype=np.uint32))
+    good = []
+    for vals in shapes:
+        for run_opt in (0, 1):
+            blob = oracle.roaring_serialize(vals, bool(run_opt))
+            good.append((np.ascontiguousarray(blob), vals))
+    for blob, vals in good:
+        assert lib.pb200_roaring_validate(blob.ctypes.data, len(blob), num_docs) == 0
+        if len(vals):
+            assert lib.pb200_roaring_validate(blob.ctypes.data, len(blob), int(vals[-1])) != 0    # largest doc id == numDocs: out of range
+            assert lib.pb200_roaring_validate(blob.ctypes.data, len(blob), int(vals[-1]) + 1) == 0
+    rejected = 0
+    for blob, vals in good:
+        if len(blob) < 9:
+            continue
+        for _ in range(80):
+            g = blob.copy()
+            if rng.integers(0, 3) == 0:
+                g = g[: int(rng.integers(1, len(g)))].copy()
+            else:
+                for pos in rng.integers(0, len(g), size=int(rng.integers(1, 4))):
+                    g[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            buf = np.ascontiguousarray(np.concatenate([g, np.zeros(1, dtype=np.uint8)]))
+            rc = lib.pb200_roaring_validate(buf.ctypes.data, len(g), num_docs)
+            rejected += rc != 0
+    assert rejected > 200
