@@ -577,7 +577,7 @@ extern "C" int32_t pb200h_segment_load_dir(pb200_ctx* ctx, const char* path, pb2
     auto so = imap.find(col + "." + kind + ".startOffset"), sz = imap.find(col + "." + kind + ".size");
     if (so == imap.end() || sz == imap.end()) return false;
     unsigned long long off = strtoull(so->second.c_str(), nullptr, 10), size = strtoull(sz->second.c_str(), nullptr, 10);
-    if (size < 8 || off + size > psf.size() || be64(psf.data() + off) != 0xdeadbeefdeafbeadull) return false;  // SingleFileIndexDirectory magic
+    if (size < 8 || off > psf.size() || size > psf.size() - off || be64(psf.data() + off) != 0xdeadbeefdeafbeadull) return false;  // SingleFileIndexDirectory magic
     dst.assign(psf.begin() + off + 8, psf.begin() + off + size);
     return true;
   };
