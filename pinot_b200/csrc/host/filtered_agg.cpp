@@ -95,6 +95,7 @@ int execute_filtered(pb200_ctx* ctx, const pb200h_query& q, pb200h_segment* cons
   if (main_info) { int rc = run(nullptr, 0, non_filtered); if (rc) return rc; }
 
   // ---- align by group key ----
+  std::vector<std::unique_ptr<pb200_result>> aligned(nres);
   for (int r = 0; r < nres; r++) {
     const pb200_result* base = main_info ? info_results.back()[r] : nullptr;  // defines the rows of a GROUP BY result
     pb200_result_meta bm;
@@ -169,8 +170,9 @@ int execute_filtered(pb200_ctx* ctx, const pb200h_query& q, pb200h_segment* cons
         }
       }
     }
-    results[r] = R.release();
+    aligned[r] = std::move(R);
   }
+  for (int r = 0; r < nres; r++) results[r] = aligned[r].release();  // only when every result was built
   if (kinds) for (int s = 0; s < nseg; s++) kinds[s] = ngb > 0 ? PB200H_OP_GROUP_BY : PB200H_OP_AGGREGATION;
   return PB200_OK;
 }
