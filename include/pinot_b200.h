@@ -310,7 +310,9 @@ int32_t pb200_comm_shutdown(pb200_ctx* ctx);
  * of the same query: all table blocks are reduced into rank `root` in ONE NCCL group on the context's stream and the root
  * extracts the groups (the result is then read with the accessors; on the other ranks it stays empty -- free it).
  * *retry = 1 on EVERY rank when a count-carrying sum was not provably safe for the reduce: all ranks free the result and
- * execute again with PB200_Q_NO_COUNT_CARRIER. */
+ * execute again with PB200_Q_NO_COUNT_CARRIER.  It is a COLLECTIVE: all ranks must call it for the same queries in the same
+ * order (calls of one context are serialised internally; concurrent queries need an agreed order across ranks, e.g. the
+ * broker's request id).  Aggregation-only results (num_groups < 0) are combined too (sums / counts add, MIN / MAX by value). */
 int32_t pb200_result_combine(pb200_ctx* ctx, pb200_result* result, int32_t root, int32_t* retry);
 
 /* ---- synthetic segments (SegmentIndexCreationDriverImpl stand-in for benchmarks; bytes are Pinot's formats) ---- */
