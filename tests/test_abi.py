@@ -54,3 +54,13 @@ def test_sql_front_end_shapes():
     assert sorted(c.type for c in q.filter.children) == ["EQ", "IN"]  # MergeEqIn
     with pytest.raises(sql.SqlError):
         sql.parse("SELECT a FROM t")
+
+
+def test_headers_are_plain_c():
+    """The boundary is a C ABI: both headers must compile as C99 on their own (what a cgo / JNI / ctypes binding includes)."""
+    import subprocess
+    for h in ("pinot_b200.h", "pinot_b200_host.h"):
+        src = f'#include "include/{h}"\nint main(void) {{ return 0; }}\n'
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", "-I", ROOT, "-"], input=src.encode(),
+                           capture_output=True, cwd=ROOT)
+        assert r.returncode == 0, r.stderr.decode()
