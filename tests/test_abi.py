@@ -64,3 +64,20 @@ def test_headers_are_plain_c():
         r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", "-I", ROOT, "-"], input=src.encode(),
                            capture_output=True, cwd=ROOT)
         assert r.returncode == 0, r.stderr.decode()
+
+
+def test_jni_stub_type_checks_against_the_header():
+    """No JDK in the image, so the JVM shim cannot be compiled -- but its C half can be TYPE-CHECKED: java/jni/pb200_jni.c against
+    include/pinot_b200.h with a stand-in <jni.h> (tests/jni_stub/): any drift between the stub's calls and the C-ABI
+    (argument count / pointer types / missing functions) fails here.  And every `native` method of B200Native.java has its
+    JNIEXPORT function, and vice versa."""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c11", "-fsyntax-only", "-Werror=implicit-function-declaration", "-Werror=incompatible-pointer-types",
+                        "-Werror=int-conversion", "-I", os.path.join(ROOT, "tests", "jni_stub"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "java", "jni", "pb200_jni.c")], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    java = open(os.path.join(ROOT, "java", "org", "apache", "pinot", "b200", "B200Native.java")).read()
+    natives = set(re.findall(r"public static native [\w\.\[\]<>]+ (\w+)\(", java))
+    stub = open(os.path.join(ROOT, "java", "jni", "pb200_jni.c")).read()
+    exported = set(re.findall(r"CLS\((\w+)\)\(", stub))
+    assert natives == exported, (sorted(natives - exported), sorted(exported - natives))
